@@ -1,0 +1,108 @@
+"""ctypes binding of libehdg.so (include/ehdg.h).  No CPU fallback: a missing library or a
+missing CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libehdg.so")
+
+MAX_ENR = 2
+
+
+class LayerExpr(C.Structure):
+    _fields_ = [("c", C.c_double * 4), ("k", C.c_double * 2)]
+
+
+class Problem(C.Structure):
+    _fields_ = [("order", C.c_int32), ("bonus_int", C.c_int32), ("epsilon", C.c_double),
+                ("beta", C.c_double * 2), ("n_enrich", C.c_int32), ("enrich_axis", C.c_int32 * MAX_ENR),
+                ("enrich_k", C.c_double * MAX_ENR), ("coeff", LayerExpr), ("exact", LayerExpr)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("nv", C.c_int32), ("ne", C.c_int32), ("nf", C.c_int32), ("verts", C.c_void_p),
+                ("tris", C.c_void_p), ("el2facet", C.c_void_p), ("facet2el", C.c_void_p)]
+
+
+class Sizes(C.Structure):
+    _fields_ = [("n_p", C.c_int32), ("nfl", C.c_int32), ("nb", C.c_int32), ("nvmax", C.c_int32),
+                ("nfmax", C.c_int32), ("nf_poly", C.c_int32), ("nq", C.c_int32), ("nqf", C.c_int32),
+                ("nq0", C.c_int32), ("nqf0", C.c_int32), ("nq_err", C.c_int32),
+                ("flops_poly_elem", C.c_int64), ("flops_quad_elem", C.c_int64)]
+
+
+class PlanSizes(C.Structure):
+    _fields_ = [("n_poly", C.c_int64), ("n_gen", C.c_int64), ("S_doubles", C.c_int64), ("g_doubles", C.c_int64),
+                ("W_doubles", C.c_int64), ("z_doubles", C.c_int64)]
+
+
+class CsrSizes(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64)]
+
+
+class GmresInfo(C.Structure):
+    _fields_ = [("restart", C.c_int32), ("max_iters", C.c_int32), ("rtol", C.c_double), ("iters", C.c_int32),
+                ("converged", C.c_int32), ("rel_residual", C.c_double), ("total_seconds", C.c_double),
+                ("spmv_calls", C.c_int64)]
+
+
+# every symbol include/ehdg.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "ehdg_version": (C.c_char_p, []),
+    "ehdg_last_error": (C.c_char_p, []),
+    "ehdg_create": (C.c_int, [C.POINTER(Problem), C.POINTER(_P)]),
+    "ehdg_destroy": (C.c_int, [_P]),
+    "ehdg_get_sizes": (C.c_int, [_P, C.POINTER(Sizes)]),
+    "ehdg_mark": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, _P, _P]),
+    "ehdg_plan_create": (C.c_int, [_P, C.POINTER(Mesh), _P, C.c_int, C.POINTER(_P), _P]),
+    "ehdg_plan_destroy": (C.c_int, [_P]),
+    "ehdg_plan_get_sizes": (C.c_int, [_P, C.POINTER(PlanSizes)]),
+    "ehdg_plan_eslot": (_P, [_P]),
+    "ehdg_prune": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, C.c_double, _P, _P, _P, _P]),
+    "ehdg_alpha": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),
+    "ehdg_assemble_condense": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ehdg_csr_symbolic": (C.c_int, [_P, C.POINTER(Mesh), _P, C.POINTER(_P), _P]),
+    "ehdg_csr_destroy": (C.c_int, [_P]),
+    "ehdg_csr_get_sizes": (C.c_int, [_P, C.POINTER(CsrSizes)]),
+    "ehdg_csr_rowptr": (_P, [_P]),
+    "ehdg_csr_colind": (_P, [_P]),
+    "ehdg_csr_row_start": (_P, [_P]),
+    "ehdg_csr_dofmask": (_P, [_P]),
+    "ehdg_csr_numeric": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
+    "ehdg_gmres": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
+    "ehdg_spmv": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "ehdg_backsolve": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
+    "ehdg_l2_error": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class EhdgError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libehdg.so and bind every symbol of include/ehdg.h.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EhdgError(f"{LIB_PATH} not built: run `python -m convectiondiffusionequation_b200.build` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().ehdg_last_error().decode()
+        raise EhdgError(f"{what} failed ({rc}): {msg}")

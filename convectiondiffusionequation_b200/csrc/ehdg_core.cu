@@ -1,0 +1,394 @@
+// libehdg core: context, marking (a1), plan, pruning (a3) and the general quadrature kernels
+// for alpha (a4) and assembly + condensation (a5-a7).  See include/ehdg.h for the contract.
+#include <cub/cub.cuh>
+#include <cstring>
+#include <string>
+
+#include "ehdg_internal.h"
+#include "ehdg_rules.h"
+
+namespace ehdg {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+static int upload_rules(int order, DeviceRules& dr) {
+    TrigRule tr = trig_rule(order);
+    SegRule sr = seg_rule(order);
+    const int nq = (int)tr.w.size(), nqf = (int)sr.w.size();
+    std::vector<double> h(3 * nq + 2 * nqf);
+    memcpy(h.data(), tr.x.data(), nq * 8);
+    memcpy(h.data() + nq, tr.y.data(), nq * 8);
+    memcpy(h.data() + 2 * nq, tr.w.data(), nq * 8);
+    memcpy(h.data() + 3 * nq, sr.t.data(), nqf * 8);
+    memcpy(h.data() + 3 * nq + nqf, sr.w.data(), nqf * 8);
+    EHDG_CUDA(cudaMalloc(&dr.buf, h.size() * 8));
+    EHDG_CUDA(cudaMemcpy(dr.buf, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    dr.rs.nq = nq;
+    dr.rs.nqf = nqf;
+    dr.rs.vx = dr.buf;
+    dr.rs.vy = dr.buf + nq;
+    dr.rs.vw = dr.buf + 2 * nq;
+    dr.rs.st = dr.buf + 3 * nq;
+    dr.rs.sw = dr.buf + 3 * nq + nqf;
+    return EHDG_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// a1 marking
+// -------------------------------------------------------------------------------------------
+__global__ void mark_elements_kernel(int ne, int nv, int nenr, const int32_t* __restrict__ tris,
+                                     const uint8_t* __restrict__ vflags, uint8_t* __restrict__ elem_mask) {
+    const int el = blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= ne) return;
+    int m = 0;
+    for (int k = 0; k < nenr; ++k) {
+        const uint8_t* f = vflags + (size_t)k * nv;
+        if (f[tris[3 * el]] | f[tris[3 * el + 1]] | f[tris[3 * el + 2]]) m |= 1 << k;   // any vertex
+    }
+    elem_mask[el] = (uint8_t)m;
+}
+
+__global__ void mark_facets_kernel(int nf, const int32_t* __restrict__ facet2el,
+                                   const uint8_t* __restrict__ elem_mask, uint8_t* __restrict__ facet_mask) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    int m = 0;
+    const int e0 = facet2el[2 * f], e1 = facet2el[2 * f + 1];
+    if (e0 >= 0) m |= elem_mask[e0];
+    if (e1 >= 0) m |= elem_mask[e1];
+    facet_mask[f] = (uint8_t)m;                       // any adjacent element marked
+}
+
+// -------------------------------------------------------------------------------------------
+// plan
+// -------------------------------------------------------------------------------------------
+__global__ void plan_flags_kernel(int ne, const int32_t* __restrict__ el2facet,
+                                  const uint8_t* __restrict__ facet_mask, int force, int32_t* __restrict__ flag) {
+    const int el = blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= ne) return;
+    int g = force;
+    if (facet_mask)
+        g |= facet_mask[el2facet[3 * el]] | facet_mask[el2facet[3 * el + 1]] | facet_mask[el2facet[3 * el + 2]];
+    flag[el] = g ? 1 : 0;
+}
+
+__global__ void plan_scatter_kernel(int ne, const int32_t* __restrict__ flag, const int32_t* __restrict__ scan,
+                                    int32_t* __restrict__ eslot, int32_t* __restrict__ list_poly,
+                                    int32_t* __restrict__ list_gen) {
+    const int el = blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= ne) return;
+    const int gi = scan[el];          // general elements before el
+    if (flag[el]) {
+        eslot[el] = EHDG_SLOT_GEN | gi;
+        list_gen[gi] = el;
+    } else {
+        eslot[el] = el - gi;
+        list_poly[el - gi] = el;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// general kernels: one warp (= one CTA of 32 threads) per element, workspace in dynamic smem
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fac_bits(const uint8_t* fm, const int32_t* el2facet, int el, int e) {
+    return fm ? (int)fm[el2facet[3 * el + e]] : 0;
+}
+
+__global__ void __launch_bounds__(32)
+prune_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __restrict__ list_gen,
+             const double* __restrict__ verts, const int32_t* __restrict__ tris,
+             const int32_t* __restrict__ el2facet, const uint8_t* __restrict__ elem_mask,
+             const uint8_t* __restrict__ facet_mask, double threshold, uint8_t* elem_active,
+             uint8_t* facet_active, double* factors) {
+    extern __shared__ double ws[];
+    const int gi = blockIdx.x;
+    if (gi >= n_gen) return;
+    const int el = list_gen[gi];
+    const int elmark = elem_mask[el];
+    if (elmark == 0) return;                      // only marked elements are visited (:285)
+    Coop co{(int)threadIdx.x, 32};
+    int facmask[3];
+    for (int e = 0; e < 3; ++e) facmask[e] = fac_bits(facet_mask, el2facet, el, e);
+    int vdrop, fdrop[3];
+    double fac[4 * EHDG_MAX_ENRICH];
+    prune_general(co, pb, rs, verts, tris + 3 * el, elmark, facmask, threshold, ws, &vdrop, fdrop, fac);
+    if (threadIdx.x == 0) {
+        if (vdrop) elem_active[el] = (uint8_t)(elmark & ~vdrop);
+        for (int e = 0; e < 3; ++e)
+            if (fdrop[e]) {
+                const int f = el2facet[3 * el + e];
+                unsigned int* word = reinterpret_cast<unsigned int*>(facet_active) + (f >> 2);
+                atomicAnd(word, ~((unsigned int)fdrop[e] << (8 * (f & 3))));
+            }
+        if (factors)
+            for (int i = 0; i < 4 * pb.nenr; ++i) factors[(size_t)el * 4 * pb.nenr + i] = fac[i];
+    }
+}
+
+__global__ void prune_init_kernel(int ne, int nf, int nenr, const uint8_t* __restrict__ elem_mask,
+                                  const uint8_t* __restrict__ facet_mask, const int32_t* __restrict__ facet2el,
+                                  uint8_t* elem_active, uint8_t* facet_active, double* factors) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ne) {
+        elem_active[i] = elem_mask[i];
+        if (factors)
+            for (int k = 0; k < 4 * nenr; ++k) factors[(size_t)i * 4 * nenr + k] = -1.0;
+    }
+    if (i < nf) facet_active[i] = (facet2el[2 * i + 1] < 0) ? 0 : facet_mask[i];   // dirichlet=".*"
+}
+
+__global__ void __launch_bounds__(32)
+alpha_general_kernel(Problem pb, RuleSet rs0, int n_gen, const int32_t* __restrict__ list_gen,
+                     const double* __restrict__ verts, const int32_t* __restrict__ tris,
+                     const uint8_t* __restrict__ elem_active, double* __restrict__ lam, int32_t* status) {
+    extern __shared__ double ws[];
+    const int gi = blockIdx.x;
+    if (gi >= n_gen) return;
+    const int el = list_gen[gi];
+    Coop co{(int)threadIdx.x, 32};
+    const int volmask = elem_active ? elem_active[el] : 0;
+    int st = 0;
+    const double l = alpha_general(co, pb, rs0, verts, tris + 3 * el, volmask, el == 0, ws, &st);
+    st = __reduce_or_sync(0xffffffffu, st);
+    if (threadIdx.x == 0) {
+        lam[el] = l;
+        if (status) status[el] = st;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+assemble_general_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __restrict__ list_gen,
+                        const double* __restrict__ verts, const int32_t* __restrict__ tris,
+                        const int32_t* __restrict__ el2facet, const double* __restrict__ lam,
+                        const uint8_t* __restrict__ elem_active, const uint8_t* __restrict__ facet_mask,
+                        double* __restrict__ S, double* __restrict__ g, double* __restrict__ W,
+                        double* __restrict__ z, int32_t* status, double* Afull) {
+    extern __shared__ double ws[];
+    const int gi = blockIdx.x;
+    if (gi >= n_gen) return;
+    const int el = list_gen[gi];
+    Coop co{(int)threadIdx.x, 32};
+    const int volmask = elem_active ? elem_active[el] : 0;
+    int facmask[3];
+    for (int e = 0; e < 3; ++e) facmask[e] = fac_bits(facet_mask, el2facet, el, e);
+    const int nv = pb.nvmax, nf = pb.nfmax;
+    const size_t afull_sz = (size_t)nv * (nv + nf + 1) + (size_t)nf * nv + (size_t)nf * nf;
+    int st = assemble_condense_general(co, pb, rs, verts, tris + 3 * el, lam[el], volmask, facmask, ws,
+                                       S + (size_t)gi * nf * nf, g + (size_t)gi * nf, W + (size_t)gi * nv * nf,
+                                       z + (size_t)gi * nv, Afull ? Afull + (size_t)gi * afull_sz : nullptr);
+    st = __reduce_or_sync(0xffffffffu, st);
+    if (threadIdx.x == 0 && status) status[el] |= st;
+}
+
+}  // namespace ehdg
+
+using namespace ehdg;
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* ehdg_version(void) { return "libehdg 0.1 (sm_100a)"; }
+const char* ehdg_last_error(void) { return g_err.c_str(); }
+
+int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out) {
+    if (!prob || !out) { set_error("ehdg_create: null argument"); return EHDG_ERR_ARG; }
+    if (!problem_valid(*prob)) { set_error("ehdg_create: invalid problem (order 1..6, n_enrich 0..2, eps > 0)"); return EHDG_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("ehdg_create: no CUDA device (libehdg has no CPU path)");
+        return EHDG_ERR_CUDA;
+    }
+    ehdg_ctx* c = new ehdg_ctx();
+    c->ep = *prob;
+    c->pb = make_problem(*prob);
+    EHDG_CUDA(cudaGetDevice(&c->device));
+    EHDG_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    int rc;
+    if ((rc = upload_rules(2 * c->pb.p + c->pb.bonus, c->rb))) return rc;
+    if ((rc = upload_rules(2 * c->pb.p, c->r0))) return rc;
+    if ((rc = upload_rules(50 + c->pb.bonus, c->rerr))) return rc;
+    c->ws_doubles = general_ws_doubles(c->pb, c->rb.rs.nq, c->rb.rs.nqf);
+    const int smem = c->ws_doubles * 8;
+    EHDG_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EHDG_CUDA(cudaFuncSetAttribute(alpha_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    EHDG_CUDA(cudaFuncSetAttribute(assemble_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if ((rc = fast_build_tensors(c))) return rc;
+    *out = c;
+    return EHDG_OK;
+}
+
+int ehdg_destroy(ehdg_ctx* c) {
+    if (!c) return EHDG_OK;
+    cudaFree(c->rb.buf);
+    cudaFree(c->r0.buf);
+    cudaFree(c->rerr.buf);
+    fast_free_tensors(c);
+    delete c;
+    return EHDG_OK;
+}
+
+int ehdg_get_sizes(const ehdg_ctx* c, ehdg_sizes* o) {
+    if (!c || !o) { set_error("ehdg_get_sizes: null argument"); return EHDG_ERR_ARG; }
+    const Problem& pb = c->pb;
+    o->n_p = pb.n_p;
+    o->nfl = pb.nfl;
+    o->nb = pb.nb;
+    o->nvmax = pb.nvmax;
+    o->nfmax = pb.nfmax;
+    o->nf_poly = 3 * pb.nfl;
+    o->nq = c->rb.rs.nq;
+    o->nqf = c->rb.rs.nqf;
+    o->nq0 = c->r0.rs.nq;
+    o->nqf0 = c->r0.rs.nqf;
+    o->nq_err = c->rerr.rs.nq;
+    o->flops_poly_elem = fast_flops_per_element(c);
+    // F_asm + F_cond of the quadrature algorithm on an unenriched element
+    const int64_t nV = pb.n_p, ne_ = pb.nfl, nF = 3 * pb.nfl, nq = o->nq, nqf = o->nqf;
+    o->flops_quad_elem = 4 * nV * nV * nq + 2 * nV * nq + 3 * nqf * (4 * nV * nV + 6 * nV * ne_ + 2 * ne_ * ne_)
+                         + (2 * nV * nV * nV) / 3 + 2 * nV * nV * (nF + 1) + 2 * nF * nV * (nF + 1);
+    return EHDG_OK;
+}
+
+int ehdg_mark(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* vert_flags, uint8_t* elem_mask, uint8_t* facet_mask,
+              void* stream) {
+    if (!c || !m || !elem_mask || !facet_mask) { set_error("ehdg_mark: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->ne > 0) mark_elements_kernel<<<(m->ne + 255) / 256, 256, 0, st>>>(m->ne, m->nv, c->pb.nenr, m->tris, vert_flags, elem_mask);
+    EHDG_LAUNCH_CHECK();
+    if (m->nf > 0) mark_facets_kernel<<<(m->nf + 255) / 256, 256, 0, st>>>(m->nf, m->facet2el, elem_mask, facet_mask);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+int ehdg_plan_create(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_mask, int force_general, ehdg_plan** out,
+                     void* stream) {
+    if (!c || !m || !out) { set_error("ehdg_plan_create: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ehdg_plan* p = new ehdg_plan();
+    p->ne = m->ne;
+    p->nf_poly = 3 * c->pb.nfl;
+    p->nfmax = c->pb.nfmax;
+    p->n_p = c->pb.n_p;
+    p->nvmax = c->pb.nvmax;
+    const int ne = m->ne;
+    int32_t *flag = nullptr, *scan = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    EHDG_CUDA(cudaMalloc(&flag, sizeof(int32_t) * (size_t)(ne + 1)));
+    EHDG_CUDA(cudaMalloc(&scan, sizeof(int32_t) * (size_t)(ne + 1)));
+    EHDG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * (size_t)(ne + 1), st));
+    EHDG_CUDA(cudaMalloc(&p->eslot, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1)));
+    if (ne > 0) plan_flags_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, m->el2facet, c->pb.nenr ? facet_mask : nullptr, force_general ? 1 : 0, flag);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, scan, ne + 1, st));
+    EHDG_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 8));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, scan, ne + 1, st));
+    int32_t ngen = 0;
+    EHDG_CUDA(cudaMemcpyAsync(&ngen, scan + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    p->n_gen = ngen;
+    p->n_poly = ne - ngen;
+    EHDG_CUDA(cudaMalloc(&p->list_gen, sizeof(int32_t) * (size_t)(ngen > 0 ? ngen : 1)));
+    EHDG_CUDA(cudaMalloc(&p->list_poly, sizeof(int32_t) * (size_t)(p->n_poly > 0 ? p->n_poly : 1)));
+    if (ne > 0) plan_scatter_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, flag, scan, p->eslot, p->list_poly, p->list_gen);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    cudaFree(flag);
+    cudaFree(scan);
+    cudaFree(tmp);
+    *out = p;
+    return EHDG_OK;
+}
+
+int ehdg_plan_destroy(ehdg_plan* p) {
+    if (!p) return EHDG_OK;
+    cudaFree(p->eslot);
+    cudaFree(p->list_poly);
+    cudaFree(p->list_gen);
+    delete p;
+    return EHDG_OK;
+}
+
+int ehdg_plan_get_sizes(const ehdg_plan* p, ehdg_plan_sizes* o) {
+    if (!p || !o) { set_error("ehdg_plan_get_sizes: null argument"); return EHDG_ERR_ARG; }
+    o->n_poly = p->n_poly;
+    o->n_gen = p->n_gen;
+    o->S_doubles = p->n_poly * p->nf_poly * p->nf_poly + p->n_gen * p->nfmax * p->nfmax;
+    o->g_doubles = p->n_poly * p->nf_poly + p->n_gen * p->nfmax;
+    o->W_doubles = p->n_poly * p->n_p * p->nf_poly + p->n_gen * p->nvmax * p->nfmax;
+    o->z_doubles = p->n_poly * p->n_p + p->n_gen * p->nvmax;
+    return EHDG_OK;
+}
+
+const int32_t* ehdg_plan_eslot(const ehdg_plan* p) { return p ? p->eslot : nullptr; }
+
+int ehdg_prune(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_mask, const uint8_t* facet_mask,
+               double threshold, uint8_t* elem_active, uint8_t* facet_active, double* factors, void* stream) {
+    if (!c || !p || !m || !elem_mask || !facet_mask || !elem_active || !facet_active) {
+        set_error("ehdg_prune: null argument");
+        return EHDG_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = m->ne > m->nf ? m->ne : m->nf;
+    if (n > 0) prune_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(m->ne, m->nf, c->pb.nenr, elem_mask, facet_mask, m->facet2el, elem_active, facet_active, factors);
+    EHDG_LAUNCH_CHECK();
+    if (c->pb.nenr > 0 && p->n_gen > 0) {
+        prune_kernel<<<(unsigned)p->n_gen, 32, c->ws_doubles * 8, st>>>(c->pb, c->rb.rs, (int)p->n_gen, p->list_gen, m->verts, m->tris,
+                                                                          m->el2facet, elem_mask, facet_mask, threshold, elem_active,
+                                                                          facet_active, factors);
+        EHDG_LAUNCH_CHECK();
+    }
+    return EHDG_OK;
+}
+
+int ehdg_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, double* lam,
+               int32_t* status, void* stream) {
+    if (!c || !p || !m || !lam) { set_error("ehdg_alpha: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->n_gen > 0) {
+        alpha_general_kernel<<<(unsigned)p->n_gen, 32, c->ws_doubles * 8, st>>>(c->pb, c->r0.rs, (int)p->n_gen, p->list_gen, m->verts,
+                                                                                  m->tris, c->pb.nenr ? elem_active : nullptr, lam, status);
+        EHDG_LAUNCH_CHECK();
+    }
+    if (p->n_poly > 0) {
+        int rc = fast_alpha(c, p, m, lam, status, st);
+        if (rc) return rc;
+    }
+    return EHDG_OK;
+}
+
+int ehdg_assemble_condense(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam,
+                           const uint8_t* elem_active, const uint8_t* facet_mask, double* S, double* g, double* W,
+                           double* z, int32_t* status, double* Afull, void* stream) {
+    if (!c || !p || !m || !lam || !S || !g || !W || !z) { set_error("ehdg_assemble_condense: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->n_poly > 0) {
+        int rc = fast_assemble(c, p, m, lam, S, g, W, z, status, st);
+        if (rc) return rc;
+    }
+    if (p->n_gen > 0) {
+        const size_t nfp = p->nf_poly, np = p->n_p;
+        double* Sg = S + (size_t)p->n_poly * nfp * nfp;
+        double* gg = g + (size_t)p->n_poly * nfp;
+        double* Wg = W + (size_t)p->n_poly * np * nfp;
+        double* zg = z + (size_t)p->n_poly * np;
+        assemble_general_kernel<<<(unsigned)p->n_gen, 32, c->ws_doubles * 8, st>>>(
+            c->pb, c->rb.rs, (int)p->n_gen, p->list_gen, m->verts, m->tris, m->el2facet, lam,
+            c->pb.nenr ? elem_active : nullptr, c->pb.nenr ? facet_mask : nullptr, Sg, gg, Wg, zg, status, Afull);
+        EHDG_LAUNCH_CHECK();
+    }
+    return EHDG_OK;
+}
+
+}  // extern "C"

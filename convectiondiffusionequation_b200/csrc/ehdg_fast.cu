@@ -1,0 +1,167 @@
+// Polynomial-path kernels: persistent CTAs, reference tensors staged once per CTA in shared
+// memory, one LG-lane group per element with its matrix rows in registers (ehdg_fast.h).
+#include "ehdg_fast.h"
+#include "ehdg_internal.h"
+
+namespace ehdg {
+
+constexpr int FAST_THREADS = 128;
+
+template <int P>
+__global__ void __launch_bounds__(FAST_THREADS)
+fast_assemble_kernel(Problem pb, RuleSet rs, const double* __restrict__ tab_g, int tab_doubles,
+                     const double* __restrict__ phi_rhs, int n, const int32_t* __restrict__ list,
+                     const double* __restrict__ verts, const int32_t* __restrict__ tris,
+                     const double* __restrict__ lam, double* __restrict__ S, double* __restrict__ g,
+                     double* __restrict__ W, double* __restrict__ z, int32_t* status) {
+    typedef FastDims<P> D;
+    constexpr int LG = D::LG, GPC = FAST_THREADS / LG;
+    extern __shared__ double smem[];
+    for (int i = threadIdx.x; i < tab_doubles; i += FAST_THREADS) smem[i] = tab_g[i];
+    __syncthreads();
+    const int gid = threadIdx.x / LG;
+    const int scratch = fast_asm_scratch_doubles<P>(rs.nq);
+    Group<LG> gc{(int)(threadIdx.x % LG), smem + ((tab_doubles + 1) & ~1) + gid * scratch};
+    for (int base = blockIdx.x * GPC; base < n; base += gridDim.x * GPC) {
+        const bool live = base + gid < n;
+        const int idx = live ? base + gid : n - 1;
+        const int el = list[idx];
+        const int st = fast_assemble_element<P>(gc, pb, rs, smem, phi_rhs, verts, tris + 3 * el, lam[el], live,
+                                                S + (size_t)idx * D::NF * D::NF, g + (size_t)idx * D::NF,
+                                                W + (size_t)idx * D::NP * D::NF, z + (size_t)idx * D::NP);
+        if (st && live && status) atomicOr(status + el, st);
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(FAST_THREADS)
+fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, const int32_t* __restrict__ list,
+                  const double* __restrict__ verts, const int32_t* __restrict__ tris, double* __restrict__ lam,
+                  int32_t* status) {
+    typedef FastDims<P> D;
+    constexpr int LG = D::LG, GPC = FAST_THREADS / LG;
+    extern __shared__ double smem[];
+    for (int i = threadIdx.x; i < tab_doubles; i += FAST_THREADS) smem[i] = tab_g[i];
+    __syncthreads();
+    const int gid = threadIdx.x / LG;
+    Group<LG> gc{(int)(threadIdx.x % LG), smem + ((tab_doubles + 1) & ~1) + gid * fast_alpha_scratch_doubles<P>()};
+    for (int base = blockIdx.x * GPC; base < n; base += gridDim.x * GPC) {
+        const bool live = base + gid < n;
+        const int idx = live ? base + gid : n - 1;
+        const int el = list[idx];
+        int st = 0;
+        const double l = fast_alpha_element<P>(gc, smem, verts, tris + 3 * el, &st);
+        if (live && gc.lane == 0) {
+            lam[el] = l;
+            if (status) status[el] = st;
+        }
+    }
+}
+
+template <int P>
+static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, double* lam, int32_t* status, cudaStream_t st) {
+    typedef FastDims<P> D;
+    constexpr int GPC = FAST_THREADS / D::LG;
+    const int tabd = c->tens.alpha_doubles;
+    const size_t smem = (size_t)(((tabd + 1) & ~1) + GPC * fast_alpha_scratch_doubles<P>()) * 8;
+    EHDG_CUDA(cudaFuncSetAttribute(fast_alpha_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    EHDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_alpha_kernel<P>, FAST_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t need = (p->n_poly + GPC - 1) / GPC;
+    const int64_t cap = (int64_t)c->sm_count * per_sm;
+    const int grid = (int)(need < cap ? need : cap);
+    fast_alpha_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->tens.alpha_tab, tabd, (int)p->n_poly, p->list_poly, m->verts, m->tris,
+                                                          lam, status);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+template <int P>
+static int launch_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, double* S, double* g,
+                           double* W, double* z, int32_t* status, cudaStream_t st) {
+    typedef FastDims<P> D;
+    constexpr int GPC = FAST_THREADS / D::LG;
+    const int tabd = c->tens.asm_doubles;
+    const size_t smem = (size_t)(((tabd + 1) & ~1) + GPC * fast_asm_scratch_doubles<P>(c->rb.rs.nq)) * 8;
+    EHDG_CUDA(cudaFuncSetAttribute(fast_assemble_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    EHDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_assemble_kernel<P>, FAST_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t need = (p->n_poly + GPC - 1) / GPC;
+    const int64_t cap = (int64_t)c->sm_count * per_sm;
+    const int grid = (int)(need < cap ? need : cap);
+    fast_assemble_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->pb, c->rb.rs, c->tens.asm_tab, tabd, c->tens.rhs_phi, (int)p->n_poly,
+                                                             p->list_poly, m->verts, m->tris, lam, S, g, W, z, status);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+int fast_build_tensors(ehdg_ctx* c) {
+    std::vector<double> asm_tab, alpha_tab, phi;
+    const int order = 2 * c->pb.p + c->pb.bonus;
+    build_tensors(c->pb.p, order, asm_tab, alpha_tab);
+    build_rhs_phi(c->pb.p, order, phi);
+    c->tens.asm_doubles = (int)asm_tab.size();
+    c->tens.alpha_doubles = (int)alpha_tab.size();
+    EHDG_CUDA(cudaMalloc(&c->tens.asm_tab, asm_tab.size() * 8));
+    EHDG_CUDA(cudaMalloc(&c->tens.alpha_tab, alpha_tab.size() * 8));
+    EHDG_CUDA(cudaMalloc(&c->tens.rhs_phi, phi.size() * 8));
+    EHDG_CUDA(cudaMemcpy(c->tens.asm_tab, asm_tab.data(), asm_tab.size() * 8, cudaMemcpyHostToDevice));
+    EHDG_CUDA(cudaMemcpy(c->tens.alpha_tab, alpha_tab.data(), alpha_tab.size() * 8, cudaMemcpyHostToDevice));
+    EHDG_CUDA(cudaMemcpy(c->tens.rhs_phi, phi.data(), phi.size() * 8, cudaMemcpyHostToDevice));
+    return EHDG_OK;
+}
+
+void fast_free_tensors(ehdg_ctx* c) {
+    cudaFree(c->tens.asm_tab);
+    cudaFree(c->tens.alpha_tab);
+    cudaFree(c->tens.rhs_phi);
+}
+
+#define EHDG_DISPATCH_P(p, CALL)                 \
+    switch (p) {                                  \
+        case 1: return CALL(1);                   \
+        case 2: return CALL(2);                   \
+        case 3: return CALL(3);                   \
+        case 4: return CALL(4);                   \
+        case 5: return CALL(5);                   \
+        case 6: return CALL(6);                   \
+        default: set_error("unsupported order %d", p); return EHDG_ERR_ARG; \
+    }
+
+int fast_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, double* lam, int32_t* status, cudaStream_t st) {
+#define CALL(PP) launch_alpha<PP>(c, p, m, lam, status, st)
+    EHDG_DISPATCH_P(c->pb.p, CALL)
+#undef CALL
+}
+
+int fast_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, double* S, double* g, double* W,
+                  double* z, int32_t* status, cudaStream_t st) {
+#define CALL(PP) launch_assemble<PP>(c, p, m, lam, S, g, W, z, status, st)
+    EHDG_DISPATCH_P(c->pb.p, CALL)
+#undef CALL
+}
+
+// FMA = 2 flops; counts the arithmetic the polynomial path executes on the matrix data of one
+// element (geometry, coefficient evaluation and pivot search excluded), see DESIGN.md.
+int64_t fast_flops_per_element(const ehdg_ctx* c) {
+    const int64_t p = c->pb.p, NP = c->pb.n_p, NFL = p + 1, NF = 3 * NFL, NC = NP + NF + 1, nq = c->rb.rs.nq, N = NP - 1;
+    int64_t f = 0;
+    f += 2 * 14 * NP * NP;          // A_VV from 5 volume + 9 edge tensors
+    f += 2 * 2 * 3 * NP * NF;       // A_VF and A_FV from 3 tensors each
+    f += 2 * nq * NP;               // f_V
+    for (int64_t k = 0; k < NP; ++k) f += 2 * NP * (NC - 1 - k);   // Gauss-Jordan on [A_VV | A_VF f_V]
+    f += 2 * NF * NP * (NF + 1);    // Schur complement and g
+    // alpha: tensors, Cholesky, two triangular solves, Householder, Sturm multisection
+    f += 2 * 12 * N * N;
+    for (int64_t k = 0; k < N; ++k) f += 2 * (N - 1 - k) * (N - 1 - k) ;
+    for (int64_t j = 0; j < N; ++j) f += 2 * 2 * (N - 1 - j) * N;
+    for (int64_t k = 0; k + 2 < N; ++k) f += 6 * (N - 1 - k) * (N - 1 - k);
+    const int64_t LG = (NP > NF ? NP : NF) <= 8 ? 8 : ((NP > NF ? NP : NF) <= 16 ? 16 : 32);
+    const int64_t rounds = LG == 32 ? 12 : (LG == 16 ? 14 : 18);
+    f += rounds * LG * N * 5;
+    return f;
+}
+
+}  // namespace ehdg

@@ -1,0 +1,545 @@
+// Polynomial-path element routines (no enriched dof on the element): alpha_K (a4) and
+// assembly + static condensation (a5-a7) from the reference tensors of ehdg_tensors.h.
+//
+// Execution model: a GROUP of LG lanes (LG = 8, 16 or 32, a power of two >= max(n_p, 3(p+1)))
+// owns one element; lane i keeps ROW i of the element matrices in registers.  Values cross
+// lanes only through the group's shared-memory scratch and three primitives (argmax / sum /
+// ballot).  The body is written in lock-step phases
+//     EHDG_FOR_LANES(l, L)  ...  EHDG_END_LANES
+// so that the same source runs on the device (each thread is one lane, L == 0, a phase ends
+// with __syncwarp) and on the host (a phase is a loop over the LG lanes, L == l); the host
+// instantiation exists only for tests/hostcheck.
+#pragma once
+#include "ehdg_general.h"
+#include "ehdg_tensors.h"
+
+namespace ehdg {
+
+#ifdef __CUDA_ARCH__
+#define EHDG_NLS(LG) 1
+#define EHDG_FOR_LANES(l, L) { const int l = gc.lane; constexpr int L = 0; (void)L;
+#define EHDG_END_LANES } __syncwarp();
+#else
+#define EHDG_NLS(LG) (LG)
+#define EHDG_FOR_LANES(l, L) for (int l = 0; l < LG; ++l) { const int L = l;
+#define EHDG_END_LANES }
+#endif
+
+template <int LG>
+struct Group {
+    int lane;       // lane inside the group (device); unused on the host
+    double* sh;     // group-private scratch
+
+    // index of the lane with the largest key (ties: lowest lane); key < 0 never wins unless all are
+    EHDG_HD int argmax(const double* key) const {
+#ifdef __CUDA_ARCH__
+        double k = key[0];
+        int idx = lane;
+#pragma unroll
+        for (int s = LG / 2; s > 0; s >>= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, k, s, LG);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, s, LG);
+            if (ok > k || (ok == k && oi < idx)) { k = ok; idx = oi; }
+        }
+        return idx;
+#else
+        int idx = 0;
+        for (int l = 1; l < LG; ++l)
+            if (key[l] > key[idx]) idx = l;
+        return idx;
+#endif
+    }
+    EHDG_HD double sum(const double* x) const {
+#ifdef __CUDA_ARCH__
+        double s = x[0];
+#pragma unroll
+        for (int d = LG / 2; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d, LG);
+        return s;
+#else
+        // same pairing as the butterfly so host and device round identically
+        double t[LG];
+        for (int l = 0; l < LG; ++l) t[l] = x[l];
+        for (int d = LG / 2; d > 0; d >>= 1) {
+            double u[LG];
+            for (int l = 0; l < LG; ++l) u[l] = t[l] + t[l ^ d];
+            for (int l = 0; l < LG; ++l) t[l] = u[l];
+        }
+        return t[0];
+#endif
+    }
+    // bit l set iff flag of lane l is non-zero
+    EHDG_HD unsigned ballot(const int* flag) const {
+#ifdef __CUDA_ARCH__
+        const unsigned b = __ballot_sync(0xffffffffu, flag[0] != 0);
+        const int base = (threadIdx.x & 31) & ~(LG - 1);
+        return (LG == 32) ? b : ((b >> base) & ((1u << LG) - 1u));
+#else
+        unsigned b = 0;
+        for (int l = 0; l < LG; ++l)
+            if (flag[l]) b |= 1u << l;
+        return b;
+#endif
+    }
+};
+
+// geometry of one element in its vertex-sorted frame (computed redundantly by every lane)
+struct SortedGeom {
+    double adet;
+    double g00, g01, g11;       // Gram of grad lam_Q0, grad lam_Q1
+    double c0, c1;              // b . grad lam_Qa
+    double len[3], h[3], bn[3]; // per sorted edge s (opposite Q_s)
+    double ga0[3], ga1[3];      // n_s . grad lam_Q0 / Q1
+    int eloc[3];                // local edge number of sorted edge s
+    int f0, f1;                 // local index of Q0, Q1
+    double omx[3], omy[3];      // 1-x, 1-y at the LOCAL vertices
+};
+
+EHDG_HD void sorted_geom(const double* verts, const int* tri, double bx, double by, SortedGeom& sg) {
+    int vn[3];
+    double P[3][2];
+    for (int v = 0; v < 3; ++v) {
+        vn[v] = tri[v];
+        P[v][0] = verts[2 * vn[v]];
+        P[v][1] = verts[2 * vn[v] + 1];
+        sg.omx[v] = 1.0 - P[v][0];
+        sg.omy[v] = 1.0 - P[v][1];
+    }
+    int o0 = 0, o1 = 1, o2 = 2, t;
+    if (vn[o1] < vn[o0]) { t = o0; o0 = o1; o1 = t; }
+    if (vn[o2] < vn[o1]) { t = o1; o1 = o2; o2 = t; }
+    if (vn[o1] < vn[o0]) { t = o0; o0 = o1; o1 = t; }
+    sg.f0 = o0;
+    sg.f1 = o1;
+    const int o[3] = {o0, o1, o2};
+    // local vertex v is opposite local edge: V0 -> e1, V1 -> e0, V2 -> e2
+    for (int s = 0; s < 3; ++s) sg.eloc[s] = (o[s] == 0) ? 1 : (o[s] == 1 ? 0 : 2);
+    const double ax = P[o0][0] - P[o2][0], ay = P[o0][1] - P[o2][1];
+    const double bx_ = P[o1][0] - P[o2][0], by_ = P[o1][1] - P[o2][1];
+    const double det = ax * by_ - bx_ * ay;
+    const double id = 1.0 / det;
+    sg.adet = fabs(det);
+    double gl[3][2];
+    gl[0][0] = by_ * id;  gl[0][1] = -bx_ * id;
+    gl[1][0] = -ay * id;  gl[1][1] = ax * id;
+    gl[2][0] = -gl[0][0] - gl[1][0];
+    gl[2][1] = -gl[0][1] - gl[1][1];
+    sg.g00 = gl[0][0] * gl[0][0] + gl[0][1] * gl[0][1];
+    sg.g01 = gl[0][0] * gl[1][0] + gl[0][1] * gl[1][1];
+    sg.g11 = gl[1][0] * gl[1][0] + gl[1][1] * gl[1][1];
+    sg.c0 = bx * gl[0][0] + by * gl[0][1];
+    sg.c1 = bx * gl[1][0] + by * gl[1][1];
+    for (int s = 0; s < 3; ++s) {
+        // outward normal of the edge opposite Q_s is -grad lam_Qs / |grad lam_Qs|, |grad lam_Qs| = 1/h_s
+        const double gn = sqrt(gl[s][0] * gl[s][0] + gl[s][1] * gl[s][1]);
+        const double nx = -gl[s][0] / gn, ny = -gl[s][1] / gn;
+        sg.h[s] = 1.0 / gn;                 // = |detJ| / |e|   
+        sg.len[s] = sg.adet * gn;
+        sg.bn[s] = bx * nx + by * ny;
+        sg.ga0[s] = nx * gl[0][0] + ny * gl[0][1];
+        sg.ga1[s] = nx * gl[1][0] + ny * gl[1][1];
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// a5-a7 on one polynomial element.  Scratch `gc.sh` needs fast_asm_scratch_doubles() doubles.
+// Outputs in LOCAL edge order (3 (p+1) facet dofs): S[NF*NF], gvec[NF], W[NP*NF], z[NP].
+// tab: assembly tensors (shared memory on the device), phi_rhs: [9][nq][NP] (global/L1),
+// rule: bonus triangle rule.
+// -------------------------------------------------------------------------------------------
+template <int P>
+struct FastDims {
+    static constexpr int NP = (P + 1) * (P + 2) / 2;
+    static constexpr int NFL = P + 1;
+    static constexpr int NF = 3 * NFL;
+    static constexpr int NC = NP + NF + 1;
+    static constexpr int M = NP > NF ? NP : NF;
+    static constexpr int LG = M <= 8 ? 8 : (M <= 16 ? 16 : 32);
+    static constexpr int NXS = (NF + 2) & ~1;          // row stride of the X scratch (even)
+};
+
+template <int P>
+EHDG_HD constexpr int fast_asm_scratch_doubles(int nq) {
+    return ((FastDims<P>::NC + 1) & ~1) + FastDims<P>::NP * FastDims<P>::NXS + ((nq + 1) & ~1);
+}
+
+template <int P>
+EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Problem& pb, const RuleSet& rs,
+                                  const double* tab, const double* phi_rhs, const double* verts, const int* tri,
+                                  double lam, bool store, double* S, double* gvec, double* W, double* z) {
+    typedef FastDims<P> D;
+    constexpr int NP = D::NP, NFL = D::NFL, NF = D::NF, NC = D::NC, LG = D::LG, NXS = D::NXS;
+    constexpr int NLS = EHDG_NLS(LG);
+    const TensorLayout TL = tensor_layout(P, rs.nq);
+    SortedGeom sg;
+    sorted_geom(verts, tri, pb.bx, pb.by, sg);
+    double* prow = gc.sh;                       // NC (padded even)
+    double* Xs = prow + ((NC + 1) & ~1);        // NP x NXS
+    double* cw = Xs + NP * NXS;                 // nq
+    // per-edge coefficients
+    double cvv[3], cvf[3], cfv[3], cff[3], eg0[3], eg1[3];
+    for (int s = 0; s < 3; ++s) {
+        const double bn = sg.bn[s];
+        const double pos = bn > 0.0 ? 1.0 : 0.0, neg = 1.0 - pos;
+        const double tau = pb.eps * (20.0 * lam) * (double)(P * P) / sg.h[s];
+        cvv[s] = sg.len[s] * (tau + pos * bn);
+        cvf[s] = sg.len[s] * (-tau + neg * bn);
+        cfv[s] = sg.len[s] * (-tau - pos * bn - pos);
+        cff[s] = sg.len[s] * (tau - neg * bn + pos);
+        eg0[s] = sg.len[s] * pb.eps * sg.ga0[s];
+        eg1[s] = sg.len[s] * pb.eps * sg.ga1[s];
+    }
+    const double kxx = sg.adet * pb.eps * sg.g00, ks = sg.adet * pb.eps * sg.g01, kyy = sg.adet * pb.eps * sg.g11;
+    const double ccx = -sg.adet * sg.c0, ccy = -sg.adet * sg.c1;
+
+    double a[NLS][NC];      // row i of [A_VV | A_VF | f_V]          (lanes i < NP)
+    double afv[NLS][NP];    // row r of A_FV in the sorted frame      (lanes r < NF)
+    double aff[NLS];
+    int mycol[NLS];
+    int status = 0;
+
+    // ---- right-hand side weights at the quadrature points: cw[q] = w_q |detJ| coeff(x_q)
+    EHDG_FOR_LANES(l, L)
+        for (int q = l; q < rs.nq; q += LG) {
+            const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
+            const double dx = l0 * sg.omx[0] + l1 * sg.omx[1] + l2 * sg.omx[2];
+            const double dy = l0 * sg.omy[0] + l1 * sg.omy[1] + l2 * sg.omy[2];
+            cw[q] = rs.vw[q] * sg.adet * layer_expr_eval(pb.coeff, dx, dy);
+        }
+    EHDG_END_LANES
+
+    // ---- build the rows from the tensors
+    EHDG_FOR_LANES(l, L)
+        const int i = l < NP ? l : NP - 1;          // clamp: surplus lanes recompute the last row
+        const double* tv = tab + TL.offV + i * NP;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            double acc = kxx * tv[j] + ks * tv[NP * NP + j] + kyy * tv[2 * NP * NP + j]
+                       + ccx * tv[3 * NP * NP + j] + ccy * tv[4 * NP * NP + j];
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const double* te = tab + TL.offE + (s * 3 * NP + i) * NP;
+                acc += cvv[s] * te[j] - eg0[s] * te[NP * NP + j] - eg1[s] * te[2 * NP * NP + j];
+            }
+            a[L][j] = acc;
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const double* tf = tab + TL.offF + (s * 3 * NP + i) * NFL;
+#pragma unroll
+            for (int k = 0; k < NFL; ++k)
+                a[L][NP + s * NFL + k] = cvf[s] * tf[k] + eg0[s] * tf[NP * NFL + k] + eg1[s] * tf[2 * NP * NFL + k];
+        }
+        // f_V[i] = sum_q cw[q] phi_i(q)
+        {
+            const double* ph = phi_rhs + (size_t)(sg.f0 * 3 + sg.f1) * rs.nq * NP + i;
+            double acc = 0.0;
+            for (int q = 0; q < rs.nq; ++q) acc += cw[q] * ph[q * NP];
+            a[L][NC - 1] = acc;
+        }
+        // A_FV row r = (s, k) in the sorted frame
+        {
+            const int r = l < NF ? l : NF - 1;
+            const int s = r / NFL, k = r % NFL;
+            const double* tf = tab + TL.offF + (s * 3 * NP) * NFL + k;
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+                afv[L][j] = cfv[s] * tf[j * NFL] + eg0[s] * tf[(NP + j) * NFL] + eg1[s] * tf[(2 * NP + j) * NFL];
+            aff[L] = cff[s] / (2.0 * k + 1.0);           // int_0^1 mu_k^2 dt
+        }
+        mycol[L] = -1;
+    EHDG_END_LANES
+
+    // ---- Gauss-Jordan with partial pivoting, rows stay in their lanes
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        double key[NLS];
+        EHDG_FOR_LANES(l, L)
+            key[L] = (l < NP && mycol[L] < 0) ? fabs(a[L][k]) : -1.0;
+        EHDG_END_LANES
+        const int r = gc.argmax(key);
+        EHDG_FOR_LANES(l, L)
+            if (l == r) {
+#pragma unroll
+                for (int j = k; j < NC; ++j) prow[j] = a[L][j];
+                mycol[L] = k;
+            }
+        EHDG_END_LANES
+        EHDG_FOR_LANES(l, L)
+            const double piv = prow[k];
+            if (!(fabs(piv) > 0.0)) status |= EHDG_ST_SINGULAR;
+            const double inv = 1.0 / piv;
+            if (l == r) {
+#pragma unroll
+                for (int j = k + 1; j < NC; ++j) a[L][j] *= inv;
+            } else if (l < NP) {
+                const double f = a[L][k] * inv;
+#pragma unroll
+                for (int j = k + 1; j < NC; ++j) a[L][j] -= f * prow[j];
+            }
+        EHDG_END_LANES
+    }
+
+    // ---- X = A_VV^-1 [A_VF | f_V]: row c sits in the lane whose pivot column was c
+    EHDG_FOR_LANES(l, L)
+        if (l < NP) {
+            const int c = mycol[L];
+#pragma unroll
+            for (int j = 0; j <= NF; ++j) Xs[c * NXS + j] = a[L][NP + j];
+            if (store) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+#pragma unroll
+                    for (int k = 0; k < NFL; ++k) W[c * NF + sg.eloc[s] * NFL + k] = a[L][NP + s * NFL + k];
+                z[c] = a[L][NC - 1];
+            }
+        }
+    EHDG_END_LANES
+
+    // ---- S = A_FF - A_FV X, g = -A_FV z ; lane r owns row r (sorted frame), written in local order
+    EHDG_FOR_LANES(l, L)
+        if (l < NF) {
+            double srow[NF + 1];
+#pragma unroll
+            for (int j = 0; j <= NF; ++j) srow[j] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NP; ++c) {
+                const double f = afv[L][c];
+#pragma unroll
+                for (int j = 0; j <= NF; ++j) srow[j] -= f * Xs[c * NXS + j];
+            }
+            const int s = l / NFL, k = l % NFL;
+            const int orow = sg.eloc[s] * NFL + k;
+#pragma unroll
+            for (int s2 = 0; s2 < 3; ++s2)
+#pragma unroll
+                for (int k2 = 0; k2 < NFL; ++k2) {
+                    double val = srow[s2 * NFL + k2];
+                    if (s2 * NFL + k2 == l) val += aff[L];
+                    if (val != val) status |= EHDG_ST_NONFINITE;
+                    if (store) S[orow * NF + sg.eloc[s2] * NFL + k2] = val;
+                }
+            if (store) gvec[orow] = srow[NF];
+        }
+    EHDG_END_LANES
+    return status;
+}
+
+// -------------------------------------------------------------------------------------------
+// a4 on one polynomial element: lambda_max of (m, a') on the non-constant modes (the constant
+// mode decouples: row 0 of m vanishes and f f^T only touches a'[0][0]).
+// Scratch: fast_alpha_scratch_doubles() doubles.
+// -------------------------------------------------------------------------------------------
+template <int P>
+EHDG_HD constexpr int fast_alpha_scratch_doubles() {
+    return (FastDims<P>::NP - 1) * (FastDims<P>::NP - 1) + 4 * 32;
+}
+
+template <int P>
+EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double* tab, const double* verts,
+                                  const int* tri, int* status_out) {
+    typedef FastDims<P> D;
+    constexpr int NP = D::NP, LG = D::LG, N = NP - 1;
+    constexpr int NLS = EHDG_NLS(LG);
+    const TensorLayout TL = tensor_layout(P, 0);
+    SortedGeom sg;
+    sorted_geom(verts, tri, 0.0, 0.0, sg);
+    double* shT = gc.sh;              // N x N
+    double* shv = shT + N * N;        // 32
+    double* shq = shv + 32;           // 32
+    double* shd = shq + 32;           // 32
+    double* she = shd + 32;           // 32
+    int status = 0;
+
+    double A[NLS][N];   // a' row -> Cholesky factor row
+    double M[NLS][N];   // m row  -> C row
+    double eown[NLS];   // sub-diagonal entry T[i][i-1] owned by lane i
+
+    // m = sum_s h_s len_s (dn u)(dn v) with dn = ga0 dX + ga1 dY ; the common factor |detJ| of a'
+    // and m is dropped (h_s len_s = |detJ|)
+    double w0[3], w1[3], w2[3];
+    for (int s = 0; s < 3; ++s) {
+        w0[s] = sg.ga0[s] * sg.ga0[s];
+        w1[s] = sg.ga0[s] * sg.ga1[s];
+        w2[s] = sg.ga1[s] * sg.ga1[s];
+    }
+    EHDG_FOR_LANES(l, L)
+        const int i = (l < N ? l : N - 1) + 1;
+        const double* tk = tab + TL.offAK + i * NP + 1;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            A[L][j] = sg.g00 * tk[j] + sg.g01 * tk[NP * NP + j] + sg.g11 * tk[2 * NP * NP + j];
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const double* tn = tab + TL.offAN + (s * 3 * NP + i) * NP + 1;
+                acc += w0[s] * tn[j] + w1[s] * tn[NP * NP + j] + w2[s] * tn[2 * NP * NP + j];
+            }
+            M[L][j] = acc;
+        }
+        eown[L] = 0.0;
+    EHDG_END_LANES
+
+    // ---- Cholesky a' = L L^T, right-looking; A[i][k] becomes l_ik (k <= i)
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        EHDG_FOR_LANES(l, L)
+            if (l == k) {
+                const double d = A[L][k];
+                if (!(d > 0.0)) status |= EHDG_ST_ALPHA_DEFICIENT;
+                shv[0] = 1.0 / sqrt(d);
+            }
+        EHDG_END_LANES
+        EHDG_FOR_LANES(l, L)
+            if (l >= k && l < N) {
+                A[L][k] *= shv[0];
+                shq[l] = A[L][k];
+            }
+        EHDG_END_LANES
+        EHDG_FOR_LANES(l, L)
+            if (l > k && l < N) {
+                const double f = A[L][k];
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) A[L][j] -= f * shq[j];
+            }
+        EHDG_END_LANES
+    }
+    // ---- two forward substitutions with a transpose in between: C = L^-1 (L^-1 m)^T
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            EHDG_FOR_LANES(l, L)
+                if (l == j) {
+                    const double inv = 1.0 / A[L][j];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) {
+                        M[L][c] *= inv;
+                        shT[c] = M[L][c];
+                    }
+                }
+            EHDG_END_LANES
+            EHDG_FOR_LANES(l, L)
+                if (l > j && l < N) {
+                    const double f = A[L][j];
+#pragma unroll
+                    for (int c = 0; c < N; ++c) M[L][c] -= f * shT[c];
+                }
+            EHDG_END_LANES
+        }
+        if (pass == 0) {
+            EHDG_FOR_LANES(l, L)
+                if (l < N) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) shT[l * N + c] = M[L][c];
+                }
+            EHDG_END_LANES
+            EHDG_FOR_LANES(l, L)
+                if (l < N) {
+#pragma unroll
+                    for (int c = 0; c < N; ++c) M[L][c] = shT[c * N + l];
+                }
+            EHDG_END_LANES
+        }
+    }
+    // ---- Householder tridiagonalisation of C (rows in M)
+#pragma unroll
+    for (int k = 0; k + 2 < N; ++k) {
+        double part[NLS], vi[NLS];
+        EHDG_FOR_LANES(l, L)
+            part[L] = (l > k && l < N) ? M[L][k] * M[L][k] : 0.0;
+            if (l == k + 1) shv[0] = M[L][k];
+        EHDG_END_LANES
+        const double sig = gc.sum(part);
+        const double x0 = shv[0];
+        const bool skip = !(sig > 0.0);
+        const double alpha = (x0 > 0.0) ? -sqrt(sig) : sqrt(sig);
+        const double beta = skip ? 0.0 : 1.0 / (sig - x0 * alpha);     // 2 / v^T v
+        EHDG_FOR_LANES(l, L)
+            vi[L] = skip ? 0.0 : ((l == k + 1) ? x0 - alpha : ((l > k + 1 && l < N) ? M[L][k] : 0.0));
+            shq[l] = vi[L];
+            if (l == k + 1) eown[L] = skip ? x0 : alpha;
+        EHDG_END_LANES
+        double pi[NLS];
+        EHDG_FOR_LANES(l, L)
+            double acc = 0.0;
+            if (l > k && l < N) {
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) acc += M[L][j] * shq[j];
+            }
+            pi[L] = beta * acc;
+            part[L] = vi[L] * pi[L];
+        EHDG_END_LANES
+        const double kk = 0.5 * beta * gc.sum(part);
+        EHDG_FOR_LANES(l, L)
+            pi[L] -= kk * vi[L];            // q_i
+            shd[l] = pi[L];
+        EHDG_END_LANES
+        EHDG_FOR_LANES(l, L)
+            if (l > k && l < N) {
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) M[L][j] -= vi[L] * shd[j] + pi[L] * shq[j];
+            }
+        EHDG_END_LANES
+    }
+    // ---- gather the tridiagonal matrix
+    EHDG_FOR_LANES(l, L)
+        double d = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (j == l) d = M[L][j];
+        if (N >= 2 && l == N - 1) eown[L] = M[L][N - 2];
+        shd[l] = d;
+        she[l] = eown[L];
+    EHDG_END_LANES
+    double dg[N], e2[N];
+    double lo = 0.0, hi = 0.0, scale = 0.0;
+    {
+        // every lane reads the whole tridiagonal matrix (uniform across lanes)
+        for (int i = 0; i < N; ++i) {
+            const double r = (i > 0 ? fabs(she[i]) : 0.0) + (i + 1 < N ? fabs(she[i + 1]) : 0.0);
+            const double up = shd[i] + r, dn = shd[i] - r;
+            if (i == 0 || up > hi) hi = up;
+            if (i == 0 || dn < lo) lo = dn;
+        }
+        scale = fabs(hi) > fabs(lo) ? fabs(hi) : fabs(lo);
+        if (!(scale > 0.0)) scale = 1.0;
+        const double is = 1.0 / scale;
+        for (int i = 0; i < N; ++i) {
+            dg[i] = shd[i] * is;
+            e2[i] = (i > 0) ? (she[i] * is) * (she[i] * is) : 0.0;
+        }
+        lo *= is;
+        hi = hi * is + 1e-15;
+    }
+    // ---- multisection on "all eigenvalues below x" (signs of the Sturm sequence alternate)
+    constexpr int ROUNDS = LG == 32 ? 12 : (LG == 16 ? 14 : 18);
+    for (int it = 0; it < ROUNDS; ++it) {
+        int below[NLS];
+        const double step = (hi - lo) / (double)(LG + 1);
+        EHDG_FOR_LANES(l, L)
+            const double x = lo + step * (double)(l + 1);
+            double pm = 1.0, pc = dg[0] - x;
+            bool ok = pc < 0.0;
+#pragma unroll
+            for (int i = 1; i < N; ++i) {
+                const double pn = (dg[i] - x) * pc - e2[i] * pm;
+                ok = ok && (pn * pc < 0.0);
+                pm = pc;
+                pc = pn;
+            }
+            below[L] = ok ? 1 : 0;
+        EHDG_END_LANES
+        const unsigned b = gc.ballot(below);
+        // first lane whose abscissa is above the spectrum
+        int f = LG;
+        for (int l = 0; l < LG; ++l)
+            if ((b >> l) & 1u) { f = l; break; }
+        const double nlo = lo + step * (double)f;          // x_{f-1}  (f = 0 -> lo)
+        const double nhi = (f < LG) ? lo + step * (double)(f + 1) : hi;
+        lo = nlo;
+        hi = nhi;
+    }
+    *status_out = status;
+    return 0.5 * (lo + hi) * scale;
+}
+
+}  // namespace ehdg

@@ -1,0 +1,89 @@
+// Internal definitions shared by the libehdg translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/ehdg.h"
+#include "ehdg_general.h"
+#include "ehdg_problem.h"
+
+namespace ehdg {
+
+void set_error(const char* fmt, ...);
+
+#define EHDG_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            ehdg::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+            return EHDG_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define EHDG_LAUNCH_CHECK() EHDG_CUDA(cudaGetLastError())
+
+struct DeviceRules {
+    RuleSet rs;                 // device pointers
+    double* buf = nullptr;
+};
+
+// reference tensors of the polynomial path (device), see ehdg_tensors.h
+struct DeviceTensors {
+    double* asm_tab = nullptr;     // assembly tensors
+    double* alpha_tab = nullptr;   // alpha pencil tensors
+    double* rhs_phi = nullptr;     // phi at the bonus-rule points, 6 vertex-order classes
+    int asm_doubles = 0, alpha_doubles = 0;
+};
+
+}  // namespace ehdg
+
+struct ehdg_ctx {
+    ehdg_problem ep;
+    ehdg::Problem pb;
+    ehdg::DeviceRules rb, r0, rerr;   // orders 2p+bonus, 2p, 50+bonus
+    ehdg::DeviceTensors tens;
+    int ws_doubles;                   // per-warp workspace of the general kernels
+    int device;
+    int sm_count;
+};
+
+struct ehdg_plan {
+    int32_t ne;
+    int64_t n_poly, n_gen;
+    int32_t* eslot = nullptr;       // [ne]
+    int32_t* list_poly = nullptr;   // [n_poly]
+    int32_t* list_gen = nullptr;    // [n_gen]
+    int nf_poly, nfmax, n_p, nvmax;
+};
+
+#define EHDG_SLOT_GEN 0x40000000
+#define EHDG_SLOT_MASK 0x3fffffff
+
+struct ehdg_csr {
+    int32_t nf;
+    int64_t n_rows, nnz;
+    int32_t* row_start = nullptr;   // [nf+1]  first row of facet f
+    int64_t* rowptr = nullptr;      // [n_rows+1]
+    int32_t* colind = nullptr;      // [nnz]
+    int64_t* blk_base = nullptr;    // [nf+1]  first nnz of the row block of facet f
+    int32_t* nbr = nullptr;         // [nf][5] neighbour facets ascending, -1 padded
+    int32_t* nbr_len = nullptr;     // [nf]    row length (sum of active dofs of the neighbours)
+    uint16_t* dofmask = nullptr;    // [nf]    active slots of the facet
+    int32_t* row_facet = nullptr;   // [n_rows] facet of each row
+    double* dinv = nullptr;         // [n_rows * nbmax] block-Jacobi inverses (set by ehdg_gmres)
+    int nb;                         // slots per facet
+};
+
+namespace ehdg {
+// polynomial-path kernels (ehdg_fast.cu)
+int fast_build_tensors(ehdg_ctx* ctx);
+void fast_free_tensors(ehdg_ctx* ctx);
+int fast_alpha(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, double* lam, int32_t* status,
+               cudaStream_t st);
+int fast_assemble(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const double* lam, double* S,
+                  double* g, double* W, double* z, int32_t* status, cudaStream_t st);
+int64_t fast_flops_per_element(const ehdg_ctx* ctx);
+}  // namespace ehdg

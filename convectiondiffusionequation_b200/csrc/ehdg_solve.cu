@@ -1,0 +1,777 @@
+// libehdg: condensed facet system -- CSR build (a8), SpMV + block-Jacobi GMRES (a9),
+// back-solve and error (a10).  See include/ehdg.h for the contract.
+#include <cub/cub.cuh>
+#include <cmath>
+#include <vector>
+
+#include "ehdg_internal.h"
+
+namespace ehdg {
+
+// ---------------------------------------------------------------------------------------------
+// a8 symbolic
+// ---------------------------------------------------------------------------------------------
+__global__ void csr_dofmask_kernel(int nf, int nfl, const int32_t* __restrict__ facet2el,
+                                   const uint8_t* __restrict__ facet_active, uint16_t* __restrict__ dofmask,
+                                   int32_t* __restrict__ nbf) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > nf) return;
+    if (f == nf) { nbf[f] = 0; return; }
+    int m = 0;
+    if (facet2el[2 * f + 1] >= 0) {                                   // interior: free (dirichlet=".*" otherwise)
+        m = (1 << nfl) - 1;
+        if (facet_active) m |= ((int)facet_active[f]) << nfl;
+    }
+    dofmask[f] = (uint16_t)m;
+    nbf[f] = __popc(m);
+}
+
+__global__ void csr_nbr_kernel(int nf, const int32_t* __restrict__ facet2el, const int32_t* __restrict__ el2facet,
+                               const int32_t* __restrict__ nbf, int32_t* __restrict__ nbr, int32_t* __restrict__ nbr_len,
+                               int64_t* __restrict__ blk) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > nf) return;
+    if (f == nf) { blk[f] = 0; return; }
+    int c[6];
+    int n = 0;
+    for (int s = 0; s < 2; ++s) {
+        const int e = facet2el[2 * f + s];
+        if (e < 0) continue;
+        for (int k = 0; k < 3; ++k) c[n++] = el2facet[3 * e + k];
+    }
+    // insertion sort + dedupe
+    for (int i = 1; i < n; ++i) {
+        const int v = c[i];
+        int j = i - 1;
+        while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; --j; }
+        c[j + 1] = v;
+    }
+    int m = 0, len = 0;
+    for (int i = 0; i < n; ++i)
+        if (i == 0 || c[i] != c[i - 1]) {
+            c[m++] = c[i];
+        }
+    for (int i = 0; i < 5; ++i) {
+        nbr[5 * f + i] = i < m ? c[i] : -1;
+        if (i < m) len += nbf[c[i]];
+    }
+    const int rows = nbf[f];
+    nbr_len[f] = rows ? len : 0;
+    blk[f] = (int64_t)rows * len;
+}
+
+__global__ void csr_fill_kernel(int nf, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
+                                const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len,
+                                int64_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t* __restrict__ row_facet) {
+    // one warp per facet
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= nf) return;
+    const int r0 = row_start[f], rows = row_start[f + 1] - r0;
+    if (rows == 0) return;
+    const int len = nbr_len[f];
+    const int64_t base = blk_base[f];
+    for (int i = lane; i < rows; i += 32) {
+        rowptr[r0 + i] = base + (int64_t)i * len;
+        row_facet[r0 + i] = f;
+    }
+    int off = 0;
+    for (int t = 0; t < 5; ++t) {
+        const int g = nbr[5 * f + t];
+        if (g < 0) break;
+        const int c0 = row_start[g], nbg = row_start[g + 1] - c0;
+        for (int idx = lane; idx < rows * nbg; idx += 32) {
+            const int i = idx / nbg, l = idx % nbg;
+            colind[base + (int64_t)i * len + off + l] = c0 + l;
+        }
+        off += nbg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8 numeric: gather, ascending element id
+// ---------------------------------------------------------------------------------------------
+struct SLayout {
+    int n_poly, nfp, nfl, nfg, nb;   // nfp = 3 nfl, nfg = 3 nb
+};
+
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n) {
+    for (int i = 0; i < n; ++i) m &= m - 1;
+    return __ffs(m) - 1;
+}
+
+__global__ void csr_numeric_kernel(int n_rows, SLayout sl, const int32_t* __restrict__ row_facet,
+                                   const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
+                                   const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask,
+                                   const int32_t* __restrict__ facet2el, const int32_t* __restrict__ el2facet,
+                                   const int32_t* __restrict__ eslot, const double* __restrict__ S,
+                                   const double* __restrict__ gv, double* __restrict__ vals, double* __restrict__ rhs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int f = row_facet[r];
+    const int k = nth_set_bit(dofmask[f], r - row_start[f]);        // slot of this row on its facet
+    // adjacent elements (ascending id) and where their blocks live
+    const double* Sb[2];
+    const double* gb[2];
+    int ld[2], nbe[2], lef[2], ef[2][3], ne = 0;
+    for (int s = 0; s < 2; ++s) {
+        const int e = facet2el[2 * f + s];
+        if (e < 0) continue;
+        const int sl_ = eslot[e];
+        const int idx = sl_ & EHDG_SLOT_MASK;
+        if (sl_ & EHDG_SLOT_GEN) {
+            Sb[ne] = S + (size_t)sl.n_poly * sl.nfp * sl.nfp + (size_t)idx * sl.nfg * sl.nfg;
+            gb[ne] = gv + (size_t)sl.n_poly * sl.nfp + (size_t)idx * sl.nfg;
+            ld[ne] = sl.nfg;
+            nbe[ne] = sl.nb;
+        } else {
+            Sb[ne] = S + (size_t)idx * sl.nfp * sl.nfp;
+            gb[ne] = gv + (size_t)idx * sl.nfp;
+            ld[ne] = sl.nfp;
+            nbe[ne] = sl.nfl;
+        }
+        lef[ne] = 0;
+        for (int t = 0; t < 3; ++t) {
+            ef[ne][t] = el2facet[3 * e + t];
+            if (ef[ne][t] == f) lef[ne] = t;
+        }
+        ++ne;
+    }
+    double b = 0.0;
+    for (int s = 0; s < ne; ++s)
+        if (k < nbe[s]) b += gb[s][lef[s] * nbe[s] + k];
+    rhs[r] = b;
+    int64_t pos = rowptr[r];
+    for (int t = 0; t < 5; ++t) {
+        const int g = nbr[5 * f + t];
+        if (g < 0) break;
+        unsigned mg = dofmask[g];
+        int leg[2];
+        for (int s = 0; s < ne; ++s) {
+            leg[s] = -1;
+            for (int u = 0; u < 3; ++u)
+                if (ef[s][u] == g) leg[s] = u;
+        }
+        while (mg) {
+            const int l = __ffs(mg) - 1;
+            mg &= mg - 1;
+            double v = 0.0;
+            for (int s = 0; s < ne; ++s)
+                if (leg[s] >= 0 && k < nbe[s] && l < nbe[s])
+                    v += Sb[s][(size_t)(lef[s] * nbe[s] + k) * ld[s] + leg[s] * nbe[s] + l];
+            vals[pos++] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpMV: CSR, TPR threads per row
+// ---------------------------------------------------------------------------------------------
+template <int TPR>
+__global__ void __launch_bounds__(256)
+spmv_kernel(int n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+            const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(gt / TPR);
+    const int lane = (int)(gt % TPR);
+    double acc = 0.0;
+    if (r < n_rows) {
+        const int64_t b = rowptr[r], e = rowptr[r + 1];
+        for (int64_t i = b + lane; i < e; i += TPR) acc += vals[i] * __ldg(x + colind[i]);
+    }
+#pragma unroll
+    for (int d = TPR / 2; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d, TPR);
+    if (r < n_rows && lane == 0) y[r] = acc;
+}
+
+static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, double* y, cudaStream_t st) {
+    if (A->n_rows == 0) return EHDG_OK;
+    constexpr int TPR = 8;
+    const int64_t threads = A->n_rows * TPR;
+    spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)A->n_rows, A->rowptr, A->colind, vals, x, y);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-Jacobi: invert the facet diagonal blocks, fold M^-1 into the matrix (A <- A M^-1)
+// ---------------------------------------------------------------------------------------------
+constexpr int NBMAX = EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH;
+
+__global__ void bj_invert_kernel(int nf, int nbs, const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ nbr, const double* __restrict__ vals, double* __restrict__ dinv,
+                                 int* __restrict__ fail) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int r0 = row_start[f], n = row_start[f + 1] - r0;
+    if (n == 0) return;
+    int off = 0;
+    for (int t = 0; t < 5; ++t) {
+        const int g = nbr[5 * f + t];
+        if (g == f) break;
+        off += row_start[g + 1] - row_start[g];
+    }
+    double a[NBMAX][2 * NBMAX];
+    for (int i = 0; i < n; ++i) {
+        const double* row = vals + rowptr[r0 + i] + off;
+        for (int j = 0; j < n; ++j) {
+            a[i][j] = row[j];
+            a[i][n + j] = (i == j) ? 1.0 : 0.0;
+        }
+    }
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        double best = fabs(a[k][k]);
+        for (int i = k + 1; i < n; ++i)
+            if (fabs(a[i][k]) > best) { best = fabs(a[i][k]); piv = i; }
+        if (!(best > 0.0)) { *fail = 1; best = 1.0; a[piv][k] = 1.0; }
+        if (piv != k)
+            for (int j = 0; j < 2 * n; ++j) { const double t = a[k][j]; a[k][j] = a[piv][j]; a[piv][j] = t; }
+        const double inv = 1.0 / a[k][k];
+        for (int j = 0; j < 2 * n; ++j) a[k][j] *= inv;
+        for (int i = 0; i < n; ++i) {
+            if (i == k) continue;
+            const double fct = a[i][k];
+            for (int j = 0; j < 2 * n; ++j) a[i][j] -= fct * a[k][j];
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) dinv[(size_t)(r0 + i) * nbs + j] = a[i][n + j];
+}
+
+__global__ void bj_fold_kernel(int n_rows, int nbs, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
+                               const int64_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
+                               const double* __restrict__ dinv, double* __restrict__ vals) {
+    // one thread per (row, neighbour block): segment <- segment * Dinv_g
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(t / 5), nb_i = (int)(t % 5);
+    if (r >= n_rows) return;
+    const int f = row_facet[r];
+    int off = 0, g = -1;
+    for (int u = 0; u <= nb_i; ++u) {
+        g = nbr[5 * f + u];
+        if (g < 0) return;
+        if (u < nb_i) off += row_start[g + 1] - row_start[g];
+    }
+    const int c0 = row_start[g], n = row_start[g + 1] - c0;
+    double seg[NBMAX], out[NBMAX];
+    double* p = vals + rowptr[r] + off;
+    for (int l = 0; l < n; ++l) seg[l] = p[l];
+    for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        for (int l = 0; l < n; ++l) acc += seg[l] * dinv[(size_t)(c0 + l) * nbs + j];
+        out[j] = acc;
+    }
+    for (int j = 0; j < n; ++j) p[j] = out[j];
+}
+
+__global__ void bj_apply_kernel(int n_rows, int nbs, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
+                                const double* __restrict__ dinv, const double* __restrict__ y, double* __restrict__ x) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int f = row_facet[r];
+    const int c0 = row_start[f], n = row_start[f + 1] - c0;
+    double acc = 0.0;
+    for (int l = 0; l < n; ++l) acc += dinv[(size_t)r * nbs + l] * y[c0 + l];
+    x[r] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GMRES vector kernels: tiles of KT Krylov vectors, deterministic two-stage reductions
+// ---------------------------------------------------------------------------------------------
+constexpr int KT = 8;
+constexpr int RED_BLOCKS = 1184;      // 148 SMs x 8
+constexpr int RED_THREADS = 256;
+
+// partial[b][t] = sum over the rows of block b of V[t][row] * w[row],  t < kt
+__global__ void __launch_bounds__(RED_THREADS)
+multi_dot_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int kt, const double* __restrict__ w,
+                 double* __restrict__ partial) {
+    double acc[KT];
+#pragma unroll
+    for (int t = 0; t < KT; ++t) acc[t] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+#pragma unroll
+        for (int t = 0; t < KT; ++t)
+            if (t < kt) acc[t] += V[t * ldv + i] * wi;
+    }
+    __shared__ double red[RED_THREADS / 32][KT];
+#pragma unroll
+    for (int t = 0; t < KT; ++t) {
+        double v = acc[t];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < KT) {
+        double v = 0.0;
+        for (int wv = 0; wv < RED_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+        partial[(size_t)blockIdx.x * KT + threadIdx.x] = v;
+    }
+}
+
+// out[t] (+)= sum_b partial[b][t], fixed order
+__global__ void reduce_partials_kernel(int nblocks, int kt, const double* __restrict__ partial, double* __restrict__ out,
+                                       int accumulate) {
+    __shared__ double red[256];
+    for (int t = 0; t < kt; ++t) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partial[(size_t)b * KT + t];
+        red[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[t] = accumulate ? out[t] + red[0] : red[0];
+        __syncthreads();
+    }
+}
+
+// w -= sum_t h[t] V[t]
+__global__ void multi_axpy_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int kt, const double* __restrict__ h,
+                                  double* __restrict__ w) {
+    double hh[KT];
+#pragma unroll
+    for (int t = 0; t < KT; ++t) hh[t] = t < kt ? h[t] : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double wi = w[i];
+#pragma unroll
+        for (int t = 0; t < KT; ++t)
+            if (t < kt) wi -= hh[t] * V[t * ldv + i];
+        w[i] = wi;
+    }
+}
+
+// out = in / sqrt(*nrm2)
+__global__ void scale_kernel(int64_t n, const double* __restrict__ in, const double* __restrict__ nrm2, double* __restrict__ out) {
+    const double s = 1.0 / sqrt(*nrm2);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i] * s;
+}
+
+// x += sum_t y[t] V[t]   (host-provided coefficients already on the device)
+__global__ void update_x_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ y,
+                                double* __restrict__ x) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double xi = x[i];
+        for (int t = 0; t < k; ++t) xi += y[t] * V[t * ldv + i];
+        x[i] = xi;
+    }
+}
+
+// r = b - r
+__global__ void residual_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        r[i] = b[i] - r[i];
+}
+
+struct VecOps {
+    cudaStream_t st;
+    double* partial;
+    int64_t n;
+    int grid() const {
+        const int64_t need = (n + RED_THREADS - 1) / RED_THREADS;
+        return (int)(need < RED_BLOCKS ? (need > 0 ? need : 1) : RED_BLOCKS);
+    }
+    // out[0..k) = V[0..k)^T w
+    int dots(const double* V, int64_t ldv, int k, const double* w, double* out) const {
+        for (int t0 = 0; t0 < k; t0 += KT) {
+            const int kt = k - t0 < KT ? k - t0 : KT;
+            multi_dot_kernel<<<grid(), RED_THREADS, 0, st>>>(n, V + t0 * ldv, ldv, kt, w, partial);
+            reduce_partials_kernel<<<1, 256, 0, st>>>(grid(), kt, partial, out + t0, 0);
+        }
+        EHDG_LAUNCH_CHECK();
+        return EHDG_OK;
+    }
+    int axpys(const double* V, int64_t ldv, int k, const double* h, double* w) const {
+        for (int t0 = 0; t0 < k; t0 += KT) {
+            const int kt = k - t0 < KT ? k - t0 : KT;
+            multi_axpy_kernel<<<grid(), RED_THREADS, 0, st>>>(n, V + t0 * ldv, ldv, kt, h + t0, w);
+        }
+        EHDG_LAUNCH_CHECK();
+        return EHDG_OK;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// a10 back-solve and error
+// ---------------------------------------------------------------------------------------------
+__global__ void backsolve_kernel(int ne, SLayout sl, int n_p, int nvmax, const int32_t* __restrict__ eslot,
+                                 const int32_t* __restrict__ el2facet, const int32_t* __restrict__ row_start,
+                                 const uint16_t* __restrict__ dofmask, const double* __restrict__ W,
+                                 const double* __restrict__ z, const double* __restrict__ xhat, double* __restrict__ u) {
+    // one warp per element
+    const int el = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (el >= ne) return;
+    const int s = eslot[el];
+    const int idx = s & EHDG_SLOT_MASK;
+    const bool gen = (s & EHDG_SLOT_GEN) != 0;
+    const int nv = gen ? nvmax : n_p, nf = gen ? sl.nfg : sl.nfp, nbe = gen ? sl.nb : sl.nfl;
+    const size_t wb = gen ? (size_t)sl.n_poly * n_p * sl.nfp + (size_t)idx * nvmax * sl.nfg : (size_t)idx * n_p * sl.nfp;
+    const size_t zb = gen ? (size_t)sl.n_poly * n_p + (size_t)idx * nvmax : (size_t)idx * n_p;
+    __shared__ double xl_all[8][3 * NBMAX];
+    double* xl = xl_all[threadIdx.x >> 5];
+    for (int c = lane; c < nf; c += 32) {
+        const int e = c / nbe, k = c % nbe;
+        const int f = el2facet[3 * el + e];
+        const unsigned m = dofmask[f];
+        double v = 0.0;
+        if ((m >> k) & 1u) v = xhat[row_start[f] + __popc(m & ((1u << k) - 1u))];
+        xl[c] = v;
+    }
+    __syncwarp();
+    for (int i = lane; i < nv; i += 32) {
+        double acc = z[zb + i];
+        const double* wr = W + wb + (size_t)i * nf;
+        for (int c = 0; c < nf; ++c) acc -= wr[c] * xl[c];
+        u[zb + i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+l2_error_kernel(Problem pb, RuleSet rs, int ne, int n_poly, const int32_t* __restrict__ eslot,
+                const double* __restrict__ verts, const int32_t* __restrict__ tris,
+                const uint8_t* __restrict__ elem_active, const double* __restrict__ u, double* __restrict__ block_out) {
+    // one warp per element, lanes over quadrature points (order 50 + bonus, conv_diff.py:393-394)
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int el = blockIdx.x * 4 + wid;
+    double e2 = 0.0, h2 = 0.0;
+    if (el < ne) {
+        ElemGeom g;
+        elem_geom(verts, tris + 3 * el, g);
+        const int s = eslot[el];
+        const int idx = s & EHDG_SLOT_MASK;
+        const bool gen = (s & EHDG_SLOT_GEN) != 0;
+        const int nv = gen ? pb.nvmax : pb.n_p;
+        const double* ul = u + (gen ? (size_t)n_poly * pb.n_p + (size_t)idx * pb.nvmax : (size_t)idx * pb.n_p);
+        const int volmask = (gen && elem_active) ? elem_active[el] : 0;
+        for (int q = lane; q < rs.nq; q += 32) {
+            const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
+            double ph[EHDG_MAX_NP + EHDG_MAX_ENRICH], gx[EHDG_MAX_NP + EHDG_MAX_ENRICH], gy[EHDG_MAX_NP + EHDG_MAX_ENRICH];
+            vol_shapes(pb, g, volmask, l0, l1, ph, gx, gy, 1);
+            double uh = 0.0, ux = 0.0, uy = 0.0;
+            for (int i = 0; i < nv; ++i) {
+                const double c = ul[i];
+                if (i < pb.n_p || ((volmask >> (i - pb.n_p)) & 1)) {
+                    uh += c * ph[i];
+                    ux += c * gx[i];
+                    uy += c * gy[i];
+                }
+            }
+            const double dx = l0 * g.omx[0] + l1 * g.omx[1] + l2 * g.omx[2];
+            const double dy = l0 * g.omy[0] + l1 * g.omy[1] + l2 * g.omy[2];
+            double ex, egx, egy;
+            layer_expr_grad(pb.exact, dx, dy, &ex, &egx, &egy);
+            const double w = rs.vw[q] * g.adet;
+            e2 += w * (uh - ex) * (uh - ex);
+            h2 += w * ((ux - egx) * (ux - egx) + (uy - egy) * (uy - egy));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        e2 += __shfl_xor_sync(0xffffffffu, e2, d);
+        h2 += __shfl_xor_sync(0xffffffffu, h2, d);
+    }
+    __shared__ double red[4][2];
+    if (lane == 0) { red[wid][0] = e2; red[wid][1] = h2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        block_out[(size_t)blockIdx.x * KT + 0] = red[0][0] + red[1][0] + red[2][0] + red[3][0];
+        block_out[(size_t)blockIdx.x * KT + 1] = red[0][1] + red[1][1] + red[2][1] + red[3][1];
+    }
+}
+
+}  // namespace ehdg
+
+using namespace ehdg;
+
+static SLayout make_slayout(const ehdg_ctx* c, const ehdg_plan* p) {
+    SLayout sl;
+    sl.n_poly = (int)p->n_poly;
+    sl.nfl = c->pb.nfl;
+    sl.nfp = 3 * c->pb.nfl;
+    sl.nb = c->pb.nb;
+    sl.nfg = c->pb.nfmax;
+    return sl;
+}
+
+extern "C" {
+
+int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_active, ehdg_csr** out, void* stream) {
+    if (!c || !m || !out) { set_error("ehdg_csr_symbolic: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nf = m->nf;
+    ehdg_csr* A = new ehdg_csr();
+    A->nf = nf;
+    A->nb = c->pb.nb;
+    int32_t* nbf = nullptr;
+    int64_t* blk = nullptr;
+    void* tmp = nullptr;
+    size_t tb1 = 0, tb2 = 0;
+    EHDG_CUDA(cudaMalloc(&nbf, sizeof(int32_t) * (size_t)(nf + 1)));
+    EHDG_CUDA(cudaMalloc(&blk, sizeof(int64_t) * (size_t)(nf + 1)));
+    EHDG_CUDA(cudaMalloc(&A->dofmask, sizeof(uint16_t) * (size_t)(nf + 1)));
+    EHDG_CUDA(cudaMalloc(&A->row_start, sizeof(int32_t) * (size_t)(nf + 1)));
+    EHDG_CUDA(cudaMalloc(&A->blk_base, sizeof(int64_t) * (size_t)(nf + 1)));
+    EHDG_CUDA(cudaMalloc(&A->nbr, sizeof(int32_t) * 5 * (size_t)(nf + 1)));
+    EHDG_CUDA(cudaMalloc(&A->nbr_len, sizeof(int32_t) * (size_t)(nf + 1)));
+    const int gb = (nf + 1 + 255) / 256;
+    csr_dofmask_kernel<<<gb, 256, 0, st>>>(nf, c->pb.nfl, m->facet2el, c->pb.nenr ? facet_active : nullptr, A->dofmask, nbf);
+    EHDG_LAUNCH_CHECK();
+    csr_nbr_kernel<<<gb, 256, 0, st>>>(nf, m->facet2el, m->el2facet, nbf, A->nbr, A->nbr_len, blk);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb1, nbf, A->row_start, nf + 1, st));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, blk, A->blk_base, nf + 1, st));
+    EHDG_CUDA(cudaMalloc(&tmp, (tb1 > tb2 ? tb1 : tb2) + 8));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb1, nbf, A->row_start, nf + 1, st));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb2, blk, A->blk_base, nf + 1, st));
+    int32_t nrows = 0;
+    int64_t nnz = 0;
+    EHDG_CUDA(cudaMemcpyAsync(&nrows, A->row_start + nf, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cudaMemcpyAsync(&nnz, A->blk_base + nf, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    A->n_rows = nrows;
+    A->nnz = nnz;
+    EHDG_CUDA(cudaMalloc(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1)));
+    EHDG_CUDA(cudaMalloc(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+    int32_t* row_facet = nullptr;
+    EHDG_CUDA(cudaMalloc(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1)));
+    if (nf > 0) csr_fill_kernel<<<(unsigned)(((int64_t)nf * 32 + 255) / 256), 256, 0, st>>>(nf, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    A->dinv = nullptr;
+    cudaFree(nbf);
+    cudaFree(blk);
+    cudaFree(tmp);
+    A->row_facet = row_facet;
+    *out = A;
+    return EHDG_OK;
+}
+
+int ehdg_csr_destroy(ehdg_csr* A) {
+    if (!A) return EHDG_OK;
+    cudaFree(A->row_start);
+    cudaFree(A->rowptr);
+    cudaFree(A->colind);
+    cudaFree(A->blk_base);
+    cudaFree(A->nbr);
+    cudaFree(A->nbr_len);
+    cudaFree(A->dofmask);
+    cudaFree(A->dinv);
+    cudaFree(A->row_facet);
+    delete A;
+    return EHDG_OK;
+}
+
+int ehdg_csr_get_sizes(const ehdg_csr* A, ehdg_csr_sizes* o) {
+    if (!A || !o) { set_error("ehdg_csr_get_sizes: null argument"); return EHDG_ERR_ARG; }
+    o->n_rows = A->n_rows;
+    o->nnz = A->nnz;
+    return EHDG_OK;
+}
+const int64_t* ehdg_csr_rowptr(const ehdg_csr* A) { return A ? A->rowptr : nullptr; }
+const int32_t* ehdg_csr_colind(const ehdg_csr* A) { return A ? A->colind : nullptr; }
+const int32_t* ehdg_csr_row_start(const ehdg_csr* A) { return A ? A->row_start : nullptr; }
+const uint16_t* ehdg_csr_dofmask(const ehdg_csr* A) { return A ? A->dofmask : nullptr; }
+
+int ehdg_csr_numeric(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehdg_mesh* m, const double* S, const double* g,
+                     double* vals, double* rhs, void* stream) {
+    if (!c || !p || !A || !m || !S || !g || !vals || !rhs) { set_error("ehdg_csr_numeric: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (A->n_rows == 0) return EHDG_OK;
+    csr_numeric_kernel<<<(unsigned)((A->n_rows + 127) / 128), 128, 0, st>>>((int)A->n_rows, make_slayout(c, p), A->row_facet, A->row_start,
+                                                                            A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,
+                                                                            p->eslot, S, g, vals, rhs);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+int ehdg_spmv(ehdg_ctx* c, const ehdg_csr* A, const double* vals, const double* x, double* y, void* stream) {
+    if (!c || !A || !vals || !x || !y) { set_error("ehdg_spmv: null argument"); return EHDG_ERR_ARG; }
+    return launch_spmv(A, vals, x, y, (cudaStream_t)stream);
+}
+
+int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream) {
+    if (!c || !A || !vals || !rhs || !x || !info) { set_error("ehdg_gmres: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = A->n_rows;
+    const int m = info->restart > 0 ? info->restart : 30;
+    const int max_iters = info->max_iters > 0 ? info->max_iters : 1000;
+    const double rtol = info->rtol > 0 ? info->rtol : 1e-10;
+    info->iters = 0;
+    info->converged = 0;
+    info->rel_residual = 0.0;
+    info->spmv_calls = 0;
+    info->total_seconds = 0.0;
+    if (n == 0) { info->converged = 1; return EHDG_OK; }
+    cudaEvent_t ev0, ev1;
+    EHDG_CUDA(cudaEventCreate(&ev0));
+    EHDG_CUDA(cudaEventCreate(&ev1));
+    EHDG_CUDA(cudaEventRecord(ev0, st));
+    const int nbs = A->nb;
+    // ---- preconditioner: Dinv, then A <- A M^-1 in place
+    if (!A->dinv) EHDG_CUDA(cudaMalloc(&A->dinv, sizeof(double) * (size_t)n * nbs));
+    int* fail = nullptr;
+    EHDG_CUDA(cudaMalloc(&fail, sizeof(int)));
+    EHDG_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
+    bj_invert_kernel<<<(A->nf + 127) / 128, 128, 0, st>>>(A->nf, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail);
+    EHDG_LAUNCH_CHECK();
+    bj_fold_kernel<<<(unsigned)((n * 5 + 255) / 256), 256, 0, st>>>((int)n, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr, A->dinv, vals);
+    EHDG_LAUNCH_CHECK();
+    // ---- workspace
+    double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr;
+    EHDG_CUDA(cudaMalloc(&V, sizeof(double) * (size_t)n * (m + 1)));
+    EHDG_CUDA(cudaMalloc(&w, sizeof(double) * (size_t)n));
+    EHDG_CUDA(cudaMalloc(&yhat, sizeof(double) * (size_t)n));
+    EHDG_CUDA(cudaMalloc(&partial, sizeof(double) * (size_t)RED_BLOCKS * KT));
+    EHDG_CUDA(cudaMalloc(&dsc, sizeof(double) * (size_t)(3 * (m + 2) + 8)));
+    double* d_h1 = dsc;                 // m+1
+    double* d_h2 = dsc + (m + 2);       // m+1
+    double* d_nrm = dsc + 2 * (m + 2);  // 1
+    double* d_y = d_nrm + 4;            // m
+    double* hbuf = nullptr;
+    EHDG_CUDA(cudaMallocHost(&hbuf, sizeof(double) * (size_t)(2 * (m + 2) + 8)));
+    EHDG_CUDA(cudaMemsetAsync(yhat, 0, sizeof(double) * (size_t)n, st));
+    VecOps vo{st, partial, n};
+    const int vgrid = vo.grid();
+    int rc;
+    // ||b||
+    if ((rc = vo.dots(rhs, n, 1, rhs, d_nrm))) return rc;
+    EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    const double bnorm = std::sqrt(hbuf[0]);
+    int fail_h = 0;
+    EHDG_CUDA(cudaMemcpy(&fail_h, fail, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(fail);
+    if (fail_h) { set_error("ehdg_gmres: singular facet diagonal block"); return EHDG_ERR_SINGULAR; }
+    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), gvec(m + 1), yv(m);
+    double rel = 1.0;
+    int iters = 0;
+    bool conv = (bnorm == 0.0);
+    if (conv) rel = 0.0;
+    while (!conv && iters < max_iters) {
+        // r = b - A yhat  (into w), beta = ||r||
+        if ((rc = launch_spmv(A, vals, yhat, w, st))) return rc;
+        info->spmv_calls++;
+        residual_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, rhs, w);
+        if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
+        EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        const double beta = std::sqrt(hbuf[0]);
+        rel = beta / bnorm;
+        if (rel <= rtol) { conv = true; break; }
+        scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, V);
+        std::fill(gvec.begin(), gvec.end(), 0.0);
+        gvec[0] = beta;
+        int j = 0;
+        for (; j < m && iters < max_iters; ++j, ++iters) {
+            double* vj1 = V + (size_t)(j + 1) * n;
+            if ((rc = launch_spmv(A, vals, V + (size_t)j * n, w, st))) return rc;
+            info->spmv_calls++;
+            // classical Gram-Schmidt, twice
+            if ((rc = vo.dots(V, n, j + 1, w, d_h1))) return rc;
+            if ((rc = vo.axpys(V, n, j + 1, d_h1, w))) return rc;
+            if ((rc = vo.dots(V, n, j + 1, w, d_h2))) return rc;
+            if ((rc = vo.axpys(V, n, j + 1, d_h2, w))) return rc;
+            if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
+            scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, vj1);
+            EHDG_CUDA(cudaMemcpyAsync(hbuf, dsc, sizeof(double) * (size_t)(2 * (m + 2) + 1), cudaMemcpyDeviceToHost, st));
+            EHDG_CUDA(cudaStreamSynchronize(st));
+            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hbuf[i] + hbuf[(m + 2) + i];
+            const double hn = std::sqrt(hbuf[2 * (m + 2)]);
+            H[(size_t)(j + 1) * m + j] = hn;
+            for (int i = 0; i < j; ++i) {
+                const double t = cs[i] * H[(size_t)i * m + j] + sn[i] * H[(size_t)(i + 1) * m + j];
+                H[(size_t)(i + 1) * m + j] = -sn[i] * H[(size_t)i * m + j] + cs[i] * H[(size_t)(i + 1) * m + j];
+                H[(size_t)i * m + j] = t;
+            }
+            const double a = H[(size_t)j * m + j], b = H[(size_t)(j + 1) * m + j];
+            const double d = std::hypot(a, b);
+            cs[j] = d > 0 ? a / d : 1.0;
+            sn[j] = d > 0 ? b / d : 0.0;
+            H[(size_t)j * m + j] = d;
+            H[(size_t)(j + 1) * m + j] = 0.0;
+            gvec[j + 1] = -sn[j] * gvec[j];
+            gvec[j] = cs[j] * gvec[j];
+            rel = std::fabs(gvec[j + 1]) / bnorm;
+            if (rel <= rtol || !(hn > 0.0)) { ++j; ++iters; break; }
+        }
+        // y = H^-1 g, yhat += V y
+        for (int i = j - 1; i >= 0; --i) {
+            double s = gvec[i];
+            for (int k = i + 1; k < j; ++k) s -= H[(size_t)i * m + k] * yv[k];
+            yv[i] = s / H[(size_t)i * m + i];
+        }
+        for (int i = 0; i < j; ++i) hbuf[i] = yv[i];
+        EHDG_CUDA(cudaMemcpyAsync(d_y, hbuf, sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, st));
+        update_x_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, V, n, j, d_y, yhat);
+        EHDG_CUDA(cudaStreamSynchronize(st));
+    }
+    // true residual at exit
+    if (!(bnorm == 0.0)) {
+        if ((rc = launch_spmv(A, vals, yhat, w, st))) return rc;
+        info->spmv_calls++;
+        residual_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, rhs, w);
+        if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
+        EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        rel = std::sqrt(hbuf[0]) / bnorm;
+        conv = rel <= rtol * 10.0;
+    }
+    // x = M^-1 yhat
+    bj_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n, nbs, A->row_facet, A->row_start, A->dinv, yhat, x);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cudaEventRecord(ev1, st));
+    EHDG_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    info->iters = iters;
+    info->converged = conv ? 1 : 0;
+    info->rel_residual = rel;
+    info->total_seconds = ms * 1e-3;
+    cudaFree(V);
+    cudaFree(w);
+    cudaFree(yhat);
+    cudaFree(partial);
+    cudaFree(dsc);
+    cudaFreeHost(hbuf);
+    return EHDG_OK;
+}
+
+int ehdg_backsolve(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehdg_mesh* m, const double* W, const double* z,
+                   const double* xhat, double* u, void* stream) {
+    if (!c || !p || !A || !m || !W || !z || !xhat || !u) { set_error("ehdg_backsolve: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->ne == 0) return EHDG_OK;
+    backsolve_kernel<<<(unsigned)(((int64_t)m->ne * 32 + 255) / 256), 256, 0, st>>>(m->ne, make_slayout(c, p), c->pb.n_p, c->pb.nvmax, p->eslot,
+                                                                                    m->el2facet, A->row_start, A->dofmask, W, z, xhat, u);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+int ehdg_l2_error(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, const double* u, double* err2,
+                  void* stream) {
+    if (!c || !p || !m || !u || !err2) { set_error("ehdg_l2_error: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblocks = (m->ne + 3) / 4;
+    if (nblocks == 0) { EHDG_CUDA(cudaMemsetAsync(err2, 0, 16, st)); return EHDG_OK; }
+    double* partial = nullptr;
+    EHDG_CUDA(cudaMalloc(&partial, sizeof(double) * (size_t)nblocks * KT));
+    l2_error_kernel<<<nblocks, 128, 0, st>>>(c->pb, c->rerr.rs, m->ne, (int)p->n_poly, p->eslot, m->verts, m->tris,
+                                             c->pb.nenr ? elem_active : nullptr, u, partial);
+    EHDG_LAUNCH_CHECK();
+    reduce_partials_kernel<<<1, 256, 0, st>>>(nblocks, 2, partial, err2, 0);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    cudaFree(partial);
+    return EHDG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+"""Host-side part of the enrichment layer (reference Python/enrichment_proxy.py).
+
+The proxy classes of the reference (EnrichmentProxy_VOL/_FAC, :83-195) only exist to state
+u = u_poly + sum c_i psi_i to NGSolve's symbolic integrators; here that statement is built into
+the kernels (csrc/ehdg_general.h: vol_shapes / facet_shapes).  What remains on the host is the
+evaluation of the Python predicates `enr_indicator(x, y, h)` on the mesh vertices
+(mark_elements, :201-208): the any-vertex / any-adjacent-element reductions run on the device
+(ehdg_mark).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def vertex_flags(verts: np.ndarray, indicators, mesh_size: float) -> np.ndarray:
+    """u8 [n_enrich, nv]: enr_indicator(x_v, y_v, mesh_size) per vertex, as the reference's
+    mark_elements evaluates it (enrichment_proxy.py:204-206)."""
+    out = np.zeros((len(indicators), verts.shape[0]), dtype=np.uint8)
+    xs, ys = verts[:, 0], verts[:, 1]
+    for i, ind in enumerate(indicators):
+        try:
+            r = np.asarray(ind(xs, ys, mesh_size))
+            if r.shape != xs.shape:
+                raise ValueError
+            out[i] = r.astype(bool)
+        except Exception:
+            out[i] = np.fromiter((bool(ind(float(a), float(b), mesh_size)) for a, b in zip(xs, ys)),
+                                 dtype=bool, count=xs.shape[0])
+    return out

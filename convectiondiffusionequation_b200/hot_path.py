@@ -1,0 +1,278 @@
+"""Device pipeline of the (E)HDG hot path: thin Python over the C ABI (include/ehdg.h).
+
+Stages mirror Convection_Diffusion._solveEHDG of the reference
+(Python/convection_diffusion.py:223-403): mark -> prune -> alpha -> assemble+condense ->
+CSR -> GMRES -> back-solve -> error.  torch is used for device buffers only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .coefficients import LayerExpr
+from .enrichment_proxy import vertex_flags
+from .mesh import TriMesh
+
+
+@dataclass
+class ProblemSpec:
+    order: int
+    epsilon: float
+    beta: tuple
+    bonus_int: int = 10
+    coeff: LayerExpr | None = None
+    exact: LayerExpr | None = None
+    enrich_functions: tuple = ()
+    enrich_domain_ind: tuple = ()
+
+    def c_struct(self) -> _lib.Problem:
+        p = _lib.Problem()
+        p.order = int(self.order)
+        p.bonus_int = int(self.bonus_int)
+        p.epsilon = float(self.epsilon)
+        p.beta[0], p.beta[1] = float(self.beta[0]), float(self.beta[1])
+        if len(self.enrich_functions) > _lib.MAX_ENR:
+            raise ValueError(f"at most {_lib.MAX_ENR} enrichment functions are supported")
+        p.n_enrich = len(self.enrich_functions)
+        for i, f in enumerate(self.enrich_functions):
+            ax, k = f.single_axis()
+            p.enrich_axis[i] = ax
+            p.enrich_k[i] = k
+        for name in ("coeff", "exact"):
+            f = getattr(self, name)
+            if f is not None:
+                c, k = f.desc()
+                for i in range(4):
+                    getattr(p, name).c[i] = c[i]
+                for i in range(2):
+                    getattr(p, name).k[i] = k[i]
+        return p
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class EHDGPipeline:
+    """One (mesh, order) instance of the hot path on one GPU."""
+
+    def __init__(self, mesh: TriMesh, spec: ProblemSpec, device="cuda:0", force_general=False):
+        if not torch.cuda.is_available():
+            raise _lib.EhdgError("no CUDA device: the (E)HDG hot path has no CPU fallback")
+        self.lib = _lib.load()
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.mesh_host = mesh
+        self.spec = spec
+        self.force_general = bool(force_general)
+        self.nenr = len(spec.enrich_functions)
+        self._cprob = spec.c_struct()
+        self.ctx = C.c_void_p()
+        _lib.check(self.lib.ehdg_create(C.byref(self._cprob), C.byref(self.ctx)), "ehdg_create")
+        self.sizes = _lib.Sizes()
+        _lib.check(self.lib.ehdg_get_sizes(self.ctx, C.byref(self.sizes)), "ehdg_get_sizes")
+        self.plan = None
+        self.csr = None
+        self.upload_mesh()
+
+    # ------------------------------------------------------------------ mesh
+    def upload_mesh(self, pinned=None):
+        m = self.mesh_host
+        src = pinned or dict(verts=torch.from_numpy(m.verts), tris=torch.from_numpy(m.tris),
+                             el2facet=torch.from_numpy(m.el2facet), facet2el=torch.from_numpy(m.facet2el))
+        self.verts = src["verts"].to(self.dev, non_blocking=True)
+        self.tris = src["tris"].to(self.dev, non_blocking=True)
+        self.el2facet = src["el2facet"].to(self.dev, non_blocking=True)
+        self.facet2el = src["facet2el"].to(self.dev, non_blocking=True)
+        self.cmesh = _lib.Mesh(m.nv, m.ne, m.nf, self.verts.data_ptr(), self.tris.data_ptr(),
+                               self.el2facet.data_ptr(), self.facet2el.data_ptr())
+        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in (self.verts, self.tris, self.el2facet, self.facet2el))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    # ------------------------------------------------------------------ a1
+    def mark(self):
+        m = self.mesh_host
+        ne, nf = m.ne, m.nf
+        self.elem_mask = torch.zeros(ne, dtype=torch.uint8, device=self.dev)
+        self.facet_mask = torch.zeros((nf + 3) // 4 * 4, dtype=torch.uint8, device=self.dev)
+        if self.nenr:
+            vf = vertex_flags(m.verts, self.spec.enrich_domain_ind, m.maxh)
+            self.vert_flags = torch.from_numpy(vf).to(self.dev)
+            _lib.check(self.lib.ehdg_mark(self.ctx, C.byref(self.cmesh), _ptr(self.vert_flags), _ptr(self.elem_mask),
+                                          _ptr(self.facet_mask), self._stream()), "ehdg_mark")
+        if self.plan is not None:
+            self.lib.ehdg_plan_destroy(self.plan)
+        self.plan = C.c_void_p()
+        _lib.check(self.lib.ehdg_plan_create(self.ctx, C.byref(self.cmesh), _ptr(self.facet_mask), int(self.force_general),
+                                             C.byref(self.plan), self._stream()), "ehdg_plan_create")
+        self.plan_sizes = _lib.PlanSizes()
+        _lib.check(self.lib.ehdg_plan_get_sizes(self.plan, C.byref(self.plan_sizes)), "ehdg_plan_get_sizes")
+        return self
+
+    def eslot(self) -> torch.Tensor:
+        """i32 [ne]: bit 30 = general path, low bits = index on that path (copy of the plan's array)."""
+        torch.cuda.synchronize(self.dev)
+        return _device_view(self.lib.ehdg_plan_eslot(self.plan), self.mesh_host.ne, torch.int32, self.dev).clone()
+
+    # ------------------------------------------------------------------ a3
+    def prune(self, threshold=1e-5, want_factors=False):
+        m = self.mesh_host
+        self.elem_active = torch.zeros(m.ne, dtype=torch.uint8, device=self.dev)
+        self.facet_active = torch.zeros((m.nf + 3) // 4 * 4, dtype=torch.uint8, device=self.dev)
+        self.factors = (torch.empty((m.ne, 4 * self.nenr), dtype=torch.float64, device=self.dev)
+                        if (want_factors and self.nenr) else None)
+        _lib.check(self.lib.ehdg_prune(self.ctx, self.plan, C.byref(self.cmesh), _ptr(self.elem_mask), _ptr(self.facet_mask),
+                                       float(threshold), _ptr(self.elem_active), _ptr(self.facet_active), _ptr(self.factors),
+                                       self._stream()), "ehdg_prune")
+        return self
+
+    # ------------------------------------------------------------------ a4
+    def alpha(self):
+        ne = self.mesh_host.ne
+        if not hasattr(self, "lam") or self.lam.numel() != ne:
+            self.lam = torch.empty(ne, dtype=torch.float64, device=self.dev)
+            self.status = torch.zeros(ne, dtype=torch.int32, device=self.dev)
+        _lib.check(self.lib.ehdg_alpha(self.ctx, self.plan, C.byref(self.cmesh), _ptr(self.elem_active), _ptr(self.lam),
+                                       _ptr(self.status), self._stream()), "ehdg_alpha")
+        return self
+
+    # ------------------------------------------------------------------ a5-a7
+    def alloc_blocks(self, want_full=False):
+        ps = self.plan_sizes
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.S = torch.empty(ps.S_doubles, **f64)
+        self.g = torch.empty(ps.g_doubles, **f64)
+        self.W = torch.empty(ps.W_doubles, **f64)
+        self.z = torch.empty(ps.z_doubles, **f64)
+        s = self.sizes
+        self.afull_stride = s.nvmax * (s.nvmax + s.nfmax + 1) + s.nfmax * s.nvmax + s.nfmax * s.nfmax
+        self.Afull = torch.zeros(ps.n_gen * self.afull_stride, **f64) if want_full else None
+
+    def assemble_condense(self, want_full=False):
+        if not hasattr(self, "S") or self.S.numel() != self.plan_sizes.S_doubles or (want_full and self.Afull is None):
+            self.alloc_blocks(want_full)
+        _lib.check(self.lib.ehdg_assemble_condense(self.ctx, self.plan, C.byref(self.cmesh), _ptr(self.lam), _ptr(self.elem_active),
+                                                   _ptr(self.facet_mask), _ptr(self.S), _ptr(self.g), _ptr(self.W), _ptr(self.z),
+                                                   _ptr(self.status), _ptr(self.Afull) if want_full else None, self._stream()),
+                   "ehdg_assemble_condense")
+        return self
+
+    # ------------------------------------------------------------------ a8
+    def csr_build(self):
+        if self.csr is not None:
+            self.lib.ehdg_csr_destroy(self.csr)
+        self.csr = C.c_void_p()
+        _lib.check(self.lib.ehdg_csr_symbolic(self.ctx, C.byref(self.cmesh), _ptr(self.facet_active) if self.nenr else None,
+                                              C.byref(self.csr), self._stream()), "ehdg_csr_symbolic")
+        self.csr_sizes = _lib.CsrSizes()
+        _lib.check(self.lib.ehdg_csr_get_sizes(self.csr, C.byref(self.csr_sizes)), "ehdg_csr_get_sizes")
+        n, nnz = self.csr_sizes.n_rows, self.csr_sizes.nnz
+        self.vals = torch.empty(max(nnz, 1), dtype=torch.float64, device=self.dev)
+        self.rhs = torch.empty(max(n, 1), dtype=torch.float64, device=self.dev)
+        self.csr_numeric()
+        return self
+
+    def csr_numeric(self):
+        _lib.check(self.lib.ehdg_csr_numeric(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.S), _ptr(self.g),
+                                             _ptr(self.vals), _ptr(self.rhs), self._stream()), "ehdg_csr_numeric")
+        return self
+
+    def csr_arrays(self):
+        """(rowptr i64, colind i32, row_start i32, dofmask u16) as torch tensors (copies)."""
+        n, nnz, nf = self.csr_sizes.n_rows, self.csr_sizes.nnz, self.mesh_host.nf
+        rp = _device_view(self.lib.ehdg_csr_rowptr(self.csr), n + 1, torch.int64, self.dev).clone()
+        ci = _device_view(self.lib.ehdg_csr_colind(self.csr), max(nnz, 1), torch.int32, self.dev)[:nnz].clone()
+        rs = _device_view(self.lib.ehdg_csr_row_start(self.csr), nf + 1, torch.int32, self.dev).clone()
+        dm = _device_view(self.lib.ehdg_csr_dofmask(self.csr), nf, torch.int16, self.dev).clone()
+        return rp, ci, rs, dm
+
+    # ------------------------------------------------------------------ a9
+    def spmv(self, x, y=None):
+        y = torch.empty_like(x) if y is None else y
+        _lib.check(self.lib.ehdg_spmv(self.ctx, self.csr, _ptr(self.vals), _ptr(x), _ptr(y), self._stream()), "ehdg_spmv")
+        return y
+
+    def gmres(self, restart=30, max_iters=20000, rtol=1e-12):
+        n = self.csr_sizes.n_rows
+        self.xhat = torch.zeros(max(n, 1), dtype=torch.float64, device=self.dev)
+        info = _lib.GmresInfo()
+        info.restart, info.max_iters, info.rtol = int(restart), int(max_iters), float(rtol)
+        _lib.check(self.lib.ehdg_gmres(self.ctx, self.csr, _ptr(self.vals), _ptr(self.rhs), _ptr(self.xhat), C.byref(info),
+                                       self._stream()), "ehdg_gmres")
+        self.gmres_info = info
+        return self
+
+    # ------------------------------------------------------------------ a10
+    def backsolve(self):
+        self.u = torch.empty(self.plan_sizes.z_doubles, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ehdg_backsolve(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.W), _ptr(self.z),
+                                           _ptr(self.xhat), _ptr(self.u), self._stream()), "ehdg_backsolve")
+        return self
+
+    def errors(self):
+        """(L2 error, H1-seminorm error) against spec.exact with the order 50+bonus rule."""
+        err2 = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ehdg_l2_error(self.ctx, self.plan, C.byref(self.cmesh), _ptr(self.elem_active), _ptr(self.u),
+                                          _ptr(err2), self._stream()), "ehdg_l2_error")
+        e = err2.cpu().numpy()
+        return float(np.sqrt(e[0])), float(np.sqrt(e[1]))
+
+    # ------------------------------------------------------------------ whole path
+    def setup(self, prune_threshold=1e-5):
+        return self.mark().prune(prune_threshold)
+
+    def assemble(self):
+        """the metric's unit of work: alpha + element blocks + static condensation of every element"""
+        return self.alpha().assemble_condense()
+
+    def solve(self, **gm):
+        return self.csr_build().gmres(**gm).backsolve()
+
+    def ndof(self) -> int:
+        """fes.ndof of the reference's compound space [V, F, Qx, QFx, Qy, QFy] (conv_diff.py:246, :396)."""
+        m, s = self.mesh_host, self.sizes
+        n = m.ne * s.n_p + m.nf * s.nfl
+        if self.nenr:
+            em = self.elem_mask.cpu().numpy()
+            fm = self.facet_mask.cpu().numpy()[:m.nf]
+            for i in range(self.nenr):
+                n += int(((em >> i) & 1).sum()) + int(((fm >> i) & 1).sum())
+        return int(n)
+
+    def close(self):
+        if self.csr is not None:
+            self.lib.ehdg_csr_destroy(self.csr)
+            self.csr = None
+        if self.plan is not None:
+            self.lib.ehdg_plan_destroy(self.plan)
+            self.plan = None
+        if self.ctx:
+            self.lib.ehdg_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _device_view(ptr, n, dtype, dev):
+    """torch view of a library-owned device buffer (no ownership transfer)."""
+    itemsize = torch.empty((), dtype=dtype).element_size()
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {
+        "shape": (int(n),), "typestr": {torch.int32: "<i4", torch.int64: "<i8", torch.int16: "<i2",
+                                        torch.float64: "<f8", torch.uint8: "|u1"}[dtype],
+        "data": (int(ptr), False), "version": 2, "strides": (itemsize,)}
+    return torch.as_tensor(h, device=dev)

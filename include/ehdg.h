@@ -1,0 +1,197 @@
+/* libehdg -- C ABI of the B200-native (E)HDG convection-diffusion hot path.
+ *
+ * The reference (aqibrahimbt/convectiondiffusionequation) has no FFI of its own: its hot path
+ * is a Python method that scripts NGSolve.  Each entry point below replaces one stage of
+ *   Python/convection_diffusion.py:223-403  (Convection_Diffusion._solveEHDG)
+ * and cites the lines it stands for.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ehdg_status otherwise; ehdg_last_error()
+ *     gives the text.  No exceptions cross the boundary.
+ *   - all array pointers are DEVICE pointers owned by the caller unless the name says `host`;
+ *     `stream` is a cudaStream_t passed as void* (0 = default stream).  Work is stream ordered.
+ *   - the library owns only: the context (quadrature rules and reference tensors on the
+ *     device), the plan (element classification lists), and scratch it allocates per call.
+ *   - there is no CPU code path: without a CUDA device ehdg_create fails with EHDG_ERR_CUDA.
+ */
+#ifndef EHDG_H
+#define EHDG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EHDG_MAX_ENR 2
+
+typedef enum {
+    EHDG_OK = 0,
+    EHDG_ERR_ARG = -1,
+    EHDG_ERR_CUDA = -2,
+    EHDG_ERR_ALLOC = -3,
+    EHDG_ERR_SINGULAR = -4,
+    EHDG_ERR_NOCONV = -5,
+    EHDG_ERR_NCCL = -6
+} ehdg_status;
+
+/* f(x,y) = c0 + c1 L(k0;x) + c2 L(k1;y) + c3 L(k0;x) L(k1;y),
+ * L(k;s) = s + (exp(k(s-1)) - exp(-k)) / (exp(-k) - 1)   (run.py:26-27, k = beta_i/eps) */
+typedef struct {
+    double c[4];
+    double k[2];
+} ehdg_layer_expr;
+
+/* Problem definition: the config keys of run.py:32-46 that reach the kernels. */
+typedef struct {
+    int32_t order;                   /* config['order'] entry, 1..6 */
+    int32_t bonus_int;               /* config['bonus_int'] */
+    double epsilon;                  /* config['epsilon'] */
+    double beta[2];                  /* config['beta'] */
+    int32_t n_enrich;                /* len(config['enrich_functions']), 0..2 */
+    int32_t enrich_axis[EHDG_MAX_ENR]; /* 0: psi = L(k; x), 1: psi = L(k; y) */
+    double enrich_k[EHDG_MAX_ENR];
+    ehdg_layer_expr coeff;           /* config['coeff']  (right-hand side) */
+    ehdg_layer_expr exact;           /* config['exact']  (error computation) */
+} ehdg_problem;
+
+/* Triangle mesh with facet topology (replaces Mesh(unit_square.GenerateMesh(maxh)),
+ * convection_diffusion.py:228).  Local edges follow NGSolve ET_TRIG: e0={V2,V0}, e1={V1,V2},
+ * e2={V0,V1}. */
+typedef struct {
+    int32_t nv, ne, nf;
+    const double* verts;       /* f64 [nv,2] */
+    const int32_t* tris;       /* i32 [ne,3] */
+    const int32_t* el2facet;   /* i32 [ne,3] facet of local edge 0,1,2 */
+    const int32_t* facet2el;   /* i32 [nf,2] adjacent elements ascending, -1 = none (boundary) */
+} ehdg_mesh;
+
+typedef struct ehdg_ctx ehdg_ctx;
+
+/* derived sizes, filled by ehdg_get_sizes */
+typedef struct {
+    int32_t n_p;      /* (p+1)(p+2)/2 polynomial volume dofs */
+    int32_t nfl;      /* p+1 polynomial dofs per facet */
+    int32_t nb;       /* nfl + n_enrich dof slots per facet */
+    int32_t nvmax;    /* n_p + n_enrich volume slots of a general element */
+    int32_t nfmax;    /* 3 nb facet slots of a general element */
+    int32_t nf_poly;  /* 3 nfl facet dofs of a polynomial (fast path) element */
+    int32_t nq, nqf;  /* points of the order 2p+bonus triangle / segment rules */
+    int32_t nq0, nqf0;/* same for order 2p (alpha integrators, convection_diffusion.py:315-320) */
+    int32_t nq_err;   /* points of the order 50+bonus rule (convection_diffusion.py:393-394) */
+    int64_t flops_poly_elem;   /* flops the polynomial path spends per element (alpha + assemble + condense) */
+    int64_t flops_quad_elem;   /* SURVEY 8(d) quadrature-algorithm flops per unenriched element */
+} ehdg_sizes;
+
+const char* ehdg_version(void);
+const char* ehdg_last_error(void);
+
+/* context: rules + reference tensors for (order, bonus, enrichment) on the current device */
+int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out);
+int ehdg_destroy(ehdg_ctx* ctx);
+int ehdg_get_sizes(const ehdg_ctx* ctx, ehdg_sizes* out);
+
+/* a1  mark_elements / mark_element_bnd  (enrichment_proxy.py:201-208, :228-251)
+ * vert_flags u8[n_enrich][nv]: the Python predicates evaluated on the vertices (host side).
+ * elem_mask u8[ne]: bit k = element marked for enrichment k (any vertex flagged).
+ * facet_mask u8[nf]: bit k = facet belongs to an element marked for k. */
+int ehdg_mark(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* vert_flags, uint8_t* elem_mask,
+              uint8_t* facet_mask, void* stream);
+
+/* plan: splits the elements into the polynomial path (no enriched dof anywhere on the element)
+ * and the general quadrature path (marked elements and their facet neighbours) and assigns
+ * each an output slot.  force_general != 0 sends every element through the quadrature path
+ * (cross-checks, order sweeps of the prescribed quadrature algorithm). */
+typedef struct ehdg_plan ehdg_plan;
+typedef struct {
+    int64_t n_poly, n_gen;        /* elements on each path */
+    int64_t S_doubles, g_doubles; /* sizes of the condensed-block stores */
+    int64_t W_doubles, z_doubles; /* sizes of the back-solve stores (= size of the solution u) */
+} ehdg_plan_sizes;
+int ehdg_plan_create(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_mask, int force_general,
+                     ehdg_plan** out, void* stream);
+int ehdg_plan_destroy(ehdg_plan* plan);
+int ehdg_plan_get_sizes(const ehdg_plan* plan, ehdg_plan_sizes* out);
+/* eslot i32[ne]: bit 30 set = general path; low bits = index on that path (device pointer, plan-owned) */
+const int32_t* ehdg_plan_eslot(const ehdg_plan* plan);
+
+/* a3  enrichment pruning (convection_diffusion.py:270-310), threshold 1e-5 there.
+ * In : elem_mask, facet_mask from ehdg_mark.
+ * Out: elem_active u8[ne]  = elem_mask minus pruned volume enrichment dofs,
+ *      facet_active u8[nf] = facet_mask minus pruned facet enrichment dofs minus boundary facets
+ *                            (dirichlet=".*", :230-232); nf rounded up to a multiple of 4 bytes,
+ *      factors f64[ne][4*n_enrich] (optional, may be null): the reference's `factor` per visited
+ *      dof in order Q_k, QF_k(e0,e1,e2); -1 where the dof does not exist / element not visited. */
+int ehdg_prune(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_mask,
+               const uint8_t* facet_mask, double threshold, uint8_t* elem_active, uint8_t* facet_active,
+               double* factors, void* stream);
+
+/* a4  stabilisation eigenvalue lambda_K = max eig(pinv(a + f f^T) m)  (convection_diffusion.py:314-351);
+ * alpha_K = 20 lambda_K is applied inside ehdg_assemble_condense (:349).
+ * lam f64[ne], status i32[ne] (optional). */
+int ehdg_alpha(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_active,
+               double* lam, int32_t* status, void* stream);
+
+/* a5+a6+a7  element blocks, right-hand side and static condensation
+ * (convection_diffusion.py:357-383; condensation = NGSolve BilinearForm(condense=True)).
+ * S,g: condensed blocks  S_K = A_FF - A_FV A_VV^-1 A_VF,  g_K = -A_FV A_VV^-1 f_V
+ * W,z: back-solve operators  A_VV^-1 A_VF,  A_VV^-1 f_V.
+ * Layout: polynomial elements first ([n_poly][nf_poly^2] ...), then general elements
+ * ([n_gen][nfmax^2] ...); an element's index on its path is eslot & 0x3fffffff.
+ * Afull (optional, general path only, [n_gen][nvmax*(nvmax+nfmax+1) + nfmax*nvmax + nfmax*nfmax]):
+ * uncondensed blocks [A_VV | A_VF | f_V], A_FV, A_FF for parity tests. */
+int ehdg_assemble_condense(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const double* lam,
+                           const uint8_t* elem_active, const uint8_t* facet_mask, double* S, double* g,
+                           double* W, double* z, int32_t* status, double* Afull, void* stream);
+
+/* a8  condensed facet system in CSR.  Rows/columns = active facet dofs, facet-major
+ * (row of (facet f, slot k) = row_start[f] + rank of k among the active slots of f),
+ * columns ascending in every row, structural zeros kept (NGSolve graph rule).
+ * Polynomial dofs of interior facets are free; enriched dof j of facet f is active iff bit j of
+ * facet_active[f] (from ehdg_prune; pass null when n_enrich = 0). */
+typedef struct ehdg_csr ehdg_csr;
+typedef struct {
+    int64_t n_rows, nnz;
+} ehdg_csr_sizes;
+int ehdg_csr_symbolic(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_active, ehdg_csr** out,
+                      void* stream);
+int ehdg_csr_destroy(ehdg_csr* csr);
+int ehdg_csr_get_sizes(const ehdg_csr* csr, ehdg_csr_sizes* out);
+const int64_t* ehdg_csr_rowptr(const ehdg_csr* csr);     /* i64 [n_rows+1] device */
+const int32_t* ehdg_csr_colind(const ehdg_csr* csr);     /* i32 [nnz]      device */
+const int32_t* ehdg_csr_row_start(const ehdg_csr* csr);  /* i32 [nf+1]     device: first row of facet f */
+const uint16_t* ehdg_csr_dofmask(const ehdg_csr* csr);   /* u16 [nf]       device: active dof slots of facet f */
+/* deterministic numeric fill: every entry gathers its <= 2 element contributions in ascending
+ * element id (a sorted-key segmented reduction with the segments read off the topology). */
+int ehdg_csr_numeric(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_csr* csr, const ehdg_mesh* mesh,
+                     const double* S, const double* g, double* vals, double* rhs, void* stream);
+
+/* a9  restarted GMRES with block-Jacobi (facet block) right preconditioning on the condensed system
+ * (replaces acd.mat.Inverse(ba_active_dofs, "pardiso"), convection_diffusion.py:385-387). */
+typedef struct {
+    int32_t restart;        /* Krylov dimension m */
+    int32_t max_iters;
+    double rtol;            /* on ||b - A x|| / ||b|| */
+    int32_t iters;          /* out */
+    int32_t converged;      /* out */
+    double rel_residual;    /* out: true residual at exit */
+    double total_seconds;   /* out: device time of the whole solve */
+    int64_t spmv_calls;     /* out */
+} ehdg_gmres_info;
+int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^-1 */,
+               const double* rhs, double* x, ehdg_gmres_info* info, void* stream);
+/* y = A x with the CSR SpMV kernel used inside GMRES (for tests and the bandwidth bench) */
+int ehdg_spmv(ehdg_ctx* ctx, const ehdg_csr* csr, const double* vals, const double* x, double* y, void* stream);
+
+/* a10 back-solve U_K = z_K - W_K Uhat_K and L2 / H1 error against `exact`
+ * (convection_diffusion.py:389-394).  u f64: polynomial elements [n_poly][n_p] then general [n_gen][nvmax].
+ * err2 f64[2] (device): sum of squared L2 and H1-seminorm errors. */
+int ehdg_backsolve(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_csr* csr, const ehdg_mesh* mesh,
+                   const double* W, const double* z, const double* xhat, double* u, void* stream);
+int ehdg_l2_error(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_active,
+                  const double* u, double* err2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EHDG_H */

@@ -114,10 +114,14 @@ def legendre_eval(p, xi):
 # ----------------------------------------------------------------------------------------------
 class Problem:
     """Problem data of run.py:24-46 as plain numpy callables (independent of the product's
-    coefficient classes).  enrich[i] = (psi, dpsi_dx, dpsi_dy), indicators[i] = f(x, y, h)."""
+    coefficient classes).  Every callable takes the DISTANCES to the outflow sides,
+    (dx, dy) = (1 - x, 1 - y), which the oracle interpolates barycentrically from the vertex
+    values 1 - x_v >= 0: the exponent beta (x - 1) / eps = -k dx is then free of cancellation
+    (k reaches 2e6 at eps = 1e-6, where forming x first would cost 2e-10 relative accuracy).
+    enrich[i] = (psi, dpsi_dx, dpsi_dy), indicators[i] = f(x, y, h) as in run.py:45."""
 
     def __init__(self, beta, eps, coeff=None, exact=None, enrich=(), indicators=(), bonus_int=10,
-                 exact_grad=None):
+                 exact_grad=None, enrich_desc=(), coeff_desc=None, exact_desc=None):
         self.beta = (float(beta[0]), float(beta[1]))
         self.eps = float(eps)
         self.coeff = coeff
@@ -126,18 +130,21 @@ class Problem:
         self.enrich = list(enrich)
         self.indicators = list(indicators)
         self.bonus = int(bonus_int)
+        self.enrich_desc = list(enrich_desc)      # [(axis, k)]      for the C-ABI under test
+        self.coeff_desc = coeff_desc              # (c[4], k[2])     "
+        self.exact_desc = exact_desc
 
 
 def layer_1d(beta, eps):
-    """p(s) of run.py:26-27 and its derivative."""
+    """p(s) of run.py:26-27 and its derivative, as functions of d = 1 - s."""
     k = beta / eps
     em = np.exp(-k)
 
-    def val(s):
-        return s + (np.exp(k * (s - 1.0)) - em) / (em - 1.0)
+    def val(d):
+        return (1.0 - d) + (np.exp(-k * d) - em) / (em - 1.0)
 
-    def der(s):
-        return 1.0 + k * np.exp(k * (s - 1.0)) / (em - 1.0)
+    def der(d):
+        return 1.0 + k * np.exp(-k * d) / (em - 1.0)
 
     return val, der
 
@@ -146,16 +153,20 @@ def run_py_problem(beta=(2.0, 0.001), eps=0.01, bonus_int=10, enriched=True):
     """run.py:24-46 verbatim: exact = p(x) q(y), coeff = beta1 p(x) + beta0 q(y)."""
     p, dp = layer_1d(beta[0], eps)
     q, dq = layer_1d(beta[1], eps)
-    zero = lambda x, y: np.zeros_like(x)
-    enrich = [(lambda x, y: p(x), lambda x, y: dp(x), zero),
-              (lambda x, y: q(y), zero, lambda x, y: dq(y))]
+    zero = lambda dx, dy: np.zeros_like(dx)
+    enrich = [(lambda dx, dy: p(dx), lambda dx, dy: dp(dx), zero),
+              (lambda dx, dy: q(dy), zero, lambda dx, dy: dq(dy))]
     inds = [lambda x, y, h: x > 1 - h, lambda x, y, h: y > 1 - h]
+    kx, ky = beta[0] / eps, beta[1] / eps
     return Problem(beta, eps,
-                   coeff=lambda x, y: beta[1] * p(x) + beta[0] * q(y),
-                   exact=lambda x, y: p(x) * q(y),
-                   exact_grad=lambda x, y: (dp(x) * q(y), p(x) * dq(y)),
+                   coeff=lambda dx, dy: beta[1] * p(dx) + beta[0] * q(dy),
+                   exact=lambda dx, dy: p(dx) * q(dy),
+                   exact_grad=lambda dx, dy: (dp(dx) * q(dy), p(dx) * dq(dy)),
                    enrich=enrich if enriched else [], indicators=inds if enriched else [],
-                   bonus_int=bonus_int)
+                   bonus_int=bonus_int,
+                   enrich_desc=[(0, kx), (1, ky)] if enriched else [],
+                   coeff_desc=((0.0, beta[1], beta[0], 0.0), (kx, ky)),
+                   exact_desc=((0.0, 0.0, 0.0, 1.0), (kx, ky)))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -264,7 +275,7 @@ class EHDGOracle:
 
     def vol_shapes(self, el, pts):
         """enriched volume shapes at reference points: phi, dphi/dx, dphi/dy  [n_p+nenr, npts],
-        plus physical points.  (enrichment_proxy.py:95-96, 133-138)"""
+        plus the distances (1-x, 1-y) of the points.  (enrichment_proxy.py:95-96, 133-138)"""
         P, J, det = self.geom(el)
         lam = np.stack([pts[:, 0], pts[:, 1], 1.0 - pts[:, 0] - pts[:, 1]])
         vn = self.tris[el]
@@ -274,12 +285,17 @@ class EHDGOracle:
         dref = dX[:, None, :] * grad_lam[f[0]][None, :, None] + dY[:, None, :] * grad_lam[f[1]][None, :, None]
         Jinv = np.linalg.inv(J)
         dphys = np.einsum("ac,kan->kcn", Jinv, dref)                    # J^{-T} grad_ref
-        xy = P[2][None, :] + pts @ J.T
+        dd = self.dist(el, lam)
         phi = [v]; gx = [dphys[:, 0]]; gy = [dphys[:, 1]]
         for (psi, dpx, dpy) in self.prob.enrich:
-            phi.append(psi(xy[:, 0], xy[:, 1])[None]); gx.append(dpx(xy[:, 0], xy[:, 1])[None])
-            gy.append(dpy(xy[:, 0], xy[:, 1])[None])
-        return np.concatenate(phi), np.concatenate(gx), np.concatenate(gy), xy
+            phi.append(psi(dd[0], dd[1])[None]); gx.append(dpx(dd[0], dd[1])[None])
+            gy.append(dpy(dd[0], dd[1])[None])
+        return np.concatenate(phi), np.concatenate(gx), np.concatenate(gy), dd
+
+    def dist(self, el, lam):
+        """(1 - x, 1 - y) at points given by local barycentrics lam [3, npts]."""
+        P = self.verts[self.tris[el]]
+        return np.stack([lam.T @ (1.0 - P[:, 0]), lam.T @ (1.0 - P[:, 1])])
 
     def edge_data(self, el, e, order):
         """points on local edge e: reference pts, weights*|e|, unit outward normal, h_e, mu."""
@@ -304,9 +320,9 @@ class EHDGOracle:
 
     def facet_shapes(self, el, e, pts, mu):
         """enriched facet shapes on edge e  [p+1+nenr, npts]  (enrichment_proxy.py:161-162)."""
-        P, J, det = self.geom(el)
-        xy = P[2][None, :] + pts @ J.T
-        rows = [mu] + [psi(xy[:, 0], xy[:, 1])[None] for (psi, _, _) in self.prob.enrich]
+        lam = np.stack([pts[:, 0], pts[:, 1], 1.0 - pts[:, 0] - pts[:, 1]])
+        dd = self.dist(el, lam)
+        rows = [mu] + [psi(dd[0], dd[1])[None] for (psi, _, _) in self.prob.enrich]
         return np.concatenate(rows)
 
     # ------------------------------------------------------------------ a3: pruning
@@ -402,13 +418,13 @@ class EHDGOracle:
         A = np.zeros((N, N)); F = np.zeros(N)
         P, J, det = self.geom(el)
         pts, w = trig_rule(order)
-        phi, gx, gy, xy = self.vol_shapes(el, pts)
+        phi, gx, gy, dd = self.vol_shapes(el, pts)
         wd = w * abs(det)
         bg = b[0] * gx + b[1] * gy
         A[np.ix_(iv, iv)] += eps * (np.einsum("in,jn,n->ij", gx, gx, wd) + np.einsum("in,jn,n->ij", gy, gy, wd))
         A[np.ix_(iv, iv)] -= np.einsum("in,jn,n->ij", bg, phi, wd)       # -(b u).grad v, rows = test
         if self.prob.coeff is not None:
-            F[iv] = np.einsum("in,n->i", phi, wd * self.prob.coeff(xy[:, 0], xy[:, 1]))
+            F[iv] = np.einsum("in,n->i", phi, wd * self.prob.coeff(dd[0], dd[1]))
         alpha = 20.0 * lam
         for e in range(3):
             epts, ew, nrm, h_e, mu = self.edge_data(el, e, order)
@@ -520,13 +536,13 @@ class EHDGOracle:
         iv = self.loc_voltype()
         for el in range(self.ne):
             P, J, det = self.geom(el)
-            phi, gx, gy, xy = self.vol_shapes(el, pts)
+            phi, gx, gy, dd = self.vol_shapes(el, pts)
             dofs = self.el_dofs(el)[iv]
             coef = np.where(dofs >= 0, x[np.maximum(dofs, 0)], 0.0)
             uh = coef @ phi
-            ex = self.prob.exact(xy[:, 0], xy[:, 1])
+            ex = self.prob.exact(dd[0], dd[1])
             err2 += np.sum(w * abs(det) * (uh - ex) ** 2)
             if h1:
-                ex_gx, ex_gy = self.prob.exact_grad(xy[:, 0], xy[:, 1])
+                ex_gx, ex_gy = self.prob.exact_grad(dd[0], dd[1])
                 h1e2 += np.sum(w * abs(det) * ((coef @ gx - ex_gx) ** 2 + (coef @ gy - ex_gy) ** 2))
         return (np.sqrt(err2), np.sqrt(h1e2)) if h1 else np.sqrt(err2)

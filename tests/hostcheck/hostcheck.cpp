@@ -1,0 +1,116 @@
+// TEST-ONLY host build of the per-element device routines (g++, no CUDA): lets the CPU test
+// suite compare the math of csrc/ehdg_general.h and the reference tensors with the numpy
+// oracle without a GPU.  Never loaded by the product package.
+#include <cstring>
+#include <vector>
+#include "../../include/ehdg.h"
+#include "../../convectiondiffusionequation_b200/csrc/ehdg_general.h"
+#include "../../convectiondiffusionequation_b200/csrc/ehdg_rules.h"
+#include "../../convectiondiffusionequation_b200/csrc/ehdg_problem.h"
+#include "../../convectiondiffusionequation_b200/csrc/ehdg_fast.h"
+
+using namespace ehdg;
+
+struct HostRules {
+    TrigRule tr;
+    SegRule sr;
+    RuleSet rs;
+    explicit HostRules(int order) : tr(trig_rule(order)), sr(seg_rule(order)) {
+        rs.nq = (int)tr.w.size();
+        rs.nqf = (int)sr.w.size();
+        rs.vx = tr.x.data(); rs.vy = tr.y.data(); rs.vw = tr.w.data();
+        rs.st = sr.t.data(); rs.sw = sr.w.data();
+    }
+};
+
+template <int P>
+static int fast_assemble_host(const Problem& pb, const double* verts, const int* tri, double lam, double* S, double* g,
+                              double* W, double* z) {
+    HostRules hr(2 * pb.p + pb.bonus);
+    std::vector<double> asm_tab, alpha_tab, phi;
+    build_tensors(P, 2 * P + pb.bonus, asm_tab, alpha_tab);
+    build_rhs_phi(P, 2 * P + pb.bonus, phi);
+    std::vector<double> sh(fast_asm_scratch_doubles<P>(hr.rs.nq));
+    Group<FastDims<P>::LG> gc{0, sh.data()};
+    return fast_assemble_element<P>(gc, pb, hr.rs, asm_tab.data(), phi.data(), verts, tri, lam, true, S, g, W, z);
+}
+template <int P>
+static double fast_alpha_host(const double* verts, const int* tri, int bonus, int* status) {
+    std::vector<double> asm_tab, alpha_tab;
+    build_tensors(P, 2 * P + bonus, asm_tab, alpha_tab);
+    std::vector<double> sh(fast_alpha_scratch_doubles<P>());
+    Group<FastDims<P>::LG> gc{0, sh.data()};
+    return fast_alpha_element<P>(gc, alpha_tab.data(), verts, tri, status);
+}
+
+extern "C" {
+
+int hc_trig_rule(int order, double* x, double* y, double* w) {
+    TrigRule r = trig_rule(order);
+    for (size_t i = 0; i < r.w.size(); ++i) { x[i] = r.x[i]; y[i] = r.y[i]; w[i] = r.w[i]; }
+    return (int)r.w.size();
+}
+int hc_seg_rule(int order, double* t, double* w) {
+    SegRule r = seg_rule(order);
+    for (size_t i = 0; i < r.w.size(); ++i) { t[i] = r.t[i]; w[i] = r.w[i]; }
+    return (int)r.w.size();
+}
+void hc_dubiner(int p, int n, const double* X, const double* Y, double* v, double* dX, double* dY) {
+    const int np = (p + 1) * (p + 2) / 2;
+    for (int i = 0; i < n; ++i) dubiner_eval(p, X[i], Y[i], v + i * np, dX + i * np, dY + i * np);
+}
+void hc_sizes(const ehdg_problem* ep, int* out) {
+    Problem pb = make_problem(*ep);
+    out[0] = pb.n_p; out[1] = pb.nb; out[2] = pb.nvmax; out[3] = pb.nfmax;
+}
+int hc_assemble(const ehdg_problem* ep, const double* verts, const int* tri, double lam, int volmask,
+                const int* facmask, double* S, double* g, double* W, double* z, double* Afull) {
+    Problem pb = make_problem(*ep);
+    HostRules hr(2 * pb.p + pb.bonus);
+    std::vector<double> ws(general_ws_doubles(pb, hr.rs.nq, hr.rs.nqf));
+    Coop co{0, 1};
+    return assemble_condense_general(co, pb, hr.rs, verts, tri, lam, volmask, facmask, ws.data(), S, g, W, z, Afull);
+}
+double hc_alpha(const ehdg_problem* ep, const double* verts, const int* tri, int volmask, int exclude_const,
+                int* status) {
+    Problem pb = make_problem(*ep);
+    HostRules hb(2 * pb.p + pb.bonus), h0(2 * pb.p);
+    std::vector<double> ws(general_ws_doubles(pb, hb.rs.nq, hb.rs.nqf));
+    Coop co{0, 1};
+    *status = 0;
+    return alpha_general(co, pb, h0.rs, verts, tri, volmask, exclude_const, ws.data(), status);
+}
+void hc_prune(const ehdg_problem* ep, const double* verts, const int* tri, int elmark, const int* facmask,
+              double threshold, int* vol_drop, int* fac_drop, double* factors) {
+    Problem pb = make_problem(*ep);
+    HostRules hb(2 * pb.p + pb.bonus);
+    std::vector<double> ws(general_ws_doubles(pb, hb.rs.nq, hb.rs.nqf));
+    Coop co{0, 1};
+    prune_general(co, pb, hb.rs, verts, tri, elmark, facmask, threshold, ws.data(), vol_drop, fac_drop, factors);
+}
+
+int hc_fast_assemble(const ehdg_problem* ep, const double* verts, const int* tri, double lam, double* S, double* g,
+                     double* W, double* z) {
+    Problem pb = make_problem(*ep);
+    switch (pb.p) {
+        case 1: return fast_assemble_host<1>(pb, verts, tri, lam, S, g, W, z);
+        case 2: return fast_assemble_host<2>(pb, verts, tri, lam, S, g, W, z);
+        case 3: return fast_assemble_host<3>(pb, verts, tri, lam, S, g, W, z);
+        case 4: return fast_assemble_host<4>(pb, verts, tri, lam, S, g, W, z);
+        case 5: return fast_assemble_host<5>(pb, verts, tri, lam, S, g, W, z);
+        case 6: return fast_assemble_host<6>(pb, verts, tri, lam, S, g, W, z);
+    }
+    return -1;
+}
+double hc_fast_alpha(const ehdg_problem* ep, const double* verts, const int* tri, int* status) {
+    switch (ep->order) {
+        case 1: return fast_alpha_host<1>(verts, tri, ep->bonus_int, status);
+        case 2: return fast_alpha_host<2>(verts, tri, ep->bonus_int, status);
+        case 3: return fast_alpha_host<3>(verts, tri, ep->bonus_int, status);
+        case 4: return fast_alpha_host<4>(verts, tri, ep->bonus_int, status);
+        case 5: return fast_alpha_host<5>(verts, tri, ep->bonus_int, status);
+        case 6: return fast_alpha_host<6>(verts, tri, ep->bonus_int, status);
+    }
+    return -1.0;
+}
+}
