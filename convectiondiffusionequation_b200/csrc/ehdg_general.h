@@ -654,32 +654,41 @@ EHDG_HD void prune_general(const Coop& co, const Problem& pb, const RuleSet& rs,
         }
         co.sync();
     }
-    // sequential factor tests (every lane computes the same result)
+    // sequential factor tests (every lane computes the same result).  The reference wraps the loop of
+    // one element in try/except (conv_diff.py:291, :309-310): a zero Gram diagonal (an enrichment
+    // function that vanishes on the whole element boundary / facet, e.g. psi on the outflow edge)
+    // raises ZeroDivisionError there and silently ends the element; factors of the dofs not visited
+    // are reported as -2.
     int vdrop = 0;
     int fdrop[3] = {0, 0, 0};
+    bool aborted = false;
     for (int k = 0; k < pb.nenr; ++k) {
         // --- Q_k against V and the earlier surviving Q's
         double fac = -1.0;
         if ((elmark >> k) & 1) {
             const int i = pb.n_p + k;
-            int act[EHDG_MAX_NP + EHDG_MAX_ENRICH];
-            int na = 0;
-            for (int j = 0; j < pb.n_p; ++j) act[na++] = j;
-            for (int kk = 0; kk < k; ++kk)
-                if (((elmark >> kk) & 1) && !((vdrop >> kk) & 1)) act[na++] = pb.n_p + kk;
-            double s1 = 0.0, s2 = 0.0;
             const double gii = Gv[i * nv + i];
-            for (int a = 0; a < na; ++a) {
-                const int j = act[a];
-                s1 += Gv[i * nv + j] * Gv[i * nv + j] / gii / Gv[j * nv + j];
-            }
-            for (int a = 0; a < na; ++a)
-                for (int b = 0; b < na; ++b) {
-                    const int j = act[a], kk = act[b];
-                    s2 += Gv[i * nv + j] * Gv[i * nv + kk] * Gv[j * nv + kk] / gii / Gv[j * nv + j] / Gv[kk * nv + kk];
+            if (aborted) fac = -2.0;
+            else if (gii == 0.0) { aborted = true; fac = -2.0; }
+            else {
+                int act[EHDG_MAX_NP + EHDG_MAX_ENRICH];
+                int na = 0;
+                for (int j = 0; j < pb.n_p; ++j) act[na++] = j;
+                for (int kk = 0; kk < k; ++kk)
+                    if (((elmark >> kk) & 1) && !((vdrop >> kk) & 1)) act[na++] = pb.n_p + kk;
+                double s1 = 0.0, s2 = 0.0;
+                for (int a = 0; a < na; ++a) {
+                    const int j = act[a];
+                    s1 += Gv[i * nv + j] * Gv[i * nv + j] / gii / Gv[j * nv + j];
                 }
-            fac = sqrt(fabs(1.0 - 2.0 * s1 + s2));
-            if (fac <= threshold) vdrop |= 1 << k;
+                for (int a = 0; a < na; ++a)
+                    for (int b = 0; b < na; ++b) {
+                        const int j = act[a], kk = act[b];
+                        s2 += Gv[i * nv + j] * Gv[i * nv + kk] * Gv[j * nv + kk] / gii / Gv[j * nv + j] / Gv[kk * nv + kk];
+                    }
+                fac = sqrt(fabs(1.0 - 2.0 * s1 + s2));
+                if (fac <= threshold) vdrop |= 1 << k;
+            }
         }
         factors[4 * k] = fac;
         // --- QF_k on each edge against F_e and the earlier surviving QF's of that edge
@@ -688,24 +697,28 @@ EHDG_HD void prune_general(const Coop& co, const Problem& pb, const RuleSet& rs,
             if ((facmask[e] >> k) & 1) {
                 const double* G = Gf + e * nb * nb;
                 const int i = pb.p + 1 + k;
-                int act[EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH];
-                int na = 0;
-                for (int j = 0; j <= pb.p; ++j) act[na++] = j;
-                for (int kk = 0; kk < k; ++kk)
-                    if (((facmask[e] >> kk) & 1) && !((fdrop[e] >> kk) & 1)) act[na++] = pb.p + 1 + kk;
-                double s1 = 0.0, s2 = 0.0;
                 const double gii = G[i * nb + i];
-                for (int a = 0; a < na; ++a) {
-                    const int j = act[a];
-                    s1 += G[i * nb + j] * G[i * nb + j] / gii / G[j * nb + j];
-                }
-                for (int a = 0; a < na; ++a)
-                    for (int b = 0; b < na; ++b) {
-                        const int j = act[a], kk = act[b];
-                        s2 += G[i * nb + j] * G[i * nb + kk] * G[j * nb + kk] / gii / G[j * nb + j] / G[kk * nb + kk];
+                if (aborted) ff = -2.0;
+                else if (gii == 0.0) { aborted = true; ff = -2.0; }
+                else {
+                    int act[EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH];
+                    int na = 0;
+                    for (int j = 0; j <= pb.p; ++j) act[na++] = j;
+                    for (int kk = 0; kk < k; ++kk)
+                        if (((facmask[e] >> kk) & 1) && !((fdrop[e] >> kk) & 1)) act[na++] = pb.p + 1 + kk;
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int a = 0; a < na; ++a) {
+                        const int j = act[a];
+                        s1 += G[i * nb + j] * G[i * nb + j] / gii / G[j * nb + j];
                     }
-                ff = sqrt(fabs(1.0 - 2.0 * s1 + s2));
-                if (ff <= threshold) fdrop[e] |= 1 << k;
+                    for (int a = 0; a < na; ++a)
+                        for (int b = 0; b < na; ++b) {
+                            const int j = act[a], kk = act[b];
+                            s2 += G[i * nb + j] * G[i * nb + kk] * G[j * nb + kk] / gii / G[j * nb + j] / G[kk * nb + kk];
+                        }
+                    ff = sqrt(fabs(1.0 - 2.0 * s1 + s2));
+                    if (ff <= threshold) fdrop[e] |= 1 << k;
+                }
             }
             factors[4 * k + 1 + e] = ff;
         }

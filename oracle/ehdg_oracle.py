@@ -273,11 +273,12 @@ class EHDGOracle:
         det = np.linalg.det(J)
         return P, J, det
 
-    def vol_shapes(self, el, pts):
+    def vol_shapes(self, el, pts, lam=None):
         """enriched volume shapes at reference points: phi, dphi/dx, dphi/dy  [n_p+nenr, npts],
         plus the distances (1-x, 1-y) of the points.  (enrichment_proxy.py:95-96, 133-138)"""
         P, J, det = self.geom(el)
-        lam = np.stack([pts[:, 0], pts[:, 1], 1.0 - pts[:, 0] - pts[:, 1]])
+        if lam is None:
+            lam = np.stack([pts[:, 0], pts[:, 1], 1.0 - pts[:, 0] - pts[:, 1]])
         vn = self.tris[el]
         f = np.argsort(vn, kind="stable")                               # ascending vertex numbers
         grad_lam = np.array([[1.0, 0.0], [0.0, 1.0], [-1.0, -1.0]])
@@ -303,6 +304,9 @@ class EHDGOracle:
         a, b = LOCAL_EDGES[e]
         t, w = seg_rule(order)
         pts = (1.0 - t)[:, None] * REF_VERTS[a][None] + t[:, None] * REF_VERTS[b][None]
+        lam = np.zeros((3, len(t)))                                      # exact barycentrics: the vertex
+        lam[a] = 1.0 - t                                                 # opposite the edge gets a true 0
+        lam[b] = t
         A, B = P[a], P[b]
         length = np.linalg.norm(B - A)
         tang = (B - A) / length
@@ -313,15 +317,14 @@ class EHDGOracle:
         h_e = abs(det) / length                                         # SURVEY A.2 [V]
         vn = self.tris[el]
         lo, hi = (a, b) if vn[a] < vn[b] else (b, a)                    # sorted edge (A.4)
-        lam = np.stack([pts[:, 0], pts[:, 1], 1.0 - pts[:, 0] - pts[:, 1]])
         xi = lam[hi] - lam[lo]
         mu = legendre_eval(self.p, xi)
+        self._edge_lam = lam
         return pts, w * length, nrm, h_e, mu
 
     def facet_shapes(self, el, e, pts, mu):
         """enriched facet shapes on edge e  [p+1+nenr, npts]  (enrichment_proxy.py:161-162)."""
-        lam = np.stack([pts[:, 0], pts[:, 1], 1.0 - pts[:, 0] - pts[:, 1]])
-        dd = self.dist(el, lam)
+        dd = self.dist(el, self._edge_lam)
         rows = [mu] + [psi(dd[0], dd[1])[None] for (psi, _, _) in self.prob.enrich]
         return np.concatenate(rows)
 
@@ -333,7 +336,7 @@ class EHDGOracle:
         iv = self.loc_voltype()
         for e in range(3):
             pts, w, nrm, h_e, mu = self.edge_data(el, e, order)
-            phi, _, _, _ = self.vol_shapes(el, pts)
+            phi, _, _, _ = self.vol_shapes(el, pts, self._edge_lam)
             fs = self.facet_shapes(el, e, pts, mu)
             jf = self.loc_factype(e)
             G[np.ix_(iv, iv)] += np.einsum("in,jn,n->ij", phi, phi, w)
@@ -387,7 +390,7 @@ class EHDGOracle:
         f[iv] = np.einsum("in,n->i", phi, wd) * hvol ** (-2.0)           # h**((-2-dim)/2), dim = 2
         for e in range(3):
             epts, ew, nrm, h_e, mu = self.edge_data(el, e, order)
-            _, egx, egy, _ = self.vol_shapes(el, epts)
+            _, egx, egy, _ = self.vol_shapes(el, epts, self._edge_lam)
             dn = egx * nrm[0] + egy * nrm[1]
             m[np.ix_(iv, iv)] += h_e * np.einsum("in,jn,n->ij", dn, dn, ew)
         return a, f, m
@@ -428,7 +431,7 @@ class EHDGOracle:
         alpha = 20.0 * lam
         for e in range(3):
             epts, ew, nrm, h_e, mu = self.edge_data(el, e, order)
-            ephi, egx, egy, _ = self.vol_shapes(el, epts)
+            ephi, egx, egy, _ = self.vol_shapes(el, epts, self._edge_lam)
             fs = self.facet_shapes(el, e, epts, mu)
             jf = self.loc_factype(e)
             dn = egx * nrm[0] + egy * nrm[1]

@@ -106,7 +106,9 @@ def test_general_path_blocks(n, order, eps, beta, kind):
     st = P.status.cpu().numpy()
     lam_ref = o.alpha_all()
     ok = st == 0
-    assert np.max(np.abs(lam_dev[ok] - lam_ref[ok]) / lam_ref[ok]) < 1e-8
+    from tests.test_hostcheck import _alpha_cond
+    for el in np.nonzero(ok)[0]:
+        assert abs(lam_dev[el] - lam_ref[el]) < max(1e-10, 1e-13 * _alpha_cond(o, el)) * lam_ref[el], el
     # elements the pseudo-inverse of the reference leaves to round-off are flagged, not matched
     assert ok.sum() >= 0.5 * mesh.ne
     P.lam.copy_(P.lam.new_tensor(lam_ref))          # same alpha on both sides for the block comparison
