@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the (E)HDG hot path (driver contract: one JSON line on rank 0).
+
+metric  : condensed EHDG elements/second (FP64) = elements whose stabilisation eigenvalue (a4),
+          element blocks + right-hand side (a5, a7) and static condensation (a6) were computed,
+          per second, whole job.  One "step" = one such pass over the whole synthetic mesh.
+value   : device-timed (CUDA events, inputs resident in HBM).
+e2e     : same metric through the public pipeline with HOST buffers: pinned mesh arrays -> device,
+          mark/plan/prune, alpha, assemble+condense, per-element alpha table + status -> host.
+solve   : CSR build + block-Jacobi GMRES + back-solve + L2 error, run once after the timed steps
+          ("full solve time" of BASELINE.json's metric), with achieved SpMV GB/s.
+--impl reference : the CPU restatement of the reference algorithm (oracle/) on the host cores,
+          bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (lattice N, kind, order, eps)      SURVEY.md 8(d)
+    "ehdg_p4_eps1e-6_unstructured_4M": (1414, "unstructured", 4, 1e-6),
+    "ehdg_p4_eps1e-6_structured_1M": (708, "structured", 4, 1e-6),
+    "ehdg_p3_eps1e-4_structured_100k": (224, "structured", 3, 1e-4),
+    "ehdg_p2_eps1e-2_runpy_512": (16, "structured", 2, 1e-2),
+}
+DEFAULT_WORKLOAD = "ehdg_p4_eps1e-6_unstructured_4M"
+BETA = (2.0, 0.001)          # run.py:24
+
+
+def make_spec(order, eps, enriched=True):
+    from convectiondiffusionequation_b200 import boundary_layer, x, y
+    from convectiondiffusionequation_b200.hot_path import ProblemSpec
+    p, q = boundary_layer(x, BETA[0], eps), boundary_layer(y, BETA[1], eps)
+    return ProblemSpec(order=order, epsilon=eps, beta=BETA, bonus_int=10, coeff=BETA[1] * p + BETA[0] * q, exact=p * q,
+                       enrich_functions=(p, q) if enriched else (),
+                       enrich_domain_ind=(lambda X, Y, h: X > 1 - h, lambda X, Y, h: Y > 1 - h) if enriched else ())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.stop = threading.Event()
+        self.index = index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.15)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    hbm, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm, hbm_src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        pass
+    fp64, fp64_src = 37.0, "nominal"
+    try:
+        fp = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))
+        fp64, fp64_src = float(fp["fp64_fma_tflops"]), "profiles/fp64_peak_r01.json (tools/fp64_peak.cu, measured on this pool's B200)"
+    except Exception:
+        pass
+    return hbm, hbm_src, fp64, fp64_src
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on the host cores, bounded sample of the workload
+# --------------------------------------------------------------------------------------------
+def cpu_reference(workload, budget_s=20.0, max_elems=None):
+    from oracle import ehdg_cpu
+    n, kind, order, eps = WORKLOADS[workload]
+    return ehdg_cpu.time_sample(n, kind, order, eps, BETA, budget_s=budget_s, max_elems=max_elems)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_reference(args.workload, budget_s=min(20.0, 120.0 / max(1, args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(info["value"])
+    v = float(np.mean(vals)) if vals else float(info["value"])
+    n, kind, order, eps = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "condensed EHDG elements/sec (FP64)", "value": v, "unit": "elements/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * info["sample_elements"] / v if v else None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "lattice_n": n, "mesh": kind, "order": order, "epsilon": eps, "beta": list(BETA),
+                       "bonus_int": 10},
+            "cpu_baseline": {"value": v, "unit": "elements/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+            "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-solve", action="store_true", help="skip the one-off GMRES solve after the timed steps")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--solve-iters", type=int, default=20000)
+    ap.add_argument("--rtol", type=float, default=1e-8)
+    ap.add_argument("--restart", type=int, default=30)
+    ap.add_argument("--plain-hdg-solve", action="store_true", help="one-off solve on the unenriched (HDG) system instead")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from convectiondiffusionequation_b200 import build
+    from convectiondiffusionequation_b200.hot_path import EHDGPipeline
+    from convectiondiffusionequation_b200.mesh import unit_square_mesh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    build.build()
+
+    n, kind, order, eps = WORKLOADS[args.workload]
+    # weak scaling: every rank owns one mesh of the named size (rank-specific seed for the jitter)
+    mesh = unit_square_mesh(n, kind=kind, seed=20261019 + rank)
+    spec = make_spec(order, eps)
+    P = EHDGPipeline(mesh, spec, device=dev)
+    P.setup()
+    ne = mesh.ne
+    sizes = P.sizes
+    ps = P.plan_sizes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # L2 flush between timed iterations: the outputs of one step (S, W: > 10 GB at 4M) exceed the 126 MB L2;
+    # for small workloads an explicit flush buffer is written.
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    need_flush = (ps.S_doubles + ps.W_doubles) * 8 < (512 << 20)
+
+    def step():
+        P.alpha()
+        P.assemble_condense()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---- timed region: K steps, device time per stage, clocks sampled meanwhile
+    t_alpha, t_asm = 0.0, 0.0
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0, e3 = ev(), ev()
+        stage = []
+        e0.record()
+        for _ in range(args.steps):
+            if need_flush:
+                flush.fill_(1)
+            a0, a1, a2 = ev(), ev(), ev()
+            a0.record()
+            P.alpha()
+            a1.record()
+            P.assemble_condense()
+            a2.record()
+            stage.append((a0, a1, a2))
+        e3.record()
+        barrier()
+    for a0, a1, a2 in stage:
+        t_alpha += a0.elapsed_time(a1)
+        t_asm += a1.elapsed_time(a2)
+    ms_step = (t_alpha + t_asm) / args.steps
+    tmax = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step_max = float(tmax.item())
+    value = world * ne / (ms_step_max * 1e-3)
+    status_bad = int((P.status != 0).sum().item())
+
+    # ---- e2e: host buffers in, alpha table + status out, every step
+    pinned = dict(verts=torch.from_numpy(mesh.verts).pin_memory(), tris=torch.from_numpy(mesh.tris).pin_memory(),
+                  el2facet=torch.from_numpy(mesh.el2facet).pin_memory(), facet2el=torch.from_numpy(mesh.facet2el).pin_memory())
+    lam_host = torch.empty(ne, dtype=torch.float64).pin_memory()
+    st_host = torch.empty(ne, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        P.upload_mesh(pinned)
+        P.setup()
+        P.alpha()
+        P.assemble_condense()
+        lam_host.copy_(P.lam, non_blocking=True)
+        st_host.copy_(P.status, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * ne / float(te.item())
+    h2d = P.h2d_bytes + (P.vert_flags.numel() if hasattr(P, "vert_flags") else 0)
+    d2h = ne * 12
+
+    # ---- one-off solve (a8-a10)
+    solve = None
+    if not args.no_solve:
+        Ps = P
+        if args.plain_hdg_solve:
+            Ps = EHDGPipeline(mesh, make_spec(order, eps, enriched=False), device=dev)
+            Ps.setup().assemble()
+        barrier()
+        s0, s1, s2, s3 = ev(), ev(), ev(), ev()
+        s0.record()
+        Ps.csr_build()
+        s1.record()
+        nrows, nnz = Ps.csr_sizes.n_rows, Ps.csr_sizes.nnz
+        # SpMV bandwidth: algorithmic bytes 12 nnz + 20 rows, 20 launches
+        xs = torch.ones(max(nrows, 1), dtype=torch.float64, device=dev)
+        ys = torch.empty_like(xs)
+        for _ in range(3):
+            Ps.spmv(xs, ys)
+        b0, b1 = ev(), ev()
+        b0.record()
+        for _ in range(20):
+            Ps.spmv(xs, ys)
+        b1.record()
+        torch.cuda.synchronize(dev)
+        spmv_ms = b0.elapsed_time(b1) / 20
+        spmv_gbs = (12.0 * nnz + 20.0 * nrows) / (spmv_ms * 1e-3) / 1e9
+        s2.record()
+        Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol)
+        Ps.backsolve()
+        l2, h1 = Ps.errors()
+        s3.record()
+        torch.cuda.synchronize(dev)
+        gi = Ps.gmres_info
+        solve = {"type": "hdg" if args.plain_hdg_solve else "ehdg", "rows": int(nrows), "nnz": int(nnz),
+                 "csr_build_ms": s0.elapsed_time(s1), "gmres_backsolve_error_ms": s2.elapsed_time(s3), "gmres_iters": int(gi.iters),
+                 "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual), "gmres_seconds": float(gi.total_seconds),
+                 "restart": args.restart, "rtol": args.rtol, "dropped_dofs": int(gi.dropped_dofs), "l2_error": l2, "h1_error": h1,
+                 "spmv_ms": spmv_ms, "spmv_gbs": spmv_gbs}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, hbm_src, fp64, fp64_src = measured_peaks()
+    # dominant kernel: the polynomial-path assembly+condensation launch (one launch per step)
+    flops_elem = int(sizes.flops_poly_elem)
+    # split of flops_poly_elem between the two kernels is reported by the library as a whole; the
+    # roofline below is for the step (alpha kernel + assemble kernel), see DESIGN.md
+    n_poly, n_gen = int(ps.n_poly), int(ps.n_gen)
+    achieved_tf = n_poly * flops_elem / (ms_step * 1e-3) / 1e12
+    out_bytes = (ps.S_doubles + ps.g_doubles + ps.W_doubles + ps.z_doubles + ne) * 8 + ne * 60
+    line = {
+        "metric": "condensed EHDG elements/sec (FP64)", "value": value, "unit": "elements/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "lattice_n": n, "mesh": kind, "order": order, "epsilon": eps, "beta": list(BETA),
+                   "bonus_int": 10, "elements_per_gpu": ne, "facets_per_gpu": mesh.nf, "enriched_path_elements": n_gen,
+                   "l2_flush": "explicit 256 MiB write between steps" if need_flush else "step outputs (S,W) exceed L2",
+                   "elements_with_status_flags": status_bad},
+        "stage_ms": {"alpha": t_alpha / args.steps, "assemble_condense": t_asm / args.steps},
+        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64, "unit": "TFLOP/s", "frac": achieved_tf / fp64,
+                     "traffic": None, "peak_source": fp64_src, "flops_per_element": flops_elem,
+                     "note": "flops of the tensor algorithm actually executed (no credit for skipped quadrature work)",
+                     "quadrature_algorithm_flops_per_element": int(sizes.flops_quad_elem),
+                     "quadrature_equivalent_tflops": value / world * int(sizes.flops_quad_elem) / 1e12,
+                     "hbm_gbs_of_outputs": out_bytes / (ms_step * 1e-3) / 1e9, "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src},
+        "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(args.steps * (2 + (2 if n_gen else 0))),
+        "clocks": clocks.summary(),
+    }
+    if solve:
+        line["solve"] = solve
+        line["solve"]["spmv_frac_of_hbm_peak"] = solve["spmv_gbs"] / hbm
+    if not args.no_cpu and world == 1:
+        try:
+            info = cpu_reference(args.workload, budget_s=15.0)
+            line["cpu_baseline"] = {"value": info["value"], "unit": "elements/s", "cores": info["cores"], "kind": info["kind"],
+                                    "sample": info["sample"]}
+        except Exception as exc:          # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "elements/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,7 @@ class CsrSizes(C.Structure):
 class GmresInfo(C.Structure):
     _fields_ = [("restart", C.c_int32), ("max_iters", C.c_int32), ("rtol", C.c_double), ("iters", C.c_int32),
                 ("converged", C.c_int32), ("rel_residual", C.c_double), ("total_seconds", C.c_double),
-                ("spmv_calls", C.c_int64)]
+                ("spmv_calls", C.c_int64), ("dropped_dofs", C.c_int32)]
 
 
 # every symbol include/ehdg.h declares: name -> (restype, argtypes)

@@ -654,28 +654,28 @@ EHDG_HD void prune_general(const Coop& co, const Problem& pb, const RuleSet& rs,
         }
         co.sync();
     }
-    // sequential factor tests (every lane computes the same result).  The reference wraps the loop of
-    // one element in try/except (conv_diff.py:291, :309-310): a zero Gram diagonal (an enrichment
-    // function that vanishes on the whole element boundary / facet, e.g. psi on the outflow edge)
-    // raises ZeroDivisionError there and silently ends the element; factors of the dofs not visited
-    // are reported as -2.
+    // sequential factor tests (every lane computes the same result).  A zero Gram diagonal means the
+    // enrichment function vanishes identically on that facet (psi on the outflow edge itself, where
+    // d = 0 exactly in the cancellation-free form).  NGSolve evaluates psi from a rounded coordinate,
+    // gets ~1e-16 rather than 0 and therefore neither divides by zero nor prunes this (Dirichlet)
+    // dof; here it is skipped (factor -3) and kept out of the later active sets.
     int vdrop = 0;
     int fdrop[3] = {0, 0, 0};
-    bool aborted = false;
+    int vzero = 0;
+    int fzero[3] = {0, 0, 0};
     for (int k = 0; k < pb.nenr; ++k) {
         // --- Q_k against V and the earlier surviving Q's
         double fac = -1.0;
         if ((elmark >> k) & 1) {
             const int i = pb.n_p + k;
             const double gii = Gv[i * nv + i];
-            if (aborted) fac = -2.0;
-            else if (gii == 0.0) { aborted = true; fac = -2.0; }
+            if (gii == 0.0) { vzero |= 1 << k; fac = -3.0; }
             else {
                 int act[EHDG_MAX_NP + EHDG_MAX_ENRICH];
                 int na = 0;
                 for (int j = 0; j < pb.n_p; ++j) act[na++] = j;
                 for (int kk = 0; kk < k; ++kk)
-                    if (((elmark >> kk) & 1) && !((vdrop >> kk) & 1)) act[na++] = pb.n_p + kk;
+                    if (((elmark >> kk) & 1) && !(((vdrop | vzero) >> kk) & 1)) act[na++] = pb.n_p + kk;
                 double s1 = 0.0, s2 = 0.0;
                 for (int a = 0; a < na; ++a) {
                     const int j = act[a];
@@ -698,14 +698,13 @@ EHDG_HD void prune_general(const Coop& co, const Problem& pb, const RuleSet& rs,
                 const double* G = Gf + e * nb * nb;
                 const int i = pb.p + 1 + k;
                 const double gii = G[i * nb + i];
-                if (aborted) ff = -2.0;
-                else if (gii == 0.0) { aborted = true; ff = -2.0; }
+                if (gii == 0.0) { fzero[e] |= 1 << k; ff = -3.0; }
                 else {
                     int act[EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH];
                     int na = 0;
                     for (int j = 0; j <= pb.p; ++j) act[na++] = j;
                     for (int kk = 0; kk < k; ++kk)
-                        if (((facmask[e] >> kk) & 1) && !((fdrop[e] >> kk) & 1)) act[na++] = pb.p + 1 + kk;
+                        if (((facmask[e] >> kk) & 1) && !(((fdrop[e] | fzero[e]) >> kk) & 1)) act[na++] = pb.p + 1 + kk;
                     double s1 = 0.0, s2 = 0.0;
                     for (int a = 0; a < na; ++a) {
                         const int j = act[a];

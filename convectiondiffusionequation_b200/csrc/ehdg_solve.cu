@@ -211,32 +211,81 @@ __global__ void bj_invert_kernel(int nf, int nbs, const int32_t* __restrict__ ro
         if (g == f) break;
         off += row_start[g + 1] - row_start[g];
     }
+    // A facet dof can be numerically dependent on the others of its facet (an enrichment function that
+    // is constant along the facet next to the Legendre mode mu_0; the reference's pruning test misses
+    // it when a second enrichment lives on the same facet).  Step 1 finds the independent dofs K by
+    // elimination with complete pivoting (pivot below 1e-10 of the block's largest entry = dependent);
+    // step 2 inverts the principal sub-block [K,K].  Dropped dofs get zero rows and columns in the block
+    // inverse, so the right-preconditioned iteration leaves their coefficient at 0: one solution of the
+    // consistent singular system, i.e. the same discrete function.
     double a[NBMAX][2 * NBMAX];
+    double w[NBMAX][NBMAX];
+    double amax = 0.0;
     for (int i = 0; i < n; ++i) {
         const double* row = vals + rowptr[r0 + i] + off;
         for (int j = 0; j < n; ++j) {
-            a[i][j] = row[j];
-            a[i][n + j] = (i == j) ? 1.0 : 0.0;
+            w[i][j] = row[j];
+            amax = fmax(amax, fabs(row[j]));
         }
     }
+    int cperm[NBMAX];
+    for (int j = 0; j < n; ++j) cperm[j] = j;
+    int rank = n;
     for (int k = 0; k < n; ++k) {
+        int pr = k, pc = k;
+        double best = -1.0;
+        for (int i = k; i < n; ++i)
+            for (int j = k; j < n; ++j)
+                if (fabs(w[i][j]) > best) { best = fabs(w[i][j]); pr = i; pc = j; }
+        if (!(best > 1e-10 * amax)) { rank = k; break; }
+        if (pr != k)
+            for (int j = 0; j < n; ++j) { const double t = w[k][j]; w[k][j] = w[pr][j]; w[pr][j] = t; }
+        if (pc != k) {
+            for (int i = 0; i < n; ++i) { const double t = w[i][k]; w[i][k] = w[i][pc]; w[i][pc] = t; }
+            const int t = cperm[k]; cperm[k] = cperm[pc]; cperm[pc] = t;
+        }
+        for (int i = k + 1; i < n; ++i) {
+            const double fct = w[i][k] / w[k][k];
+            for (int j = k + 1; j < n; ++j) w[i][j] -= fct * w[k][j];
+        }
+    }
+    if (rank == 0) *fail = 1;
+    if (rank < n) atomicAdd(fail + 1, n - rank);
+    // kept dofs in ascending order
+    int keep[NBMAX];
+    int nk = 0;
+    for (int j = 0; j < n; ++j) {
+        bool in = false;
+        for (int k = 0; k < rank; ++k) in = in || (cperm[k] == j);
+        if (in) keep[nk++] = j;
+    }
+    for (int i = 0; i < nk; ++i) {
+        const double* row = vals + rowptr[r0 + keep[i]] + off;
+        for (int j = 0; j < nk; ++j) {
+            a[i][j] = row[keep[j]];
+            a[i][nk + j] = (i == j) ? 1.0 : 0.0;
+        }
+    }
+    for (int k = 0; k < nk; ++k) {
         int piv = k;
         double best = fabs(a[k][k]);
-        for (int i = k + 1; i < n; ++i)
+        for (int i = k + 1; i < nk; ++i)
             if (fabs(a[i][k]) > best) { best = fabs(a[i][k]); piv = i; }
-        if (!(best > 0.0)) { *fail = 1; best = 1.0; a[piv][k] = 1.0; }
+        if (!(best > 0.0)) { *fail = 1; a[piv][k] = 1.0; }
         if (piv != k)
-            for (int j = 0; j < 2 * n; ++j) { const double t = a[k][j]; a[k][j] = a[piv][j]; a[piv][j] = t; }
+            for (int j = 0; j < 2 * nk; ++j) { const double t = a[k][j]; a[k][j] = a[piv][j]; a[piv][j] = t; }
         const double inv = 1.0 / a[k][k];
-        for (int j = 0; j < 2 * n; ++j) a[k][j] *= inv;
-        for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < 2 * nk; ++j) a[k][j] *= inv;
+        for (int i = 0; i < nk; ++i) {
             if (i == k) continue;
             const double fct = a[i][k];
-            for (int j = 0; j < 2 * n; ++j) a[i][j] -= fct * a[k][j];
+            for (int j = 0; j < 2 * nk; ++j) a[i][j] -= fct * a[k][j];
         }
     }
     for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) dinv[(size_t)(r0 + i) * nbs + j] = a[i][n + j];
+        for (int j = 0; j < n; ++j) dinv[(size_t)(r0 + i) * nbs + j] = 0.0;
+    for (int i = 0; i < nk; ++i)
+        for (int j = 0; j < nk; ++j) dinv[(size_t)(r0 + keep[i]) * nbs + keep[j]] = a[i][nk + j];
 }
 
 __global__ void bj_fold_kernel(int n_rows, int nbs, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
@@ -617,8 +666,8 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     // ---- preconditioner: Dinv, then A <- A M^-1 in place
     if (!A->dinv) EHDG_CUDA(cudaMalloc(&A->dinv, sizeof(double) * (size_t)n * nbs));
     int* fail = nullptr;
-    EHDG_CUDA(cudaMalloc(&fail, sizeof(int)));
-    EHDG_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
+    EHDG_CUDA(cudaMalloc(&fail, 2 * sizeof(int)));
+    EHDG_CUDA(cudaMemsetAsync(fail, 0, 2 * sizeof(int), st));
     bj_invert_kernel<<<(A->nf + 127) / 128, 128, 0, st>>>(A->nf, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail);
     EHDG_LAUNCH_CHECK();
     bj_fold_kernel<<<(unsigned)((n * 5 + 255) / 256), 256, 0, st>>>((int)n, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr, A->dinv, vals);
@@ -645,9 +694,11 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
     const double bnorm = std::sqrt(hbuf[0]);
-    int fail_h = 0;
-    EHDG_CUDA(cudaMemcpy(&fail_h, fail, sizeof(int), cudaMemcpyDeviceToHost));
+    int fail_h2[2] = {0, 0};
+    EHDG_CUDA(cudaMemcpy(fail_h2, fail, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(fail);
+    const int fail_h = fail_h2[0];
+    info->dropped_dofs = fail_h2[1];
     if (fail_h) { set_error("ehdg_gmres: singular facet diagonal block"); return EHDG_ERR_SINGULAR; }
     std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), gvec(m + 1), yv(m);
     double rel = 1.0;

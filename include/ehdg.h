@@ -121,7 +121,8 @@ const int32_t* ehdg_plan_eslot(const ehdg_plan* plan);
  *      facet_active u8[nf] = facet_mask minus pruned facet enrichment dofs minus boundary facets
  *                            (dirichlet=".*", :230-232); nf rounded up to a multiple of 4 bytes,
  *      factors f64[ne][4*n_enrich] (optional, may be null): the reference's `factor` per visited
- *      dof in order Q_k, QF_k(e0,e1,e2); -1 where the dof does not exist / element not visited. */
+ *      dof in order Q_k, QF_k(e0,e1,e2); -1 where the dof does not exist / element not visited,
+ *      -3 where the enrichment function vanishes identically on the facet (skipped). */
 int ehdg_prune(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_mask,
                const uint8_t* facet_mask, double threshold, uint8_t* elem_active, uint8_t* facet_active,
                double* factors, void* stream);
@@ -177,6 +178,7 @@ typedef struct {
     double rel_residual;    /* out: true residual at exit */
     double total_seconds;   /* out: device time of the whole solve */
     int64_t spmv_calls;     /* out */
+    int32_t dropped_dofs;   /* out: facet dofs found dependent inside their facet block (coefficient kept 0) */
 } ehdg_gmres_info;
 int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^-1 */,
                const double* rhs, double* x, ehdg_gmres_info* info, void* stream);

@@ -359,6 +359,14 @@ class EHDGOracle:
             try:
                 for i in range(self.n_p, N):
                     if important[i]:
+                        if elmat[i][i] == 0.0:
+                            # psi vanishes identically on this facet (the outflow edge itself, d = 0 in the
+                            # cancellation-free form used here).  NGSolve evaluates psi from a rounded x and
+                            # gets ~1e-16 instead of 0, so the reference neither divides by zero nor prunes
+                            # this (Dirichlet) dof: skip it, and keep it out of the later `active` lists.
+                            important[i] = False
+                            factors.append((i, -3.0))
+                            continue
                         act = [j for j in range(i) if important[j]]
                         factor = 1 - 2 * sum([elmat[i][j] ** 2 / elmat[i][i] / elmat[j][j] for j in act])
                         factor += sum([elmat[i][j] * elmat[i][k] * elmat[j][k] / elmat[i][i]
