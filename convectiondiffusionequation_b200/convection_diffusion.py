@@ -1,0 +1,76 @@
+"""Host-side mirror of the reference's solver class (Python/convection_diffusion.py).
+
+Same class name, method names, config keys, returned tables and printed line; the body of
+`_solveEHDG` (reference :223-403) is re-pointed at the CUDA hot path through the C ABI
+(include/ehdg.h).  Differences that are deliberate and documented in DESIGN.md:
+  * meshes come from the synthetic generator (Netgen is not available), config key `mesh_kind`;
+  * `exact`, `coeff`, `enrich_functions` are LayerExpr objects (coefficients.py) instead of NGSolve
+    CoefficientFunctions;
+  * the direct PARDISO solve of the uncondensed system (:385-387) is replaced by static condensation
+    + block-Jacobi GMRES on the facet system (mathematically the same discrete solution);
+  * no GUI: `Draw` / `input('')` (:398-399) are dropped; the instance gets its own config dict
+    (the reference mutates a class-level dict, :28-33).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+from .hot_path import EHDGPipeline, ProblemSpec
+from .mesh import mesh_for_size
+
+
+class Convection_Diffusion():
+
+    # default parameters (reference :28-30)
+    config = {}
+
+    def __init__(self, new_config={}):
+        self.config = dict(type(self).config)
+        self.config.update(new_config)
+        self.columns = ['Order', 'DOFs', 'Mesh Size', 'Error', 'Bonus Int', 'Type']
+        self.col = ['alpha', 'type', 'mesh_size', 'order']
+        self.results = pd.DataFrame(columns=self.columns)
+        self.alphas = pd.DataFrame(columns=self.col)
+        self.last_pipeline = None
+        self.solver_info = []
+
+    '''Enriched Discontinuous Galerkin Methods'''
+
+    def _solveEDG(self):
+        raise NotImplementedError("the EDG (interior-penalty) path of the reference (convection_diffusion.py:42-219) is the "
+                                  "next row of the hot-path scope table (SURVEY.md 8f-1); only _solveEHDG is built")
+
+    '''Enriched (Hybrid) Discontinuous Galerkin Methods'''
+
+    def _solveEHDG(self):
+        cfg = self.config
+        enrich = tuple(cfg.get('enrich_functions') or ())
+        inds = tuple(cfg.get('enrich_domain_ind') or ())
+        if len(enrich) != len(inds):
+            raise ValueError("enrich_functions and enrich_domain_ind must have the same length")
+        for order in cfg['order']:
+            for size in cfg['mesh_size']:
+                mesh = mesh_for_size(size, kind=cfg.get('mesh_kind', 'structured'))
+                spec = ProblemSpec(order=order, epsilon=cfg['epsilon'], beta=tuple(cfg['beta']), bonus_int=cfg['bonus_int'],
+                                   coeff=cfg['coeff'], exact=cfg['exact'], enrich_functions=enrich, enrich_domain_ind=inds)
+                pipe = EHDGPipeline(mesh, spec, device=cfg.get('device', 'cuda:0'))
+                type = 'ehdg' if len(enrich) > 0 else 'hdg'
+                pipe.setup(prune_threshold=1e-5)            # marking + pruning            (:240-244, :270-310)
+                pipe.alpha()                                # lambda_K per element         (:314-351)
+                lam = pipe.lam.cpu().numpy()
+                alp = 0.5 * np.sqrt(1.0 + lam)              # value the reference tabulates (:350-351)
+                frame = pd.DataFrame({'alpha': alp, 'type': type, 'mesh_size': size, 'order': order}, columns=self.col)
+                self.alphas = frame if len(self.alphas) == 0 else pd.concat([self.alphas, frame], ignore_index=True)
+                pipe.assemble_condense()                    # forms + assembly + rhs       (:357-383)
+                pipe.solve(restart=cfg.get('gmres_restart', 60), max_iters=cfg.get('gmres_max_iters', 20000),
+                           rtol=cfg.get('gmres_rtol', 1e-12))   # replaces Inverse(..., "pardiso")   (:385-387)
+                error, _ = pipe.errors()                    # recombination + L2 error     (:389-394)
+                ndof = pipe.ndof()
+                gi = pipe.gmres_info
+                self.solver_info.append(dict(order=order, mesh_size=size, type=type, iters=int(gi.iters), converged=bool(gi.converged),
+                                             rel_residual=float(gi.rel_residual), dropped_dofs=int(gi.dropped_dofs)))
+                self.results.loc[len(self.results)] = [order, ndof, size, error, cfg['bonus_int'], type]
+                print('order:', order, 'DOFs:', ndof, 'mesh:', size, "err:", error, 'type:', type)
+                self.last_pipeline = pipe
+        return self.results, self.alphas

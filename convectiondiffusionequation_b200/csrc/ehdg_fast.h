@@ -154,7 +154,7 @@ struct FastDims {
     static constexpr int NC = NP + NF + 1;
     static constexpr int M = NP > NF ? NP : NF;
     static constexpr int LG = M <= 8 ? 8 : (M <= 16 ? 16 : 32);
-    static constexpr int NXS = (NF + 2) & ~1;          // row stride of the X scratch (even)
+    static constexpr int NXS = (NF + 1) | 1;           // row stride of the X scratch (odd: conflict-free column writes)
 };
 
 template <int P>

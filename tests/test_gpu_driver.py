@@ -1,0 +1,57 @@
+"""The reference-facing entry points (Convection_Diffusion._solveEHDG, run.py) on the GPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_solve_ehdg_tables_match_reference_layout_and_oracle():
+    from convectiondiffusionequation_b200 import boundary_layer, x, y
+    from convectiondiffusionequation_b200.convection_diffusion import Convection_Diffusion
+    from convectiondiffusionequation_b200.mesh import mesh_for_size
+    from oracle import ehdg_oracle as orc
+    beta, eps = (2.0, 0.5), 0.05
+    p, q = boundary_layer(x, beta[0], eps), boundary_layer(y, beta[1], eps)
+    cfg = {'order': [1, 2], 'beta': beta, 'mesh_size': [0.25], 'epsilon': eps, 'exact': p * q, 'coeff': beta[1] * p + beta[0] * q,
+           'bonus_int': 10, 'theta': 1e-5, 'enrich_functions': [], 'enrich_domain_ind': []}
+    CT = Convection_Diffusion(cfg)
+    results, alphas = CT._solveEHDG()
+    assert list(results.columns) == ['Order', 'DOFs', 'Mesh Size', 'Error', 'Bonus Int', 'Type']
+    assert list(alphas.columns) == ['alpha', 'type', 'mesh_size', 'order']
+    assert list(results['Type']) == ['hdg', 'hdg'] and len(alphas) == 2 * 32
+    mesh = mesh_for_size(0.25)
+    for row, order in zip(results.itertuples(index=False), (1, 2)):
+        o = orc.EHDGOracle(mesh.verts, mesh.tris, mesh.el2facet, mesh.facet2el, mesh.maxh, order,
+                           orc.run_py_problem(beta=beta, eps=eps, enriched=False))
+        lams = o.alpha_all()
+        err = o.l2_error(o.solve_condensed(lams))
+        assert row.DOFs == o.ndof
+        assert abs(row.Error - err) < 1e-8 * err
+        a = alphas[alphas['order'] == order]['alpha'].to_numpy()
+        assert np.max(np.abs(a - 0.5 * np.sqrt(1 + lams))) < 1e-12
+    with pytest.raises(NotImplementedError):
+        CT._solveEDG()
+
+
+def test_run_py_default_problem():
+    """run.py's own configuration (enriched, then plain HDG): errors agree with the oracle's direct solve as
+    functions (the enriched system is numerically singular in the reference too)."""
+    from convectiondiffusionequation_b200 import run
+    from convectiondiffusionequation_b200.mesh import mesh_for_size
+    from oracle import ehdg_oracle as orc
+    old = dict(run.config)
+    try:
+        run.config.update({'order': [1], 'mesh_size': [0.25]})
+        table, alphas = run.main(write_csv=False)
+    finally:
+        run.config.clear()
+        run.config.update(old)
+    assert sorted(table['Type']) == ['ehdg', 'hdg']
+    mesh = mesh_for_size(0.25)
+    for typ in ('hdg', 'ehdg'):
+        o = orc.EHDGOracle(mesh.verts, mesh.tris, mesh.el2facet, mesh.facet2el, mesh.maxh, 1, orc.run_py_problem(enriched=typ == 'ehdg'))
+        o.prune()
+        err = o.l2_error(o.solve_condensed(o.alpha_all()))
+        got = float(table[table['Type'] == typ]['Error'].iloc[0])
+        assert abs(got - err) < (1e-8 if typ == 'hdg' else 1e-4) * err, (typ, got, err)
+        assert int(table[table['Type'] == typ]['DOFs'].iloc[0]) == o.ndof
