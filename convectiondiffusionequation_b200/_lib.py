@@ -45,7 +45,8 @@ class CsrSizes(C.Structure):
 class GmresInfo(C.Structure):
     _fields_ = [("restart", C.c_int32), ("max_iters", C.c_int32), ("rtol", C.c_double), ("iters", C.c_int32),
                 ("converged", C.c_int32), ("rel_residual", C.c_double), ("total_seconds", C.c_double),
-                ("spmv_calls", C.c_int64), ("dropped_dofs", C.c_int32)]
+                ("spmv_calls", C.c_int64), ("dropped_dofs", C.c_int32),
+                ("use_strip_block", C.c_int32), ("strip_dofs", C.c_int32), ("strip_blocks", C.c_int32)]
 
 
 # every symbol include/ehdg.h declares: name -> (restype, argtypes)
@@ -64,7 +65,7 @@ SYMBOLS = {
     "ehdg_prune": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, C.c_double, _P, _P, _P, _P]),
     "ehdg_alpha": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),
     "ehdg_assemble_condense": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "ehdg_csr_symbolic": (C.c_int, [_P, C.POINTER(Mesh), _P, C.POINTER(_P), _P]),
+    "ehdg_csr_symbolic": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.POINTER(_P), _P]),
     "ehdg_csr_destroy": (C.c_int, [_P]),
     "ehdg_csr_get_sizes": (C.c_int, [_P, C.POINTER(CsrSizes)]),
     "ehdg_csr_rowptr": (_P, [_P]),

@@ -73,6 +73,7 @@ struct ehdg_csr {
     int32_t* nbr_len = nullptr;     // [nf]    row length (sum of active dofs of the neighbours)
     uint16_t* dofmask = nullptr;    // [nf]    active slots of the facet
     int32_t* row_facet = nullptr;   // [n_rows] facet of each row
+    uint8_t* strip = nullptr;       // [nf]    1 = free facet of a marked element (enriched strip), null if none
     double* dinv = nullptr;         // [n_rows * nbmax] block-Jacobi inverses (set by ehdg_gmres)
     int nb;                         // slots per facet
 };

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "ehdg_internal.h"
+#include "ehdg_strip.h"
 
 namespace ehdg {
 
@@ -12,8 +13,8 @@ namespace ehdg {
 // a8 symbolic
 // ---------------------------------------------------------------------------------------------
 __global__ void csr_dofmask_kernel(int nf, int nfl, const int32_t* __restrict__ facet2el,
-                                   const uint8_t* __restrict__ facet_active, uint16_t* __restrict__ dofmask,
-                                   int32_t* __restrict__ nbf) {
+                                   const uint8_t* __restrict__ facet_active, const uint8_t* __restrict__ facet_mask,
+                                   uint16_t* __restrict__ dofmask, int32_t* __restrict__ nbf, uint8_t* __restrict__ strip) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f > nf) return;
     if (f == nf) { nbf[f] = 0; return; }
@@ -24,6 +25,7 @@ __global__ void csr_dofmask_kernel(int nf, int nfl, const int32_t* __restrict__ 
     }
     dofmask[f] = (uint16_t)m;
     nbf[f] = __popc(m);
+    if (strip) strip[f] = (m != 0 && facet_mask[f] != 0) ? 1 : 0;      // free facet of a marked element
 }
 
 __global__ void csr_nbr_kernel(int nf, const int32_t* __restrict__ facet2el, const int32_t* __restrict__ el2facet,
@@ -200,7 +202,7 @@ constexpr int NBMAX = EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH;
 
 __global__ void bj_invert_kernel(int nf, int nbs, const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ nbr, const double* __restrict__ vals, double* __restrict__ dinv,
-                                 int* __restrict__ fail) {
+                                 int* __restrict__ fail, uint8_t* __restrict__ rowdrop) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;
     const int r0 = row_start[f], n = row_start[f + 1] - r0;
@@ -282,15 +284,18 @@ __global__ void bj_invert_kernel(int nf, int nbs, const int32_t* __restrict__ ro
             for (int j = 0; j < 2 * nk; ++j) a[i][j] -= fct * a[k][j];
         }
     }
-    for (int i = 0; i < n; ++i)
+    for (int i = 0; i < n; ++i) {
+        rowdrop[r0 + i] = 1;
         for (int j = 0; j < n; ++j) dinv[(size_t)(r0 + i) * nbs + j] = 0.0;
+    }
+    for (int i = 0; i < nk; ++i) rowdrop[r0 + keep[i]] = 0;
     for (int i = 0; i < nk; ++i)
         for (int j = 0; j < nk; ++j) dinv[(size_t)(r0 + keep[i]) * nbs + keep[j]] = a[i][nk + j];
 }
 
 __global__ void bj_fold_kernel(int n_rows, int nbs, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
                                const int64_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
-                               const double* __restrict__ dinv, double* __restrict__ vals) {
+                               const double* __restrict__ dinv, const uint8_t* __restrict__ strip, double* __restrict__ vals) {
     // one thread per (row, neighbour block): segment <- segment * Dinv_g
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = (int)(t / 5), nb_i = (int)(t % 5);
@@ -302,6 +307,7 @@ __global__ void bj_fold_kernel(int n_rows, int nbs, const int32_t* __restrict__ 
         if (g < 0) return;
         if (u < nb_i) off += row_start[g + 1] - row_start[g];
     }
+    if (strip && strip[g]) return;          // strip columns stay unscaled: their block is solved exactly (ehdg_strip.cu)
     const int c0 = row_start[g], n = row_start[g + 1] - c0;
     double seg[NBMAX], out[NBMAX];
     double* p = vals + rowptr[r] + off;
@@ -550,7 +556,8 @@ static SLayout make_slayout(const ehdg_ctx* c, const ehdg_plan* p) {
 
 extern "C" {
 
-int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_active, ehdg_csr** out, void* stream) {
+int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_active, const uint8_t* facet_mask, ehdg_csr** out,
+                      void* stream) {
     if (!c || !m || !out) { set_error("ehdg_csr_symbolic: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int nf = m->nf;
@@ -569,7 +576,10 @@ int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_acti
     EHDG_CUDA(cudaMalloc(&A->nbr, sizeof(int32_t) * 5 * (size_t)(nf + 1)));
     EHDG_CUDA(cudaMalloc(&A->nbr_len, sizeof(int32_t) * (size_t)(nf + 1)));
     const int gb = (nf + 1 + 255) / 256;
-    csr_dofmask_kernel<<<gb, 256, 0, st>>>(nf, c->pb.nfl, m->facet2el, c->pb.nenr ? facet_active : nullptr, A->dofmask, nbf);
+    const bool want_strip = c->pb.nenr > 0 && facet_mask != nullptr;
+    if (want_strip) EHDG_CUDA(cudaMalloc(&A->strip, (size_t)(nf + 1)));
+    csr_dofmask_kernel<<<gb, 256, 0, st>>>(nf, c->pb.nfl, m->facet2el, c->pb.nenr ? facet_active : nullptr, facet_mask, A->dofmask, nbf,
+                                           want_strip ? A->strip : nullptr);
     EHDG_LAUNCH_CHECK();
     csr_nbr_kernel<<<gb, 256, 0, st>>>(nf, m->facet2el, m->el2facet, nbf, A->nbr, A->nbr_len, blk);
     EHDG_LAUNCH_CHECK();
@@ -613,6 +623,7 @@ int ehdg_csr_destroy(ehdg_csr* A) {
     cudaFree(A->dofmask);
     cudaFree(A->dinv);
     cudaFree(A->row_facet);
+    cudaFree(A->strip);
     delete A;
     return EHDG_OK;
 }
@@ -668,12 +679,24 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     int* fail = nullptr;
     EHDG_CUDA(cudaMalloc(&fail, 2 * sizeof(int)));
     EHDG_CUDA(cudaMemsetAsync(fail, 0, 2 * sizeof(int), st));
-    bj_invert_kernel<<<(A->nf + 127) / 128, 128, 0, st>>>(A->nf, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail);
+    uint8_t* rowdrop = nullptr;
+    EHDG_CUDA(cudaMalloc(&rowdrop, (size_t)n));
+    bj_invert_kernel<<<(A->nf + 127) / 128, 128, 0, st>>>(A->nf, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop);
     EHDG_LAUNCH_CHECK();
-    bj_fold_kernel<<<(unsigned)((n * 5 + 255) / 256), 256, 0, st>>>((int)n, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr, A->dinv, vals);
+    // strip of marked elements: one exactly solved block (needs the unscaled matrix values)
+    StripSolver* strip = nullptr;
+    if (info->use_strip_block) {
+        const int rcs = strip_setup(A, vals, rowdrop, st, &strip);
+        if (rcs) return rcs;
+    }
+    info->strip_dofs = strip ? strip->n_dofs : 0;
+    info->strip_blocks = strip ? strip->n_blocks : 0;
+    bj_fold_kernel<<<(unsigned)((n * 5 + 255) / 256), 256, 0, st>>>((int)n, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr, A->dinv,
+                                                                     strip ? A->strip : nullptr, vals);
     EHDG_LAUNCH_CHECK();
     // ---- workspace
-    double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr;
+    double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr, *tvec = nullptr;
+    if (strip) EHDG_CUDA(cudaMalloc(&tvec, sizeof(double) * (size_t)n));
     EHDG_CUDA(cudaMalloc(&V, sizeof(double) * (size_t)n * (m + 1)));
     EHDG_CUDA(cudaMalloc(&w, sizeof(double) * (size_t)n));
     EHDG_CUDA(cudaMalloc(&yhat, sizeof(double) * (size_t)n));
@@ -687,6 +710,18 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     EHDG_CUDA(cudaMallocHost(&hbuf, sizeof(double) * (size_t)(2 * (m + 2) + 8)));
     EHDG_CUDA(cudaMemsetAsync(yhat, 0, sizeof(double) * (size_t)n, st));
     VecOps vo{st, partial, n};
+    // w = A~ P(v):  P leaves the bulk entries (their M^-1 is folded into A~) and solves the strip block
+    auto apply_op = [&](const double* v, double* out) -> int {
+        const double* in = v;
+        if (strip) {
+            EHDG_CUDA(cudaMemcpyAsync(tvec, v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            const int r2 = strip_apply(strip, v, tvec, st);
+            if (r2) return r2;
+            in = tvec;
+        }
+        info->spmv_calls++;
+        return launch_spmv(A, vals, in, out, st);
+    };
     const int vgrid = vo.grid();
     int rc;
     // ||b||
@@ -707,8 +742,7 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     if (conv) rel = 0.0;
     while (!conv && iters < max_iters) {
         // r = b - A yhat  (into w), beta = ||r||
-        if ((rc = launch_spmv(A, vals, yhat, w, st))) return rc;
-        info->spmv_calls++;
+        if ((rc = apply_op(yhat, w))) return rc;
         residual_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, rhs, w);
         if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
         EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -722,8 +756,7 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
         int j = 0;
         for (; j < m && iters < max_iters; ++j, ++iters) {
             double* vj1 = V + (size_t)(j + 1) * n;
-            if ((rc = launch_spmv(A, vals, V + (size_t)j * n, w, st))) return rc;
-            info->spmv_calls++;
+            if ((rc = apply_op(V + (size_t)j * n, w))) return rc;
             // classical Gram-Schmidt, twice
             if ((rc = vo.dots(V, n, j + 1, w, d_h1))) return rc;
             if ((rc = vo.axpys(V, n, j + 1, d_h1, w))) return rc;
@@ -765,8 +798,7 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     }
     // true residual at exit
     if (!(bnorm == 0.0)) {
-        if ((rc = launch_spmv(A, vals, yhat, w, st))) return rc;
-        info->spmv_calls++;
+        if ((rc = apply_op(yhat, w))) return rc;
         residual_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, rhs, w);
         if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
         EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -777,6 +809,7 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     // x = M^-1 yhat
     bj_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n, nbs, A->row_facet, A->row_start, A->dinv, yhat, x);
     EHDG_LAUNCH_CHECK();
+    if (strip && (rc = strip_apply(strip, yhat, x, st))) return rc;
     EHDG_CUDA(cudaEventRecord(ev1, st));
     EHDG_CUDA(cudaEventSynchronize(ev1));
     float ms = 0.f;
@@ -787,6 +820,10 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     info->converged = conv ? 1 : 0;
     info->rel_residual = rel;
     info->total_seconds = ms * 1e-3;
+    info->dropped_dofs += strip ? strip->dropped : 0;
+    strip_free(strip);
+    cudaFree(rowdrop);
+    cudaFree(tvec);
     cudaFree(V);
     cudaFree(w);
     cudaFree(yhat);

@@ -169,7 +169,7 @@ class EHDGPipeline:
             self.lib.ehdg_csr_destroy(self.csr)
         self.csr = C.c_void_p()
         _lib.check(self.lib.ehdg_csr_symbolic(self.ctx, C.byref(self.cmesh), _ptr(self.facet_active) if self.nenr else None,
-                                              C.byref(self.csr), self._stream()), "ehdg_csr_symbolic")
+                                              _ptr(self.facet_mask) if self.nenr else None, C.byref(self.csr), self._stream()), "ehdg_csr_symbolic")
         self.csr_sizes = _lib.CsrSizes()
         _lib.check(self.lib.ehdg_csr_get_sizes(self.csr, C.byref(self.csr_sizes)), "ehdg_csr_get_sizes")
         n, nnz = self.csr_sizes.n_rows, self.csr_sizes.nnz
@@ -198,11 +198,12 @@ class EHDGPipeline:
         _lib.check(self.lib.ehdg_spmv(self.ctx, self.csr, _ptr(self.vals), _ptr(x), _ptr(y), self._stream()), "ehdg_spmv")
         return y
 
-    def gmres(self, restart=30, max_iters=20000, rtol=1e-12):
+    def gmres(self, restart=30, max_iters=20000, rtol=1e-12, strip_block=True):
         n = self.csr_sizes.n_rows
         self.xhat = torch.zeros(max(n, 1), dtype=torch.float64, device=self.dev)
         info = _lib.GmresInfo()
         info.restart, info.max_iters, info.rtol = int(restart), int(max_iters), float(rtol)
+        info.use_strip_block = int(bool(strip_block) and self.nenr > 0)
         _lib.check(self.lib.ehdg_gmres(self.ctx, self.csr, _ptr(self.vals), _ptr(self.rhs), _ptr(self.xhat), C.byref(info),
                                        self._stream()), "ehdg_gmres")
         self.gmres_info = info

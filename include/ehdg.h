@@ -149,13 +149,14 @@ int ehdg_assemble_condense(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh
  * (row of (facet f, slot k) = row_start[f] + rank of k among the active slots of f),
  * columns ascending in every row, structural zeros kept (NGSolve graph rule).
  * Polynomial dofs of interior facets are free; enriched dof j of facet f is active iff bit j of
- * facet_active[f] (from ehdg_prune; pass null when n_enrich = 0). */
+ * facet_active[f] (from ehdg_prune; pass null when n_enrich = 0).  facet_mask (from ehdg_mark, may be null)
+ * tells which facets belong to marked elements: they form the strip block of the preconditioner. */
 typedef struct ehdg_csr ehdg_csr;
 typedef struct {
     int64_t n_rows, nnz;
 } ehdg_csr_sizes;
-int ehdg_csr_symbolic(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_active, ehdg_csr** out,
-                      void* stream);
+int ehdg_csr_symbolic(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_active, const uint8_t* facet_mask,
+                      ehdg_csr** out, void* stream);
 int ehdg_csr_destroy(ehdg_csr* csr);
 int ehdg_csr_get_sizes(const ehdg_csr* csr, ehdg_csr_sizes* out);
 const int64_t* ehdg_csr_rowptr(const ehdg_csr* csr);     /* i64 [n_rows+1] device */
@@ -179,6 +180,9 @@ typedef struct {
     double total_seconds;   /* out: device time of the whole solve */
     int64_t spmv_calls;     /* out */
     int32_t dropped_dofs;   /* out: facet dofs found dependent inside their facet block (coefficient kept 0) */
+    int32_t use_strip_block;/* in : 1 = facets of marked elements form one exactly solved preconditioner block */
+    int32_t strip_dofs;     /* out */
+    int32_t strip_blocks;   /* out */
 } ehdg_gmres_info;
 int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^-1 */,
                const double* rhs, double* x, ehdg_gmres_info* info, void* stream);
