@@ -156,7 +156,8 @@ def main():
     ap.add_argument("--solve-iters", type=int, default=20000)
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--restart", type=int, default=30)
-    ap.add_argument("--plain-hdg-solve", action="store_true", help="one-off solve on the unenriched (HDG) system instead")
+    ap.add_argument("--solve-type", default="hdg", choices=["hdg", "ehdg", "both"],
+                    help="system of the one-off solve: plain HDG (well posed at every size) and/or the enriched one")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -266,44 +267,53 @@ def main():
     h2d = P.h2d_bytes + (P.vert_flags.numel() if hasattr(P, "vert_flags") else 0)
     d2h = ne * 12
 
-    # ---- one-off solve (a8-a10)
-    solve = None
-    if not args.no_solve:
-        Ps = P
-        if args.plain_hdg_solve:
-            Ps = EHDGPipeline(mesh, make_spec(order, eps, enriched=False), device=dev)
-            Ps.setup().assemble()
-        barrier()
-        s0, s1, s2, s3 = ev(), ev(), ev(), ev()
-        s0.record()
-        Ps.csr_build()
-        s1.record()
-        nrows, nnz = Ps.csr_sizes.n_rows, Ps.csr_sizes.nnz
-        # SpMV bandwidth: algorithmic bytes 12 nnz + 20 rows, 20 launches
-        xs = torch.ones(max(nrows, 1), dtype=torch.float64, device=dev)
-        ys = torch.empty_like(xs)
-        for _ in range(3):
-            Ps.spmv(xs, ys)
-        b0, b1 = ev(), ev()
-        b0.record()
-        for _ in range(20):
-            Ps.spmv(xs, ys)
-        b1.record()
-        torch.cuda.synchronize(dev)
-        spmv_ms = b0.elapsed_time(b1) / 20
-        spmv_gbs = (12.0 * nnz + 20.0 * nrows) / (spmv_ms * 1e-3) / 1e9
-        s2.record()
-        Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol)
-        Ps.backsolve()
-        l2, h1 = Ps.errors()
-        s3.record()
-        torch.cuda.synchronize(dev)
-        gi = Ps.gmres_info
-        solve = {"type": "hdg" if args.plain_hdg_solve else "ehdg", "rows": int(nrows), "nnz": int(nnz),
-                 "csr_build_ms": s0.elapsed_time(s1), "gmres_backsolve_error_ms": s2.elapsed_time(s3), "gmres_iters": int(gi.iters),
-                 "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual), "gmres_seconds": float(gi.total_seconds),
-                 "restart": args.restart, "rtol": args.rtol, "dropped_dofs": int(gi.dropped_dofs), "l2_error": l2, "h1_error": h1,
-                 "spmv_ms": spmv_ms, "spmv_gbs": spmv_gbs}
+    # ---- one-off solve (a8-a10); N = 1 only (the distributed GMRES is not built yet)
+    solves = []
+    if not args.no_solve and world == 1:
+        for styp in (["hdg", "ehdg"] if args.solve_type == "both" else [args.solve_type]):
+            Ps = P
+            if styp == "hdg":
+                Ps = EHDGPipeline(mesh, make_spec(order, eps, enriched=False), device=dev)
+                Ps.setup().assemble()
+            barrier()
+            s0, s1, s2, s3 = ev(), ev(), ev(), ev()
+            s0.record()
+            Ps.csr_build()
+            s1.record()
+            nrows, nnz = Ps.csr_sizes.n_rows, Ps.csr_sizes.nnz
+            # SpMV bandwidth: algorithmic bytes 12 nnz + 20 rows, 20 launches
+            xs = torch.ones(max(nrows, 1), dtype=torch.float64, device=dev)
+            ys = torch.empty_like(xs)
+            for _ in range(3):
+                Ps.spmv(xs, ys)
+            b0, b1 = ev(), ev()
+            b0.record()
+            for _ in range(20):
+                Ps.spmv(xs, ys)
+            b1.record()
+            torch.cuda.synchronize(dev)
+            spmv_ms = b0.elapsed_time(b1) / 20
+            spmv_gbs = (12.0 * nnz + 20.0 * nrows) / (spmv_ms * 1e-3) / 1e9
+            del xs, ys
+            s2.record()
+            Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol)
+            Ps.backsolve()
+            l2, h1 = Ps.errors()
+            s3.record()
+            torch.cuda.synchronize(dev)
+            gi = Ps.gmres_info
+            solves.append({"type": styp, "rows": int(nrows), "nnz": int(nnz), "csr_build_ms": s0.elapsed_time(s1),
+                           "gmres_backsolve_error_ms": s2.elapsed_time(s3), "gmres_iters": int(gi.iters),
+                           "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual),
+                           "gmres_seconds": float(gi.total_seconds), "ms_per_iteration": 1e3 * float(gi.total_seconds) / max(1, int(gi.iters)),
+                           "restart": args.restart, "rtol": args.rtol, "dropped_dofs": int(gi.dropped_dofs),
+                           "strip_dofs": int(gi.strip_dofs), "strip_blocks": int(gi.strip_blocks), "l2_error": l2, "h1_error": h1,
+                           "spmv_ms": spmv_ms, "spmv_gbs": spmv_gbs})
+            if Ps is not P:
+                Ps.close()
+                del Ps
+                torch.cuda.empty_cache()
+    solve = solves[0] if solves else None
 
     if rank != 0:
         if world > 1:
@@ -338,9 +348,12 @@ def main():
         "gpu_launches": int(args.steps * (2 + (2 if n_gen else 0))),
         "clocks": clocks.summary(),
     }
-    if solve:
-        line["solve"] = solve
-        line["solve"]["spmv_frac_of_hbm_peak"] = solve["spmv_gbs"] / hbm
+    for sv in solves:
+        sv["spmv_frac_of_hbm_peak"] = sv["spmv_gbs"] / hbm
+    if solves:
+        line["solve"] = solves[0]
+        if len(solves) > 1:
+            line["solve_enriched"] = solves[1]
     if not args.no_cpu and world == 1:
         try:
             info = cpu_reference(args.workload, budget_s=15.0)

