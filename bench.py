@@ -153,9 +153,10 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-solve", action="store_true", help="skip the one-off GMRES solve after the timed steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--solve-iters", type=int, default=20000)
+    ap.add_argument("--solve-iters", type=int, default=400)
     ap.add_argument("--rtol", type=float, default=1e-8)
-    ap.add_argument("--restart", type=int, default=30)
+    ap.add_argument("--restart", type=int, default=40)
+    ap.add_argument("--sweeps", type=int, default=0, help="block-Jacobi sweeps per preconditioner application (0 = 4.5 N / restart)")
     ap.add_argument("--solve-type", default="hdg", choices=["hdg", "ehdg", "both"],
                     help="system of the one-off solve: plain HDG (well posed at every size) and/or the enriched one")
     args = ap.parse_args()
@@ -296,7 +297,8 @@ def main():
             spmv_gbs = (12.0 * nnz + 20.0 * nrows) / (spmv_ms * 1e-3) / 1e9
             del xs, ys
             s2.record()
-            Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol)
+            sweeps = args.sweeps if args.sweeps > 0 else max(1, int(np.ceil(4.5 * n / args.restart)))
+            Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol, jacobi_sweeps=sweeps)
             Ps.backsolve()
             l2, h1 = Ps.errors()
             s3.record()
@@ -306,7 +308,7 @@ def main():
                            "gmres_backsolve_error_ms": s2.elapsed_time(s3), "gmres_iters": int(gi.iters),
                            "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual),
                            "gmres_seconds": float(gi.total_seconds), "ms_per_iteration": 1e3 * float(gi.total_seconds) / max(1, int(gi.iters)),
-                           "restart": args.restart, "rtol": args.rtol, "dropped_dofs": int(gi.dropped_dofs),
+                           "restart": args.restart, "jacobi_sweeps": sweeps, "spmv_calls": int(gi.spmv_calls), "rtol": args.rtol, "dropped_dofs": int(gi.dropped_dofs),
                            "strip_dofs": int(gi.strip_dofs), "strip_blocks": int(gi.strip_blocks), "l2_error": l2, "h1_error": h1,
                            "spmv_ms": spmv_ms, "spmv_gbs": spmv_gbs})
             if Ps is not P:

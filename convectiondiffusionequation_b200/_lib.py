@@ -46,7 +46,8 @@ class GmresInfo(C.Structure):
     _fields_ = [("restart", C.c_int32), ("max_iters", C.c_int32), ("rtol", C.c_double), ("iters", C.c_int32),
                 ("converged", C.c_int32), ("rel_residual", C.c_double), ("total_seconds", C.c_double),
                 ("spmv_calls", C.c_int64), ("dropped_dofs", C.c_int32),
-                ("use_strip_block", C.c_int32), ("strip_dofs", C.c_int32), ("strip_blocks", C.c_int32)]
+                ("use_strip_block", C.c_int32), ("strip_dofs", C.c_int32), ("strip_blocks", C.c_int32),
+                ("jacobi_sweeps", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/ehdg.h declares: name -> (restype, argtypes)

@@ -417,6 +417,17 @@ __global__ void update_x_kernel(int64_t n, const double* __restrict__ V, int64_t
     }
 }
 
+// t = v + t - w   (one block-Jacobi Richardson sweep in the preconditioned variables)
+__global__ void poly_update_kernel(int64_t n, const double* __restrict__ v, const double* __restrict__ w, double* __restrict__ t) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        t[i] = v[i] + t[i] - w[i];
+}
+
+// y += x
+__global__ void add_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
+}
+
 // r = b - r
 __global__ void residual_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -722,6 +733,32 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
         info->spmv_calls++;
         return launch_spmv(A, vals, in, out, st);
     };
+    // polynomial block-Jacobi preconditioner: t = sum_{i<s} (I - B)^i v, i.e. s Richardson sweeps.  B (I + N + ... +
+    // N^{s-1}) = I - N^s with N = I - B: for convection-dominated systems N is (nearly) nilpotent along the streamlines,
+    // so one application moves information s facet layers downstream (restarted GMRES on B alone stagnates: all
+    // eigenvalues are 1 and the minimal polynomial has the degree of the longest streamline).
+    const int sweeps = info->jacobi_sweeps > 1 ? info->jacobi_sweeps : 1;
+    double *pt = nullptr, *pw = nullptr;
+    if (sweeps > 1) {
+        EHDG_CUDA(cudaMalloc(&pt, sizeof(double) * (size_t)n));
+        EHDG_CUDA(cudaMalloc(&pw, sizeof(double) * (size_t)n));
+    }
+    const int vgrid0 = vo.grid();
+    auto poly = [&](const double* v, double* t) -> int {          // t = P^ v  (t != v)
+        EHDG_CUDA(cudaMemcpyAsync(t, v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        for (int i = 1; i < sweeps; ++i) {
+            const int r2 = apply_op(t, pw);
+            if (r2) return r2;
+            poly_update_kernel<<<vgrid0, RED_THREADS, 0, st>>>(n, v, pw, t);
+        }
+        return EHDG_OK;
+    };
+    auto apply_prec_op = [&](const double* v, double* out) -> int {   // out = B P^ v
+        if (sweeps == 1) return apply_op(v, out);
+        const int r2 = poly(v, pt);
+        if (r2) return r2;
+        return apply_op(pt, out);
+    };
     const int vgrid = vo.grid();
     int rc;
     // ||b||
@@ -756,7 +793,7 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
         int j = 0;
         for (; j < m && iters < max_iters; ++j, ++iters) {
             double* vj1 = V + (size_t)(j + 1) * n;
-            if ((rc = apply_op(V + (size_t)j * n, w))) return rc;
+            if ((rc = apply_prec_op(V + (size_t)j * n, w))) return rc;
             // classical Gram-Schmidt, twice
             if ((rc = vo.dots(V, n, j + 1, w, d_h1))) return rc;
             if ((rc = vo.axpys(V, n, j + 1, d_h1, w))) return rc;
@@ -793,7 +830,15 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
         }
         for (int i = 0; i < j; ++i) hbuf[i] = yv[i];
         EHDG_CUDA(cudaMemcpyAsync(d_y, hbuf, sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, st));
-        update_x_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, V, n, j, d_y, yhat);
+        if (sweeps == 1) {
+            update_x_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, V, n, j, d_y, yhat);
+        } else {
+            // yhat += P^ (V y)
+            EHDG_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)n, st));
+            update_x_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, V, n, j, d_y, w);
+            if ((rc = poly(w, pt))) return rc;
+            add_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, pt, yhat);
+        }
         EHDG_CUDA(cudaStreamSynchronize(st));
     }
     // true residual at exit
@@ -824,6 +869,8 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     strip_free(strip);
     cudaFree(rowdrop);
     cudaFree(tvec);
+    cudaFree(pt);
+    cudaFree(pw);
     cudaFree(V);
     cudaFree(w);
     cudaFree(yhat);

@@ -183,6 +183,9 @@ typedef struct {
     int32_t use_strip_block;/* in : 1 = facets of marked elements form one exactly solved preconditioner block */
     int32_t strip_dofs;     /* out */
     int32_t strip_blocks;   /* out */
+    int32_t jacobi_sweeps;  /* in : s >= 1 block-Jacobi Richardson sweeps per preconditioner application (polynomial
+                             *      block-Jacobi); s * restart should exceed the number of facet layers along a streamline */
+    int32_t reserved;
 } ehdg_gmres_info;
 int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^-1 */,
                const double* rhs, double* x, ehdg_gmres_info* info, void* stream);

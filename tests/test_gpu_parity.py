@@ -261,6 +261,13 @@ def test_csr_solve_and_error(order, eps, beta, enriched, kind):
         assert abs(l2_dev - l2_o) <= tol * l2_o
         assert abs(h1_dev - h1_o) <= 10 * tol * h1_o
     assert P.ndof() == o.ndof
+    # polynomial block-Jacobi (Richardson sweeps inside the preconditioner): same solution, fewer outer iterations
+    if condS < 1e10:
+        it_plain = P.gmres_info.iters
+        x1 = P.xhat.clone()
+        P.csr_build().gmres(restart=60, max_iters=6000, rtol=1e-11, jacobi_sweeps=8)
+        assert P.gmres_info.converged == 1 and P.gmres_info.iters < it_plain
+        assert rel(P.xhat.cpu().numpy(), x1.cpu().numpy()) < 1e-7
 
 
 def _conds(o, lams):
