@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--solve-iters", type=int, default=400)
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--restart", type=int, default=40)
-    ap.add_argument("--sweeps", type=int, default=0, help="block-Jacobi sweeps per preconditioner application (0 = 4.5 N / restart)")
+    ap.add_argument("--sweeps", type=int, default=1, help="block-Jacobi sweeps per preconditioner application")
     ap.add_argument("--solve-type", default="hdg", choices=["hdg", "ehdg", "both"],
                     help="system of the one-off solve: plain HDG (well posed at every size) and/or the enriched one")
     args = ap.parse_args()
@@ -297,7 +297,7 @@ def main():
             spmv_gbs = (12.0 * nnz + 20.0 * nrows) / (spmv_ms * 1e-3) / 1e9
             del xs, ys
             s2.record()
-            sweeps = args.sweeps if args.sweeps > 0 else max(1, int(np.ceil(4.5 * n / args.restart)))
+            sweeps = max(1, args.sweeps)
             Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol, jacobi_sweeps=sweeps)
             Ps.backsolve()
             l2, h1 = Ps.errors()

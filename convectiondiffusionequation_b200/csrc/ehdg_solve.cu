@@ -428,6 +428,25 @@ __global__ void add_kernel(int64_t n, const double* __restrict__ x, double* __re
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
 }
 
+// BiCGStab vector updates
+__global__ void bicg_p_kernel(int64_t n, const double* __restrict__ r, const double* __restrict__ v, double beta, double omega,
+                              double* __restrict__ p) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = r[i] + beta * (p[i] - omega * v[i]);
+}
+__global__ void bicg_s_kernel(int64_t n, const double* __restrict__ r, const double* __restrict__ v, double alpha,
+                              double* __restrict__ s) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s[i] = r[i] - alpha * v[i];
+}
+__global__ void bicg_x_kernel(int64_t n, const double* __restrict__ p, const double* __restrict__ s, const double* __restrict__ t,
+                              double alpha, double omega, double* __restrict__ u, double* __restrict__ r) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        u[i] += alpha * p[i] + omega * s[i];
+        r[i] = s[i] - omega * t[i];
+    }
+}
+
 // r = b - r
 __global__ void residual_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -667,7 +686,8 @@ int ehdg_spmv(ehdg_ctx* c, const ehdg_csr* A, const double* vals, const double* 
     return launch_spmv(A, vals, x, y, (cudaStream_t)stream);
 }
 
-int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream) {
+static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream,
+                        int method) {
     if (!c || !A || !vals || !rhs || !x || !info) { set_error("ehdg_gmres: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = A->n_rows;
@@ -708,7 +728,7 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     // ---- workspace
     double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr, *tvec = nullptr;
     if (strip) EHDG_CUDA(cudaMalloc(&tvec, sizeof(double) * (size_t)n));
-    EHDG_CUDA(cudaMalloc(&V, sizeof(double) * (size_t)n * (m + 1)));
+    EHDG_CUDA(cudaMalloc(&V, sizeof(double) * (size_t)n * (method == 0 ? (m + 1) : 6)));
     EHDG_CUDA(cudaMalloc(&w, sizeof(double) * (size_t)n));
     EHDG_CUDA(cudaMalloc(&yhat, sizeof(double) * (size_t)n));
     EHDG_CUDA(cudaMalloc(&partial, sizeof(double) * (size_t)RED_BLOCKS * KT));
@@ -777,7 +797,64 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     int iters = 0;
     bool conv = (bnorm == 0.0);
     if (conv) rel = 0.0;
-    while (!conv && iters < max_iters) {
+    if (method == 1 && !conv) {
+        // ---- BiCGStab on Op = B P^ (right preconditioned by the polynomial block-Jacobi when sweeps > 1);
+        // the short recurrence avoids the restart stagnation of GMRES(m) on the penalty-dominated (elliptic-like)
+        // facet systems of the fine meshes.
+        double* r = V;
+        double* rh = V + (size_t)n;
+        double* pv = V + 2 * (size_t)n;
+        double* vv = V + 3 * (size_t)n;
+        double* sv = V + 4 * (size_t)n;     // s and t are contiguous: one fused dot launch gives (t,s) and (t,t)
+        double* tv = V + 5 * (size_t)n;
+        double* u = yhat;                   // solution in the Op variables; yhat = P^ u at the end
+        EHDG_CUDA(cudaMemcpyAsync(r, rhs, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        EHDG_CUDA(cudaMemcpyAsync(rh, rhs, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        EHDG_CUDA(cudaMemsetAsync(pv, 0, sizeof(double) * (size_t)n, st));
+        EHDG_CUDA(cudaMemsetAsync(vv, 0, sizeof(double) * (size_t)n, st));
+        double rho = 1.0, alpha = 1.0, omega = 1.0;
+        auto dot1 = [&](const double* a, const double* b2, double* out) -> int {
+            int r3 = vo.dots(a, n, 1, b2, d_nrm);
+            if (r3) return r3;
+            EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
+            EHDG_CUDA(cudaStreamSynchronize(st));
+            *out = hbuf[0];
+            return EHDG_OK;
+        };
+        double best_rel = 1.0;
+        for (; iters < max_iters; ++iters) {
+            double rho_new;
+            if ((rc = dot1(rh, r, &rho_new))) return rc;
+            if (rho_new == 0.0 || !std::isfinite(rho_new)) break;
+            const double beta = (rho_new / rho) * (alpha / omega);
+            rho = rho_new;
+            bicg_p_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, r, vv, beta, omega, pv);
+            if ((rc = apply_prec_op(pv, vv))) return rc;
+            double rhv;
+            if ((rc = dot1(rh, vv, &rhv))) return rc;
+            if (rhv == 0.0 || !std::isfinite(rhv)) break;
+            alpha = rho / rhv;
+            bicg_s_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, r, vv, alpha, sv);
+            if ((rc = apply_prec_op(sv, tv))) return rc;
+            if ((rc = vo.dots(sv, n, 2, tv, d_h1))) return rc;        // (s,t), (t,t)
+            EHDG_CUDA(cudaMemcpyAsync(hbuf, d_h1, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+            EHDG_CUDA(cudaStreamSynchronize(st));
+            omega = hbuf[1] > 0.0 ? hbuf[0] / hbuf[1] : 0.0;
+            bicg_x_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, pv, sv, tv, alpha, omega, u, r);
+            double rr;
+            if ((rc = dot1(r, r, &rr))) return rc;
+            rel = std::sqrt(rr) / bnorm;
+            if (rel < best_rel) best_rel = rel;
+            if (rel <= rtol) { ++iters; break; }
+            if (omega == 0.0 || !std::isfinite(rel)) break;
+        }
+        if (sweeps > 1) {      // yhat = P^ u
+            EHDG_CUDA(cudaMemcpyAsync(w, u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            if ((rc = poly(w, pt))) return rc;
+            EHDG_CUDA(cudaMemcpyAsync(yhat, pt, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    while (method == 0 && !conv && iters < max_iters) {
         // r = b - A yhat  (into w), beta = ||r||
         if ((rc = apply_op(yhat, w))) return rc;
         residual_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, rhs, w);
@@ -878,6 +955,14 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
     cudaFree(dsc);
     cudaFreeHost(hbuf);
     return EHDG_OK;
+}
+
+int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream) {
+    return krylov_solve(c, A, vals, rhs, x, info, stream, 0);
+}
+
+int ehdg_bicgstab(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream) {
+    return krylov_solve(c, A, vals, rhs, x, info, stream, 1);
 }
 
 int ehdg_backsolve(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehdg_mesh* m, const double* W, const double* z,

@@ -198,15 +198,16 @@ class EHDGPipeline:
         _lib.check(self.lib.ehdg_spmv(self.ctx, self.csr, _ptr(self.vals), _ptr(x), _ptr(y), self._stream()), "ehdg_spmv")
         return y
 
-    def gmres(self, restart=30, max_iters=20000, rtol=1e-12, strip_block=True, jacobi_sweeps=1):
+    def gmres(self, restart=30, max_iters=20000, rtol=1e-12, strip_block=True, jacobi_sweeps=1, method="gmres"):
         n = self.csr_sizes.n_rows
         self.xhat = torch.zeros(max(n, 1), dtype=torch.float64, device=self.dev)
         info = _lib.GmresInfo()
         info.restart, info.max_iters, info.rtol = int(restart), int(max_iters), float(rtol)
         info.use_strip_block = int(bool(strip_block) and self.nenr > 0)
         info.jacobi_sweeps = int(jacobi_sweeps)
-        _lib.check(self.lib.ehdg_gmres(self.ctx, self.csr, _ptr(self.vals), _ptr(self.rhs), _ptr(self.xhat), C.byref(info),
-                                       self._stream()), "ehdg_gmres")
+        fn = self.lib.ehdg_gmres if method == "gmres" else self.lib.ehdg_bicgstab
+        _lib.check(fn(self.ctx, self.csr, _ptr(self.vals), _ptr(self.rhs), _ptr(self.xhat), C.byref(info), self._stream()),
+                   "ehdg_" + method)
         self.gmres_info = info
         return self
 
