@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libehdg.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("EHDG_LIB_NAME", "libehdg.so"))
 
 MAX_ENR = 2
 

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "libehdg.so")
+LIB = os.path.join(HERE, os.environ.get("EHDG_LIB_NAME", "libehdg.so"))     # variant builds for A/B timing
 SOURCES = ["ehdg_core.cu", "ehdg_fast.cu", "ehdg_solve.cu", "ehdg_strip.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -26,14 +26,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
     hdrs.append(os.path.join(ROOT, "include", "ehdg.h"))
-    objdir = os.path.join(ROOT, "build")
+    objdir = os.path.join(ROOT, "build", os.environ.get("EHDG_LIB_NAME", "libehdg.so").replace(".so", ""))
+    extra = os.environ.get("EHDG_NVCC_DEFS", "").split()
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         path = os.path.join(CSRC, src)
         if force or _stale(obj, [path] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode:
                 sys.stderr.write(r.stdout + r.stderr)

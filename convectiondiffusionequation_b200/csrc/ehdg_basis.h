@@ -100,6 +100,24 @@ EHDG_HD void layer_eval(double k, double d, double* val, double* der) {
     *der = 1.0 + k * E / den;
 }
 
+// Same function with the per-problem constants hoisted: e0 = exp(-k), inv = 1 / (e0 - 1).
+// exp(-k d) underflows to exactly 0 beyond k d = 745.2, so the exponential is skipped there (bit-identical).
+struct LayerConst {
+    double k, e0, inv;
+};
+EHDG_HD LayerConst layer_const(double k) {
+    LayerConst c;
+    c.k = k;
+    c.e0 = exp(-k);
+    c.inv = 1.0 / (c.e0 - 1.0);
+    return c;
+}
+EHDG_HD double layer_val(const LayerConst& c, double d) {
+    const double kd = c.k * d;
+    const double E = kd > 746.0 ? 0.0 : exp(-kd);
+    return (1.0 - d) + (E - c.e0) * c.inv;
+}
+
 // f(x, y) = c0 + c1 L(k0; x) + c2 L(k1; y) + c3 L(k0; x) L(k1; y), given dx = 1 - x, dy = 1 - y.
 // Covers coeff = beta1 p(x) + beta0 q(y) (run.py:30) and exact = p(x) q(y) (run.py:29).
 struct LayerExpr {

@@ -6,9 +6,15 @@
 namespace ehdg {
 
 constexpr int FAST_THREADS = 128;
+#ifndef EHDG_ASM_MINBLOCKS
+#define EHDG_ASM_MINBLOCKS 3
+#endif
+#ifndef EHDG_ALPHA_MINBLOCKS
+#define EHDG_ALPHA_MINBLOCKS 4
+#endif
 
 template <int P>
-__global__ void __launch_bounds__(FAST_THREADS)
+__global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ASM_MINBLOCKS : (P == 5 ? 2 : 1)))
 fast_assemble_kernel(Problem pb, RuleSet rs, const double* __restrict__ tab_g, int tab_doubles,
                      const double* __restrict__ phi_rhs, int n, const int32_t* __restrict__ list,
                      const double* __restrict__ verts, const int32_t* __restrict__ tris,
@@ -34,7 +40,7 @@ fast_assemble_kernel(Problem pb, RuleSet rs, const double* __restrict__ tab_g, i
 }
 
 template <int P>
-__global__ void __launch_bounds__(FAST_THREADS)
+__global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ALPHA_MINBLOCKS : 2))
 fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, const int32_t* __restrict__ list,
                   const double* __restrict__ verts, const int32_t* __restrict__ tris, double* __restrict__ lam,
                   int32_t* status) {

@@ -10,6 +10,8 @@
 // with __syncwarp) and on the host (a phase is a loop over the LG lanes, L == l); the host
 // instantiation exists only for tests/hostcheck.
 #pragma once
+#include <string.h>
+
 #include "ehdg_general.h"
 #include "ehdg_tensors.h"
 
@@ -30,23 +32,35 @@ struct Group {
     int lane;       // lane inside the group (device); unused on the host
     double* sh;     // group-private scratch
 
-    // index of the lane with the largest key (ties: lowest lane); key < 0 never wins unless all are
+    // Lane holding the largest key (keys are magnitudes >= 0, or -1 for "not a candidate").  The keys
+    // are compared through the top 32 bits of the double with the low bits replaced by the lane, so
+    // the search is ONE 32-bit warp reduction (redux.sync) per group; pivots that agree to ~15 bits
+    // of mantissa are tie-broken towards the lower lane (immaterial for partial pivoting).
+    static EHDG_HD unsigned order_key(double key, int lane_) {
+        if (!(key >= 0.0)) return 0u;                       // -1 / NaN: never wins against a real candidate
+        unsigned long long bits;
+#ifdef __CUDA_ARCH__
+        bits = (unsigned long long)__double_as_longlong(key);
+#else
+        memcpy(&bits, &key, 8);
+#endif
+        const unsigned hi = (unsigned)(bits >> 32);
+        return ((hi | 0x80000000u) & ~(unsigned)(LG - 1)) | (unsigned)(LG - 1 - lane_);
+    }
     EHDG_HD int argmax(const double* key) const {
 #ifdef __CUDA_ARCH__
-        double k = key[0];
-        int idx = lane;
-#pragma unroll
-        for (int s = LG / 2; s > 0; s >>= 1) {
-            const double ok = __shfl_xor_sync(0xffffffffu, k, s, LG);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, s, LG);
-            if (ok > k || (ok == k && oi < idx)) { k = ok; idx = oi; }
-        }
-        return idx;
+        const unsigned k = order_key(key[0], lane);
+        const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(LG - 1);
+        const unsigned mask = (LG == 32) ? 0xffffffffu : (((1u << LG) - 1u) << base);
+        const unsigned best = __reduce_max_sync(mask, k);
+        return LG - 1 - (int)(best & (unsigned)(LG - 1));
 #else
-        int idx = 0;
-        for (int l = 1; l < LG; ++l)
-            if (key[l] > key[idx]) idx = l;
-        return idx;
+        unsigned best = 0u;
+        for (int l = 0; l < LG; ++l) {
+            const unsigned k = order_key(key[l], l);
+            if (k > best) best = k;
+        }
+        return LG - 1 - (int)(best & (unsigned)(LG - 1));
 #endif
     }
     EHDG_HD double sum(const double* x) const {
@@ -130,10 +144,15 @@ EHDG_HD void sorted_geom(const double* verts, const int* tri, double bx, double 
     sg.c1 = bx * gl[1][0] + by * gl[1][1];
     for (int s = 0; s < 3; ++s) {
         // outward normal of the edge opposite Q_s is -grad lam_Qs / |grad lam_Qs|, |grad lam_Qs| = 1/h_s
-        const double gn = sqrt(gl[s][0] * gl[s][0] + gl[s][1] * gl[s][1]);
-        const double nx = -gl[s][0] / gn, ny = -gl[s][1] / gn;
-        sg.h[s] = 1.0 / gn;                 // = |detJ| / |e|   
-        sg.len[s] = sg.adet * gn;
+        const double g2 = gl[s][0] * gl[s][0] + gl[s][1] * gl[s][1];
+#ifdef __CUDA_ARCH__
+        const double ign = rsqrt(g2);
+#else
+        const double ign = 1.0 / sqrt(g2);
+#endif
+        const double nx = -gl[s][0] * ign, ny = -gl[s][1] * ign;
+        sg.h[s] = ign;                      // = |detJ| / |e|   
+        sg.len[s] = sg.adet * (g2 * ign);
         sg.bn[s] = bx * nx + by * ny;
         sg.ga0[s] = nx * gl[0][0] + ny * gl[0][1];
         sg.ga1[s] = nx * gl[1][0] + ny * gl[1][1];
@@ -198,14 +217,19 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     int status = 0;
 
     // ---- right-hand side weights at the quadrature points: cw[q] = w_q |detJ| coeff(x_q)
-    EHDG_FOR_LANES(l, L)
-        for (int q = l; q < rs.nq; q += LG) {
-            const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
-            const double dx = l0 * sg.omx[0] + l1 * sg.omx[1] + l2 * sg.omx[2];
-            const double dy = l0 * sg.omy[0] + l1 * sg.omy[1] + l2 * sg.omy[2];
-            cw[q] = rs.vw[q] * sg.adet * layer_expr_eval(pb.coeff, dx, dy);
-        }
-    EHDG_END_LANES
+    {
+        const LayerConst cx = layer_const(pb.coeff.k[0]), cy = layer_const(pb.coeff.k[1]);
+        const bool ux = pb.coeff.c[1] != 0.0 || pb.coeff.c[3] != 0.0, uy = pb.coeff.c[2] != 0.0 || pb.coeff.c[3] != 0.0;
+        EHDG_FOR_LANES(l, L)
+            for (int q = l; q < rs.nq; q += LG) {
+                const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
+                const double dx = l0 * sg.omx[0] + l1 * sg.omx[1] + l2 * sg.omx[2];
+                const double dy = l0 * sg.omy[0] + l1 * sg.omy[1] + l2 * sg.omy[2];
+                const double lx = ux ? layer_val(cx, dx) : 0.0, ly = uy ? layer_val(cy, dy) : 0.0;
+                cw[q] = rs.vw[q] * sg.adet * (pb.coeff.c[0] + pb.coeff.c[1] * lx + pb.coeff.c[2] * ly + pb.coeff.c[3] * lx * ly);
+            }
+        EHDG_END_LANES
+    }
 
     // ---- build the rows from the tensors
     EHDG_FOR_LANES(l, L)
@@ -267,7 +291,11 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
         EHDG_FOR_LANES(l, L)
             const double piv = prow[k];
             if (!(fabs(piv) > 0.0)) status |= EHDG_ST_SINGULAR;
+#ifdef __CUDA_ARCH__
+            const double inv = __drcp_rn(piv);
+#else
             const double inv = 1.0 / piv;
+#endif
             if (l == r) {
 #pragma unroll
                 for (int j = k + 1; j < NC; ++j) a[L][j] *= inv;
@@ -353,6 +381,7 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
     double A[NLS][N];   // a' row -> Cholesky factor row
     double M[NLS][N];   // m row  -> C row
     double eown[NLS];   // sub-diagonal entry T[i][i-1] owned by lane i
+    double invd[NLS];   // 1 / l_ii of the Cholesky factor (lane i)
 
     // m = sum_s h_s len_s (dn u)(dn v) with dn = ga0 dX + ga1 dY ; the common factor |detJ| of a'
     // and m is dropped (h_s len_s = |detJ|)
@@ -377,6 +406,7 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
             M[L][j] = acc;
         }
         eown[L] = 0.0;
+        invd[L] = 0.0;
     EHDG_END_LANES
 
     // ---- Cholesky a' = L L^T, right-looking; A[i][k] becomes l_ik (k <= i)
@@ -386,7 +416,12 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
             if (l == k) {
                 const double d = A[L][k];
                 if (!(d > 0.0)) status |= EHDG_ST_ALPHA_DEFICIENT;
+#ifdef __CUDA_ARCH__
+                shv[0] = rsqrt(d);
+#else
                 shv[0] = 1.0 / sqrt(d);
+#endif
+                invd[L] = shv[0];
             }
         EHDG_END_LANES
         EHDG_FOR_LANES(l, L)
@@ -409,7 +444,7 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
         for (int j = 0; j < N; ++j) {
             EHDG_FOR_LANES(l, L)
                 if (l == j) {
-                    const double inv = 1.0 / A[L][j];
+                    const double inv = invd[L];
 #pragma unroll
                     for (int c = 0; c < N; ++c) {
                         M[L][c] *= inv;
@@ -531,8 +566,12 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
         const unsigned b = gc.ballot(below);
         // first lane whose abscissa is above the spectrum
         int f = LG;
+#ifdef __CUDA_ARCH__
+        if (b) f = __ffs((int)b) - 1;
+#else
         for (int l = 0; l < LG; ++l)
             if ((b >> l) & 1u) { f = l; break; }
+#endif
         const double nlo = lo + step * (double)f;          // x_{f-1}  (f = 0 -> lo)
         const double nhi = (f < LG) ? lo + step * (double)(f + 1) : hi;
         lo = nlo;
