@@ -1,6 +1,7 @@
 // libehdg core: context, marking (a1), plan, pruning (a3) and the general quadrature kernels
 // for alpha (a4) and assembly + condensation (a5-a7).  See include/ehdg.h for the contract.
 #include <cub/cub.cuh>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -97,13 +98,15 @@ __global__ void plan_scatter_kernel(int ne, const int32_t* __restrict__ flag, co
 }
 
 // -------------------------------------------------------------------------------------------
-// general kernels: one warp (= one CTA of 32 threads) per element, workspace in dynamic smem
+// general kernels: one CTA of GEN_THREADS threads per element, workspace in dynamic smem
 // -------------------------------------------------------------------------------------------
+constexpr int GEN_THREADS = 128;
+
 __device__ __forceinline__ int fac_bits(const uint8_t* fm, const int32_t* el2facet, int el, int e) {
     return fm ? (int)fm[el2facet[3 * el + e]] : 0;
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(GEN_THREADS)
 prune_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __restrict__ list_gen,
              const double* __restrict__ verts, const int32_t* __restrict__ tris,
              const int32_t* __restrict__ el2facet, const uint8_t* __restrict__ elem_mask,
@@ -115,7 +118,7 @@ prune_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __restrict__ list
     const int el = list_gen[gi];
     const int elmark = elem_mask[el];
     if (elmark == 0) return;                      // only marked elements are visited (:285)
-    Coop co{(int)threadIdx.x, 32};
+    Coop co{(int)threadIdx.x, GEN_THREADS};
     int facmask[3];
     for (int e = 0; e < 3; ++e) facmask[e] = fac_bits(facet_mask, el2facet, el, e);
     int vdrop, fdrop[3];
@@ -146,7 +149,7 @@ __global__ void prune_init_kernel(int ne, int nf, int nenr, const uint8_t* __res
     if (i < nf) facet_active[i] = (facet2el[2 * i + 1] < 0) ? 0 : facet_mask[i];   // dirichlet=".*"
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(GEN_THREADS)
 alpha_general_kernel(Problem pb, RuleSet rs0, int n_gen, const int32_t* __restrict__ list_gen,
                      const double* __restrict__ verts, const int32_t* __restrict__ tris,
                      const uint8_t* __restrict__ elem_active, double* __restrict__ lam, int32_t* status) {
@@ -154,18 +157,18 @@ alpha_general_kernel(Problem pb, RuleSet rs0, int n_gen, const int32_t* __restri
     const int gi = blockIdx.x;
     if (gi >= n_gen) return;
     const int el = list_gen[gi];
-    Coop co{(int)threadIdx.x, 32};
+    Coop co{(int)threadIdx.x, GEN_THREADS};
     const int volmask = elem_active ? elem_active[el] : 0;
     int st = 0;
     const double l = alpha_general(co, pb, rs0, verts, tris + 3 * el, volmask, el == 0, ws, &st);
-    st = __reduce_or_sync(0xffffffffu, st);
+    st = __syncthreads_or(st);
     if (threadIdx.x == 0) {
         lam[el] = l;
         if (status) status[el] = st;
     }
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(GEN_THREADS)
 assemble_general_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __restrict__ list_gen,
                         const double* __restrict__ verts, const int32_t* __restrict__ tris,
                         const int32_t* __restrict__ el2facet, const double* __restrict__ lam,
@@ -176,7 +179,7 @@ assemble_general_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __rest
     const int gi = blockIdx.x;
     if (gi >= n_gen) return;
     const int el = list_gen[gi];
-    Coop co{(int)threadIdx.x, 32};
+    Coop co{(int)threadIdx.x, GEN_THREADS};
     const int volmask = elem_active ? elem_active[el] : 0;
     int facmask[3];
     for (int e = 0; e < 3; ++e) facmask[e] = fac_bits(facet_mask, el2facet, el, e);
@@ -185,7 +188,7 @@ assemble_general_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __rest
     int st = assemble_condense_general(co, pb, rs, verts, tris + 3 * el, lam[el], volmask, facmask, ws,
                                        S + (size_t)gi * nf * nf, g + (size_t)gi * nf, W + (size_t)gi * nv * nf,
                                        z + (size_t)gi * nv, Afull ? Afull + (size_t)gi * afull_sz : nullptr);
-    st = __reduce_or_sync(0xffffffffu, st);
+    st = __syncthreads_or(st);
     if (threadIdx.x == 0 && status) status[el] |= st;
 }
 
@@ -224,6 +227,9 @@ int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out) {
     EHDG_CUDA(cudaFuncSetAttribute(alpha_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     EHDG_CUDA(cudaFuncSetAttribute(assemble_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if ((rc = fast_build_tensors(c))) return rc;
+    EHDG_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    EHDG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    EHDG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     *out = c;
     return EHDG_OK;
 }
@@ -234,6 +240,12 @@ int ehdg_destroy(ehdg_ctx* c) {
     cudaFree(c->r0.buf);
     cudaFree(c->rerr.buf);
     fast_free_tensors(c);
+    cudaFree(c->scratch);
+    cudaFree(c->pool_eslot);
+    cudaFree(c->pool_lists);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     return EHDG_OK;
 }
@@ -271,51 +283,76 @@ int ehdg_mark(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* vert_flags, uint8_
     return EHDG_OK;
 }
 
+static int ctx_scratch(ehdg_ctx* c, size_t bytes, void** out) {
+    if (bytes > c->scratch_bytes) {
+        if (c->scratch) cudaFree(c->scratch);
+        c->scratch = nullptr;
+        c->scratch_bytes = 0;
+        EHDG_CUDA(cudaMalloc(&c->scratch, bytes));
+        c->scratch_bytes = bytes;
+    }
+    *out = c->scratch;
+    return EHDG_OK;
+}
+
 int ehdg_plan_create(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_mask, int force_general, ehdg_plan** out,
                      void* stream) {
     if (!c || !m || !out) { set_error("ehdg_plan_create: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     ehdg_plan* p = new ehdg_plan();
+    p->ctx = c;
     p->ne = m->ne;
     p->nf_poly = 3 * c->pb.nfl;
     p->nfmax = c->pb.nfmax;
     p->n_p = c->pb.n_p;
     p->nvmax = c->pb.nvmax;
     const int ne = m->ne;
-    int32_t *flag = nullptr, *scan = nullptr;
-    void* tmp = nullptr;
+    const size_t nint = (size_t)(ne + 1);
     size_t tmp_bytes = 0;
-    EHDG_CUDA(cudaMalloc(&flag, sizeof(int32_t) * (size_t)(ne + 1)));
-    EHDG_CUDA(cudaMalloc(&scan, sizeof(int32_t) * (size_t)(ne + 1)));
-    EHDG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * (size_t)(ne + 1), st));
-    EHDG_CUDA(cudaMalloc(&p->eslot, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1)));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (int32_t*)nullptr, (int32_t*)nullptr, ne + 1, st));
+    const size_t off_scan = (nint * 4 + 255) & ~(size_t)255, off_tmp = 2 * off_scan;
+    void* base = nullptr;
+    int rc = ctx_scratch(c, off_tmp + tmp_bytes + 256, &base);
+    if (rc) return rc;
+    int32_t* flag = (int32_t*)base;
+    int32_t* scan = (int32_t*)((char*)base + off_scan);
+    void* tmp = (char*)base + off_tmp;
+    if (c->pool_eslot && c->pool_ne == ne) {             // reuse the buffers of the last destroyed plan
+        p->eslot = c->pool_eslot;
+        p->lists = c->pool_lists;
+        c->pool_eslot = c->pool_lists = nullptr;
+    } else {
+        EHDG_CUDA(cudaMalloc(&p->eslot, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1)));
+        EHDG_CUDA(cudaMalloc(&p->lists, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1)));
+    }
+    EHDG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * nint, st));
     if (ne > 0) plan_flags_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, m->el2facet, c->pb.nenr ? facet_mask : nullptr, force_general ? 1 : 0, flag);
     EHDG_LAUNCH_CHECK();
-    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flag, scan, ne + 1, st));
-    EHDG_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 8));
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, scan, ne + 1, st));
     int32_t ngen = 0;
     EHDG_CUDA(cudaMemcpyAsync(&ngen, scan + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
     p->n_gen = ngen;
     p->n_poly = ne - ngen;
-    EHDG_CUDA(cudaMalloc(&p->list_gen, sizeof(int32_t) * (size_t)(ngen > 0 ? ngen : 1)));
-    EHDG_CUDA(cudaMalloc(&p->list_poly, sizeof(int32_t) * (size_t)(p->n_poly > 0 ? p->n_poly : 1)));
+    p->list_poly = p->lists;
+    p->list_gen = p->lists + p->n_poly;
     if (ne > 0) plan_scatter_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, flag, scan, p->eslot, p->list_poly, p->list_gen);
     EHDG_LAUNCH_CHECK();
-    EHDG_CUDA(cudaStreamSynchronize(st));
-    cudaFree(flag);
-    cudaFree(scan);
-    cudaFree(tmp);
     *out = p;
     return EHDG_OK;
 }
 
 int ehdg_plan_destroy(ehdg_plan* p) {
     if (!p) return EHDG_OK;
-    cudaFree(p->eslot);
-    cudaFree(p->list_poly);
-    cudaFree(p->list_gen);
+    ehdg_ctx* c = p->ctx;
+    if (c && !c->pool_eslot) {
+        c->pool_eslot = p->eslot;
+        c->pool_lists = p->lists;
+        c->pool_ne = p->ne;
+    } else {
+        cudaFree(p->eslot);
+        cudaFree(p->lists);
+    }
     delete p;
     return EHDG_OK;
 }
@@ -344,7 +381,7 @@ int ehdg_prune(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_
     if (n > 0) prune_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(m->ne, m->nf, c->pb.nenr, elem_mask, facet_mask, m->facet2el, elem_active, facet_active, factors);
     EHDG_LAUNCH_CHECK();
     if (c->pb.nenr > 0 && p->n_gen > 0) {
-        prune_kernel<<<(unsigned)p->n_gen, 32, c->ws_doubles * 8, st>>>(c->pb, c->rb.rs, (int)p->n_gen, p->list_gen, m->verts, m->tris,
+        prune_kernel<<<(unsigned)p->n_gen, GEN_THREADS, c->ws_doubles * 8, st>>>(c->pb, c->rb.rs, (int)p->n_gen, p->list_gen, m->verts, m->tris,
                                                                           m->el2facet, elem_mask, facet_mask, threshold, elem_active,
                                                                           facet_active, factors);
         EHDG_LAUNCH_CHECK();
@@ -356,14 +393,24 @@ int ehdg_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_
                int32_t* status, void* stream) {
     if (!c || !p || !m || !lam) { set_error("ehdg_alpha: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
+    const bool fork = p->n_gen > 0 && p->n_poly > 0 && !getenv("EHDG_NO_FORK");   // O(sqrt(ne)) enriched elements beside the bulk
+    cudaStream_t sg = fork ? c->side : st;
+    if (fork) {
+        EHDG_CUDA(cudaEventRecord(c->ev_fork, st));
+        EHDG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    }
     if (p->n_gen > 0) {
-        alpha_general_kernel<<<(unsigned)p->n_gen, 32, c->ws_doubles * 8, st>>>(c->pb, c->r0.rs, (int)p->n_gen, p->list_gen, m->verts,
+        alpha_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, c->ws_doubles * 8, sg>>>(c->pb, c->r0.rs, (int)p->n_gen, p->list_gen, m->verts,
                                                                                   m->tris, c->pb.nenr ? elem_active : nullptr, lam, status);
         EHDG_LAUNCH_CHECK();
     }
     if (p->n_poly > 0) {
         int rc = fast_alpha(c, p, m, lam, status, st);
         if (rc) return rc;
+    }
+    if (fork) {
+        EHDG_CUDA(cudaEventRecord(c->ev_join, c->side));
+        EHDG_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
     }
     return EHDG_OK;
 }
@@ -373,9 +420,11 @@ int ehdg_assemble_condense(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
                            double* z, int32_t* status, double* Afull, void* stream) {
     if (!c || !p || !m || !lam || !S || !g || !W || !z) { set_error("ehdg_assemble_condense: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (p->n_poly > 0) {
-        int rc = fast_assemble(c, p, m, lam, S, g, W, z, status, st);
-        if (rc) return rc;
+    const bool fork = p->n_gen > 0 && p->n_poly > 0 && !getenv("EHDG_NO_FORK");
+    cudaStream_t sg = fork ? c->side : st;
+    if (fork) {
+        EHDG_CUDA(cudaEventRecord(c->ev_fork, st));
+        EHDG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     }
     if (p->n_gen > 0) {
         const size_t nfp = p->nf_poly, np = p->n_p;
@@ -383,10 +432,18 @@ int ehdg_assemble_condense(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
         double* gg = g + (size_t)p->n_poly * nfp;
         double* Wg = W + (size_t)p->n_poly * np * nfp;
         double* zg = z + (size_t)p->n_poly * np;
-        assemble_general_kernel<<<(unsigned)p->n_gen, 32, c->ws_doubles * 8, st>>>(
+        assemble_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, c->ws_doubles * 8, sg>>>(
             c->pb, c->rb.rs, (int)p->n_gen, p->list_gen, m->verts, m->tris, m->el2facet, lam,
             c->pb.nenr ? elem_active : nullptr, c->pb.nenr ? facet_mask : nullptr, Sg, gg, Wg, zg, status, Afull);
         EHDG_LAUNCH_CHECK();
+    }
+    if (p->n_poly > 0) {
+        int rc = fast_assemble(c, p, m, lam, S, g, W, z, status, st);
+        if (rc) return rc;
+    }
+    if (fork) {
+        EHDG_CUDA(cudaEventRecord(c->ev_join, c->side));
+        EHDG_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
     }
     return EHDG_OK;
 }

@@ -27,6 +27,36 @@ namespace ehdg {
 #define EHDG_END_LANES }
 #endif
 
+// strict sign change between two doubles (both non-zero), on the integer pipe
+EHDG_HD bool opposite_signs(double a, double b) {
+#ifdef __CUDA_ARCH__
+    const int ha = __double2hiint(a), hb = __double2hiint(b);
+    return ((ha ^ hb) < 0) && a != 0.0 && b != 0.0;
+#else
+    return (a < 0.0 && b > 0.0) || (a > 0.0 && b < 0.0);
+#endif
+}
+
+// 16-byte shared-memory accesses (p must be 16-byte aligned): one wavefront moves two doubles
+EHDG_HD void ld2(const double* p, double& a, double& b) {
+#ifdef __CUDA_ARCH__
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    a = v.x;
+    b = v.y;
+#else
+    a = p[0];
+    b = p[1];
+#endif
+}
+EHDG_HD void st2(double* p, double a, double b) {
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+#else
+    p[0] = a;
+    p[1] = b;
+#endif
+}
+
 template <int LG>
 struct Group {
     int lane;       // lane inside the group (device); unused on the host
@@ -173,7 +203,7 @@ struct FastDims {
     static constexpr int NC = NP + NF + 1;
     static constexpr int M = NP > NF ? NP : NF;
     static constexpr int LG = M <= 8 ? 8 : (M <= 16 ? 16 : 32);
-    static constexpr int NXS = (NF + 1) | 1;           // row stride of the X scratch (odd: conflict-free column writes)
+    static constexpr int NXS = ((NF + 2) & ~1) + 2;    // row stride of the X scratch: even (16-byte rows), 2-way conflicts at most
 };
 
 template <int P>
@@ -214,6 +244,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     double afv[NLS][NP];    // row r of A_FV in the sorted frame      (lanes r < NF)
     double aff[NLS];
     int mycol[NLS];
+    double myinv[NLS];
     int status = 0;
 
     // ---- right-hand side weights at the quadrature points: cw[q] = w_q |detJ| coeff(x_q)
@@ -257,7 +288,14 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
         {
             const double* ph = phi_rhs + (size_t)(sg.f0 * 3 + sg.f1) * rs.nq * NP + i;
             double acc = 0.0;
-            for (int q = 0; q < rs.nq; ++q) acc += cw[q] * ph[q * NP];
+            int q = 0;
+            for (; q + 1 < rs.nq; q += 2) {
+                double c0, c1;
+                ld2(cw + q, c0, c1);
+                acc += c0 * ph[q * NP];
+                acc += c1 * ph[(q + 1) * NP];
+            }
+            if (q < rs.nq) acc += cw[q] * ph[q * NP];
             a[L][NC - 1] = acc;
         }
         // A_FV row r = (s, k) in the sorted frame
@@ -271,6 +309,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             aff[L] = cff[s] / (2.0 * k + 1.0);           // int_0^1 mu_k^2 dt
         }
         mycol[L] = -1;
+        myinv[L] = 1.0;
     EHDG_END_LANES
 
     // ---- Gauss-Jordan with partial pivoting, rows stay in their lanes
@@ -284,7 +323,8 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
         EHDG_FOR_LANES(l, L)
             if (l == r) {
 #pragma unroll
-                for (int j = k; j < NC; ++j) prow[j] = a[L][j];
+                for (int jp = k >> 1; jp <= (NC - 1) >> 1; ++jp)
+                    st2(prow + 2 * jp, a[L][2 * jp], (2 * jp + 1 < NC) ? a[L][2 * jp + 1] : 0.0);
                 mycol[L] = k;
             }
         EHDG_END_LANES
@@ -297,12 +337,16 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             const double inv = 1.0 / piv;
 #endif
             if (l == r) {
-#pragma unroll
-                for (int j = k + 1; j < NC; ++j) a[L][j] *= inv;
+                myinv[L] = inv;          // the pivot row stays unscaled; its lane scales the solution once at the end
             } else if (l < NP) {
                 const double f = a[L][k] * inv;
 #pragma unroll
-                for (int j = k + 1; j < NC; ++j) a[L][j] -= f * prow[j];
+                for (int jp = (k + 1) >> 1; jp <= (NC - 1) >> 1; ++jp) {
+                    double x0, x1;
+                    ld2(prow + 2 * jp, x0, x1);
+                    if (2 * jp >= k + 1) a[L][2 * jp] -= f * x0;
+                    if (2 * jp + 1 < NC) a[L][2 * jp + 1] -= f * x1;
+                }
             }
         EHDG_END_LANES
     }
@@ -311,8 +355,12 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     EHDG_FOR_LANES(l, L)
         if (l < NP) {
             const int c = mycol[L];
+            const double sc = myinv[L];
 #pragma unroll
-            for (int j = 0; j <= NF; ++j) Xs[c * NXS + j] = a[L][NP + j];
+            for (int j = 0; j <= NF; ++j) a[L][NP + j] *= sc;
+#pragma unroll
+            for (int jp = 0; jp <= NF >> 1; ++jp)
+                st2(Xs + c * NXS + 2 * jp, a[L][NP + 2 * jp], (2 * jp + 1 <= NF) ? a[L][NP + 2 * jp + 1] : 0.0);
             if (store) {
 #pragma unroll
                 for (int s = 0; s < 3; ++s)
@@ -333,7 +381,12 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             for (int c = 0; c < NP; ++c) {
                 const double f = afv[L][c];
 #pragma unroll
-                for (int j = 0; j <= NF; ++j) srow[j] -= f * Xs[c * NXS + j];
+                for (int jp = 0; jp <= NF >> 1; ++jp) {
+                    double x0, x1;
+                    ld2(Xs + c * NXS + 2 * jp, x0, x1);
+                    srow[2 * jp] -= f * x0;
+                    if (2 * jp + 1 <= NF) srow[2 * jp + 1] -= f * x1;
+                }
             }
             const int s = l / NFL, k = l % NFL;
             const int orow = sg.eloc[s] * NFL + k;
@@ -359,7 +412,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 // -------------------------------------------------------------------------------------------
 template <int P>
 EHDG_HD constexpr int fast_alpha_scratch_doubles() {
-    return (FastDims<P>::NP - 1) * (FastDims<P>::NP - 1) + 4 * 32;
+    return (((FastDims<P>::NP - 1) * (FastDims<P>::NP - 1) + 1) & ~1) + 4 * 32;     // even: groups stay 16-byte aligned
 }
 
 template <int P>
@@ -372,7 +425,7 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
     SortedGeom sg;
     sorted_geom(verts, tri, 0.0, 0.0, sg);
     double* shT = gc.sh;              // N x N
-    double* shv = shT + N * N;        // 32
+    double* shv = shT + ((N * N + 1) & ~1);   // 32
     double* shq = shv + 32;           // 32
     double* shd = shq + 32;           // 32
     double* she = shd + 32;           // 32
@@ -438,28 +491,37 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
             }
         EHDG_END_LANES
     }
-    // ---- two forward substitutions with a transpose in between: C = L^-1 (L^-1 m)^T
+    // ---- two forward substitutions with a transpose in between: C = L^-1 (L^-1 m)^T.
+    // Row j is broadcast UNSCALED (Y~_j = l_jj Y_j) together with 1/l_jj; the lanes below subtract
+    // (l_ij / l_jj) Y~_j and every lane scales its own finished row once (all lanes busy, one pass).
     for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             EHDG_FOR_LANES(l, L)
                 if (l == j) {
-                    const double inv = invd[L];
 #pragma unroll
-                    for (int c = 0; c < N; ++c) {
-                        M[L][c] *= inv;
-                        shT[c] = M[L][c];
-                    }
+                    for (int cp = 0; cp <= (N - 1) >> 1; ++cp)
+                        st2(shT + 2 * cp, M[L][2 * cp], (2 * cp + 1 < N) ? M[L][2 * cp + 1] : 0.0);
+                    shv[0] = invd[L];
                 }
             EHDG_END_LANES
             EHDG_FOR_LANES(l, L)
                 if (l > j && l < N) {
-                    const double f = A[L][j];
+                    const double f = A[L][j] * shv[0];
 #pragma unroll
-                    for (int c = 0; c < N; ++c) M[L][c] -= f * shT[c];
+                    for (int cp = 0; cp <= (N - 1) >> 1; ++cp) {
+                        double x0, x1;
+                        ld2(shT + 2 * cp, x0, x1);
+                        M[L][2 * cp] -= f * x0;
+                        if (2 * cp + 1 < N) M[L][2 * cp + 1] -= f * x1;
+                    }
                 }
             EHDG_END_LANES
         }
+        EHDG_FOR_LANES(l, L)
+#pragma unroll
+            for (int c = 0; c < N; ++c) M[L][c] *= invd[L];
+        EHDG_END_LANES
         if (pass == 0) {
             EHDG_FOR_LANES(l, L)
                 if (l < N) {
@@ -557,7 +619,7 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
 #pragma unroll
             for (int i = 1; i < N; ++i) {
                 const double pn = (dg[i] - x) * pc - e2[i] * pm;
-                ok = ok && (pn * pc < 0.0);
+                ok = ok && opposite_signs(pn, pc);
                 pm = pc;
                 pc = pn;
             }

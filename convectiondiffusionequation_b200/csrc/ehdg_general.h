@@ -34,7 +34,8 @@ struct Coop {
     int lane, nl;
     EHDG_HD void sync() const {
 #ifdef __CUDA_ARCH__
-        __syncwarp();
+        if (nl > 32) __syncthreads();      // one CTA per element
+        else __syncwarp();                 // one warp per element
 #endif
     }
 };
@@ -318,6 +319,7 @@ EHDG_HD int assemble_condense_general(const Coop& co, const Problem& pb, const R
             if (a > best) { best = a; piv = i; }
         }
         if (!(best > 0.0) || best != best) status |= EHDG_ST_SINGULAR;
+        co.sync();                      // every lane has finished scanning column k before rows move
         if (piv != k) {
             for (int j = k + co.lane; j < ncol; j += co.nl) {
                 const double t = Aug[k * ldA + j];

@@ -48,9 +48,19 @@ struct ehdg_ctx {
     int ws_doubles;                   // per-warp workspace of the general kernels
     int device;
     int sm_count;
+    // grow-only scratch and a one-deep pool of plan buffers: cudaMalloc/cudaFree cost milliseconds, a plan
+    // is rebuilt for every mesh upload in the end-to-end path
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int32_t *pool_eslot = nullptr, *pool_lists = nullptr;
+    int32_t pool_ne = 0;
+    cudaStream_t side = nullptr;      // the general (enriched) kernels run beside the polynomial ones
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 struct ehdg_plan {
+    ehdg_ctx* ctx = nullptr;
+    int32_t* lists = nullptr;       // [ne] backing store of list_poly | list_gen
     int32_t ne;
     int64_t n_poly, n_gen;
     int32_t* eslot = nullptr;       // [ne]

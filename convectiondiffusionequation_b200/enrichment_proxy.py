@@ -16,7 +16,7 @@ def vertex_flags(verts: np.ndarray, indicators, mesh_size: float) -> np.ndarray:
     """u8 [n_enrich, nv]: enr_indicator(x_v, y_v, mesh_size) per vertex, as the reference's
     mark_elements evaluates it (enrichment_proxy.py:204-206)."""
     out = np.zeros((len(indicators), verts.shape[0]), dtype=np.uint8)
-    xs, ys = verts[:, 0], verts[:, 1]
+    xs, ys = np.ascontiguousarray(verts[:, 0]), np.ascontiguousarray(verts[:, 1])
     for i, ind in enumerate(indicators):
         try:
             r = np.asarray(ind(xs, ys, mesh_size))

@@ -1,0 +1,128 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties and sampled oracle checks
+(the numpy oracle cannot reach these sizes; the C oracle checks a strided sample)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BETA = (2.0, 0.001)
+
+
+def _pipe(n, kind, order, eps, enriched=True):
+    from bench import make_spec
+    from convectiondiffusionequation_b200.hot_path import EHDGPipeline
+    from convectiondiffusionequation_b200.mesh import unit_square_mesh
+    mesh = unit_square_mesh(n, kind=kind)
+    return mesh, EHDGPipeline(mesh, make_spec(order, eps, enriched=enriched))
+
+
+@pytest.mark.parametrize("n,kind,order,eps", [(708, "structured", 4, 1e-6), (1414, "unstructured", 4, 1e-6), (224, "structured", 3, 1e-4)])
+def test_sampled_oracle_parity_at_full_size(n, kind, order, eps):
+    import torch
+    from oracle import ehdg_cpu
+    from oracle import ehdg_oracle as orc
+    mesh, P = _pipe(n, kind, order, eps)
+    P.setup().assemble()
+    torch.cuda.synchronize()
+    prob = orc.run_py_problem(beta=BETA, eps=eps)
+    # marking: vectorised restatement of mark_elements / mark_element_bnd
+    em, fm = ehdg_cpu.marks(mesh, prob)
+    assert np.array_equal(P.elem_mask.cpu().numpy(), em)
+    assert np.array_equal(P.facet_mask.cpu().numpy()[:mesh.nf], fm)
+    slot = P.eslot().cpu().numpy()
+    poly = (slot & 0x40000000) == 0
+    assert poly.sum() == P.plan_sizes.n_poly and (~poly).sum() == P.plan_sizes.n_gen
+    # general path = exactly the elements with an enriched facet
+    assert np.array_equal(~poly, (fm[mesh.el2facet] != 0).any(axis=1))
+    # strided sample of polynomial-path elements against the C oracle (alpha, S_K, g_K)
+    els = np.nonzero(poly)[0][:: max(1, int(poly.sum()) // 1500)].astype(np.int32)
+    co = ehdg_cpu.COracle(order, prob)
+    ref = co.batch(mesh.verts, mesh.tris, els, np.zeros(len(els), np.uint8), np.zeros((len(els), 3), np.uint8))
+    lam = P.lam.cpu().numpy()
+    assert np.max(np.abs(lam[els] - ref["lam"]) / ref["lam"]) < 1e-11
+    ref = co.batch(mesh.verts, mesh.tris, els, np.zeros(len(els), np.uint8), np.zeros((len(els), 3), np.uint8), lam=lam[els])
+    nfp, nb, nfl = P.sizes.nf_poly, P.sizes.nb, P.sizes.nfl
+    keep = np.concatenate([e * nb + np.arange(nfl) for e in range(3)])
+    idx = torch.as_tensor(slot[els].astype(np.int64), device=P.dev)
+    S = P.S[: P.plan_sizes.n_poly * nfp * nfp].view(-1, nfp, nfp)[idx].cpu().numpy()
+    g = P.g[: P.plan_sizes.n_poly * nfp].view(-1, nfp)[idx].cpu().numpy()
+    So = ref["S"][:, keep][:, :, keep]
+    go = ref["g"][:, keep]
+    errS = np.linalg.norm((S - So).reshape(len(els), -1), axis=1) / np.linalg.norm(So.reshape(len(els), -1), axis=1)
+    assert errS.max() < 1e-10, errS.max()       # eps = 1e-6: cond(A_VV) ~ 1e4 on these elements
+    gn = np.linalg.norm(go, axis=1)
+    errg = np.linalg.norm(g - go, axis=1)[gn > 0] / gn[gn > 0]
+    assert errg.size == 0 or errg.max() < 1e-8
+    # enriched-path sample: alpha where the eigenproblem is well posed, S_K with the device's alpha
+    gel = np.nonzero(~poly)[0][:: max(1, int((~poly).sum()) // 300)].astype(np.int32)
+    ea = P.elem_active.cpu().numpy()
+    refg = co.batch(mesh.verts, mesh.tris, gel, ea[gel], fm[mesh.el2facet[gel]], lam=lam[gel])
+    nfg = P.sizes.nfmax
+    idxg = torch.as_tensor((slot[gel] & 0x3fffffff).astype(np.int64), device=P.dev)
+    Sg = P.S[P.plan_sizes.n_poly * nfp * nfp:].view(-1, nfg, nfg)[idxg].cpu().numpy()
+    err = np.linalg.norm((Sg - refg["S"]).reshape(len(gel), -1), axis=1) / np.linalg.norm(refg["S"].reshape(len(gel), -1), axis=1)
+    # the enriched A_VV are ill-conditioned: the bulk of the sample still agrees to 1e-6
+    assert np.median(err) < 1e-6, np.median(err)
+    assert np.all(np.isfinite(P.S.cpu().numpy() if mesh.ne < 200000 else Sg))
+
+
+def test_fast_and_quadrature_paths_agree_at_scale():
+    """100k elements through both product paths: tensor path == quadrature path (same alpha)."""
+    import torch
+    mesh, Pf = _pipe(224, "unstructured", 4, 1e-6, enriched=False)
+    Pf.setup().assemble()
+    from bench import make_spec
+    from convectiondiffusionequation_b200.hot_path import EHDGPipeline
+    Pq = EHDGPipeline(mesh, make_spec(4, 1e-6, enriched=False), force_general=True)
+    Pq.setup().alpha()
+    lam_f, lam_q = Pf.lam, Pq.lam
+    assert float(((lam_f - lam_q).abs() / lam_q).max()) < 1e-11
+    Pq.lam.copy_(lam_f)
+    Pq.assemble_condense()
+    nf = Pf.sizes.nf_poly
+    Sf = Pf.S.view(-1, nf * nf)
+    Sq = Pq.S.view(-1, nf * nf)
+    err = ((Sf - Sq).norm(dim=1) / Sq.norm(dim=1)).max()
+    assert float(err) < 1e-10
+    gerr = (Pf.g - Pq.g).norm() / Pq.g.norm()
+    assert float(gerr) < 1e-9
+    assert int(Pf.status.abs().sum()) == 0 and int(Pq.status.abs().sum()) == 0
+
+
+def test_condensed_system_properties_at_1m():
+    """CSR invariants at the 1M-element size: sorted columns, exact nnz formula, conservation of the scattered blocks,
+    linearity of the SpMV, back-solve of the zero facet solution returns z."""
+    import torch
+    mesh, P = _pipe(708, "structured", 4, 1e-6, enriched=False)
+    P.setup().assemble().csr_build()
+    n, nnz = P.csr_sizes.n_rows, P.csr_sizes.nnz
+    N = 708
+    assert n == (mesh.nf - 4 * N) * 5
+    rp, ci, rs, dm = P.csr_arrays()
+    assert int(rp[-1]) == nnz and bool((rp[1:] > rp[:-1]).all())
+    # columns strictly ascending inside every row
+    d = ci[1:].to(torch.int64) - ci[:-1].to(torch.int64)
+    row_end = torch.zeros(nnz, dtype=torch.bool, device=P.dev)
+    row_end[(rp[1:-1] - 1).long()] = True
+    assert bool((d[~row_end[:-1]] > 0).all())
+    # sum of all matrix entries == sum over elements of the interior-facet part of S_K (each entry lands exactly once)
+    nf = P.sizes.nf_poly
+    interior = torch.as_tensor(mesh.facet2el[:, 1] >= 0, device=P.dev)
+    e2f = torch.as_tensor(mesh.el2facet.astype(np.int64), device=P.dev)
+    act = interior[e2f].repeat_interleave(5, dim=1).to(torch.float64)          # [ne, 15] active local facet dofs
+    S = P.S.view(-1, nf, nf)
+    total_blocks = torch.einsum("ek,ekl,el->", act, S, act)
+    total_csr = P.vals[:nnz].sum()
+    assert abs(float(total_blocks - total_csr)) <= 1e-9 * float(P.vals[:nnz].abs().sum())
+    gsum = (P.g.view(-1, nf) * act).sum()
+    assert abs(float(gsum - P.rhs[:n].sum())) <= 1e-9 * float(P.rhs[:n].abs().sum() + 1e-300)
+    # SpMV linearity
+    x = torch.randn(n, dtype=torch.float64, device=P.dev, generator=torch.Generator(device=P.dev).manual_seed(1))
+    y = torch.randn(n, dtype=torch.float64, device=P.dev, generator=torch.Generator(device=P.dev).manual_seed(2))
+    lhs = P.spmv(2.0 * x - 3.0 * y)
+    rhs = 2.0 * P.spmv(x) - 3.0 * P.spmv(y)
+    assert float((lhs - rhs).norm() / rhs.norm()) < 1e-13
+    # back-solve with a zero facet solution returns z
+    P.xhat = torch.zeros(n, dtype=torch.float64, device=P.dev)
+    P.backsolve()
+    assert torch.equal(P.u, P.z)
