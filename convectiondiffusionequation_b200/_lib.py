@@ -76,6 +76,7 @@ SYMBOLS = {
     "ehdg_csr_numeric": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
     "ehdg_gmres": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
     "ehdg_bicgstab": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
+    "ehdg_dqgmres": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
     "ehdg_spmv": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ehdg_backsolve": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
     "ehdg_l2_error": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),

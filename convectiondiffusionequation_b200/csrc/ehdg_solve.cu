@@ -447,6 +447,15 @@ __global__ void bicg_x_kernel(int64_t n, const double* __restrict__ p, const dou
     }
 }
 
+// p *= inv_d ; u += gamma p
+__global__ void dq_update_kernel(int64_t n, double inv_d, double gamma, double* __restrict__ p, double* __restrict__ u) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = p[i] * inv_d;
+        p[i] = v;
+        u[i] += gamma * v;
+    }
+}
+
 // r = b - r
 __global__ void residual_kernel(int64_t n, const double* __restrict__ b, double* __restrict__ r) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -728,7 +737,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     // ---- workspace
     double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr, *tvec = nullptr;
     if (strip) EHDG_CUDA(cudaMalloc(&tvec, sizeof(double) * (size_t)n));
-    EHDG_CUDA(cudaMalloc(&V, sizeof(double) * (size_t)n * (method == 0 ? (m + 1) : 6)));
+    EHDG_CUDA(cudaMalloc(&V, sizeof(double) * (size_t)n * (method == 0 ? (m + 1) : (method == 1 ? 6 : 2 * (m + 1)))));
     EHDG_CUDA(cudaMalloc(&w, sizeof(double) * (size_t)n));
     EHDG_CUDA(cudaMalloc(&yhat, sizeof(double) * (size_t)n));
     EHDG_CUDA(cudaMalloc(&partial, sizeof(double) * (size_t)RED_BLOCKS * KT));
@@ -854,6 +863,88 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
             EHDG_CUDA(cudaMemcpyAsync(yhat, pt, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         }
     }
+    if (method == 2 && !conv) {
+        // ---- DQGMRES(k) (Saad, Alg. 6.13): incomplete orthogonalisation against the last k Krylov vectors with a
+        // progressively updated solution.  No restart: the Krylov space keeps growing, which the facet systems need
+        // (information has to cross the mesh; GMRES(m) with m below that length stagnates), at the per-iteration
+        // cost of GMRES(k).
+        const int k = m, ring = m + 1;
+        double* Vr = V;                              // ring of k+1 Krylov vectors
+        double* Pr = V + (size_t)ring * n;           // ring of k+1 direction vectors
+        double* u = yhat;
+        std::vector<double> cq(max_iters + 2, 1.0), sq(max_iters + 2, 0.0), t(k + 3), coef(k + 2);
+        EHDG_CUDA(cudaMemcpyAsync(w, rhs, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
+        scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, Vr);          // v_0 in slot 0
+        double gamma = bnorm;
+        for (int it = 0; it < max_iters; ++it, ++iters) {
+            const int lo = it - k + 1 > 0 ? it - k + 1 : 0;                     // window of Krylov vectors lo..it
+            if ((rc = apply_prec_op(Vr + (size_t)(it % ring) * n, w))) return rc;
+            // h_i = (w, v_i), i = lo..it : up to two contiguous slot ranges of the ring
+            const int s_lo = lo % ring, s_hi = it % ring;
+            if (s_lo <= s_hi) {
+                if ((rc = vo.dots(Vr + (size_t)s_lo * n, n, s_hi - s_lo + 1, w, d_h1))) return rc;
+                if ((rc = vo.axpys(Vr + (size_t)s_lo * n, n, s_hi - s_lo + 1, d_h1, w))) return rc;
+            } else {
+                const int n1 = ring - s_lo;
+                if ((rc = vo.dots(Vr + (size_t)s_lo * n, n, n1, w, d_h1))) return rc;
+                if ((rc = vo.dots(Vr, n, s_hi + 1, w, d_h1 + n1))) return rc;
+                if ((rc = vo.axpys(Vr + (size_t)s_lo * n, n, n1, d_h1, w))) return rc;
+                if ((rc = vo.axpys(Vr, n, s_hi + 1, d_h1 + n1, w))) return rc;
+            }
+            if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
+            scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, Vr + (size_t)((it + 1) % ring) * n);
+            EHDG_CUDA(cudaMemcpyAsync(hbuf, dsc, sizeof(double) * (size_t)(2 * (m + 2) + 1), cudaMemcpyDeviceToHost, st));
+            EHDG_CUDA(cudaStreamSynchronize(st));
+            const int nw = it - lo + 1;
+            const double hn = std::sqrt(hbuf[2 * (m + 2)]);
+            // column of the band Hessenberg matrix: rows lo-1 (fill), lo..it, it+1
+            t[0] = 0.0;
+            for (int i = 0; i < nw; ++i) t[i + 1] = hbuf[i];
+            t[nw + 1] = hn;
+            const int first_rot = lo - 1 >= 0 ? lo - 1 : 0;                    // rotations first_rot..it-1 touch this column
+            for (int i = first_rot; i < it; ++i) {
+                const int j = i - (lo - 1);                                     // position of row i in t
+                const double a = cq[i] * t[j] + sq[i] * t[j + 1];
+                t[j + 1] = -sq[i] * t[j] + cq[i] * t[j + 1];
+                t[j] = a;
+            }
+            const int jm = it - (lo - 1);
+            const double a = t[jm], b2 = t[jm + 1];
+            const double d = std::hypot(a, b2);
+            cq[it] = d > 0 ? a / d : 1.0;
+            sq[it] = d > 0 ? b2 / d : 0.0;
+            const double gnext = -sq[it] * gamma;
+            gamma = cq[it] * gamma;
+            // p_it = (v_it - sum_{i=lo-1}^{it-1} t_i p_i) / d ;  u += gamma p_it
+            double* pnew = Pr + (size_t)(it % ring) * n;
+            EHDG_CUDA(cudaMemcpyAsync(pnew, Vr + (size_t)(it % ring) * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            const int plo = lo - 1 >= 0 ? lo - 1 : 0;
+            if (it > plo) {
+                const int np_ = it - plo;
+                for (int i = 0; i < np_; ++i) hbuf[i] = t[(plo + i) - (lo - 1)];
+                EHDG_CUDA(cudaMemcpyAsync(d_h2, hbuf, sizeof(double) * (size_t)np_, cudaMemcpyHostToDevice, st));
+                const int q_lo = plo % ring, q_hi = (it - 1) % ring;
+                if (q_lo <= q_hi) {
+                    if ((rc = vo.axpys(Pr + (size_t)q_lo * n, n, q_hi - q_lo + 1, d_h2, pnew))) return rc;
+                } else {
+                    const int n1 = ring - q_lo;
+                    if ((rc = vo.axpys(Pr + (size_t)q_lo * n, n, n1, d_h2, pnew))) return rc;
+                    if ((rc = vo.axpys(Pr, n, q_hi + 1, d_h2 + n1, pnew))) return rc;
+                }
+                EHDG_CUDA(cudaStreamSynchronize(st));      // hbuf is reused next iteration
+            }
+            dq_update_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, d > 0 ? 1.0 / d : 0.0, gamma, pnew, u);
+            gamma = gnext;
+            rel = std::fabs(gamma) / bnorm;
+            if (rel * std::sqrt((double)(it - lo + 2)) <= rtol || !(hn > 0.0) || !std::isfinite(rel)) { ++iters; break; }
+        }
+        if (sweeps > 1) {      // yhat = P^ u
+            EHDG_CUDA(cudaMemcpyAsync(w, u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            if ((rc = poly(w, pt))) return rc;
+            EHDG_CUDA(cudaMemcpyAsync(yhat, pt, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        }
+    }
     while (method == 0 && !conv && iters < max_iters) {
         // r = b - A yhat  (into w), beta = ||r||
         if ((rc = apply_op(yhat, w))) return rc;
@@ -963,6 +1054,10 @@ int ehdg_gmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double
 
 int ehdg_bicgstab(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream) {
     return krylov_solve(c, A, vals, rhs, x, info, stream, 1);
+}
+
+int ehdg_dqgmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream) {
+    return krylov_solve(c, A, vals, rhs, x, info, stream, 2);
 }
 
 int ehdg_backsolve(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehdg_mesh* m, const double* W, const double* z,

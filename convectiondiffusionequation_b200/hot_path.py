@@ -205,7 +205,7 @@ class EHDGPipeline:
         info.restart, info.max_iters, info.rtol = int(restart), int(max_iters), float(rtol)
         info.use_strip_block = int(bool(strip_block) and self.nenr > 0)
         info.jacobi_sweeps = int(jacobi_sweeps)
-        fn = self.lib.ehdg_gmres if method == "gmres" else self.lib.ehdg_bicgstab
+        fn = {"gmres": self.lib.ehdg_gmres, "bicgstab": self.lib.ehdg_bicgstab, "dqgmres": self.lib.ehdg_dqgmres}[method]
         _lib.check(fn(self.ctx, self.csr, _ptr(self.vals), _ptr(self.rhs), _ptr(self.xhat), C.byref(info), self._stream()),
                    "ehdg_" + method)
         self.gmres_info = info

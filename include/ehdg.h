@@ -192,6 +192,10 @@ int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^
 /* Same preconditioner (block-Jacobi, strip block, optional sweeps) with BiCGStab: short recurrence, no restart.
  * GMRES(m) stalls on the penalty-dominated facet systems of fine meshes; `restart` is ignored here. */
 int ehdg_bicgstab(ehdg_ctx* ctx, ehdg_csr* csr, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream);
+/* DQGMRES(k), k = info->restart: GMRES with the orthogonalisation truncated to the last k Krylov vectors and a
+ * progressively updated solution -- no restart, per-iteration cost of GMRES(k).  The method of choice for the
+ * large facet systems, where information has to cross the mesh and restarted GMRES stagnates. */
+int ehdg_dqgmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream);
 /* y = A x with the CSR SpMV kernel used inside GMRES (for tests and the bandwidth bench) */
 int ehdg_spmv(ehdg_ctx* ctx, const ehdg_csr* csr, const double* vals, const double* x, double* y, void* stream);
 

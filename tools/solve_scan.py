@@ -18,10 +18,10 @@ def run(n, order, eps, sweeps, restart=40, iters=300, enriched=False, kind="stru
     P.close()
 
 if __name__ == "__main__":
-    for n, it in ((32, 2000), (64, 4000), (128, 8000), (224, 8000)):
-        for eps in (1e-2, 1e-6):
-            run(n, 4, eps, 1, iters=it, method="bicgstab")
-    run(224, 3, 1e-4, 1, iters=8000, method="bicgstab")
-    run(224, 3, 1e-4, 1, iters=8000, method="bicgstab", enriched=True)
-    run(64, 2, 1e-2, 1, iters=8000, method="bicgstab", enriched=True)
-    run(708, 4, 1e-6, 1, iters=20000, method="bicgstab")
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "4m":
+        run(1414, 4, 1e-6, 8, restart=40, iters=12000, method="dqgmres", kind="unstructured")
+    else:
+        for sw in (4, 8, 16):
+            run(708, 4, 1e-6, sw, restart=40, iters=30000 // sw, method="dqgmres")
+        run(224, 3, 1e-4, 8, restart=40, iters=3000, method="dqgmres")
