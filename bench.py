@@ -153,7 +153,10 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-solve", action="store_true", help="skip the one-off GMRES solve after the timed steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--solve-iters", type=int, default=400)
+    ap.add_argument("--solve-iters", type=int, default=60000)
+    ap.add_argument("--solve-method", default="dqgmres", choices=["gmres", "dqgmres", "bicgstab"])
+    ap.add_argument("--solve-workload", default="ehdg_p4_eps1e-6_structured_1M",
+                    help="mesh of the one-off solve leg ('same' = the timed workload; the 4M solve takes minutes)")
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--restart", type=int, default=40)
     ap.add_argument("--sweeps", type=int, default=1, help="block-Jacobi sweeps per preconditioner application")
@@ -271,10 +274,14 @@ def main():
     # ---- one-off solve (a8-a10); N = 1 only (the distributed GMRES is not built yet)
     solves = []
     if not args.no_solve and world == 1:
+        swl = args.workload if args.solve_workload == "same" else args.solve_workload
+        sn, skind, sorder, seps = WORKLOADS[swl]
+        smesh = mesh if swl == args.workload else unit_square_mesh(sn, kind=skind)
         for styp in (["hdg", "ehdg"] if args.solve_type == "both" else [args.solve_type]):
-            Ps = P
-            if styp == "hdg":
-                Ps = EHDGPipeline(mesh, make_spec(order, eps, enriched=False), device=dev)
+            if styp == "ehdg" and swl == args.workload:
+                Ps = P
+            else:
+                Ps = EHDGPipeline(smesh, make_spec(sorder, seps, enriched=(styp == "ehdg")), device=dev)
                 Ps.setup().assemble()
             barrier()
             s0, s1, s2, s3 = ev(), ev(), ev(), ev()
@@ -298,13 +305,13 @@ def main():
             del xs, ys
             s2.record()
             sweeps = max(1, args.sweeps)
-            Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol, jacobi_sweeps=sweeps)
+            Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol, jacobi_sweeps=sweeps, method=args.solve_method)
             Ps.backsolve()
             l2, h1 = Ps.errors()
             s3.record()
             torch.cuda.synchronize(dev)
             gi = Ps.gmres_info
-            solves.append({"type": styp, "rows": int(nrows), "nnz": int(nnz), "csr_build_ms": s0.elapsed_time(s1),
+            solves.append({"type": styp, "workload": swl, "method": args.solve_method, "elements": int(smesh.ne), "rows": int(nrows), "nnz": int(nnz), "csr_build_ms": s0.elapsed_time(s1),
                            "gmres_backsolve_error_ms": s2.elapsed_time(s3), "gmres_iters": int(gi.iters),
                            "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual),
                            "gmres_seconds": float(gi.total_seconds), "ms_per_iteration": 1e3 * float(gi.total_seconds) / max(1, int(gi.iters)),

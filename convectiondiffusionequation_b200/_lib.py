@@ -77,6 +77,10 @@ SYMBOLS = {
     "ehdg_gmres": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
     "ehdg_bicgstab": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
     "ehdg_dqgmres": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
+    "ehdg_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "ehdg_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int]),
+    "ehdg_comm_set_partition": (C.c_int, [_P, _P, _P, _P]),
+    "ehdg_comm_destroy": (C.c_int, [_P]),
     "ehdg_spmv": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ehdg_backsolve": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
     "ehdg_l2_error": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, os.environ.get("EHDG_LIB_NAME", "libehdg.so"))     # variant builds for A/B timing
-SOURCES = ["ehdg_core.cu", "ehdg_fast.cu", "ehdg_solve.cu", "ehdg_strip.cu"]
+SOURCES = ["ehdg_core.cu", "ehdg_fast.cu", "ehdg_solve.cu", "ehdg_strip.cu", "ehdg_dist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

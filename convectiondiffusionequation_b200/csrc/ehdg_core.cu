@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 
+#include "ehdg_dist.h"
 #include "ehdg_internal.h"
 #include "ehdg_rules.h"
 
@@ -239,6 +240,7 @@ int ehdg_destroy(ehdg_ctx* c) {
     cudaFree(c->rb.buf);
     cudaFree(c->r0.buf);
     cudaFree(c->rerr.buf);
+    ehdg_comm_destroy(c);
     fast_free_tensors(c);
     cudaFree(c->scratch);
     cudaFree(c->pool_eslot);

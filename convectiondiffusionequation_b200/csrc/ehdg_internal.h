@@ -12,6 +12,7 @@
 
 namespace ehdg {
 
+struct DistComm;
 void set_error(const char* fmt, ...);
 
 #define EHDG_CUDA(call)                                                                       \
@@ -54,6 +55,7 @@ struct ehdg_ctx {
     size_t scratch_bytes = 0;
     int32_t *pool_eslot = nullptr, *pool_lists = nullptr;
     int32_t pool_ne = 0;
+    ehdg::DistComm* dist = nullptr;   // NCCL communicator + row partition of the distributed facet solve
     cudaStream_t side = nullptr;      // the general (enriched) kernels run beside the polynomial ones
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <vector>
 
+#include "ehdg_dist.h"
 #include "ehdg_internal.h"
 #include "ehdg_strip.h"
 
@@ -171,10 +172,11 @@ __global__ void csr_numeric_kernel(int n_rows, SLayout sl, const int32_t* __rest
 // ---------------------------------------------------------------------------------------------
 template <int TPR>
 __global__ void __launch_bounds__(256)
-spmv_kernel(int n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+spmv_kernel(int row0, int n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
             const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+    // rows [row0, n_rows); y is indexed by the global row
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = (int)(gt / TPR);
+    const int r = row0 + (int)(gt / TPR);
     const int lane = (int)(gt % TPR);
     double acc = 0.0;
     if (r < n_rows) {
@@ -186,11 +188,13 @@ spmv_kernel(int n_rows, const int64_t* __restrict__ rowptr, const int32_t* __res
     if (r < n_rows && lane == 0) y[r] = acc;
 }
 
-static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, double* y, cudaStream_t st) {
-    if (A->n_rows == 0) return EHDG_OK;
+static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, double* y, cudaStream_t st, int64_t row0 = 0,
+                       int64_t row1 = -1) {
+    if (row1 < 0) row1 = A->n_rows;
+    if (row1 <= row0) return EHDG_OK;
     constexpr int TPR = 8;
-    const int64_t threads = A->n_rows * TPR;
-    spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)A->n_rows, A->rowptr, A->colind, vals, x, y);
+    const int64_t threads = (row1 - row0) * TPR;
+    spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)row0, (int)row1, A->rowptr, A->colind, vals, x, y);
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -320,9 +324,10 @@ __global__ void bj_fold_kernel(int n_rows, int nbs, const int32_t* __restrict__ 
     for (int j = 0; j < n; ++j) p[j] = out[j];
 }
 
-__global__ void bj_apply_kernel(int n_rows, int nbs, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
+__global__ void bj_apply_kernel(int row0, int n_rows, int nbs, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
                                 const double* __restrict__ dinv, const double* __restrict__ y, double* __restrict__ x) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    // rows [row0, n_rows); x, y indexed by the global row
+    const int r = row0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const int f = row_facet[r];
     const int c0 = row_start[f], n = row_start[f + 1] - c0;
@@ -466,6 +471,7 @@ struct VecOps {
     cudaStream_t st;
     double* partial;
     int64_t n;
+    const DistComm* dc = nullptr;       // set: n is the local row count, dots are summed over the ranks
     int grid() const {
         const int64_t need = (n + RED_THREADS - 1) / RED_THREADS;
         return (int)(need < RED_BLOCKS ? (need > 0 ? need : 1) : RED_BLOCKS);
@@ -478,6 +484,7 @@ struct VecOps {
             reduce_partials_kernel<<<1, 256, 0, st>>>(grid(), kt, partial, out + t0, 0);
         }
         EHDG_LAUNCH_CHECK();
+        if (dc) return dc->allreduce_sum(out, (size_t)k, st);      // one collective per batch of dot products
         return EHDG_OK;
     }
     int axpys(const double* V, int64_t ldv, int k, const double* h, double* w) const {
@@ -699,7 +706,15 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
                         int method) {
     if (!c || !A || !vals || !rhs || !x || !info) { set_error("ehdg_gmres: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n = A->n_rows;
+    const int64_t ng = A->n_rows;                                   // global system size
+    const DistComm* dc = (c->dist && c->dist->active()) ? c->dist : nullptr;
+    if (dc && dc->row_begin[dc->nranks] != ng) { set_error("ehdg_gmres: partition does not match the system size"); return EHDG_ERR_ARG; }
+    const int64_t r0 = dc ? dc->row_begin[dc->rank] : 0, r1 = dc ? dc->row_begin[dc->rank + 1] : ng;
+    const int64_t n = r1 - r0;                                      // rows this rank iterates on
+    if (dc) {
+        if (info->use_strip_block) { set_error("ehdg_gmres: the strip block is not available in the distributed solve"); return EHDG_ERR_ARG; }
+        rhs += r0;
+    }
     const int m = info->restart > 0 ? info->restart : 30;
     const int max_iters = info->max_iters > 0 ? info->max_iters : 1000;
     const double rtol = info->rtol > 0 ? info->rtol : 1e-10;
@@ -708,19 +723,19 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     info->rel_residual = 0.0;
     info->spmv_calls = 0;
     info->total_seconds = 0.0;
-    if (n == 0) { info->converged = 1; return EHDG_OK; }
+    if (ng == 0) { info->converged = 1; return EHDG_OK; }
     cudaEvent_t ev0, ev1;
     EHDG_CUDA(cudaEventCreate(&ev0));
     EHDG_CUDA(cudaEventCreate(&ev1));
     EHDG_CUDA(cudaEventRecord(ev0, st));
     const int nbs = A->nb;
     // ---- preconditioner: Dinv, then A <- A M^-1 in place
-    if (!A->dinv) EHDG_CUDA(cudaMalloc(&A->dinv, sizeof(double) * (size_t)n * nbs));
+    if (!A->dinv) EHDG_CUDA(cudaMalloc(&A->dinv, sizeof(double) * (size_t)ng * nbs));
     int* fail = nullptr;
     EHDG_CUDA(cudaMalloc(&fail, 2 * sizeof(int)));
     EHDG_CUDA(cudaMemsetAsync(fail, 0, 2 * sizeof(int), st));
     uint8_t* rowdrop = nullptr;
-    EHDG_CUDA(cudaMalloc(&rowdrop, (size_t)n));
+    EHDG_CUDA(cudaMalloc(&rowdrop, (size_t)ng));
     bj_invert_kernel<<<(A->nf + 127) / 128, 128, 0, st>>>(A->nf, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop);
     EHDG_LAUNCH_CHECK();
     // strip of marked elements: one exactly solved block (needs the unscaled matrix values)
@@ -731,12 +746,16 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     }
     info->strip_dofs = strip ? strip->n_dofs : 0;
     info->strip_blocks = strip ? strip->n_blocks : 0;
-    bj_fold_kernel<<<(unsigned)((n * 5 + 255) / 256), 256, 0, st>>>((int)n, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr, A->dinv,
+    bj_fold_kernel<<<(unsigned)((ng * 5 + 255) / 256), 256, 0, st>>>((int)ng, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr, A->dinv,
                                                                      strip ? A->strip : nullptr, vals);
     EHDG_LAUNCH_CHECK();
     // ---- workspace
-    double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr, *tvec = nullptr;
+    double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr, *tvec = nullptr, *xg = nullptr;
     if (strip) EHDG_CUDA(cudaMalloc(&tvec, sizeof(double) * (size_t)n));
+    if (dc) {
+        EHDG_CUDA(cudaMalloc(&xg, sizeof(double) * (size_t)ng));          // full-length SpMV input: own rows + halo
+        EHDG_CUDA(cudaMemsetAsync(xg, 0, sizeof(double) * (size_t)ng, st));
+    }
     EHDG_CUDA(cudaMalloc(&V, sizeof(double) * (size_t)n * (method == 0 ? (m + 1) : (method == 1 ? 6 : 2 * (m + 1)))));
     EHDG_CUDA(cudaMalloc(&w, sizeof(double) * (size_t)n));
     EHDG_CUDA(cudaMalloc(&yhat, sizeof(double) * (size_t)n));
@@ -749,7 +768,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     double* hbuf = nullptr;
     EHDG_CUDA(cudaMallocHost(&hbuf, sizeof(double) * (size_t)(2 * (m + 2) + 8)));
     EHDG_CUDA(cudaMemsetAsync(yhat, 0, sizeof(double) * (size_t)n, st));
-    VecOps vo{st, partial, n};
+    VecOps vo{st, partial, n, dc};
     // w = A~ P(v):  P leaves the bulk entries (their M^-1 is folded into A~) and solves the strip block
     auto apply_op = [&](const double* v, double* out) -> int {
         const double* in = v;
@@ -760,6 +779,13 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
             in = tvec;
         }
         info->spmv_calls++;
+        if (dc) {
+            // own rows into the full-length buffer, halo rows from the two neighbouring ranks, SpMV on own rows
+            EHDG_CUDA(cudaMemcpyAsync(xg + r0, in, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            const int r3 = dc->halo_exchange(xg, st);
+            if (r3) return r3;
+            return launch_spmv(A, vals, xg, out - r0, st, r0, r1);
+        }
         return launch_spmv(A, vals, in, out, st);
     };
     // polynomial block-Jacobi preconditioner: t = sum_{i<s} (I - B)^i v, i.e. s Richardson sweeps.  B (I + N + ... +
@@ -1020,9 +1046,10 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         conv = rel <= rtol * 10.0;
     }
     // x = M^-1 yhat
-    bj_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)n, nbs, A->row_facet, A->row_start, A->dinv, yhat, x);
+    bj_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)r0, (int)r1, nbs, A->row_facet, A->row_start, A->dinv, yhat - r0, x);
     EHDG_LAUNCH_CHECK();
     if (strip && (rc = strip_apply(strip, yhat, x, st))) return rc;
+    if (dc && (rc = dc->allgather_rows(x, st))) return rc;
     EHDG_CUDA(cudaEventRecord(ev1, st));
     EHDG_CUDA(cudaEventSynchronize(ev1));
     float ms = 0.f;
@@ -1037,6 +1064,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     strip_free(strip);
     cudaFree(rowdrop);
     cudaFree(tvec);
+    cudaFree(xg);
     cudaFree(pt);
     cudaFree(pw);
     cudaFree(V);

@@ -199,6 +199,17 @@ int ehdg_dqgmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals, const double* rhs, 
 /* y = A x with the CSR SpMV kernel used inside GMRES (for tests and the bandwidth bench) */
 int ehdg_spmv(ehdg_ctx* ctx, const ehdg_csr* csr, const double* vals, const double* x, double* y, void* stream);
 
+/* Multi-GPU facet solve (one process per GPU).  Rows of the condensed system are split into contiguous
+ * ranges; every rank holds the (replicated) matrix, iterates on its own rows, exchanges the SpMV halo rows
+ * with its two neighbouring ranks (ncclSend/ncclRecv) and reduces every batch of dot products with one
+ * ncclAllReduce.  libnccl.so.2 is resolved at run time.  id128: the 128-byte ncclUniqueId of rank 0
+ * (ehdg_comm_unique_id), distributed by the caller (torch.distributed broadcast).
+ * row_begin[nranks+1]; col_lo/col_hi[nranks]: column range referenced by each rank's rows. */
+int ehdg_comm_unique_id(char* out128);
+int ehdg_comm_init(ehdg_ctx* ctx, const char* id128, int nranks, int rank);
+int ehdg_comm_set_partition(ehdg_ctx* ctx, const int64_t* row_begin, const int64_t* col_lo, const int64_t* col_hi);
+int ehdg_comm_destroy(ehdg_ctx* ctx);
+
 /* a10 back-solve U_K = z_K - W_K Uhat_K and L2 / H1 error against `exact`
  * (convection_diffusion.py:389-394).  u f64: polynomial elements [n_poly][n_p] then general [n_gen][nvmax].
  * err2 f64[2] (device): sum of squared L2 and H1-seminorm errors. */

@@ -1,0 +1,60 @@
+"""Multi-GPU facet solve check (launch with torchrun, one rank per GPU): every rank assembles the same HDG
+system, the Krylov iteration runs row-partitioned over NCCL (halo exchange + all-reduced dots) and the result is
+compared with the single-GPU solve of rank 0's own copy.  Prints one JSON line on rank 0."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from bench import make_spec
+from convectiondiffusionequation_b200 import parallel
+from convectiondiffusionequation_b200.hot_path import EHDGPipeline
+from convectiondiffusionequation_b200.mesh import unit_square_mesh
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n = int(os.environ.get("DS_N", "64"))
+    order, eps = int(os.environ.get("DS_P", "3")), float(os.environ.get("DS_EPS", "1e-6"))
+    method, k = os.environ.get("DS_METHOD", "dqgmres"), int(os.environ.get("DS_K", "40"))
+    iters = int(os.environ.get("DS_ITERS", "20000"))
+    mesh = unit_square_mesh(n, kind=os.environ.get("DS_KIND", "unstructured"))
+    spec = make_spec(order, eps, enriched=False)
+    # single-GPU reference (every rank computes it; cheap at the check size)
+    ref = None
+    if os.environ.get("DS_REF", "1") == "1":
+        Pr = EHDGPipeline(mesh, spec, device=dev).setup().assemble().csr_build()
+        Pr.gmres(restart=k, max_iters=iters, rtol=1e-10, method=method)
+        ref = (Pr.xhat.clone(), Pr.gmres_info.iters, Pr.gmres_info.total_seconds, Pr.gmres_info.rel_residual)
+        Pr.close()
+    P = EHDGPipeline(mesh, spec, device=dev).setup().assemble().csr_build()
+    parallel.init_communicator(P)
+    rb, lo, hi = parallel.set_partition(P, world)
+    dist.barrier()
+    P.gmres(restart=k, max_iters=iters, rtol=1e-10, method=method, strip_block=False)
+    gi = P.gmres_info
+    out = dict(world=world, n=n, p=order, eps=eps, method=method, rows=int(P.csr_sizes.n_rows), iters=int(gi.iters), converged=bool(gi.converged),
+               rel_residual=float(gi.rel_residual), seconds=float(gi.total_seconds), rows_per_rank=[int(b - a) for a, b in zip(rb[:-1], rb[1:])],
+               halo_rows=[int((hi[r] - lo[r]) - (rb[r + 1] - rb[r])) for r in range(world)])
+    if ref is not None:
+        x1, it1, t1, res1 = ref
+        out.update(single_iters=int(it1), single_seconds=float(t1), single_rel_residual=float(res1),
+                   rel_diff_vs_single=float((P.xhat - x1).norm() / x1.norm()))
+    # all ranks hold the same full solution
+    chk = torch.tensor([float(P.xhat.double().sum())], dtype=torch.float64, device=dev)
+    lst = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(lst, chk)
+    out["solution_identical_on_all_ranks"] = bool(all(float(t) == float(lst[0]) for t in lst))
+    P.backsolve()
+    l2, _ = P.errors()
+    out["l2_error"] = l2
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    P.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
