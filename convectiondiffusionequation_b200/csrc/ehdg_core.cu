@@ -395,7 +395,9 @@ int ehdg_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_
                int32_t* status, void* stream) {
     if (!c || !p || !m || !lam) { set_error("ehdg_alpha: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fork = p->n_gen > 0 && p->n_poly > 0 && !getenv("EHDG_NO_FORK");   // O(sqrt(ne)) enriched elements beside the bulk
+    // running the O(sqrt(ne)) enriched elements on a side stream beside the bulk kernel was measured slower on B200
+    // (the persistent bulk CTAs already fill every SM; +0.5 ms at 1M elements), so it is opt-in
+    const bool fork = p->n_gen > 0 && p->n_poly > 0 && getenv("EHDG_FORK");
     cudaStream_t sg = fork ? c->side : st;
     if (fork) {
         EHDG_CUDA(cudaEventRecord(c->ev_fork, st));
@@ -422,7 +424,7 @@ int ehdg_assemble_condense(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
                            double* z, int32_t* status, double* Afull, void* stream) {
     if (!c || !p || !m || !lam || !S || !g || !W || !z) { set_error("ehdg_assemble_condense: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fork = p->n_gen > 0 && p->n_poly > 0 && !getenv("EHDG_NO_FORK");
+    const bool fork = p->n_gen > 0 && p->n_poly > 0 && getenv("EHDG_FORK");
     cudaStream_t sg = fork ? c->side : st;
     if (fork) {
         EHDG_CUDA(cudaEventRecord(c->ev_fork, st));

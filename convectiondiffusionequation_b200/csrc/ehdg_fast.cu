@@ -7,10 +7,10 @@ namespace ehdg {
 
 constexpr int FAST_THREADS = 128;
 #ifndef EHDG_ASM_MINBLOCKS
-#define EHDG_ASM_MINBLOCKS 3
+#define EHDG_ASM_MINBLOCKS (EHDG_ASM_R == 2 ? 2 : 3)
 #endif
 #ifndef EHDG_ALPHA_MINBLOCKS
-#define EHDG_ALPHA_MINBLOCKS 4
+#define EHDG_ALPHA_MINBLOCKS (EHDG_ALPHA_R == 2 ? 3 : 4)
 #endif
 
 template <int P>
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ALPHA_MINBLOCKS :
 fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, const int32_t* __restrict__ list,
                   const double* __restrict__ verts, const int32_t* __restrict__ tris, double* __restrict__ lam,
                   int32_t* status) {
-    typedef FastDims<P> D;
+    typedef AlphaDims<P> D;
     constexpr int LG = D::LG, GPC = FAST_THREADS / LG;
     extern __shared__ double smem[];
     for (int i = threadIdx.x; i < tab_doubles; i += FAST_THREADS) smem[i] = tab_g[i];
@@ -66,7 +66,7 @@ fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, cons
 
 template <int P>
 static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, double* lam, int32_t* status, cudaStream_t st) {
-    typedef FastDims<P> D;
+    typedef AlphaDims<P> D;
     constexpr int GPC = FAST_THREADS / D::LG;
     const int tabd = c->tens.alpha_doubles;
     const size_t smem = (size_t)(((tabd + 1) & ~1) + GPC * fast_alpha_scratch_doubles<P>()) * 8;

@@ -62,11 +62,13 @@ struct Group {
     int lane;       // lane inside the group (device); unused on the host
     double* sh;     // group-private scratch
 
-    // Lane holding the largest key (keys are magnitudes >= 0, or -1 for "not a candidate").  The keys
-    // are compared through the top 32 bits of the double with the low bits replaced by the lane, so
-    // the search is ONE 32-bit warp reduction (redux.sync) per group; pivots that agree to ~15 bits
-    // of mantissa are tie-broken towards the lower lane (immaterial for partial pivoting).
-    static EHDG_HD unsigned order_key(double key, int lane_) {
+    // Row holding the largest key.  Every lane offers R candidate rows (row = h * LG + lane); keys are
+    // magnitudes >= 0, or -1 for "not a candidate".  They are compared through the top 32 bits of the
+    // double with the low bits replaced by the row number, so the search is ONE 32-bit warp reduction
+    // (redux.sync) per group; pivots that agree to ~15 bits of mantissa are tie-broken towards the
+    // lower row (immaterial for partial pivoting).
+    template <int ROWS>
+    static EHDG_HD unsigned order_key(double key, int row) {
         if (!(key >= 0.0)) return 0u;                       // -1 / NaN: never wins against a real candidate
         unsigned long long bits;
 #ifdef __CUDA_ARCH__
@@ -75,22 +77,31 @@ struct Group {
         memcpy(&bits, &key, 8);
 #endif
         const unsigned hi = (unsigned)(bits >> 32);
-        return ((hi | 0x80000000u) & ~(unsigned)(LG - 1)) | (unsigned)(LG - 1 - lane_);
+        return ((hi | 0x80000000u) & ~(unsigned)(ROWS - 1)) | (unsigned)(ROWS - 1 - row);
     }
-    EHDG_HD int argmax(const double* key) const {
+    // key[L][h]: candidate of (lane, slot h); returns the winning row
+    template <int R>
+    EHDG_HD int argmax_row(const double (*key)[R]) const {
+        constexpr int ROWS = LG * R;
 #ifdef __CUDA_ARCH__
-        const unsigned k = order_key(key[0], lane);
+        unsigned k = 0u;
+#pragma unroll
+        for (int h = 0; h < R; ++h) {
+            const unsigned kh = order_key<ROWS>(key[0][h], h * LG + lane);
+            k = kh > k ? kh : k;
+        }
         const unsigned base = (threadIdx.x & 31u) & ~(unsigned)(LG - 1);
         const unsigned mask = (LG == 32) ? 0xffffffffu : (((1u << LG) - 1u) << base);
         const unsigned best = __reduce_max_sync(mask, k);
-        return LG - 1 - (int)(best & (unsigned)(LG - 1));
+        return ROWS - 1 - (int)(best & (unsigned)(ROWS - 1));
 #else
         unsigned best = 0u;
-        for (int l = 0; l < LG; ++l) {
-            const unsigned k = order_key(key[l], l);
-            if (k > best) best = k;
-        }
-        return LG - 1 - (int)(best & (unsigned)(LG - 1));
+        for (int l = 0; l < LG; ++l)
+            for (int h = 0; h < R; ++h) {
+                const unsigned k = order_key<ROWS>(key[l][h], h * LG + l);
+                if (k > best) best = k;
+            }
+        return ROWS - 1 - (int)(best & (unsigned)(ROWS - 1));
 #endif
     }
     EHDG_HD double sum(const double* x) const {
@@ -190,40 +201,60 @@ EHDG_HD void sorted_geom(const double* verts, const int* tri, double bx, double 
 }
 
 // -------------------------------------------------------------------------------------------
-// a5-a7 on one polynomial element.  Scratch `gc.sh` needs fast_asm_scratch_doubles() doubles.
-// Outputs in LOCAL edge order (3 (p+1) facet dofs): S[NF*NF], gvec[NF], W[NP*NF], z[NP].
-// tab: assembly tensors (shared memory on the device), phi_rhs: [9][nq][NP] (global/L1),
-// rule: bonus triangle rule.
+// Layout: a group of LG lanes owns one element, every lane keeps R rows of the element matrices in
+// registers, row = h * LG + lane (h < R).  Two rows per lane halve the shared-memory broadcast volume
+// and the pivot-search / synchronisation overhead per element (ncu: the kernels are bound by issue
+// slots and the shared-memory pipe, not by latency).
 // -------------------------------------------------------------------------------------------
-template <int P>
-struct FastDims {
+template <int P, int RR>
+struct FastDimsR {
     static constexpr int NP = (P + 1) * (P + 2) / 2;
     static constexpr int NFL = P + 1;
     static constexpr int NF = 3 * NFL;
     static constexpr int NC = NP + NF + 1;
     static constexpr int M = NP > NF ? NP : NF;
-    static constexpr int LG = M <= 8 ? 8 : (M <= 16 ? 16 : 32);
+    static constexpr int R = RR;                        // rows per lane
+    static constexpr int LG = R == 2 ? (M <= 8 ? 4 : (M <= 16 ? 8 : 16)) : (M <= 8 ? 8 : (M <= 16 ? 16 : 32));
+    static constexpr int ROWS = LG * R;
     static constexpr int NXS = ((NF + 2) & ~1) + 2;    // row stride of the X scratch: even (16-byte rows), 2-way conflicts at most
 };
 
+// measured on B200 (tools/ab_time.py, A/B builds): two rows per lane pay off in the alpha kernel (-23 %) but not in
+// the assembly kernel (254 registers, 2 CTAs/SM: +7 %)
+#ifndef EHDG_ASM_R
+#define EHDG_ASM_R 1
+#endif
+#ifndef EHDG_ALPHA_R
+#define EHDG_ALPHA_R 2
+#endif
+template <int P>
+using FastDims = FastDimsR<P, (EHDG_ASM_R == 2 && P <= 4) ? 2 : 1>;
+template <int P>
+using AlphaDims = FastDimsR<P, (EHDG_ALPHA_R == 2 && P <= 4) ? 2 : 1>;
+
 template <int P>
 EHDG_HD constexpr int fast_asm_scratch_doubles(int nq) {
-    return ((FastDims<P>::NC + 1) & ~1) + FastDims<P>::NP * FastDims<P>::NXS + ((nq + 1) & ~1);
+    typedef FastDims<P> D;
+    constexpr int xs = D::NP * D::NXS, ss = D::NF * D::NF + D::NF;      // X scratch doubles as the S/g staging area
+    return ((D::NC + 1) & ~1) + (((xs > ss ? xs : ss) + 1) & ~1) + ((nq + 1) & ~1);
 }
 
+// a5-a7 on one polynomial element.  Scratch `gc.sh` needs fast_asm_scratch_doubles() doubles.
+// Outputs in LOCAL edge order (3 (p+1) facet dofs): S[NF*NF], gvec[NF], W[NP*NF], z[NP].
+// tab: assembly tensors (shared memory on the device), phi_rhs: [9][nq][NP] (global/L1), rs: bonus rule.
 template <int P>
 EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Problem& pb, const RuleSet& rs,
                                   const double* tab, const double* phi_rhs, const double* verts, const int* tri,
                                   double lam, bool store, double* S, double* gvec, double* W, double* z) {
     typedef FastDims<P> D;
-    constexpr int NP = D::NP, NFL = D::NFL, NF = D::NF, NC = D::NC, LG = D::LG, NXS = D::NXS;
+    constexpr int NP = D::NP, NFL = D::NFL, NF = D::NF, NC = D::NC, LG = D::LG, R = D::R, NXS = D::NXS;
     constexpr int NLS = EHDG_NLS(LG);
     const TensorLayout TL = tensor_layout(P, rs.nq);
     SortedGeom sg;
     sorted_geom(verts, tri, pb.bx, pb.by, sg);
     double* prow = gc.sh;                       // NC (padded even)
-    double* Xs = prow + ((NC + 1) & ~1);        // NP x NXS
-    double* cw = Xs + NP * NXS;                 // nq
+    double* Xs = prow + ((NC + 1) & ~1);        // NP x NXS, later the staging area of S (NF x NF) and g (NF)
+    double* cw = Xs + (((NP * NXS > NF * NF + NF ? NP * NXS : NF * NF + NF) + 1) & ~1);   // nq
     // per-edge coefficients
     double cvv[3], cvf[3], cfv[3], cff[3], eg0[3], eg1[3];
     for (int s = 0; s < 3; ++s) {
@@ -240,11 +271,11 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     const double kxx = sg.adet * pb.eps * sg.g00, ks = sg.adet * pb.eps * sg.g01, kyy = sg.adet * pb.eps * sg.g11;
     const double ccx = -sg.adet * sg.c0, ccy = -sg.adet * sg.c1;
 
-    double a[NLS][NC];      // row i of [A_VV | A_VF | f_V]          (lanes i < NP)
-    double afv[NLS][NP];    // row r of A_FV in the sorted frame      (lanes r < NF)
-    double aff[NLS];
-    int mycol[NLS];
-    double myinv[NLS];
+    double a[NLS][R][NC];      // rows of [A_VV | A_VF | f_V]          (rows < NP)
+    double afv[NLS][R][NP];    // rows of A_FV in the sorted frame      (rows < NF)
+    double aff[NLS][R];
+    int mycol[NLS][R];
+    double myinv[NLS][R];
     int status = 0;
 
     // ---- right-hand side weights at the quadrature points: cw[q] = w_q |detJ| coeff(x_q)
@@ -264,68 +295,114 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 
     // ---- build the rows from the tensors
     EHDG_FOR_LANES(l, L)
-        const int i = l < NP ? l : NP - 1;          // clamp: surplus lanes recompute the last row
-        const double* tv = tab + TL.offV + i * NP;
 #pragma unroll
-        for (int j = 0; j < NP; ++j) {
-            double acc = kxx * tv[j] + ks * tv[NP * NP + j] + kyy * tv[2 * NP * NP + j]
-                       + ccx * tv[3 * NP * NP + j] + ccy * tv[4 * NP * NP + j];
+        for (int h = 0; h < R; ++h) {
+            const int row = h * LG + l;
+            const int i = row < NP ? row : NP - 1;          // clamp: surplus rows recompute the last row
+            const double* tv = tab + TL.offV + i * NP;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+#ifdef EHDG_EXP_SKIP_TABLES
+                double acc = kxx * (i + 1) + ks * j + (i == j ? 10.0 * kyy + 100.0 : 0.0) + cvv[0] * 0.01;
+#else
+                double acc = kxx * tv[j] + ks * tv[NP * NP + j] + kyy * tv[2 * NP * NP + j]
+                           + ccx * tv[3 * NP * NP + j] + ccy * tv[4 * NP * NP + j];
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const double* te = tab + TL.offE + (s * 3 * NP + i) * NP;
+                    acc += cvv[s] * te[j] - eg0[s] * te[NP * NP + j] - eg1[s] * te[2 * NP * NP + j];
+                }
+#endif
+                a[L][h][j] = acc;
+            }
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const double* te = tab + TL.offE + (s * 3 * NP + i) * NP;
-                acc += cvv[s] * te[j] - eg0[s] * te[NP * NP + j] - eg1[s] * te[2 * NP * NP + j];
+                const double* tf = tab + TL.offF + (s * 3 * NP + i) * NFL;
+#pragma unroll
+                for (int k = 0; k < NFL; ++k)
+                    a[L][h][NP + s * NFL + k] = cvf[s] * tf[k] + eg0[s] * tf[NP * NFL + k] + eg1[s] * tf[2 * NP * NFL + k];
             }
-            a[L][j] = acc;
+            mycol[L][h] = -1;
+            myinv[L][h] = 1.0;
         }
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const double* tf = tab + TL.offF + (s * 3 * NP + i) * NFL;
-#pragma unroll
-            for (int k = 0; k < NFL; ++k)
-                a[L][NP + s * NFL + k] = cvf[s] * tf[k] + eg0[s] * tf[NP * NFL + k] + eg1[s] * tf[2 * NP * NFL + k];
-        }
-        // f_V[i] = sum_q cw[q] phi_i(q)
+        // f_V[i] = sum_q cw[q] phi_i(q), the R rows of the lane share the cw reads
         {
-            const double* ph = phi_rhs + (size_t)(sg.f0 * 3 + sg.f1) * rs.nq * NP + i;
-            double acc = 0.0;
+            const double* ph = phi_rhs + (size_t)(sg.f0 * 3 + sg.f1) * rs.nq * NP;
+            int ii[R];
+            double acc[R][4];                      // four independent accumulation chains per row
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                ii[h] = h * LG + l < NP ? h * LG + l : NP - 1;
+                acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.0;
+            }
             int q = 0;
-            for (; q + 1 < rs.nq; q += 2) {
-                double c0, c1;
+#ifdef EHDG_EXP_SKIP_RHS
+            q = rs.nq & ~3;
+#endif
+            for (; q + 3 < rs.nq; q += 4) {
+                double c0, c1, c2, c3;
                 ld2(cw + q, c0, c1);
-                acc += c0 * ph[q * NP];
-                acc += c1 * ph[(q + 1) * NP];
+                ld2(cw + q + 2, c2, c3);
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    acc[h][0] += c0 * ph[q * NP + ii[h]];
+                    acc[h][1] += c1 * ph[(q + 1) * NP + ii[h]];
+                    acc[h][2] += c2 * ph[(q + 2) * NP + ii[h]];
+                    acc[h][3] += c3 * ph[(q + 3) * NP + ii[h]];
+                }
             }
-            if (q < rs.nq) acc += cw[q] * ph[q * NP];
-            a[L][NC - 1] = acc;
+            for (; q < rs.nq; ++q) {
+#pragma unroll
+                for (int h = 0; h < R; ++h) acc[h][0] += cw[q] * ph[q * NP + ii[h]];
+            }
+#pragma unroll
+            for (int h = 0; h < R; ++h) a[L][h][NC - 1] = (acc[h][0] + acc[h][1]) + (acc[h][2] + acc[h][3]);
         }
-        // A_FV row r = (s, k) in the sorted frame
-        {
-            const int r = l < NF ? l : NF - 1;
+        // A_FV rows r = (s, k) in the sorted frame
+#pragma unroll
+        for (int h = 0; h < R; ++h) {
+            const int row = h * LG + l;
+            const int r = row < NF ? row : NF - 1;
             const int s = r / NFL, k = r % NFL;
             const double* tf = tab + TL.offF + (s * 3 * NP) * NFL + k;
 #pragma unroll
             for (int j = 0; j < NP; ++j)
-                afv[L][j] = cfv[s] * tf[j * NFL] + eg0[s] * tf[(NP + j) * NFL] + eg1[s] * tf[(2 * NP + j) * NFL];
-            aff[L] = cff[s] / (2.0 * k + 1.0);           // int_0^1 mu_k^2 dt
+                afv[L][h][j] = cfv[s] * tf[j * NFL] + eg0[s] * tf[(NP + j) * NFL] + eg1[s] * tf[(2 * NP + j) * NFL];
+            aff[L][h] = cff[s] / (2.0 * k + 1.0);           // int_0^1 mu_k^2 dt
         }
-        mycol[L] = -1;
-        myinv[L] = 1.0;
     EHDG_END_LANES
 
-    // ---- Gauss-Jordan with partial pivoting, rows stay in their lanes
+    // ---- Gauss-Jordan with partial pivoting, rows stay where they are
+#ifdef EHDG_EXP_SKIP_GJ
+#define EHDG_GJ_STEPS 1
+#else
+#define EHDG_GJ_STEPS NP
+#endif
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        double key[NLS];
+    for (int k = 0; k < EHDG_GJ_STEPS; ++k) {
+        double key[NLS][R];
         EHDG_FOR_LANES(l, L)
-            key[L] = (l < NP && mycol[L] < 0) ? fabs(a[L][k]) : -1.0;
+#pragma unroll
+            for (int h = 0; h < R; ++h) key[L][h] = (h * LG + l < NP && mycol[L][h] < 0) ? fabs(a[L][h][k]) : -1.0;
         EHDG_END_LANES
-        const int r = gc.argmax(key);
+        const int rw = gc.template argmax_row<R>(key);
+        const int lo = rw % LG, ho = rw / LG;
         EHDG_FOR_LANES(l, L)
-            if (l == r) {
+            if (l == lo) {
 #pragma unroll
-                for (int jp = k >> 1; jp <= (NC - 1) >> 1; ++jp)
-                    st2(prow + 2 * jp, a[L][2 * jp], (2 * jp + 1 < NC) ? a[L][2 * jp + 1] : 0.0);
-                mycol[L] = k;
+                for (int jp = k >> 1; jp <= (NC - 1) >> 1; ++jp) {
+                    double v0 = a[L][0][2 * jp], v1 = (2 * jp + 1 < NC) ? a[L][0][2 * jp + 1] : 0.0;
+#pragma unroll
+                    for (int h = 1; h < R; ++h)
+                        if (h == ho) {
+                            v0 = a[L][h][2 * jp];
+                            v1 = (2 * jp + 1 < NC) ? a[L][h][2 * jp + 1] : 0.0;
+                        }
+                    st2(prow + 2 * jp, v0, v1);
+                }
+#pragma unroll
+                for (int h = 0; h < R; ++h)
+                    if (h == ho) mycol[L][h] = k;
             }
         EHDG_END_LANES
         EHDG_FOR_LANES(l, L)
@@ -336,70 +413,103 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 #else
             const double inv = 1.0 / piv;
 #endif
-            if (l == r) {
-                myinv[L] = inv;          // the pivot row stays unscaled; its lane scales the solution once at the end
-            } else if (l < NP) {
-                const double f = a[L][k] * inv;
+            // multipliers: 0 for the pivot row (it stays unscaled; scaled once at the end) and for surplus rows
+            double f[R];
 #pragma unroll
-                for (int jp = (k + 1) >> 1; jp <= (NC - 1) >> 1; ++jp) {
-                    double x0, x1;
-                    ld2(prow + 2 * jp, x0, x1);
-                    if (2 * jp >= k + 1) a[L][2 * jp] -= f * x0;
-                    if (2 * jp + 1 < NC) a[L][2 * jp + 1] -= f * x1;
+            for (int h = 0; h < R; ++h) {
+                const bool is_piv = (l == lo) && (h == ho);
+                if (is_piv) myinv[L][h] = inv;
+                f[h] = (is_piv || h * LG + l >= NP) ? 0.0 : a[L][h][k] * inv;
+            }
+#pragma unroll
+            for (int jp = (k + 1) >> 1; jp <= (NC - 1) >> 1; ++jp) {
+                double x0, x1;
+                ld2(prow + 2 * jp, x0, x1);
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    if (2 * jp >= k + 1) a[L][h][2 * jp] -= f[h] * x0;
+                    if (2 * jp + 1 < NC) a[L][h][2 * jp + 1] -= f[h] * x1;
                 }
             }
         EHDG_END_LANES
     }
 
-    // ---- X = A_VV^-1 [A_VF | f_V]: row c sits in the lane whose pivot column was c
+    // ---- X = A_VV^-1 [A_VF | f_V]: row c sits where pivot column c was chosen
     EHDG_FOR_LANES(l, L)
-        if (l < NP) {
-            const int c = mycol[L];
-            const double sc = myinv[L];
 #pragma unroll
-            for (int j = 0; j <= NF; ++j) a[L][NP + j] *= sc;
+        for (int h = 0; h < R; ++h)
+            if (h * LG + l < NP) {
+                const int c = mycol[L][h];
+                const double sc = myinv[L][h];
 #pragma unroll
-            for (int jp = 0; jp <= NF >> 1; ++jp)
-                st2(Xs + c * NXS + 2 * jp, a[L][NP + 2 * jp], (2 * jp + 1 <= NF) ? a[L][NP + 2 * jp + 1] : 0.0);
-            if (store) {
+                for (int j = 0; j <= NF; ++j) a[L][h][NP + j] *= sc;
 #pragma unroll
-                for (int s = 0; s < 3; ++s)
+                for (int jp = 0; jp <= NF >> 1; ++jp)
+                    st2(Xs + c * NXS + 2 * jp, a[L][h][NP + 2 * jp], (2 * jp + 1 <= NF) ? a[L][h][NP + 2 * jp + 1] : 0.0);
+            }
+    EHDG_END_LANES
+
+    // ---- S = A_FF - A_FV X, g = -A_FV z ; rows in the sorted frame.  W, z leave from the X scratch and S, g from a
+    // staging copy with contiguous (full-sector) global stores in local edge order.
+    int sinv[3];                                    // sorted edge of local edge e
+    for (int s2 = 0; s2 < 3; ++s2) sinv[sg.eloc[s2]] = s2;
+    double srow[NLS][R][NF + 1];
+    EHDG_FOR_LANES(l, L)
+        if (store) {
+            for (int gi = l; gi < NP * NF; gi += LG) {
+                const int c = gi / NF, col = gi % NF;
+                W[gi] = Xs[c * NXS + sinv[col / NFL] * NFL + col % NFL];
+            }
+            for (int c = l; c < NP; c += LG) z[c] = Xs[c * NXS + NF];
+        }
 #pragma unroll
-                    for (int k = 0; k < NFL; ++k) W[c * NF + sg.eloc[s] * NFL + k] = a[L][NP + s * NFL + k];
-                z[c] = a[L][NC - 1];
+        for (int h = 0; h < R; ++h)
+#pragma unroll
+            for (int j = 0; j <= NF; ++j) srow[L][h][j] = 0.0;
+#ifdef EHDG_EXP_SKIP_SCHUR
+#define EHDG_SCHUR_N 1
+#else
+#define EHDG_SCHUR_N NP
+#endif
+#pragma unroll
+        for (int c = 0; c < EHDG_SCHUR_N; ++c) {
+#pragma unroll
+            for (int jp = 0; jp <= NF >> 1; ++jp) {
+                double x0, x1;
+                ld2(Xs + c * NXS + 2 * jp, x0, x1);
+#pragma unroll
+                for (int h = 0; h < R; ++h) {
+                    srow[L][h][2 * jp] -= afv[L][h][c] * x0;
+                    if (2 * jp + 1 <= NF) srow[L][h][2 * jp + 1] -= afv[L][h][c] * x1;
+                }
             }
         }
     EHDG_END_LANES
-
-    // ---- S = A_FF - A_FV X, g = -A_FV z ; lane r owns row r (sorted frame), written in local order
+    double* Ss = Xs;                                // every lane is done reading X
     EHDG_FOR_LANES(l, L)
-        if (l < NF) {
-            double srow[NF + 1];
 #pragma unroll
-            for (int j = 0; j <= NF; ++j) srow[j] = 0.0;
+        for (int h = 0; h < R; ++h) {
+            const int row = h * LG + l;
+            if (row < NF) {
+                const int s = row / NFL, k = row % NFL;
+                const int orow = sg.eloc[s] * NFL + k;
 #pragma unroll
-            for (int c = 0; c < NP; ++c) {
-                const double f = afv[L][c];
+                for (int s2 = 0; s2 < 3; ++s2)
 #pragma unroll
-                for (int jp = 0; jp <= NF >> 1; ++jp) {
-                    double x0, x1;
-                    ld2(Xs + c * NXS + 2 * jp, x0, x1);
-                    srow[2 * jp] -= f * x0;
-                    if (2 * jp + 1 <= NF) srow[2 * jp + 1] -= f * x1;
-                }
+                    for (int k2 = 0; k2 < NFL; ++k2) {
+                        double val = srow[L][h][s2 * NFL + k2];
+                        if (s2 * NFL + k2 == row) val += aff[L][h];
+                        if (val != val) status |= EHDG_ST_NONFINITE;
+                        Ss[orow * NF + sg.eloc[s2] * NFL + k2] = val;
+                    }
+                Ss[NF * NF + orow] = srow[L][h][NF];
             }
-            const int s = l / NFL, k = l % NFL;
-            const int orow = sg.eloc[s] * NFL + k;
-#pragma unroll
-            for (int s2 = 0; s2 < 3; ++s2)
-#pragma unroll
-                for (int k2 = 0; k2 < NFL; ++k2) {
-                    double val = srow[s2 * NFL + k2];
-                    if (s2 * NFL + k2 == l) val += aff[L];
-                    if (val != val) status |= EHDG_ST_NONFINITE;
-                    if (store) S[orow * NF + sg.eloc[s2] * NFL + k2] = val;
-                }
-            if (store) gvec[orow] = srow[NF];
+        }
+    EHDG_END_LANES
+    EHDG_FOR_LANES(l, L)
+        if (store) {
+            for (int gi = l; gi < NF * NF; gi += LG) S[gi] = Ss[gi];
+            for (int r = l; r < NF; r += LG) gvec[r] = Ss[NF * NF + r];
         }
     EHDG_END_LANES
     return status;
@@ -412,29 +522,29 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 // -------------------------------------------------------------------------------------------
 template <int P>
 EHDG_HD constexpr int fast_alpha_scratch_doubles() {
-    return (((FastDims<P>::NP - 1) * (FastDims<P>::NP - 1) + 1) & ~1) + 4 * 32;     // even: groups stay 16-byte aligned
+    return (((AlphaDims<P>::NP - 1) * (AlphaDims<P>::NP - 1) + 1) & ~1) + 4 * 32;     // even: groups stay 16-byte aligned
 }
 
 template <int P>
-EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double* tab, const double* verts,
+EHDG_HD double fast_alpha_element(const Group<AlphaDims<P>::LG>& gc, const double* tab, const double* verts,
                                   const int* tri, int* status_out) {
-    typedef FastDims<P> D;
-    constexpr int NP = D::NP, LG = D::LG, N = NP - 1;
+    typedef AlphaDims<P> D;
+    constexpr int NP = D::NP, LG = D::LG, R = D::R, N = NP - 1;
     constexpr int NLS = EHDG_NLS(LG);
     const TensorLayout TL = tensor_layout(P, 0);
     SortedGeom sg;
     sorted_geom(verts, tri, 0.0, 0.0, sg);
-    double* shT = gc.sh;              // N x N
+    double* shT = gc.sh;                      // N x N
     double* shv = shT + ((N * N + 1) & ~1);   // 32
-    double* shq = shv + 32;           // 32
-    double* shd = shq + 32;           // 32
-    double* she = shd + 32;           // 32
+    double* shq = shv + 32;                   // 32
+    double* shd = shq + 32;                   // 32
+    double* she = shd + 32;                   // 32
     int status = 0;
 
-    double A[NLS][N];   // a' row -> Cholesky factor row
-    double M[NLS][N];   // m row  -> C row
-    double eown[NLS];   // sub-diagonal entry T[i][i-1] owned by lane i
-    double invd[NLS];   // 1 / l_ii of the Cholesky factor (lane i)
+    double A[NLS][R][N];   // a' rows -> Cholesky factor rows
+    double M[NLS][R][N];   // m rows  -> C rows
+    double eown[NLS][R];   // sub-diagonal entry T[i][i-1] owned by row i
+    double invd[NLS][R];   // 1 / l_ii of the Cholesky factor
 
     // m = sum_s h_s len_s (dn u)(dn v) with dn = ga0 dX + ga1 dY ; the common factor |detJ| of a'
     // and m is dropped (h_s len_s = |detJ|)
@@ -445,94 +555,137 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
         w2[s] = sg.ga1[s] * sg.ga1[s];
     }
     EHDG_FOR_LANES(l, L)
-        const int i = (l < N ? l : N - 1) + 1;
-        const double* tk = tab + TL.offAK + i * NP + 1;
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            A[L][j] = sg.g00 * tk[j] + sg.g01 * tk[NP * NP + j] + sg.g11 * tk[2 * NP * NP + j];
-            double acc = 0.0;
+        for (int h = 0; h < R; ++h) {
+            const int row = h * LG + l;
+            const int i = (row < N ? row : N - 1) + 1;
+            const double* tk = tab + TL.offAK + i * NP + 1;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const double* tn = tab + TL.offAN + (s * 3 * NP + i) * NP + 1;
-                acc += w0[s] * tn[j] + w1[s] * tn[NP * NP + j] + w2[s] * tn[2 * NP * NP + j];
+            for (int j = 0; j < N; ++j) {
+                A[L][h][j] = sg.g00 * tk[j] + sg.g01 * tk[NP * NP + j] + sg.g11 * tk[2 * NP * NP + j];
+                double acc = 0.0;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const double* tn = tab + TL.offAN + (s * 3 * NP + i) * NP + 1;
+                    acc += w0[s] * tn[j] + w1[s] * tn[NP * NP + j] + w2[s] * tn[2 * NP * NP + j];
+                }
+                M[L][h][j] = acc;
             }
-            M[L][j] = acc;
+            eown[L][h] = 0.0;
+            invd[L][h] = 0.0;
         }
-        eown[L] = 0.0;
-        invd[L] = 0.0;
     EHDG_END_LANES
 
-    // ---- Cholesky a' = L L^T, right-looking; A[i][k] becomes l_ik (k <= i)
+    // ---- Cholesky a' = L L^T, right-looking; A[row][k] becomes l_{row,k} (k <= row)
 #pragma unroll
     for (int k = 0; k < N; ++k) {
+        const int kl = k % LG, kh = k / LG;         // owner of row k (compile-time after unrolling)
         EHDG_FOR_LANES(l, L)
-            if (l == k) {
-                const double d = A[L][k];
+            if (l == kl) {
+                double d = 0.0;
+#pragma unroll
+                for (int h = 0; h < R; ++h)
+                    if (h == kh) d = A[L][h][k];
                 if (!(d > 0.0)) status |= EHDG_ST_ALPHA_DEFICIENT;
 #ifdef __CUDA_ARCH__
                 shv[0] = rsqrt(d);
 #else
                 shv[0] = 1.0 / sqrt(d);
 #endif
-                invd[L] = shv[0];
-            }
-        EHDG_END_LANES
-        EHDG_FOR_LANES(l, L)
-            if (l >= k && l < N) {
-                A[L][k] *= shv[0];
-                shq[l] = A[L][k];
-            }
-        EHDG_END_LANES
-        EHDG_FOR_LANES(l, L)
-            if (l > k && l < N) {
-                const double f = A[L][k];
 #pragma unroll
-                for (int j = k + 1; j < N; ++j) A[L][j] -= f * shq[j];
+                for (int h = 0; h < R; ++h)
+                    if (h == kh) invd[L][h] = shv[0];
+            }
+        EHDG_END_LANES
+        EHDG_FOR_LANES(l, L)
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const int row = h * LG + l;
+                if (row >= k && row < N) {
+                    A[L][h][k] *= shv[0];
+                    shq[row] = A[L][h][k];
+                }
+            }
+        EHDG_END_LANES
+        EHDG_FOR_LANES(l, L)
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const int row = h * LG + l;
+                const double f = (row > k && row < N) ? A[L][h][k] : 0.0;
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) A[L][h][j] -= f * shq[j];
             }
         EHDG_END_LANES
     }
     // ---- two forward substitutions with a transpose in between: C = L^-1 (L^-1 m)^T.
-    // Row j is broadcast UNSCALED (Y~_j = l_jj Y_j) together with 1/l_jj; the lanes below subtract
-    // (l_ij / l_jj) Y~_j and every lane scales its own finished row once (all lanes busy, one pass).
+    // Row j is broadcast UNSCALED (Y~_j = l_jj Y_j) together with 1/l_jj; the rows below subtract
+    // (l_ij / l_jj) Y~_j and every row is scaled once when the pass is finished.
     for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
+            const int jl = j % LG, jh = j / LG;
             EHDG_FOR_LANES(l, L)
-                if (l == j) {
+                if (l == jl) {
 #pragma unroll
-                    for (int cp = 0; cp <= (N - 1) >> 1; ++cp)
-                        st2(shT + 2 * cp, M[L][2 * cp], (2 * cp + 1 < N) ? M[L][2 * cp + 1] : 0.0);
-                    shv[0] = invd[L];
+                    for (int cp = 0; cp <= (N - 1) >> 1; ++cp) {
+                        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                        for (int h = 0; h < R; ++h)
+                            if (h == jh) {
+                                v0 = M[L][h][2 * cp];
+                                v1 = (2 * cp + 1 < N) ? M[L][h][2 * cp + 1] : 0.0;
+                            }
+                        st2(shT + 2 * cp, v0, v1);
+                    }
+#pragma unroll
+                    for (int h = 0; h < R; ++h)
+                        if (h == jh) shv[0] = invd[L][h];
                 }
             EHDG_END_LANES
             EHDG_FOR_LANES(l, L)
-                if (l > j && l < N) {
-                    const double f = A[L][j] * shv[0];
+                double f[R];
 #pragma unroll
-                    for (int cp = 0; cp <= (N - 1) >> 1; ++cp) {
-                        double x0, x1;
-                        ld2(shT + 2 * cp, x0, x1);
-                        M[L][2 * cp] -= f * x0;
-                        if (2 * cp + 1 < N) M[L][2 * cp + 1] -= f * x1;
+                for (int h = 0; h < R; ++h) {
+                    const int row = h * LG + l;
+                    f[h] = (row > j && row < N) ? A[L][h][j] * shv[0] : 0.0;
+                }
+#pragma unroll
+                for (int cp = 0; cp <= (N - 1) >> 1; ++cp) {
+                    double x0, x1;
+                    ld2(shT + 2 * cp, x0, x1);
+#pragma unroll
+                    for (int h = 0; h < R; ++h) {
+                        M[L][h][2 * cp] -= f[h] * x0;
+                        if (2 * cp + 1 < N) M[L][h][2 * cp + 1] -= f[h] * x1;
                     }
                 }
             EHDG_END_LANES
         }
         EHDG_FOR_LANES(l, L)
 #pragma unroll
-            for (int c = 0; c < N; ++c) M[L][c] *= invd[L];
+            for (int h = 0; h < R; ++h)
+#pragma unroll
+                for (int c = 0; c < N; ++c) M[L][h][c] *= invd[L][h];
         EHDG_END_LANES
         if (pass == 0) {
             EHDG_FOR_LANES(l, L)
-                if (l < N) {
 #pragma unroll
-                    for (int c = 0; c < N; ++c) shT[l * N + c] = M[L][c];
+                for (int h = 0; h < R; ++h) {
+                    const int row = h * LG + l;
+                    if (row < N) {
+#pragma unroll
+                        for (int c = 0; c < N; ++c) shT[row * N + c] = M[L][h][c];
+                    }
                 }
             EHDG_END_LANES
             EHDG_FOR_LANES(l, L)
-                if (l < N) {
 #pragma unroll
-                    for (int c = 0; c < N; ++c) M[L][c] = shT[c * N + l];
+                for (int h = 0; h < R; ++h) {
+                    const int row = h * LG + l;
+                    if (row < N) {
+#pragma unroll
+                        for (int c = 0; c < N; ++c) M[L][h][c] = shT[c * N + row];
+                    }
                 }
             EHDG_END_LANES
         }
@@ -540,52 +693,89 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
     // ---- Householder tridiagonalisation of C (rows in M)
 #pragma unroll
     for (int k = 0; k + 2 < N; ++k) {
-        double part[NLS], vi[NLS];
+        const int ol = (k + 1) % LG, oh = (k + 1) / LG;       // owner of row k+1
+        double part[NLS], vi[NLS][R], pi[NLS][R];
         EHDG_FOR_LANES(l, L)
-            part[L] = (l > k && l < N) ? M[L][k] * M[L][k] : 0.0;
-            if (l == k + 1) shv[0] = M[L][k];
+            double acc = 0.0;
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const int row = h * LG + l;
+                if (row > k && row < N) acc += M[L][h][k] * M[L][h][k];
+                if (l == ol && h == oh) shv[0] = M[L][h][k];
+            }
+            part[L] = acc;
         EHDG_END_LANES
         const double sig = gc.sum(part);
         const double x0 = shv[0];
         const bool skip = !(sig > 0.0);
-        const double alpha = (x0 > 0.0) ? -sqrt(sig) : sqrt(sig);
+#ifdef __CUDA_ARCH__
+        const double nrm = skip ? 0.0 : sig * rsqrt(sig);
+#else
+        const double nrm = sqrt(sig);
+#endif
+        const double alpha = (x0 > 0.0) ? -nrm : nrm;
         const double beta = skip ? 0.0 : 1.0 / (sig - x0 * alpha);     // 2 / v^T v
         EHDG_FOR_LANES(l, L)
-            vi[L] = skip ? 0.0 : ((l == k + 1) ? x0 - alpha : ((l > k + 1 && l < N) ? M[L][k] : 0.0));
-            shq[l] = vi[L];
-            if (l == k + 1) eown[L] = skip ? x0 : alpha;
-        EHDG_END_LANES
-        double pi[NLS];
-        EHDG_FOR_LANES(l, L)
-            double acc = 0.0;
-            if (l > k && l < N) {
 #pragma unroll
-                for (int j = k + 1; j < N; ++j) acc += M[L][j] * shq[j];
+            for (int h = 0; h < R; ++h) {
+                const int row = h * LG + l;
+                vi[L][h] = skip ? 0.0 : ((row == k + 1) ? x0 - alpha : ((row > k + 1 && row < N) ? M[L][h][k] : 0.0));
+                if (row < 32) shq[row] = vi[L][h];
+                if (row == k + 1) eown[L][h] = skip ? x0 : alpha;
             }
-            pi[L] = beta * acc;
-            part[L] = vi[L] * pi[L];
+        EHDG_END_LANES
+        EHDG_FOR_LANES(l, L)
+            double acc2 = 0.0;
+            double ps[R];
+#pragma unroll
+            for (int h = 0; h < R; ++h) ps[h] = 0.0;
+#pragma unroll
+            for (int j = k + 1; j < N; ++j) {
+                const double vj = shq[j];
+#pragma unroll
+                for (int h = 0; h < R; ++h) ps[h] += M[L][h][j] * vj;
+            }
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const int row = h * LG + l;
+                pi[L][h] = (row > k && row < N) ? beta * ps[h] : 0.0;
+                acc2 += vi[L][h] * pi[L][h];
+            }
+            part[L] = acc2;
         EHDG_END_LANES
         const double kk = 0.5 * beta * gc.sum(part);
         EHDG_FOR_LANES(l, L)
-            pi[L] -= kk * vi[L];            // q_i
-            shd[l] = pi[L];
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const int row = h * LG + l;
+                pi[L][h] -= kk * vi[L][h];            // q_i
+                if (row < 32) shd[row] = pi[L][h];
+            }
         EHDG_END_LANES
         EHDG_FOR_LANES(l, L)
-            if (l > k && l < N) {
 #pragma unroll
-                for (int j = k + 1; j < N; ++j) M[L][j] -= vi[L] * shd[j] + pi[L] * shq[j];
+            for (int j = k + 1; j < N; ++j) {
+                const double qj = shd[j], vj = shq[j];
+#pragma unroll
+                for (int h = 0; h < R; ++h) M[L][h][j] -= vi[L][h] * qj + pi[L][h] * vj;     // rows <= k: vi = pi = 0
             }
         EHDG_END_LANES
     }
     // ---- gather the tridiagonal matrix
     EHDG_FOR_LANES(l, L)
-        double d = 0.0;
 #pragma unroll
-        for (int j = 0; j < N; ++j)
-            if (j == l) d = M[L][j];
-        if (N >= 2 && l == N - 1) eown[L] = M[L][N - 2];
-        shd[l] = d;
-        she[l] = eown[L];
+        for (int h = 0; h < R; ++h) {
+            const int row = h * LG + l;
+            double d = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                if (j == row) d = M[L][h][j];
+            if (N >= 2 && row == N - 1) eown[L][h] = M[L][h][N - 2];
+            if (row < 32) {
+                shd[row] = d;
+                she[row] = eown[L][h];
+            }
+        }
     EHDG_END_LANES
     double dg[N], e2[N];
     double lo = 0.0, hi = 0.0, scale = 0.0;
@@ -607,8 +797,8 @@ EHDG_HD double fast_alpha_element(const Group<FastDims<P>::LG>& gc, const double
         lo *= is;
         hi = hi * is + 1e-15;
     }
-    // ---- multisection on "all eigenvalues below x" (signs of the Sturm sequence alternate)
-    constexpr int ROUNDS = LG == 32 ? 12 : (LG == 16 ? 14 : 18);
+    // ---- multisection on "all eigenvalues below x" (signs of the Sturm sequence alternate): LG + 1 sections per round
+    constexpr int ROUNDS = LG >= 32 ? 12 : (LG == 16 ? 14 : (LG == 8 ? 18 : 24));
     for (int it = 0; it < ROUNDS; ++it) {
         int below[NLS];
         const double step = (hi - lo) / (double)(LG + 1);

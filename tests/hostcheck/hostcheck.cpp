@@ -39,7 +39,7 @@ static double fast_alpha_host(const double* verts, const int* tri, int bonus, in
     std::vector<double> asm_tab, alpha_tab;
     build_tensors(P, 2 * P + bonus, asm_tab, alpha_tab);
     std::vector<double> sh(fast_alpha_scratch_doubles<P>());
-    Group<FastDims<P>::LG> gc{0, sh.data()};
+    Group<AlphaDims<P>::LG> gc{0, sh.data()};
     return fast_alpha_element<P>(gc, alpha_tab.data(), verts, tri, status);
 }
 
