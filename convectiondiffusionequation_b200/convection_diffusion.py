@@ -64,7 +64,7 @@ class Convection_Diffusion():
                 self.alphas = frame if len(self.alphas) == 0 else pd.concat([self.alphas, frame], ignore_index=True)
                 pipe.assemble_condense()                    # forms + assembly + rhs       (:357-383)
                 pipe.solve(restart=cfg.get('gmres_restart', 60), max_iters=cfg.get('gmres_max_iters', 20000),
-                           rtol=cfg.get('gmres_rtol', 1e-12))   # replaces Inverse(..., "pardiso")   (:385-387)
+                           rtol=cfg.get('gmres_rtol', 1e-12), method=cfg.get('solver', 'gmres'))   # replaces Inverse(..., "pardiso") (:385-387)
                 error, _ = pipe.errors()                    # recombination + L2 error     (:389-394)
                 ndof = pipe.ndof()
                 gi = pipe.gmres_info

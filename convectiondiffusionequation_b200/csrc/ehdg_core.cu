@@ -153,13 +153,14 @@ __global__ void prune_init_kernel(int ne, int nf, int nenr, const uint8_t* __res
 __global__ void __launch_bounds__(GEN_THREADS)
 alpha_general_kernel(Problem pb, RuleSet rs0, int n_gen, const int32_t* __restrict__ list_gen,
                      const double* __restrict__ verts, const int32_t* __restrict__ tris,
-                     const uint8_t* __restrict__ elem_active, double* __restrict__ lam, int32_t* status) {
+                     const uint8_t* __restrict__ elem_active, int skip_unenriched, double* __restrict__ lam, int32_t* status) {
     extern __shared__ double ws[];
     const int gi = blockIdx.x;
     if (gi >= n_gen) return;
     const int el = list_gen[gi];
     Coop co{(int)threadIdx.x, GEN_THREADS};
     const int volmask = elem_active ? elem_active[el] : 0;
+    if (skip_unenriched && volmask == 0) return;      // polynomial alpha: done by the tensor kernel (CTA-uniform exit)
     int st = 0;
     const double l = alpha_general(co, pb, rs0, verts, tris + 3 * el, volmask, el == 0, ws, &st);
     st = __syncthreads_or(st);
@@ -303,6 +304,7 @@ int ehdg_plan_create(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_mask,
     cudaStream_t st = (cudaStream_t)stream;
     ehdg_plan* p = new ehdg_plan();
     p->ctx = c;
+    p->forced = force_general ? 1 : 0;
     p->ne = m->ne;
     p->nf_poly = 3 * c->pb.nfl;
     p->nfmax = c->pb.nfmax;
@@ -405,11 +407,16 @@ int ehdg_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_
     }
     if (p->n_gen > 0) {
         alpha_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, c->ws_doubles * 8, sg>>>(c->pb, c->r0.rs, (int)p->n_gen, p->list_gen, m->verts,
-                                                                                  m->tris, c->pb.nenr ? elem_active : nullptr, lam, status);
+                                                                                  m->tris, c->pb.nenr ? elem_active : nullptr, (c->pb.nenr && !p->forced) ? 1 : 0, lam, status);
         EHDG_LAUNCH_CHECK();
     }
     if (p->n_poly > 0) {
-        int rc = fast_alpha(c, p, m, lam, status, st);
+        int rc = fast_alpha(c, p, m, p->list_poly, (int)p->n_poly, nullptr, lam, status, st);
+        if (rc) return rc;
+    }
+    if (p->n_gen > 0 && c->pb.nenr && !p->forced) {
+        // facet neighbours of the marked elements carry no volume enrichment: their alpha is the polynomial one
+        int rc = fast_alpha(c, p, m, p->list_gen, (int)p->n_gen, elem_active, lam, status, sg);
         if (rc) return rc;
     }
     if (fork) {

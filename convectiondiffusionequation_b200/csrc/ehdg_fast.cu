@@ -42,8 +42,8 @@ fast_assemble_kernel(Problem pb, RuleSet rs, const double* __restrict__ tab_g, i
 template <int P>
 __global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ALPHA_MINBLOCKS : 2))
 fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, const int32_t* __restrict__ list,
-                  const double* __restrict__ verts, const int32_t* __restrict__ tris, double* __restrict__ lam,
-                  int32_t* status) {
+                  const uint8_t* __restrict__ skip_if_set, const double* __restrict__ verts, const int32_t* __restrict__ tris,
+                  double* __restrict__ lam, int32_t* status) {
     typedef AlphaDims<P> D;
     constexpr int LG = D::LG, GPC = FAST_THREADS / LG;
     extern __shared__ double smem[];
@@ -57,7 +57,7 @@ fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, cons
         const int el = list[idx];
         int st = 0;
         const double l = fast_alpha_element<P>(gc, smem, verts, tris + 3 * el, &st);
-        if (live && gc.lane == 0) {
+        if (live && gc.lane == 0 && !(skip_if_set && skip_if_set[el])) {
             lam[el] = l;
             if (status) status[el] = st;
         }
@@ -65,7 +65,8 @@ fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, cons
 }
 
 template <int P>
-static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, double* lam, int32_t* status, cudaStream_t st) {
+static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const int32_t* list, int n, const uint8_t* skip_if_set,
+                        double* lam, int32_t* status, cudaStream_t st) {
     typedef AlphaDims<P> D;
     constexpr int GPC = FAST_THREADS / D::LG;
     const int tabd = c->tens.alpha_doubles;
@@ -74,11 +75,11 @@ static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, dou
     int per_sm = 1;
     EHDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_alpha_kernel<P>, FAST_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t need = (p->n_poly + GPC - 1) / GPC;
+    (void)p;
+    const int64_t need = ((int64_t)n + GPC - 1) / GPC;
     const int64_t cap = (int64_t)c->sm_count * per_sm;
     const int grid = (int)(need < cap ? need : cap);
-    fast_alpha_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->tens.alpha_tab, tabd, (int)p->n_poly, p->list_poly, m->verts, m->tris,
-                                                          lam, status);
+    fast_alpha_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->tens.alpha_tab, tabd, n, list, skip_if_set, m->verts, m->tris, lam, status);
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -136,8 +137,10 @@ void fast_free_tensors(ehdg_ctx* c) {
         default: set_error("unsupported order %d", p); return EHDG_ERR_ARG; \
     }
 
-int fast_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, double* lam, int32_t* status, cudaStream_t st) {
-#define CALL(PP) launch_alpha<PP>(c, p, m, lam, status, st)
+int fast_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const int32_t* list, int n, const uint8_t* skip_if_set, double* lam,
+               int32_t* status, cudaStream_t st) {
+    if (n <= 0) return EHDG_OK;
+#define CALL(PP) launch_alpha<PP>(c, p, m, list, n, skip_if_set, lam, status, st)
     EHDG_DISPATCH_P(c->pb.p, CALL)
 #undef CALL
 }

@@ -37,6 +37,10 @@ EHDG_HD bool opposite_signs(double a, double b) {
 #endif
 }
 
+// v[s] for s in {0,1,2} without dynamic indexing (keeps small per-edge arrays in registers)
+EHDG_HD double sel3(const double* v, int s) { return s == 0 ? v[0] : (s == 1 ? v[1] : v[2]); }
+EHDG_HD int sel3i(const int* v, int s) { return s == 0 ? v[0] : (s == 1 ? v[1] : v[2]); }
+
 // 16-byte shared-memory accesses (p must be 16-byte aligned): one wavefront moves two doubles
 EHDG_HD void ld2(const double* p, double& a, double& b) {
 #ifdef __CUDA_ARCH__
@@ -142,7 +146,7 @@ struct SortedGeom {
     double adet;
     double g00, g01, g11;       // Gram of grad lam_Q0, grad lam_Q1
     double c0, c1;              // b . grad lam_Qa
-    double len[3], h[3], bn[3]; // per sorted edge s (opposite Q_s)
+    double len[3], h[3], ih[3], bn[3]; // per sorted edge s (opposite Q_s); ih = 1/h
     double ga0[3], ga1[3];      // n_s . grad lam_Q0 / Q1
     int eloc[3];                // local edge number of sorted edge s
     int f0, f1;                 // local index of Q0, Q1
@@ -150,26 +154,35 @@ struct SortedGeom {
 };
 
 EHDG_HD void sorted_geom(const double* verts, const int* tri, double bx, double by, SortedGeom& sg) {
-    int vn[3];
-    double P[3][2];
-    for (int v = 0; v < 3; ++v) {
-        vn[v] = tri[v];
-        P[v][0] = verts[2 * vn[v]];
-        P[v][1] = verts[2 * vn[v] + 1];
-        sg.omx[v] = 1.0 - P[v][0];
-        sg.omy[v] = 1.0 - P[v][1];
+    // vertex triples (global number, x, y, local index), sorted by global number with three compare-exchanges;
+    // scalars only, so nothing is indexed dynamically (no local memory)
+    int n0 = tri[0], n1 = tri[1], n2 = tri[2];
+    double x0 = verts[2 * n0], y0 = verts[2 * n0 + 1];
+    double x1 = verts[2 * n1], y1 = verts[2 * n1 + 1];
+    double x2 = verts[2 * n2], y2 = verts[2 * n2 + 1];
+    sg.omx[0] = 1.0 - x0; sg.omy[0] = 1.0 - y0;
+    sg.omx[1] = 1.0 - x1; sg.omy[1] = 1.0 - y1;
+    sg.omx[2] = 1.0 - x2; sg.omy[2] = 1.0 - y2;
+    int i0 = 0, i1 = 1, i2 = 2;
+#define EHDG_CSWAP(na, xa, ya, ia, nb, xb, yb, ib)                 \
+    if (nb < na) {                                                 \
+        const int tn = na; na = nb; nb = tn;                       \
+        const double tx = xa; xa = xb; xb = tx;                    \
+        const double ty = ya; ya = yb; yb = ty;                    \
+        const int ti = ia; ia = ib; ib = ti;                       \
     }
-    int o0 = 0, o1 = 1, o2 = 2, t;
-    if (vn[o1] < vn[o0]) { t = o0; o0 = o1; o1 = t; }
-    if (vn[o2] < vn[o1]) { t = o1; o1 = o2; o2 = t; }
-    if (vn[o1] < vn[o0]) { t = o0; o0 = o1; o1 = t; }
-    sg.f0 = o0;
-    sg.f1 = o1;
-    const int o[3] = {o0, o1, o2};
+    EHDG_CSWAP(n0, x0, y0, i0, n1, x1, y1, i1)
+    EHDG_CSWAP(n1, x1, y1, i1, n2, x2, y2, i2)
+    EHDG_CSWAP(n0, x0, y0, i0, n1, x1, y1, i1)
+#undef EHDG_CSWAP
+    sg.f0 = i0;
+    sg.f1 = i1;
     // local vertex v is opposite local edge: V0 -> e1, V1 -> e0, V2 -> e2
-    for (int s = 0; s < 3; ++s) sg.eloc[s] = (o[s] == 0) ? 1 : (o[s] == 1 ? 0 : 2);
-    const double ax = P[o0][0] - P[o2][0], ay = P[o0][1] - P[o2][1];
-    const double bx_ = P[o1][0] - P[o2][0], by_ = P[o1][1] - P[o2][1];
+    sg.eloc[0] = (i0 == 0) ? 1 : (i0 == 1 ? 0 : 2);
+    sg.eloc[1] = (i1 == 0) ? 1 : (i1 == 1 ? 0 : 2);
+    sg.eloc[2] = (i2 == 0) ? 1 : (i2 == 1 ? 0 : 2);
+    const double ax = x0 - x2, ay = y0 - y2;
+    const double bx_ = x1 - x2, by_ = y1 - y2;
     const double det = ax * by_ - bx_ * ay;
     const double id = 1.0 / det;
     sg.adet = fabs(det);
@@ -193,6 +206,7 @@ EHDG_HD void sorted_geom(const double* verts, const int* tri, double bx, double 
 #endif
         const double nx = -gl[s][0] * ign, ny = -gl[s][1] * ign;
         sg.h[s] = ign;                      // = |detJ| / |e|   
+        sg.ih[s] = g2 * ign;
         sg.len[s] = sg.adet * (g2 * ign);
         sg.bn[s] = bx * nx + by * ny;
         sg.ga0[s] = nx * gl[0][0] + ny * gl[0][1];
@@ -260,7 +274,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     for (int s = 0; s < 3; ++s) {
         const double bn = sg.bn[s];
         const double pos = bn > 0.0 ? 1.0 : 0.0, neg = 1.0 - pos;
-        const double tau = pb.eps * (20.0 * lam) * (double)(P * P) / sg.h[s];
+        const double tau = pb.eps * (20.0 * lam) * (double)(P * P) * sg.ih[s];
         cvv[s] = sg.len[s] * (tau + pos * bn);
         cvf[s] = sg.len[s] * (-tau + neg * bn);
         cfv[s] = sg.len[s] * (-tau - pos * bn - pos);
@@ -365,10 +379,15 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             const int r = row < NF ? row : NF - 1;
             const int s = r / NFL, k = r % NFL;
             const double* tf = tab + TL.offF + (s * 3 * NP) * NFL + k;
+            const double c_fv = sel3(cfv, s), c_g0 = sel3(eg0, s), c_g1 = sel3(eg1, s);
 #pragma unroll
             for (int j = 0; j < NP; ++j)
-                afv[L][h][j] = cfv[s] * tf[j * NFL] + eg0[s] * tf[(NP + j) * NFL] + eg1[s] * tf[(2 * NP + j) * NFL];
-            aff[L][h] = cff[s] / (2.0 * k + 1.0);           // int_0^1 mu_k^2 dt
+                afv[L][h][j] = c_fv * tf[j * NFL] + c_g0 * tf[(NP + j) * NFL] + c_g1 * tf[(2 * NP + j) * NFL];
+            double rk = 1.0;                                 // 1 / (2k+1) = int_0^1 mu_k^2 dt, k <= 6
+#pragma unroll
+            for (int kk = 1; kk < NFL; ++kk)
+                if (k == kk) rk = 1.0 / (2.0 * kk + 1.0);
+            aff[L][h] = sel3(cff, s) * rk;
         }
     EHDG_END_LANES
 
@@ -458,7 +477,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
         if (store) {
             for (int gi = l; gi < NP * NF; gi += LG) {
                 const int c = gi / NF, col = gi % NF;
-                W[gi] = Xs[c * NXS + sinv[col / NFL] * NFL + col % NFL];
+                W[gi] = Xs[c * NXS + sel3i(sinv, col / NFL) * NFL + col % NFL];
             }
             for (int c = l; c < NP; c += LG) z[c] = Xs[c * NXS + NF];
         }
@@ -492,7 +511,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             const int row = h * LG + l;
             if (row < NF) {
                 const int s = row / NFL, k = row % NFL;
-                const int orow = sg.eloc[s] * NFL + k;
+                const int orow = sel3i(sg.eloc, s) * NFL + k;
 #pragma unroll
                 for (int s2 = 0; s2 < 3; ++s2)
 #pragma unroll

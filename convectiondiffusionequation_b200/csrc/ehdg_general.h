@@ -480,20 +480,37 @@ EHDG_HD double pencil_lambda_max(const Coop& co, int n, double* A, double* M, do
     const double scale = fabs(hi) > fabs(lo) ? fabs(hi) : fabs(lo);
     const double tiny = 1e-300 + 1e-32 * scale * scale;
     hi += 1e-14 * scale;
+    // (nl + 1)-section on the Sturm count: lane l tests the abscissa lo + (l + 1) step; with one lane this is
+    // plain bisection.  flags live in the v / pv scratch (2 n doubles >= nl bytes for nl <= 128, n >= 8; else serial).
+    unsigned char* flag = reinterpret_cast<unsigned char*>(v);
+    const int nsec = (co.nl > 1 && 2 * n * 8 >= co.nl) ? co.nl : 1;
     for (int it = 0; it < 200; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        if (!(mid > lo) || !(mid < hi)) break;
-        // number of eigenvalues > mid  == number of positive pivots of T - mid I... count negatives
+        const double step = (hi - lo) / (double)(nsec + 1);
+        const double x = lo + step * (double)((nsec > 1 ? co.lane : 0) + 1);
+        if (!(x > lo) || !(lo + step * (double)nsec < hi) || !(step > 0.0)) break;     // uniform: same lo, hi on every lane
+        // all eigenvalues below x  <=>  every pivot of the LDL^T of T - x I is negative
         int nneg = 0;
-        double q = dg[0] - mid;
+        double q = dg[0] - x;
         if (q < 0.0) ++nneg;
         for (int i = 1; i < n; ++i) {
             if (fabs(q) < tiny) q = (q < 0.0) ? -tiny : tiny;
-            q = (dg[i] - mid) - of[i - 1] * of[i - 1] / q;
+            q = (dg[i] - x) - of[i - 1] * of[i - 1] / q;
             if (q < 0.0) ++nneg;
         }
-        if (nneg == n) hi = mid;      // all eigenvalues below mid
-        else lo = mid;
+        int f = nsec;                      // first abscissa above the whole spectrum
+        if (nsec > 1) {
+            co.sync();
+            flag[co.lane] = (nneg == n) ? 1 : 0;
+            co.sync();
+            for (int l = 0; l < nsec; ++l)
+                if (flag[l]) { f = l; break; }
+        } else if (nneg == n) {
+            f = 0;
+        }
+        const double nlo = lo + step * (double)f;
+        const double nhi = (f < nsec) ? lo + step * (double)(f + 1) : hi;
+        lo = nlo;
+        hi = nhi;
     }
     co.sync();
     return 0.5 * (lo + hi);

@@ -69,6 +69,7 @@ struct ehdg_plan {
     int32_t* list_poly = nullptr;   // [n_poly]
     int32_t* list_gen = nullptr;    // [n_gen]
     int nf_poly, nfmax, n_p, nvmax;
+    int forced = 0;                 // every element on the quadrature path (cross-checks)
 };
 
 #define EHDG_SLOT_GEN 0x40000000
@@ -94,8 +95,9 @@ namespace ehdg {
 // polynomial-path kernels (ehdg_fast.cu)
 int fast_build_tensors(ehdg_ctx* ctx);
 void fast_free_tensors(ehdg_ctx* ctx);
-int fast_alpha(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, double* lam, int32_t* status,
-               cudaStream_t st);
+// list/n: elements to process; skip_if_set (optional u8 per element): elements whose byte is non-zero are left untouched
+int fast_alpha(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const int32_t* list, int n, const uint8_t* skip_if_set,
+               double* lam, int32_t* status, cudaStream_t st);
 int fast_assemble(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const double* lam, double* S,
                   double* g, double* W, double* z, int32_t* status, cudaStream_t st);
 int64_t fast_flops_per_element(const ehdg_ctx* ctx);

@@ -235,6 +235,7 @@ class EHDGPipeline:
         return self.alpha().assemble_condense()
 
     def solve(self, **gm):
+        """CSR build + Krylov solve (method = 'gmres' | 'dqgmres' | 'bicgstab') + back-solve"""
         return self.csr_build().gmres(**gm).backsolve()
 
     def ndof(self) -> int:

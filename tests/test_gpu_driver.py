@@ -41,19 +41,19 @@ def test_run_py_default_problem():
     from oracle import ehdg_oracle as orc
     old = dict(run.config)
     try:
-        run.config.update({'order': [1], 'mesh_size': [0.25]})
+        run.config.update({'order': [1]})            # run.py's own mesh_size 0.0625, first of its two orders
         table, alphas = run.main(write_csv=False)
     finally:
         run.config.clear()
         run.config.update(old)
     assert sorted(table['Type']) == ['ehdg', 'hdg']
-    mesh = mesh_for_size(0.25)
+    mesh = mesh_for_size(0.0625)
     for typ in ('hdg', 'ehdg'):
         o = orc.EHDGOracle(mesh.verts, mesh.tris, mesh.el2facet, mesh.facet2el, mesh.maxh, 1, orc.run_py_problem(enriched=typ == 'ehdg'))
         o.prune()
         err = o.l2_error(o.solve_condensed(o.alpha_all()))
         got = float(table[table['Type'] == typ]['Error'].iloc[0])
-        # ehdg: run.py's beta_y = 0.001 makes q(y) a near-parabola, the enriched system is singular to working
-        # precision and even two direct solves of it agree only to ~1e-2 as functions
-        assert abs(got - err) < (1e-8 if typ == 'hdg' else 2e-2) * err, (typ, got, err)
+        # ehdg: run.py's beta_y = 0.001 makes q(y) a near-parabola; the enriched system is ill-conditioned
+        # (cond ~ 1e16), so the two solves agree as functions to ~1e-6 only
+        assert abs(got - err) < (1e-8 if typ == 'hdg' else 1e-5) * err, (typ, got, err)
         assert int(table[table['Type'] == typ]['DOFs'].iloc[0]) == o.ndof
