@@ -224,7 +224,8 @@ int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out) {
     if ((rc = upload_rules(2 * c->pb.p, c->r0))) return rc;
     if ((rc = upload_rules(50 + c->pb.bonus, c->rerr))) return rc;
     c->ws_doubles = general_ws_doubles(c->pb, c->rb.rs.nq, c->rb.rs.nqf);
-    const int smem = c->ws_doubles * 8;
+    const int a_ws = alpha_ws_doubles(c->pb, c->r0.rs.nq, c->r0.rs.nqf);
+    const int smem = (c->ws_doubles > a_ws ? c->ws_doubles : a_ws) * 8;
     EHDG_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     EHDG_CUDA(cudaFuncSetAttribute(alpha_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     EHDG_CUDA(cudaFuncSetAttribute(assemble_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -406,7 +407,8 @@ int ehdg_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_
         EHDG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     }
     if (p->n_gen > 0) {
-        alpha_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, c->ws_doubles * 8, sg>>>(c->pb, c->r0.rs, (int)p->n_gen, p->list_gen, m->verts,
+        // the alpha integrators use the order-2p rule: a quarter of the assembly workspace, 3x the resident CTAs
+        alpha_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, alpha_ws_doubles(c->pb, c->r0.rs.nq, c->r0.rs.nqf) * 8, sg>>>(c->pb, c->r0.rs, (int)p->n_gen, p->list_gen, m->verts,
                                                                                   m->tris, c->pb.nenr ? elem_active : nullptr, (c->pb.nenr && !p->forced) ? 1 : 0, lam, status);
         EHDG_LAUNCH_CHECK();
     }

@@ -11,6 +11,7 @@
 // instantiation exists only for tests/hostcheck.
 #pragma once
 #include <string.h>
+#include <cmath>
 
 #include "ehdg_general.h"
 #include "ehdg_tensors.h"
@@ -30,10 +31,10 @@ namespace ehdg {
 // strict sign change between two doubles (both non-zero), on the integer pipe
 EHDG_HD bool opposite_signs(double a, double b) {
 #ifdef __CUDA_ARCH__
-    const int ha = __double2hiint(a), hb = __double2hiint(b);
-    return ((ha ^ hb) < 0) && a != 0.0 && b != 0.0;
+    // exact zeros are a set of measure zero in the bracket refinement; the sign bit alone decides
+    return (__double2hiint(a) ^ __double2hiint(b)) < 0;
 #else
-    return (a < 0.0 && b > 0.0) || (a > 0.0 && b < 0.0);
+    return std::signbit(a) != std::signbit(b);
 #endif
 }
 
@@ -475,9 +476,11 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     double srow[NLS][R][NF + 1];
     EHDG_FOR_LANES(l, L)
         if (store) {
-            for (int gi = l; gi < NP * NF; gi += LG) {
-                const int c = gi / NF, col = gi % NF;
-                W[gi] = Xs[c * NXS + sel3i(sinv, col / NFL) * NFL + col % NFL];
+            // lane l owns the output columns l, l + LG, ...: source column fixed per lane, rows by constant strides
+            for (int col = l; col < NF; col += LG) {
+                const int src = sel3i(sinv, col / NFL) * NFL + col % NFL;
+#pragma unroll
+                for (int c = 0; c < NP; ++c) W[c * NF + col] = Xs[c * NXS + src];
             }
             for (int c = l; c < NP; c += LG) z[c] = Xs[c * NXS + NF];
         }
@@ -527,7 +530,10 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     EHDG_END_LANES
     EHDG_FOR_LANES(l, L)
         if (store) {
-            for (int gi = l; gi < NF * NF; gi += LG) S[gi] = Ss[gi];
+            for (int col = l; col < NF; col += LG) {
+#pragma unroll
+                for (int r = 0; r < NF; ++r) S[r * NF + col] = Ss[r * NF + col];
+            }
             for (int r = l; r < NF; r += LG) gvec[r] = Ss[NF * NF + r];
         }
     EHDG_END_LANES

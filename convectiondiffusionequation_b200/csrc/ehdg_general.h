@@ -158,11 +158,27 @@ EHDG_HD void facet_shapes(const Problem& pb, const ElemGeom& g, const EdgeGeom& 
 // -------------------------------------------------------------------------------------------
 EHDG_HD int pad_odd(int n) { return n | 1; }
 
-EHDG_HD int general_ws_doubles(const Problem& pb, int nq, int nqf) {
-    const int ldq = pad_odd(nq), ldf = pad_odd(nqf);
-    int tabs = 3 * pb.nvmax * ldq + 2 * nq;
-    const int etabs = (2 * pb.nvmax + pb.nb) * ldf + nqf;
+// volume points are processed in chunks of GEN_QCHUNK so that the shape tables stay small (more resident CTAs)
+#define EHDG_GEN_QCHUNK 32
+EHDG_HD int general_tabs_doubles(const Problem& pb, int nq, int nqf) {
+    const int qc = nq < EHDG_GEN_QCHUNK ? nq : EHDG_GEN_QCHUNK;
+    int tabs = 3 * pb.nvmax * pad_odd(qc) + 2 * qc;
+    const int etabs = (2 * pb.nvmax + pb.nb) * pad_odd(nqf) + nqf;
     if (etabs > tabs) tabs = etabs;
+    return (tabs + 1) & ~1;
+}
+
+// workspace of alpha_general (whole order-2p rule at once)
+EHDG_HD int alpha_ws_doubles(const Problem& pb, int nq0, int nqf0) {
+    int tabs = 3 * pb.nvmax * pad_odd(nq0) + 2 * nq0;
+    const int etabs = (2 * pb.nvmax + pb.nb) * pad_odd(nqf0) + nqf0;
+    if (etabs > tabs) tabs = etabs;
+    tabs = (tabs + 1) & ~1;
+    return tabs + 3 * pb.nvmax * pb.nvmax + 6 * pb.nvmax + 8;
+}
+
+EHDG_HD int general_ws_doubles(const Problem& pb, int nq, int nqf) {
+    const int tabs = general_tabs_doubles(pb, nq, nqf);
     const int ldA = pb.nvmax + pb.nfmax + 1;
     // blocks (assemble) or a, m, work (alpha) or Gram (prune): assemble is the largest
     int blocks = pb.nvmax * ldA + pb.nfmax * pb.nvmax + pb.nfmax * pb.nfmax;
@@ -187,53 +203,55 @@ EHDG_HD int assemble_condense_general(const Coop& co, const Problem& pb, const R
     ElemGeom g;
     elem_geom(verts, tri, g);
     const int nv = pb.nvmax, nf = pb.nfmax, nb = pb.nb, nq = rs.nq, nqf = rs.nqf;
-    const int ldq = pad_odd(nq), ldf = pad_odd(nqf), ldA = nv + nf + 1;
-    int tabs = 3 * nv * ldq + 2 * nq;
-    {
-        const int etabs = (2 * nv + nb) * ldf + nqf;
-        if (etabs > tabs) tabs = etabs;
-    }
+    const int qc = nq < EHDG_GEN_QCHUNK ? nq : EHDG_GEN_QCHUNK;
+    const int ldq = pad_odd(qc), ldf = pad_odd(nqf), ldA = nv + nf + 1;
+    const int tabs = general_tabs_doubles(pb, nq, nqf);
     double* Tphi = ws;
     double* Tgx = Tphi + nv * ldq;
     double* Tgy = Tgx + nv * ldq;
     double* wq = Tgy + nv * ldq;
-    double* cq = wq + nq;
+    double* cq = wq + qc;
     double* Aug = ws + tabs;
     double* Afv = Aug + nv * ldA;
     double* Aff = Afv + nf * nv;
     int status = 0;
 
-    // ---- volume points
-    for (int q = co.lane; q < nq; q += co.nl) {
-        const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
-        vol_shapes(pb, g, volmask, l0, l1, Tphi + q, Tgx + q, Tgy + q, ldq);
-        wq[q] = rs.vw[q] * g.adet;
-        const double dx = l0 * g.omx[0] + l1 * g.omx[1] + l2 * g.omx[2];
-        const double dy = l0 * g.omy[0] + l1 * g.omy[1] + l2 * g.omy[2];
-        cq[q] = layer_expr_eval(pb.coeff, dx, dy);
-    }
     for (int idx = co.lane; idx < nf * nf; idx += co.nl) Aff[idx] = 0.0;
+    for (int idx = co.lane; idx < nv * ldA; idx += co.nl) Aug[idx] = 0.0;
     co.sync();
-    for (int idx = co.lane; idx < nv * (nv + 1); idx += co.nl) {
-        const int i = idx / (nv + 1), j = idx % (nv + 1);
-        const double* pi = Tphi + i * ldq;
-        const double* gxi = Tgx + i * ldq;
-        const double* gyi = Tgy + i * ldq;
-        double acc = 0.0;
-        if (j < nv) {
-            const double* pj = Tphi + j * ldq;
-            const double* gxj = Tgx + j * ldq;
-            const double* gyj = Tgy + j * ldq;
-            for (int q = 0; q < nq; ++q)
-                acc += wq[q] * (pb.eps * (gxi[q] * gxj[q] + gyi[q] * gyj[q])
-                                - (pb.bx * gxi[q] + pb.by * gyi[q]) * pj[q]);
-            Aug[i * ldA + j] = acc;
-        } else {
-            for (int q = 0; q < nq; ++q) acc += wq[q] * cq[q] * pi[q];
-            Aug[i * ldA + nv + nf] = acc;
+    // ---- volume points, one chunk of the rule at a time
+    for (int q0 = 0; q0 < nq; q0 += qc) {
+        const int nqc = nq - q0 < qc ? nq - q0 : qc;
+        for (int q = co.lane; q < nqc; q += co.nl) {
+            const double l0 = rs.vx[q0 + q], l1 = rs.vy[q0 + q], l2 = 1.0 - l0 - l1;
+            vol_shapes(pb, g, volmask, l0, l1, Tphi + q, Tgx + q, Tgy + q, ldq);
+            wq[q] = rs.vw[q0 + q] * g.adet;
+            const double dx = l0 * g.omx[0] + l1 * g.omx[1] + l2 * g.omx[2];
+            const double dy = l0 * g.omy[0] + l1 * g.omy[1] + l2 * g.omy[2];
+            cq[q] = layer_expr_eval(pb.coeff, dx, dy);
         }
+        co.sync();
+        for (int idx = co.lane; idx < nv * (nv + 1); idx += co.nl) {
+            const int i = idx / (nv + 1), j = idx % (nv + 1);
+            const double* pi = Tphi + i * ldq;
+            const double* gxi = Tgx + i * ldq;
+            const double* gyi = Tgy + i * ldq;
+            double acc = 0.0;
+            if (j < nv) {
+                const double* pj = Tphi + j * ldq;
+                const double* gxj = Tgx + j * ldq;
+                const double* gyj = Tgy + j * ldq;
+                for (int q = 0; q < nqc; ++q)
+                    acc += wq[q] * (pb.eps * (gxi[q] * gxj[q] + gyi[q] * gyj[q])
+                                    - (pb.bx * gxi[q] + pb.by * gyi[q]) * pj[q]);
+                Aug[i * ldA + j] += acc;
+            } else {
+                for (int q = 0; q < nqc; ++q) acc += wq[q] * cq[q] * pi[q];
+                Aug[i * ldA + nv + nf] += acc;
+            }
+        }
+        co.sync();
     }
-    co.sync();
 
     // ---- element boundary
     double* Ephi = ws;
@@ -528,12 +546,14 @@ EHDG_HD double alpha_general(const Coop& co, const Problem& pb, const RuleSet& r
     ElemGeom g;
     elem_geom(verts, tri, g);
     const int nv = pb.nvmax, nq = rs0.nq, nqf = rs0.nqf;
+    // the order-2p rule of the alpha integrators is small (nq0 <= 49): processed in one piece
     const int ldq = pad_odd(nq), ldf = pad_odd(nqf);
     int tabs = 3 * nv * ldq + 2 * nq;
     {
         const int etabs = (2 * nv + pb.nb) * ldf + nqf;
         if (etabs > tabs) tabs = etabs;
     }
+    tabs = (tabs + 1) & ~1;
     double* Tphi = ws;
     double* Tgx = Tphi + nv * ldq;
     double* Tgy = Tgx + nv * ldq;
@@ -634,11 +654,7 @@ EHDG_HD void prune_general(const Coop& co, const Problem& pb, const RuleSet& rs,
     ElemGeom g;
     elem_geom(verts, tri, g);
     const int nv = pb.nvmax, nb = pb.nb, nqf = rs.nqf, ldf = pad_odd(nqf);
-    int tabs = 3 * nv * pad_odd(rs.nq) + 2 * rs.nq;
-    {
-        const int etabs = (2 * nv + nb) * ldf + nqf;
-        if (etabs > tabs) tabs = etabs;
-    }
+    const int tabs = general_tabs_doubles(pb, rs.nq, nqf);
     double* Ephi = ws;
     double* Efs = Ephi + nv * ldf;
     double* we = Efs + nb * ldf;

@@ -75,7 +75,7 @@ double hc_alpha(const ehdg_problem* ep, const double* verts, const int* tri, int
                 int* status) {
     Problem pb = make_problem(*ep);
     HostRules hb(2 * pb.p + pb.bonus), h0(2 * pb.p);
-    std::vector<double> ws(general_ws_doubles(pb, hb.rs.nq, hb.rs.nqf));
+    std::vector<double> ws(alpha_ws_doubles(pb, h0.rs.nq, h0.rs.nqf));
     Coop co{0, 1};
     *status = 0;
     return alpha_general(co, pb, h0.rs, verts, tri, volmask, exclude_const, ws.data(), status);
