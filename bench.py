@@ -337,12 +337,21 @@ def main():
         return
 
     hbm, hbm_src, fp64, fp64_src = measured_peaks()
-    # dominant kernel: the polynomial-path assembly+condensation launch (one launch per step)
-    flops_elem = int(sizes.flops_poly_elem)
-    # split of flops_poly_elem between the two kernels is reported by the library as a whole; the
-    # roofline below is for the step (alpha kernel + assemble kernel), see DESIGN.md
+    # dominant kernel: fast_assemble_kernel<P> (one launch per step, ~55 % of the step; fast_alpha_kernel<P> ~37 %)
     n_poly, n_gen = int(ps.n_poly), int(ps.n_gen)
-    achieved_tf = n_poly * flops_elem / (ms_step * 1e-3) / 1e12
+    f_asm, f_alpha = int(sizes.flops_poly_assemble), int(sizes.flops_poly_alpha)
+    asm_ms = float(np.mean(k_asm)) if k_asm else None
+    alpha_ms = float(np.mean(k_alpha)) if k_alpha else None
+    achieved_tf = n_poly * f_asm / (asm_ms * 1e-3) / 1e12 if asm_ms else None
+    alpha_tf = n_poly * f_alpha / (alpha_ms * 1e-3) / 1e12 if alpha_ms else None
+    step_tf = n_poly * (f_asm + f_alpha) / (ms_step * 1e-3) / 1e12
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_assemble_traffic.json")))
+        if tr.get("workload") == args.workload:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     out_bytes = (ps.S_doubles + ps.g_doubles + ps.W_doubles + ps.z_doubles + ne) * 8 + ne * 60
     line = {
         "metric": "condensed EHDG elements/sec (FP64)", "value": value, "unit": "elements/s", "n_gpus": world,
@@ -353,15 +362,22 @@ def main():
                    "l2_flush": "explicit 256 MiB write between steps" if need_flush else "step outputs (S,W) exceed L2",
                    "elements_with_status_flags": status_bad},
         "stage_ms": {"alpha": t_alpha / args.steps, "assemble_condense": t_asm / args.steps},
-        "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64, "unit": "TFLOP/s", "frac": achieved_tf / fp64,
-                     "traffic": None, "peak_source": fp64_src, "flops_per_element": flops_elem,
-                     "note": "flops of the tensor algorithm actually executed (no credit for skipped quadrature work)",
+        "roofline": {"bound": "fp64", "kernel": f"fast_assemble_kernel<{order}>", "achieved": achieved_tf, "peak": fp64, "unit": "TFLOP/s",
+                     "frac": (achieved_tf / fp64) if achieved_tf else None, "traffic": traffic, "kernel_ms": asm_ms,
+                     "peak_source": fp64_src, "flops_per_element": f_asm,
+                     "note": "FP64-FMA-bound kernel (neither hbm nor tensor); flops = tensor algorithm actually executed, "
+                             "no credit for the quadrature work it avoids",
+                     "algorithmic_hbm_bytes_per_launch": int((ps.S_doubles + ps.g_doubles + ps.W_doubles + ps.z_doubles) * 8 + n_poly * 80),
+                     "alpha_kernel": {"kernel": f"fast_alpha_kernel<{order}>", "kernel_ms": alpha_ms, "achieved": alpha_tf,
+                                      "frac": (alpha_tf / fp64) if alpha_tf else None, "flops_per_element": f_alpha},
+                     "step": {"achieved": step_tf, "frac": step_tf / fp64, "flops_per_element": f_asm + f_alpha},
                      "quadrature_algorithm_flops_per_element": int(sizes.flops_quad_elem),
                      "quadrature_equivalent_tflops": value / world * int(sizes.flops_quad_elem) / 1e12,
+                     "quadrature_equivalent_frac": value / world * int(sizes.flops_quad_elem) / 1e12 / fp64,
                      "hbm_gbs_of_outputs": out_bytes / (ms_step * 1e-3) / 1e9, "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src},
         "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3},
-        "gpu_launches": int(args.steps * (2 + (2 if n_gen else 0))),
+        "gpu_launches": int(args.steps * (2 + (3 if n_gen else 0))),
         "clocks": clocks.summary(),
     }
     for sv in solves:

@@ -30,7 +30,8 @@ class Sizes(C.Structure):
     _fields_ = [("n_p", C.c_int32), ("nfl", C.c_int32), ("nb", C.c_int32), ("nvmax", C.c_int32),
                 ("nfmax", C.c_int32), ("nf_poly", C.c_int32), ("nq", C.c_int32), ("nqf", C.c_int32),
                 ("nq0", C.c_int32), ("nqf0", C.c_int32), ("nq_err", C.c_int32),
-                ("flops_poly_elem", C.c_int64), ("flops_quad_elem", C.c_int64)]
+                ("flops_poly_elem", C.c_int64), ("flops_quad_elem", C.c_int64),
+                ("flops_poly_alpha", C.c_int64), ("flops_poly_assemble", C.c_int64)]
 
 
 class PlanSizes(C.Structure):
@@ -58,6 +59,8 @@ SYMBOLS = {
     "ehdg_create": (C.c_int, [C.POINTER(Problem), C.POINTER(_P)]),
     "ehdg_destroy": (C.c_int, [_P]),
     "ehdg_get_sizes": (C.c_int, [_P, C.POINTER(Sizes)]),
+    "ehdg_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "ehdg_kernel_times_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ehdg_mark": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, _P, _P]),
     "ehdg_plan_create": (C.c_int, [_P, C.POINTER(Mesh), _P, C.c_int, C.POINTER(_P), _P]),
     "ehdg_plan_destroy": (C.c_int, [_P]),

@@ -250,7 +250,26 @@ int ehdg_destroy(ehdg_ctx* c) {
     if (c->side) cudaStreamDestroy(c->side);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (int i = 0; i < 4; ++i)
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     delete c;
+    return EHDG_OK;
+}
+
+int ehdg_kernel_timing(ehdg_ctx* c, int enable) {
+    if (!c) { set_error("ehdg_kernel_timing: null argument"); return EHDG_ERR_ARG; }
+    if (enable && !c->ev_k[0])
+        for (int i = 0; i < 4; ++i) EHDG_CUDA(cudaEventCreate(&c->ev_k[i]));
+    c->time_kernels = enable ? 1 : 0;
+    return EHDG_OK;
+}
+
+int ehdg_kernel_times_ms(ehdg_ctx* c, float* alpha_ms, float* assemble_ms) {
+    if (!c || !c->ev_k[0] || !alpha_ms || !assemble_ms) { set_error("ehdg_kernel_times_ms: timing not enabled"); return EHDG_ERR_ARG; }
+    EHDG_CUDA(cudaEventSynchronize(c->ev_k[1]));
+    EHDG_CUDA(cudaEventSynchronize(c->ev_k[3]));
+    EHDG_CUDA(cudaEventElapsedTime(alpha_ms, c->ev_k[0], c->ev_k[1]));
+    EHDG_CUDA(cudaEventElapsedTime(assemble_ms, c->ev_k[2], c->ev_k[3]));
     return EHDG_OK;
 }
 
@@ -269,6 +288,8 @@ int ehdg_get_sizes(const ehdg_ctx* c, ehdg_sizes* o) {
     o->nqf0 = c->r0.rs.nqf;
     o->nq_err = c->rerr.rs.nq;
     o->flops_poly_elem = fast_flops_per_element(c);
+    o->flops_poly_alpha = fast_flops_alpha(c);
+    o->flops_poly_assemble = fast_flops_assemble(c);
     // F_asm + F_cond of the quadrature algorithm on an unenriched element
     const int64_t nV = pb.n_p, ne_ = pb.nfl, nF = 3 * pb.nfl, nq = o->nq, nqf = o->nqf;
     o->flops_quad_elem = 4 * nV * nV * nq + 2 * nV * nq + 3 * nqf * (4 * nV * nV + 6 * nV * ne_ + 2 * ne_ * ne_)

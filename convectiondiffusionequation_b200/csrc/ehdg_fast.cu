@@ -75,11 +75,13 @@ static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, con
     int per_sm = 1;
     EHDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_alpha_kernel<P>, FAST_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    (void)p;
     const int64_t need = ((int64_t)n + GPC - 1) / GPC;
     const int64_t cap = (int64_t)c->sm_count * per_sm;
     const int grid = (int)(need < cap ? need : cap);
+    const bool timed = c->time_kernels && list == p->list_poly;
+    if (timed) EHDG_CUDA(cudaEventRecord(c->ev_k[0], st));
     fast_alpha_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->tens.alpha_tab, tabd, n, list, skip_if_set, m->verts, m->tris, lam, status);
+    if (timed) EHDG_CUDA(cudaEventRecord(c->ev_k[1], st));
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -98,8 +100,10 @@ static int launch_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
     const int64_t need = (p->n_poly + GPC - 1) / GPC;
     const int64_t cap = (int64_t)c->sm_count * per_sm;
     const int grid = (int)(need < cap ? need : cap);
+    if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[2], st));
     fast_assemble_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->pb, c->rb.rs, c->tens.asm_tab, tabd, c->tens.rhs_phi, (int)p->n_poly,
                                                              p->list_poly, m->verts, m->tris, lam, S, g, W, z, status);
+    if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[3], st));
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -154,23 +158,32 @@ int fast_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const dou
 
 // FMA = 2 flops; counts the arithmetic the polynomial path executes on the matrix data of one
 // element (geometry, coefficient evaluation and pivot search excluded), see DESIGN.md.
-int64_t fast_flops_per_element(const ehdg_ctx* c) {
-    const int64_t p = c->pb.p, NP = c->pb.n_p, NFL = p + 1, NF = 3 * NFL, NC = NP + NF + 1, nq = c->rb.rs.nq, N = NP - 1;
+int64_t fast_flops_assemble(const ehdg_ctx* c) {
+    const int64_t p = c->pb.p, NP = c->pb.n_p, NFL = p + 1, NF = 3 * NFL, NC = NP + NF + 1, nq = c->rb.rs.nq;
     int64_t f = 0;
     f += 2 * 14 * NP * NP;          // A_VV from 5 volume + 9 edge tensors
     f += 2 * 2 * 3 * NP * NF;       // A_VF and A_FV from 3 tensors each
     f += 2 * nq * NP;               // f_V
     for (int64_t k = 0; k < NP; ++k) f += 2 * NP * (NC - 1 - k);   // Gauss-Jordan on [A_VV | A_VF f_V]
     f += 2 * NF * NP * (NF + 1);    // Schur complement and g
-    // alpha: tensors, Cholesky, two triangular solves, Householder, Sturm multisection
-    f += 2 * 12 * N * N;
-    for (int64_t k = 0; k < N; ++k) f += 2 * (N - 1 - k) * (N - 1 - k) ;
+    return f;
+}
+
+int64_t fast_flops_alpha(const ehdg_ctx* c) {
+    // tensors, Cholesky, two triangular solves, Householder, Sturm multisection
+    const int64_t NP = c->pb.n_p, NF = 3 * (c->pb.p + 1), N = NP - 1;
+    int64_t f = 2 * 12 * N * N;
+    for (int64_t k = 0; k < N; ++k) f += 2 * (N - 1 - k) * (N - 1 - k);
     for (int64_t j = 0; j < N; ++j) f += 2 * 2 * (N - 1 - j) * N;
     for (int64_t k = 0; k + 2 < N; ++k) f += 6 * (N - 1 - k) * (N - 1 - k);
-    const int64_t LG = (NP > NF ? NP : NF) <= 8 ? 8 : ((NP > NF ? NP : NF) <= 16 ? 16 : 32);
-    const int64_t rounds = LG == 32 ? 12 : (LG == 16 ? 14 : 18);
+    const int64_t M = NP > NF ? NP : NF;
+    const bool two = c->pb.p <= 4 && EHDG_ALPHA_R == 2;
+    const int64_t LG = two ? (M <= 8 ? 4 : (M <= 16 ? 8 : 16)) : (M <= 8 ? 8 : (M <= 16 ? 16 : 32));
+    const int64_t rounds = LG >= 32 ? 12 : (LG == 16 ? 14 : (LG == 8 ? 18 : 24));
     f += rounds * LG * N * 5;
     return f;
 }
+
+int64_t fast_flops_per_element(const ehdg_ctx* c) { return fast_flops_alpha(c) + fast_flops_assemble(c); }
 
 }  // namespace ehdg

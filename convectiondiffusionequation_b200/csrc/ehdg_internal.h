@@ -58,6 +58,9 @@ struct ehdg_ctx {
     ehdg::DistComm* dist = nullptr;   // NCCL communicator + row partition of the distributed facet solve
     cudaStream_t side = nullptr;      // the general (enriched) kernels run beside the polynomial ones
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // optional CUDA-event timing of the two polynomial-path kernels on their launching stream
+    int time_kernels = 0;
+    cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};   // alpha start/stop, assemble start/stop
 };
 
 struct ehdg_plan {
@@ -101,4 +104,6 @@ int fast_alpha(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, cons
 int fast_assemble(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const double* lam, double* S,
                   double* g, double* W, double* z, int32_t* status, cudaStream_t st);
 int64_t fast_flops_per_element(const ehdg_ctx* ctx);
+int64_t fast_flops_alpha(const ehdg_ctx* ctx);
+int64_t fast_flops_assemble(const ehdg_ctx* ctx);
 }  // namespace ehdg

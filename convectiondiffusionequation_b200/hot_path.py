@@ -226,6 +226,16 @@ class EHDGPipeline:
         e = err2.cpu().numpy()
         return float(np.sqrt(e[0])), float(np.sqrt(e[1]))
 
+    def kernel_timing(self, enable=True):
+        _lib.check(self.lib.ehdg_kernel_timing(self.ctx, int(enable)), "ehdg_kernel_timing")
+        return self
+
+    def kernel_times_ms(self):
+        """(alpha kernel, assemble+condense kernel) durations of the most recent polynomial-path launches"""
+        a, b = C.c_float(0), C.c_float(0)
+        _lib.check(self.lib.ehdg_kernel_times_ms(self.ctx, C.byref(a), C.byref(b)), "ehdg_kernel_times_ms")
+        return float(a.value), float(b.value)
+
     # ------------------------------------------------------------------ whole path
     def setup(self, prune_threshold=1e-5):
         return self.mark().prune(prune_threshold)

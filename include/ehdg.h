@@ -81,6 +81,8 @@ typedef struct {
     int32_t nq_err;   /* points of the order 50+bonus rule (convection_diffusion.py:393-394) */
     int64_t flops_poly_elem;   /* flops the polynomial path spends per element (alpha + assemble + condense) */
     int64_t flops_quad_elem;   /* SURVEY 8(d) quadrature-algorithm flops per unenriched element */
+    int64_t flops_poly_alpha;    /* ... of which the alpha kernel */
+    int64_t flops_poly_assemble; /* ... and the assemble + condense kernel */
 } ehdg_sizes;
 
 const char* ehdg_version(void);
@@ -90,6 +92,10 @@ const char* ehdg_last_error(void);
 int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out);
 int ehdg_destroy(ehdg_ctx* ctx);
 int ehdg_get_sizes(const ehdg_ctx* ctx, ehdg_sizes* out);
+/* CUDA-event timing of the two polynomial-path kernels (recorded on the launching stream); off by default.
+ * ehdg_kernel_times_ms returns the durations of the most recent launches. */
+int ehdg_kernel_timing(ehdg_ctx* ctx, int enable);
+int ehdg_kernel_times_ms(ehdg_ctx* ctx, float* alpha_ms, float* assemble_ms);
 
 /* a1  mark_elements / mark_element_bnd  (enrichment_proxy.py:201-208, :228-251)
  * vert_flags u8[n_enrich][nv]: the Python predicates evaluated on the vertices (host side).
