@@ -213,6 +213,8 @@ def main():
     barrier()
     # ---- timed region: K steps, device time per stage, clocks sampled meanwhile
     t_alpha, t_asm = 0.0, 0.0
+    k_alpha, k_asm = [], []          # the two polynomial-path kernels alone (events recorded inside libehdg)
+    P.kernel_timing(True)
     with ClockSampler(local) as clocks:
         barrier()
         e0, e3 = ev(), ev()
@@ -228,6 +230,10 @@ def main():
             P.assemble_condense()
             a2.record()
             stage.append((a0, a1, a2))
+            if P.plan_sizes.n_poly > 0:
+                ka, kb = P.kernel_times_ms()      # waits for this step's kernels: the next step starts after it anyway
+                k_alpha.append(ka)
+                k_asm.append(kb)
         e3.record()
         barrier()
     for a0, a1, a2 in stage:
