@@ -27,3 +27,21 @@ def vertex_flags(verts: np.ndarray, indicators, mesh_size: float) -> np.ndarray:
             out[i] = np.fromiter((bool(ind(float(a), float(b), mesh_size)) for a, b in zip(xs, ys)),
                                  dtype=bool, count=xs.shape[0])
     return out
+
+
+def vertex_flags_device(verts_dev, indicators, mesh_size):
+    """Same flags evaluated on the device copy of the vertices (torch): the predicates of run.py:45 are plain
+    comparisons, which torch tensors support; returns None when a predicate cannot take tensors (the caller
+    then evaluates it on the host with vertex_flags)."""
+    import torch
+    xs, ys = verts_dev[:, 0], verts_dev[:, 1]
+    out = torch.zeros((len(indicators), verts_dev.shape[0]), dtype=torch.uint8, device=verts_dev.device)
+    try:
+        for i, ind in enumerate(indicators):
+            r = ind(xs, ys, mesh_size)
+            if not torch.is_tensor(r) or r.shape != xs.shape:
+                return None
+            out[i] = r.to(torch.uint8)
+    except Exception:
+        return None
+    return out

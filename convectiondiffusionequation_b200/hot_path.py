@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from .coefficients import LayerExpr
-from .enrichment_proxy import vertex_flags
+from .enrichment_proxy import vertex_flags, vertex_flags_device
 from .mesh import TriMesh
 
 
@@ -102,8 +102,10 @@ class EHDGPipeline:
         self.elem_mask = torch.zeros(ne, dtype=torch.uint8, device=self.dev)
         self.facet_mask = torch.zeros((nf + 3) // 4 * 4, dtype=torch.uint8, device=self.dev)
         if self.nenr:
-            vf = vertex_flags(m.verts, self.spec.enrich_domain_ind, m.maxh)
-            self.vert_flags = torch.from_numpy(vf).to(self.dev)
+            self.vert_flags = vertex_flags_device(self.verts, self.spec.enrich_domain_ind, m.maxh)
+            if self.vert_flags is None:            # predicate needs Python scalars: evaluate on the host copy
+                vf = vertex_flags(m.verts, self.spec.enrich_domain_ind, m.maxh)
+                self.vert_flags = torch.from_numpy(vf).to(self.dev)
             _lib.check(self.lib.ehdg_mark(self.ctx, C.byref(self.cmesh), _ptr(self.vert_flags), _ptr(self.elem_mask),
                                           _ptr(self.facet_mask), self._stream()), "ehdg_mark")
         if self.plan is not None:

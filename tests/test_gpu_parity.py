@@ -51,6 +51,9 @@ def test_marks_and_pruning(n, order, eps, kind):
     P = _pipe(mesh, spec).setup()
     assert np.array_equal(P.elem_mask.cpu().numpy(), em)
     assert np.array_equal(P.facet_mask.cpu().numpy()[:mesh.nf], fm)
+    # device-evaluated predicates == host-evaluated ones
+    from convectiondiffusionequation_b200.enrichment_proxy import vertex_flags
+    assert np.array_equal(P.vert_flags.cpu().numpy(), vertex_flags(mesh.verts, spec.enrich_domain_ind, mesh.maxh))
     assert np.array_equal(P.elem_active.cpu().numpy(), ea)
     assert np.array_equal(P.facet_active.cpu().numpy()[:mesh.nf], fa)
     # the reference's per-dof `factor` values (conv_diff.py:296-301)
