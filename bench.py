@@ -140,11 +140,31 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "elements/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
             "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly one JSON line: everything else that libraries print there (NCCL's version banner,
+    torchrun notices) is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -399,7 +419,7 @@ def main():
                                     "sample": info["sample"]}
         except Exception as exc:          # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "elements/s", "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
