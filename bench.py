@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--solve-workload", default="ehdg_p4_eps1e-6_structured_1M",
                     help="mesh of the one-off solve leg ('same' = the timed workload; the 4M solve takes minutes)")
     ap.add_argument("--rtol", type=float, default=1e-8)
-    ap.add_argument("--restart", type=int, default=40)
+    ap.add_argument("--restart", type=int, default=16)
     ap.add_argument("--sweeps", type=int, default=1, help="block-Jacobi sweeps per preconditioner application")
     ap.add_argument("--solve-type", default="hdg", choices=["hdg", "ehdg", "both"],
                     help="system of the one-off solve: plain HDG (well posed at every size) and/or the enriched one")

@@ -188,13 +188,92 @@ spmv_kernel(int row0, int n_rows, const int64_t* __restrict__ rowptr, const int3
     if (r < n_rows && lane == 0) y[r] = acc;
 }
 
+// Facet-block SpMV.  All rows of a facet share one column set (the dofs of its <= 5 neighbour facets, ascending), and
+// csr_fill_kernel lays the facet's values out as a dense rows x len block at blk_base[f].  One warp per facet: lanes own
+// columns, x is gathered once per facet, and neither colind nor rowptr is read (8 B/nnz instead of 12 B/nnz).
+template <int NBM, int CHUNKS>
+__global__ void __launch_bounds__(256)
+spmv_facet_kernel(int nf, int row0, int row1, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
+                  const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len, const double* __restrict__ vals,
+                  const double* __restrict__ x, double* __restrict__ y) {
+    const int f = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= nf) return;
+    // first level of the dependency chain: everything addressed by f alone
+    const int g = lane < 5 ? nbr[5 * f + lane] : -1;
+    const int r0 = row_start[f], rows = row_start[f + 1] - r0;
+    const int len = nbr_len[f];
+    const int64_t base = blk_base[f];
+    if (rows == 0 || r0 + rows <= row0 || r0 >= row1) return;
+    // second level: the matrix block and the neighbours' column ranges
+    const double* __restrict__ blk = vals + base;
+    double a[CHUNKS][NBM];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+        for (int i = 0; i < NBM; ++i) a[c][i] = (i < rows && lane + 32 * c < len) ? blk[i * len + lane + 32 * c] : 0.0;
+    int c0 = 0, ng = 0;
+    if (g >= 0) {
+        c0 = row_start[g];
+        ng = row_start[g + 1] - c0;
+    }
+    int off = ng;                                          // exclusive scan over lanes 0..4
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, off, d);
+        if (lane >= d) off += t;
+    }
+    off -= ng;
+    // third level: x gathered once per facet
+    double xv[CHUNKS];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) xv[c] = 0.0;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+        const int ot = __shfl_sync(0xffffffffu, off, t), nt = __shfl_sync(0xffffffffu, ng, t), ct = __shfl_sync(0xffffffffu, c0, t);
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int l = lane + 32 * c - ot;
+            if (l >= 0 && l < nt) xv[c] = __ldg(x + ct + l);
+        }
+    }
+    double out = 0.0;
+#pragma unroll
+    for (int i = 0; i < NBM; ++i) {
+        if (i < rows) {                                   // warp-uniform
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) v += a[c][i] * xv[c];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == i) out = v;
+        }
+    }
+    if (lane < rows && r0 + lane >= row0 && r0 + lane < row1) y[r0 + lane] = out;
+}
+
+static bool spmv_use_csr_kernel() {
+    static const bool v = [] { const char* e = getenv("EHDG_SPMV_CSR"); return e && e[0] == '1'; }();
+    return v;
+}
+
 static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, double* y, cudaStream_t st, int64_t row0 = 0,
                        int64_t row1 = -1) {
     if (row1 < 0) row1 = A->n_rows;
     if (row1 <= row0) return EHDG_OK;
-    constexpr int TPR = 8;
-    const int64_t threads = (row1 - row0) * TPR;
-    spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)row0, (int)row1, A->rowptr, A->colind, vals, x, y);
+    if (spmv_use_csr_kernel()) {
+        constexpr int TPR = 8;
+        const int64_t threads = (row1 - row0) * TPR;
+        spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)row0, (int)row1, A->rowptr, A->colind, vals, x, y);
+    } else {
+        const int64_t threads = (int64_t)A->nf * 32;
+        const unsigned gb = (unsigned)((threads + 255) / 256);
+        if (A->nb <= 6)      // rows <= 6, row length <= 30: one column per lane
+            spmv_facet_kernel<6, 1><<<gb, 256, 0, st>>>(A->nf, (int)row0, (int)row1, A->row_start, A->blk_base, A->nbr, A->nbr_len, vals, x, y);
+        else
+            spmv_facet_kernel<EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH, 2><<<gb, 256, 0, st>>>(A->nf, (int)row0, (int)row1, A->row_start, A->blk_base,
+                                                                                            A->nbr, A->nbr_len, vals, x, y);
+    }
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -339,67 +418,70 @@ __global__ void bj_apply_kernel(int row0, int n_rows, int nbs, const int32_t* __
 // ---------------------------------------------------------------------------------------------
 // GMRES vector kernels: tiles of KT Krylov vectors, deterministic two-stage reductions
 // ---------------------------------------------------------------------------------------------
-constexpr int KT = 8;
+constexpr int KT = 8;                  // Krylov vectors handled by one launch (stride of `partial`)
 constexpr int RED_BLOCKS = 1184;      // 148 SMs x 8
 constexpr int RED_THREADS = 256;
 
-// partial[b][t] = sum over the rows of block b of V[t][row] * w[row],  t < kt
+// partial[b][t] = sum over the rows of block b of V[t][row] * w[row],  t < kt <= K.
+// (Wider tiles were measured: 48 vectors per launch costs 173 registers and halves the throughput.)
+template <int K>
 __global__ void __launch_bounds__(RED_THREADS)
 multi_dot_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int kt, const double* __restrict__ w,
                  double* __restrict__ partial) {
-    double acc[KT];
+    double acc[K];
 #pragma unroll
-    for (int t = 0; t < KT; ++t) acc[t] = 0.0;
+    for (int t = 0; t < K; ++t) acc[t] = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double wi = w[i];
 #pragma unroll
-        for (int t = 0; t < KT; ++t)
+        for (int t = 0; t < K; ++t)
             if (t < kt) acc[t] += V[t * ldv + i] * wi;
     }
-    __shared__ double red[RED_THREADS / 32][KT];
+    __shared__ double red[RED_THREADS / 32][K];
 #pragma unroll
-    for (int t = 0; t < KT; ++t) {
+    for (int t = 0; t < K; ++t) {
         double v = acc[t];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
     }
     __syncthreads();
-    if (threadIdx.x < KT) {
+    if (threadIdx.x < K) {
         double v = 0.0;
         for (int wv = 0; wv < RED_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
         partial[(size_t)blockIdx.x * KT + threadIdx.x] = v;
     }
 }
 
-// out[t] (+)= sum_b partial[b][t], fixed order
+// out[t] (+)= sum_b partial[b][t], fixed order; block t reduces column t
 __global__ void reduce_partials_kernel(int nblocks, int kt, const double* __restrict__ partial, double* __restrict__ out,
                                        int accumulate) {
     __shared__ double red[256];
-    for (int t = 0; t < kt; ++t) {
-        double v = 0.0;
-        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partial[(size_t)b * KT + t];
-        red[threadIdx.x] = v;
-        __syncthreads();
-        for (int d = 128; d > 0; d >>= 1) {
-            if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) out[t] = accumulate ? out[t] + red[0] : red[0];
+    const int t = blockIdx.x;
+    if (t >= kt) return;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partial[(size_t)b * KT + t];
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
         __syncthreads();
     }
+    if (threadIdx.x == 0) out[t] = accumulate ? out[t] + red[0] : red[0];
 }
 
-// w -= sum_t h[t] V[t]
-__global__ void multi_axpy_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int kt, const double* __restrict__ h,
-                                  double* __restrict__ w) {
-    double hh[KT];
+// w -= sum_t h[t] V[t],  t < kt <= K
+template <int K>
+__global__ void __launch_bounds__(RED_THREADS)
+multi_axpy_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int kt, const double* __restrict__ h,
+                  double* __restrict__ w) {
+    double hh[K];
 #pragma unroll
-    for (int t = 0; t < KT; ++t) hh[t] = t < kt ? h[t] : 0.0;
+    for (int t = 0; t < K; ++t) hh[t] = t < kt ? h[t] : 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double wi = w[i];
 #pragma unroll
-        for (int t = 0; t < KT; ++t)
+        for (int t = 0; t < K; ++t)
             if (t < kt) wi -= hh[t] * V[t * ldv + i];
         w[i] = wi;
     }
@@ -467,6 +549,80 @@ __global__ void residual_kernel(int64_t n, const double* __restrict__ b, double*
         r[i] = b[i] - r[i];
 }
 
+// ---- DQGMRES ring kernels: vector t of a tile lives in slot (s0 + t) % ring of V ----
+template <int K>
+__global__ void __launch_bounds__(RED_THREADS)
+ring_dot_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring, int s0, int kt, const double* __restrict__ w,
+                double* __restrict__ partial) {
+    double acc[K];
+    const double* vp[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        acc[t] = 0.0;
+        vp[t] = V + (int64_t)((s0 + (t < kt ? t : 0)) % ring) * ldv;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+#pragma unroll
+        for (int t = 0; t < K; ++t)
+            if (t < kt) acc[t] += vp[t][i] * wi;
+    }
+    __shared__ double red[RED_THREADS / 32][K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        double v = acc[t];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double v = 0.0;
+        for (int wv = 0; wv < RED_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
+        partial[(size_t)blockIdx.x * KT + threadIdx.x] = v;
+    }
+}
+
+// out = in - sum_t h[t] V[slot t].  MODE 1: also partial[b][0] = sum of out^2 over the rows of block b.
+// MODE 2: out *= inv_d, then u += gamma * out (the DQGMRES direction and solution update).
+template <int K, int MODE>
+__global__ void __launch_bounds__(RED_THREADS)
+ring_axpy_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring, int s0, int kt, const double* __restrict__ h,
+                 const double* in, double* out, double* __restrict__ partial, double inv_d, double gamma, double* __restrict__ u) {
+    double hh[K];
+    const double* vp[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        hh[t] = t < kt ? h[t] : 0.0;
+        vp[t] = V + (int64_t)((s0 + (t < kt ? t : 0)) % ring) * ldv;
+    }
+    double nrm = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double wi = in[i];
+#pragma unroll
+        for (int t = 0; t < K; ++t)
+            if (t < kt) wi -= hh[t] * vp[t][i];
+        if (MODE == 2) {
+            wi *= inv_d;
+            u[i] += gamma * wi;
+        }
+        out[i] = wi;
+        if (MODE == 1) nrm += wi * wi;
+    }
+    if (MODE == 1) {
+        __shared__ double red[RED_THREADS / 32];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, d);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double v = 0.0;
+            for (int wv = 0; wv < RED_THREADS / 32; ++wv) v += red[wv];
+            partial[(size_t)blockIdx.x * KT] = v;
+        }
+    }
+}
+
 struct VecOps {
     cudaStream_t st;
     double* partial;
@@ -480,17 +636,53 @@ struct VecOps {
     int dots(const double* V, int64_t ldv, int k, const double* w, double* out) const {
         for (int t0 = 0; t0 < k; t0 += KT) {
             const int kt = k - t0 < KT ? k - t0 : KT;
-            multi_dot_kernel<<<grid(), RED_THREADS, 0, st>>>(n, V + t0 * ldv, ldv, kt, w, partial);
-            reduce_partials_kernel<<<1, 256, 0, st>>>(grid(), kt, partial, out + t0, 0);
+            const double* Vt = V + t0 * ldv;
+            if (kt <= 2) multi_dot_kernel<2><<<grid(), RED_THREADS, 0, st>>>(n, Vt, ldv, kt, w, partial);
+            else multi_dot_kernel<KT><<<grid(), RED_THREADS, 0, st>>>(n, Vt, ldv, kt, w, partial);
+            reduce_partials_kernel<<<kt, 256, 0, st>>>(grid(), kt, partial, out + t0, 0);
         }
         EHDG_LAUNCH_CHECK();
         if (dc) return dc->allreduce_sum(out, (size_t)k, st);      // one collective per batch of dot products
         return EHDG_OK;
     }
+    // ring variants: vectors in slots (s0 + t) % ring, t < k.  out[0..k) = V^T w (summed over the ranks)
+    int ring_dots(const double* V, int64_t ldv, int ring, int s0, int k, const double* w, double* out) const {
+        for (int t0 = 0; t0 < k; t0 += KT) {
+            const int kt = k - t0 < KT ? k - t0 : KT;
+            if (kt <= 2) ring_dot_kernel<2><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, (s0 + t0) % ring, kt, w, partial);
+            else ring_dot_kernel<KT><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, (s0 + t0) % ring, kt, w, partial);
+            reduce_partials_kernel<<<kt, 256, 0, st>>>(grid(), kt, partial, out + t0, 0);
+        }
+        EHDG_LAUNCH_CHECK();
+        if (dc) return dc->allreduce_sum(out, (size_t)k, st);
+        return EHDG_OK;
+    }
+    // out = in - sum h_t V_t, last tile per `mode`: 1 = nrm2[0] = ||out||^2 (summed over the ranks); 2 = out *= inv_d, u += gamma out
+    int ring_axpys(const double* V, int64_t ldv, int ring, int s0, int k, const double* h, const double* in, double* out, int mode,
+                   double* nrm2, double inv_d, double gamma, double* u) const {
+        int t0 = 0;
+        do {
+            const int kt = k - t0 < KT ? k - t0 : KT;
+            const bool last = t0 + kt >= k;
+            const int sl = (s0 + t0) % ring;
+            const double* src = t0 == 0 ? in : out;
+            if (!last) ring_axpy_kernel<KT, 0><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
+            else if (mode == 1) ring_axpy_kernel<KT, 1><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
+            else if (mode == 2) ring_axpy_kernel<KT, 2><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, inv_d, gamma, u);
+            else ring_axpy_kernel<KT, 0><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
+            t0 += kt;
+        } while (t0 < k);
+        if (mode == 1) reduce_partials_kernel<<<1, 256, 0, st>>>(grid(), 1, partial, nrm2, 0);
+        EHDG_LAUNCH_CHECK();
+        if (mode == 1 && dc) return dc->allreduce_sum(nrm2, 1, st);
+        return EHDG_OK;
+    }
     int axpys(const double* V, int64_t ldv, int k, const double* h, double* w) const {
         for (int t0 = 0; t0 < k; t0 += KT) {
             const int kt = k - t0 < KT ? k - t0 : KT;
-            multi_axpy_kernel<<<grid(), RED_THREADS, 0, st>>>(n, V + t0 * ldv, ldv, kt, h + t0, w);
+            const double* Vt = V + t0 * ldv;
+            if (kt <= 2) multi_axpy_kernel<2><<<grid(), RED_THREADS, 0, st>>>(n, Vt, ldv, kt, h + t0, w);
+            else multi_axpy_kernel<KT><<<grid(), RED_THREADS, 0, st>>>(n, Vt, ldv, kt, h + t0, w);
         }
         EHDG_LAUNCH_CHECK();
         return EHDG_OK;
@@ -766,7 +958,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     double* d_nrm = dsc + 2 * (m + 2);  // 1
     double* d_y = d_nrm + 4;            // m
     double* hbuf = nullptr;
-    EHDG_CUDA(cudaMallocHost(&hbuf, sizeof(double) * (size_t)(2 * (m + 2) + 8)));
+    EHDG_CUDA(cudaMallocHost(&hbuf, sizeof(double) * (size_t)(2 * (m + 2) + 16)));
     EHDG_CUDA(cudaMemsetAsync(yhat, 0, sizeof(double) * (size_t)n, st));
     VecOps vo{st, partial, n, dc};
     // w = A~ P(v):  P leaves the bulk entries (their M^-1 is folded into A~) and solves the strip block
@@ -893,78 +1085,120 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         // ---- DQGMRES(k) (Saad, Alg. 6.13): incomplete orthogonalisation against the last k Krylov vectors with a
         // progressively updated solution.  No restart: the Krylov space keeps growing, which the facet systems need
         // (information has to cross the mesh; GMRES(m) with m below that length stagnates), at the per-iteration
-        // cost of GMRES(k).
+        // cost of GMRES(k).  The quasi-residual is only an estimate and the truncated recurrence can break down, so the
+        // iteration is guarded: the iterate is snapshotted while the estimate improves, a blow-up rolls back to the
+        // snapshot, and every cycle (re)starts from the true residual of the current iterate.
         const int k = m, ring = m + 1;
         double* Vr = V;                              // ring of k+1 Krylov vectors
         double* Pr = V + (size_t)ring * n;           // ring of k+1 direction vectors
         double* u = yhat;
-        std::vector<double> cq(max_iters + 2, 1.0), sq(max_iters + 2, 0.0), t(k + 3), coef(k + 2);
-        EHDG_CUDA(cudaMemcpyAsync(w, rhs, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-        if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
-        scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, Vr);          // v_0 in slot 0
-        double gamma = bnorm;
-        for (int it = 0; it < max_iters; ++it, ++iters) {
-            const int lo = it - k + 1 > 0 ? it - k + 1 : 0;                     // window of Krylov vectors lo..it
-            if ((rc = apply_prec_op(Vr + (size_t)(it % ring) * n, w))) return rc;
-            // h_i = (w, v_i), i = lo..it : up to two contiguous slot ranges of the ring
-            const int s_lo = lo % ring, s_hi = it % ring;
-            if (s_lo <= s_hi) {
-                if ((rc = vo.dots(Vr + (size_t)s_lo * n, n, s_hi - s_lo + 1, w, d_h1))) return rc;
-                if ((rc = vo.axpys(Vr + (size_t)s_lo * n, n, s_hi - s_lo + 1, d_h1, w))) return rc;
-            } else {
-                const int n1 = ring - s_lo;
-                if ((rc = vo.dots(Vr + (size_t)s_lo * n, n, n1, w, d_h1))) return rc;
-                if ((rc = vo.dots(Vr, n, s_hi + 1, w, d_h1 + n1))) return rc;
-                if ((rc = vo.axpys(Vr + (size_t)s_lo * n, n, n1, d_h1, w))) return rc;
-                if ((rc = vo.axpys(Vr, n, s_hi + 1, d_h1 + n1, w))) return rc;
-            }
-            if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
-            scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, Vr + (size_t)((it + 1) % ring) * n);
-            EHDG_CUDA(cudaMemcpyAsync(hbuf, dsc, sizeof(double) * (size_t)(2 * (m + 2) + 1), cudaMemcpyDeviceToHost, st));
+        double* usnap = nullptr;
+        EHDG_CUDA(cudaMalloc(&usnap, sizeof(double) * (size_t)n));
+        EHDG_CUDA(cudaMemsetAsync(usnap, 0, sizeof(double) * (size_t)n, st));
+        std::vector<double> cq, sq, t(k + 3);
+        double* hb[2] = {hbuf, hbuf + (m + 2) + 4};   // pinned staging, alternating per iteration
+        const int check_every = 100;                  // iterations between true-residual checks
+        // rel = ||b - Op u|| / ||b||, residual left in w
+        auto true_residual = [&](double* out_rel) -> int {
+            int r2 = apply_prec_op(u, w);
+            if (r2) return r2;
+            residual_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, rhs, w);
+            if ((r2 = vo.dots(w, n, 1, w, d_nrm))) return r2;
+            EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
             EHDG_CUDA(cudaStreamSynchronize(st));
-            const int nw = it - lo + 1;
-            const double hn = std::sqrt(hbuf[2 * (m + 2)]);
-            // column of the band Hessenberg matrix: rows lo-1 (fill), lo..it, it+1
-            t[0] = 0.0;
-            for (int i = 0; i < nw; ++i) t[i + 1] = hbuf[i];
-            t[nw + 1] = hn;
-            const int first_rot = lo - 1 >= 0 ? lo - 1 : 0;                    // rotations first_rot..it-1 touch this column
-            for (int i = first_rot; i < it; ++i) {
-                const int j = i - (lo - 1);                                     // position of row i in t
-                const double a = cq[i] * t[j] + sq[i] * t[j + 1];
-                t[j + 1] = -sq[i] * t[j] + cq[i] * t[j + 1];
-                t[j] = a;
-            }
-            const int jm = it - (lo - 1);
-            const double a = t[jm], b2 = t[jm + 1];
-            const double d = std::hypot(a, b2);
-            cq[it] = d > 0 ? a / d : 1.0;
-            sq[it] = d > 0 ? b2 / d : 0.0;
-            const double gnext = -sq[it] * gamma;
-            gamma = cq[it] * gamma;
-            // p_it = (v_it - sum_{i=lo-1}^{it-1} t_i p_i) / d ;  u += gamma p_it
-            double* pnew = Pr + (size_t)(it % ring) * n;
-            EHDG_CUDA(cudaMemcpyAsync(pnew, Vr + (size_t)(it % ring) * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-            const int plo = lo - 1 >= 0 ? lo - 1 : 0;
-            if (it > plo) {
-                const int np_ = it - plo;
-                for (int i = 0; i < np_; ++i) hbuf[i] = t[(plo + i) - (lo - 1)];
-                EHDG_CUDA(cudaMemcpyAsync(d_h2, hbuf, sizeof(double) * (size_t)np_, cudaMemcpyHostToDevice, st));
-                const int q_lo = plo % ring, q_hi = (it - 1) % ring;
-                if (q_lo <= q_hi) {
-                    if ((rc = vo.axpys(Pr + (size_t)q_lo * n, n, q_hi - q_lo + 1, d_h2, pnew))) return rc;
-                } else {
-                    const int n1 = ring - q_lo;
-                    if ((rc = vo.axpys(Pr + (size_t)q_lo * n, n, n1, d_h2, pnew))) return rc;
-                    if ((rc = vo.axpys(Pr, n, q_hi + 1, d_h2 + n1, pnew))) return rc;
+            *out_rel = std::sqrt(hbuf[0]) / bnorm;
+            return EHDG_OK;
+        };
+        double snap_rel = 1.0;                        // true relative residual of the snapshot (u = 0 at first)
+        bool done = false;
+        for (int cycle = 0; cycle < 1000 && !done && iters < max_iters; ++cycle) {
+            // r = b - Op u into w (u = 0 in the first cycle), gamma = ||r||
+            if (cycle == 0) {
+                EHDG_CUDA(cudaMemcpyAsync(w, rhs, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+                if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
+                rel = 1.0;
+            } else {
+                if ((rc = true_residual(&rel))) return rc;
+                if (!std::isfinite(rel) || rel > snap_rel * 10.0) {             // the iterate went bad: back to the snapshot
+                    EHDG_CUDA(cudaMemcpyAsync(u, usnap, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+                    if ((rc = true_residual(&rel))) return rc;
                 }
-                EHDG_CUDA(cudaStreamSynchronize(st));      // hbuf is reused next iteration
             }
-            dq_update_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, d > 0 ? 1.0 / d : 0.0, gamma, pnew, u);
-            gamma = gnext;
-            rel = std::fabs(gamma) / bnorm;
-            if (rel * std::sqrt((double)(it - lo + 2)) <= rtol || !(hn > 0.0) || !std::isfinite(rel)) { ++iters; break; }
+            if (rel <= rtol) { done = true; break; }
+            const double cycle_start_rel = rel;
+            if (rel < snap_rel) {
+                snap_rel = rel;
+                EHDG_CUDA(cudaMemcpyAsync(usnap, u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            }
+            double gamma = rel * bnorm;
+            scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, Vr);       // v_0 in slot 0
+            cq.assign(1, 1.0);
+            sq.assign(1, 0.0);
+            bool blown = false;
+            for (int it = 0; iters < max_iters; ++it, ++iters) {
+                const int lo = it - k + 1 > 0 ? it - k + 1 : 0;                 // window of Krylov vectors lo..it
+                const int nw = it - lo + 1;
+                const double* vit = Vr + (size_t)(it % ring) * n;
+                double* hcur = hb[it & 1];
+                if ((rc = apply_prec_op(vit, w))) return rc;
+                // h_i = (w, v_i), w -= h_i v_i for i = lo..it ; ||w||^2 comes out of the same pass
+                if ((rc = vo.ring_dots(Vr, n, ring, lo % ring, nw, w, d_h1))) return rc;
+                if ((rc = vo.ring_axpys(Vr, n, ring, lo % ring, nw, d_h1, w, w, 1, d_nrm, 0.0, 0.0, nullptr))) return rc;
+                scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, Vr + (size_t)((it + 1) % ring) * n);
+                EHDG_CUDA(cudaMemcpyAsync(hcur, d_h1, sizeof(double) * (size_t)nw, cudaMemcpyDeviceToHost, st));
+                EHDG_CUDA(cudaMemcpyAsync(hcur + (m + 2), d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
+                EHDG_CUDA(cudaStreamSynchronize(st));
+                const double hn = std::sqrt(hcur[m + 2]);
+                // column of the band Hessenberg matrix: rows lo-1 (fill), lo..it, it+1
+                t[0] = 0.0;
+                for (int i = 0; i < nw; ++i) t[i + 1] = hcur[i];
+                t[nw + 1] = hn;
+                const int first_rot = lo - 1 >= 0 ? lo - 1 : 0;                // rotations first_rot..it-1 touch this column
+                for (int i = first_rot; i < it; ++i) {
+                    const int j = i - (lo - 1);                                 // position of row i in t
+                    const double a = cq[i] * t[j] + sq[i] * t[j + 1];
+                    t[j + 1] = -sq[i] * t[j] + cq[i] * t[j + 1];
+                    t[j] = a;
+                }
+                const int jm = it - (lo - 1);
+                const double a = t[jm], b2 = t[jm + 1];
+                const double d = std::hypot(a, b2);
+                if ((int)cq.size() <= it) { cq.resize(it + 1); sq.resize(it + 1); }
+                cq[it] = d > 0 ? a / d : 1.0;
+                sq[it] = d > 0 ? b2 / d : 0.0;
+                const double gnext = -sq[it] * gamma;
+                gamma = cq[it] * gamma;
+                // p_it = (v_it - sum_{i=lo-1}^{it-1} t_i p_i) / d ;  u += gamma p_it   (one fused pass)
+                double* pnew = Pr + (size_t)(it % ring) * n;
+                const int plo = lo - 1 >= 0 ? lo - 1 : 0;
+                const int np_ = it - plo;
+                for (int i = 0; i < np_; ++i) hcur[i] = t[(plo + i) - (lo - 1)];
+                if (np_ > 0) EHDG_CUDA(cudaMemcpyAsync(d_h2, hcur, sizeof(double) * (size_t)np_, cudaMemcpyHostToDevice, st));
+                if ((rc = vo.ring_axpys(Pr, n, ring, plo % ring, np_, d_h2, vit, pnew, 2, nullptr, d > 0 ? 1.0 / d : 0.0, gamma, u))) return rc;
+                gamma = gnext;
+                rel = std::fabs(gamma) / bnorm;
+                if (!std::isfinite(rel)) { blown = true; ++iters; break; }
+                if (rel * std::sqrt((double)(it - lo + 2)) <= rtol || !(hn > 0.0)) { ++iters; break; }
+                if ((it + 1) % check_every == 0) {
+                    // the quasi-residual keeps shrinking even when the truncated recurrence has broken down:
+                    // measure the true residual (w is free here), snapshot on progress, roll back on a blow-up
+                    double tr;
+                    if ((rc = true_residual(&tr))) return rc;
+                    if (!std::isfinite(tr) || tr > snap_rel * 10.0) { blown = true; ++iters; break; }
+                    if (tr < snap_rel) {
+                        snap_rel = tr;
+                        EHDG_CUDA(cudaMemcpyAsync(usnap, u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+                    }
+                }
+            }
+            if (blown) {
+                EHDG_CUDA(cudaMemcpyAsync(u, usnap, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+                if (!(snap_rel < 0.9 * cycle_start_rel)) break;                 // no progress between two breakdowns
+            }
+            // the next cycle measures the true residual of u: leaves when it meets rtol, otherwise iterates on
         }
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(usnap);
         if (sweeps > 1) {      // yhat = P^ u
             EHDG_CUDA(cudaMemcpyAsync(w, u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
             if ((rc = poly(w, pt))) return rc;
@@ -1110,7 +1344,7 @@ int ehdg_l2_error(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uin
     l2_error_kernel<<<nblocks, 128, 0, st>>>(c->pb, c->rerr.rs, m->ne, (int)p->n_poly, p->eslot, m->verts, m->tris,
                                              c->pb.nenr ? elem_active : nullptr, u, partial);
     EHDG_LAUNCH_CHECK();
-    reduce_partials_kernel<<<1, 256, 0, st>>>(nblocks, 2, partial, err2, 0);
+    reduce_partials_kernel<<<2, 256, 0, st>>>(nblocks, 2, partial, err2, 0);
     EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cudaStreamSynchronize(st));
     cudaFree(partial);
