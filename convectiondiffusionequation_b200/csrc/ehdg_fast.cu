@@ -7,7 +7,7 @@ namespace ehdg {
 
 constexpr int FAST_THREADS = 128;
 #ifndef EHDG_ASM_MINBLOCKS
-#define EHDG_ASM_MINBLOCKS (EHDG_ASM_R == 2 ? 2 : 3)
+#define EHDG_ASM_MINBLOCKS (EHDG_ASM_R == 2 ? 2 : 4)     // 128 registers without spills since A_FV is built after the elimination
 #endif
 #ifndef EHDG_ALPHA_MINBLOCKS
 #define EHDG_ALPHA_MINBLOCKS (EHDG_ALPHA_R == 2 ? 3 : 4)
@@ -30,7 +30,7 @@ fast_assemble_kernel(Problem pb, RuleSet rs, const double* __restrict__ tab_g, i
     Group<LG> gc{(int)(threadIdx.x % LG), smem + ((tab_doubles + 1) & ~1) + gid * scratch};
     for (int base = blockIdx.x * GPC; base < n; base += gridDim.x * GPC) {
         const bool live = base + gid < n;
-        const int idx = live ? base + gid : n - 1;
+        const int idx = base + gid < n ? base + gid : n - 1;
         const int el = list[idx];
         const int st = fast_assemble_element<P>(gc, pb, rs, smem, phi_rhs, verts, tris + 3 * el, lam[el], live,
                                                 S + (size_t)idx * D::NF * D::NF, g + (size_t)idx * D::NF,

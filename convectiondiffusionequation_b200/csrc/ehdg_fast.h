@@ -251,7 +251,7 @@ template <int P>
 EHDG_HD constexpr int fast_asm_scratch_doubles(int nq) {
     typedef FastDims<P> D;
     constexpr int xs = D::NP * D::NXS, ss = D::NF * D::NF + D::NF;      // X scratch doubles as the S/g staging area
-    return ((D::NC + 1) & ~1) + (((xs > ss ? xs : ss) + 1) & ~1) + ((nq + 1) & ~1);
+    return ((D::NC + 1) & ~1) + 2 + (((xs > ss ? xs : ss) + 1) & ~1) + ((nq + 1) & ~1);
 }
 
 // a5-a7 on one polynomial element.  Scratch `gc.sh` needs fast_asm_scratch_doubles() doubles.
@@ -263,23 +263,21 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
                                   double lam, bool store, double* S, double* gvec, double* W, double* z) {
     typedef FastDims<P> D;
     constexpr int NP = D::NP, NFL = D::NFL, NF = D::NF, NC = D::NC, LG = D::LG, R = D::R, NXS = D::NXS;
-    constexpr int NLS = EHDG_NLS(LG);
+    constexpr int NLS = EHDG_NLS(LG), NFS = NF | 1;     // NFS: row stride of the facet tensors
     const TensorLayout TL = tensor_layout(P, rs.nq);
     SortedGeom sg;
     sorted_geom(verts, tri, pb.bx, pb.by, sg);
-    double* prow = gc.sh;                       // NC (padded even)
-    double* Xs = prow + ((NC + 1) & ~1);        // NP x NXS, later the staging area of S (NF x NF) and g (NF)
+    double* prow = gc.sh;                       // NC (padded even) + 2: pivot row and the reciprocal of the pivot
+    double* Xs = prow + ((NC + 1) & ~1) + 2;    // NP x NXS, later the staging area of S (NF x NF) and g (NF)
     double* cw = Xs + (((NP * NXS > NF * NF + NF ? NP * NXS : NF * NF + NF) + 1) & ~1);   // nq
     // per-edge coefficients
-    double cvv[3], cvf[3], cfv[3], cff[3], eg0[3], eg1[3];
+    double cvv[3], cvf[3], eg0[3], eg1[3];
     for (int s = 0; s < 3; ++s) {
         const double bn = sg.bn[s];
         const double pos = bn > 0.0 ? 1.0 : 0.0, neg = 1.0 - pos;
         const double tau = pb.eps * (20.0 * lam) * (double)(P * P) * sg.ih[s];
         cvv[s] = sg.len[s] * (tau + pos * bn);
         cvf[s] = sg.len[s] * (-tau + neg * bn);
-        cfv[s] = sg.len[s] * (-tau - pos * bn - pos);
-        cff[s] = sg.len[s] * (tau - neg * bn + pos);
         eg0[s] = sg.len[s] * pb.eps * sg.ga0[s];
         eg1[s] = sg.len[s] * pb.eps * sg.ga1[s];
     }
@@ -287,22 +285,49 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     const double ccx = -sg.adet * sg.c0, ccy = -sg.adet * sg.c1;
 
     double a[NLS][R][NC];      // rows of [A_VV | A_VF | f_V]          (rows < NP)
-    double afv[NLS][R][NP];    // rows of A_FV in the sorted frame      (rows < NF)
-    double aff[NLS][R];
     int mycol[NLS][R];
     double myinv[NLS][R];
     int status = 0;
 
-    // ---- right-hand side weights at the quadrature points: cw[q] = w_q |detJ| coeff(x_q)
+    // ---- right-hand side.  Where both layer functions of `coeff` have underflowed on the whole element
+    // (k d > 746 at the vertex nearest to the outflow side, hence at every point) the coefficient is a quadratic
+    // polynomial in the local barycentrics: f_V comes from the six moment vectors behind the phi table.
+    // Otherwise: weights at the quadrature points, cw[q] = w_q |detJ| coeff(x_q).
+    const LayerConst cx = layer_const(pb.coeff.k[0]), cy = layer_const(pb.coeff.k[1]);
+    const bool ux = pb.coeff.c[1] != 0.0 || pb.coeff.c[3] != 0.0, uy = pb.coeff.c[2] != 0.0 || pb.coeff.c[3] != 0.0;
+    const double dminx = fmin(sg.omx[0], fmin(sg.omx[1], sg.omx[2])), dminy = fmin(sg.omy[0], fmin(sg.omy[1], sg.omy[2]));
+#ifdef EHDG_NO_RHS_MOMENTS
+    const bool poly_rhs = false;
+#else
+    const bool poly_rhs = (!ux || cx.k * dminx > 747.0) && (!uy || cy.k * dminy > 747.0);     // uniform over the group
+#endif
+    const bool zx = cx.k * dminx > 747.0, zy = cy.k * dminy > 747.0;
+    double cm[EHDG_RHS_MOMENTS];
+    if (poly_rhs) {
+        // L(d) = (1 - d) - e0 inv with d = d_2 + l0 (d_0 - d_2) + l1 (d_1 - d_2)
+        const double ax = ux ? (1.0 - sg.omx[2]) - cx.e0 * cx.inv : 0.0, ay = uy ? (1.0 - sg.omy[2]) - cy.e0 * cy.inv : 0.0;
+        const double bx0 = ux ? sg.omx[2] - sg.omx[0] : 0.0, bx1 = ux ? sg.omx[2] - sg.omx[1] : 0.0;
+        const double by0 = uy ? sg.omy[2] - sg.omy[0] : 0.0, by1 = uy ? sg.omy[2] - sg.omy[1] : 0.0;
+        const double c0 = pb.coeff.c[0], c1 = pb.coeff.c[1], c2 = pb.coeff.c[2], c3 = pb.coeff.c[3];
+        cm[0] = sg.adet * (c0 + c1 * ax + c2 * ay + c3 * ax * ay);
+        cm[1] = sg.adet * (c1 * bx0 + c2 * by0 + c3 * (ax * by0 + ay * bx0));
+        cm[2] = sg.adet * (c1 * bx1 + c2 * by1 + c3 * (ax * by1 + ay * bx1));
+        cm[3] = sg.adet * (c3 * bx0 * by0);
+        cm[4] = sg.adet * (c3 * (bx0 * by1 + bx1 * by0));
+        cm[5] = sg.adet * (c3 * bx1 * by1);
+    } else {
+        for (int m = 0; m < EHDG_RHS_MOMENTS; ++m) cm[m] = 0.0;
+    }
     {
-        const LayerConst cx = layer_const(pb.coeff.k[0]), cy = layer_const(pb.coeff.k[1]);
-        const bool ux = pb.coeff.c[1] != 0.0 || pb.coeff.c[3] != 0.0, uy = pb.coeff.c[2] != 0.0 || pb.coeff.c[3] != 0.0;
         EHDG_FOR_LANES(l, L)
+            if (!poly_rhs)
             for (int q = l; q < rs.nq; q += LG) {
                 const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
                 const double dx = l0 * sg.omx[0] + l1 * sg.omx[1] + l2 * sg.omx[2];
                 const double dy = l0 * sg.omy[0] + l1 * sg.omy[1] + l2 * sg.omy[2];
-                const double lx = ux ? layer_val(cx, dx) : 0.0, ly = uy ? layer_val(cy, dy) : 0.0;
+                // an axis whose exponential has underflowed on the whole element (uniform over the group) skips exp()
+                const double lx = ux ? (zx ? (1.0 - dx) - cx.e0 * cx.inv : layer_val(cx, dx)) : 0.0;
+                const double ly = uy ? (zy ? (1.0 - dy) - cy.e0 * cy.inv : layer_val(cy, dy)) : 0.0;
                 cw[q] = rs.vw[q] * sg.adet * (pb.coeff.c[0] + pb.coeff.c[1] * lx + pb.coeff.c[2] * ly + pb.coeff.c[3] * lx * ly);
             }
         EHDG_END_LANES
@@ -332,16 +357,26 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             }
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const double* tf = tab + TL.offF + (s * 3 * NP + i) * NFL;
+                const double* tf = tab + TL.offFT + i * NFS + s * NFL;      // [t][i][(s,k)]: odd lane stride NFS
 #pragma unroll
                 for (int k = 0; k < NFL; ++k)
-                    a[L][h][NP + s * NFL + k] = cvf[s] * tf[k] + eg0[s] * tf[NP * NFL + k] + eg1[s] * tf[2 * NP * NFL + k];
+                    a[L][h][NP + s * NFL + k] = cvf[s] * tf[k] + eg0[s] * tf[NP * NFS + k] + eg1[s] * tf[2 * NP * NFS + k];
             }
             mycol[L][h] = -1;
             myinv[L][h] = 1.0;
         }
         // f_V[i] = sum_q cw[q] phi_i(q), the R rows of the lane share the cw reads
-        {
+        if (poly_rhs) {
+            const double* mo = phi_rhs + (size_t)9 * rs.nq * NP + (size_t)(sg.f0 * 3 + sg.f1) * EHDG_RHS_MOMENTS * NP;
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const int i = h * LG + l < NP ? h * LG + l : NP - 1;
+                double acc = 0.0;
+#pragma unroll
+                for (int m = EHDG_RHS_MOMENTS - 1; m >= 0; --m) acc += cm[m] * mo[m * NP + i];     // small terms first
+                a[L][h][NC - 1] = acc;
+            }
+        } else {
             const double* ph = phi_rhs + (size_t)(sg.f0 * 3 + sg.f1) * rs.nq * NP;
             int ii[R];
             double acc[R][4];                      // four independent accumulation chains per row
@@ -373,44 +408,44 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 #pragma unroll
             for (int h = 0; h < R; ++h) a[L][h][NC - 1] = (acc[h][0] + acc[h][1]) + (acc[h][2] + acc[h][3]);
         }
-        // A_FV rows r = (s, k) in the sorted frame
-#pragma unroll
-        for (int h = 0; h < R; ++h) {
-            const int row = h * LG + l;
-            const int r = row < NF ? row : NF - 1;
-            const int s = r / NFL, k = r % NFL;
-            const double* tf = tab + TL.offF + (s * 3 * NP) * NFL + k;
-            const double c_fv = sel3(cfv, s), c_g0 = sel3(eg0, s), c_g1 = sel3(eg1, s);
-#pragma unroll
-            for (int j = 0; j < NP; ++j)
-                afv[L][h][j] = c_fv * tf[j * NFL] + c_g0 * tf[(NP + j) * NFL] + c_g1 * tf[(2 * NP + j) * NFL];
-            double rk = 1.0;                                 // 1 / (2k+1) = int_0^1 mu_k^2 dt, k <= 6
-#pragma unroll
-            for (int kk = 1; kk < NFL; ++kk)
-                if (k == kk) rk = 1.0 / (2.0 * kk + 1.0);
-            aff[L][h] = sel3(cff, s) * rk;
-        }
     EHDG_END_LANES
 
-    // ---- Gauss-Jordan with partial pivoting, rows stay where they are
+    // ---- Gauss-Jordan with partial pivoting, rows stay where they are.  The pivot of step k+1 is searched as soon
+    // as column k+1 has been updated in step k, so that the warp reduction and the reciprocal of the next pivot
+    // overlap the rest of the update instead of heading the dependency chain of every step.
 #ifdef EHDG_EXP_SKIP_GJ
 #define EHDG_GJ_STEPS 1
 #else
 #define EHDG_GJ_STEPS NP
 #endif
-#pragma unroll
-    for (int k = 0; k < EHDG_GJ_STEPS; ++k) {
+    constexpr int NCP = (NC + 1) & ~1;          // prow[NCP] = 1 / pivot
+    int rw;
+    {
         double key[NLS][R];
         EHDG_FOR_LANES(l, L)
 #pragma unroll
-            for (int h = 0; h < R; ++h) key[L][h] = (h * LG + l < NP && mycol[L][h] < 0) ? fabs(a[L][h][k]) : -1.0;
+            for (int h = 0; h < R; ++h) key[L][h] = (h * LG + l < NP) ? fabs(a[L][h][0]) : -1.0;
         EHDG_END_LANES
-        const int rw = gc.template argmax_row<R>(key);
+        rw = gc.template argmax_row<R>(key);
+    }
+#pragma unroll
+    for (int k = 0; k < EHDG_GJ_STEPS; ++k) {
         const int lo = rw % LG, ho = rw / LG;
+        double f[NLS][R];
         EHDG_FOR_LANES(l, L)
             if (l == lo) {
+                double piv = a[L][0][k];
 #pragma unroll
-                for (int jp = k >> 1; jp <= (NC - 1) >> 1; ++jp) {
+                for (int h = 1; h < R; ++h)
+                    if (h == ho) piv = a[L][h][k];
+                if (!(fabs(piv) > 0.0)) status |= EHDG_ST_SINGULAR;
+#ifdef __CUDA_ARCH__
+                const double inv = __drcp_rn(piv);
+#else
+                const double inv = 1.0 / piv;
+#endif
+#pragma unroll
+                for (int jp = (k + 1) >> 1; jp <= (NC - 1) >> 1; ++jp) {
                     double v0 = a[L][0][2 * jp], v1 = (2 * jp + 1 < NC) ? a[L][0][2 * jp + 1] : 0.0;
 #pragma unroll
                     for (int h = 1; h < R; ++h)
@@ -420,35 +455,38 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
                         }
                     st2(prow + 2 * jp, v0, v1);
                 }
+                prow[NCP] = inv;
 #pragma unroll
                 for (int h = 0; h < R; ++h)
-                    if (h == ho) mycol[L][h] = k;
+                    if (h == ho) {
+                        mycol[L][h] = k;
+                        myinv[L][h] = inv;
+                    }
             }
         EHDG_END_LANES
+        double key[NLS][R];
         EHDG_FOR_LANES(l, L)
-            const double piv = prow[k];
-            if (!(fabs(piv) > 0.0)) status |= EHDG_ST_SINGULAR;
-#ifdef __CUDA_ARCH__
-            const double inv = __drcp_rn(piv);
-#else
-            const double inv = 1.0 / piv;
-#endif
+            const double inv = prow[NCP];
             // multipliers: 0 for the pivot row (it stays unscaled; scaled once at the end) and for surplus rows
-            double f[R];
+            const double x1 = prow[k + 1];
 #pragma unroll
             for (int h = 0; h < R; ++h) {
                 const bool is_piv = (l == lo) && (h == ho);
-                if (is_piv) myinv[L][h] = inv;
-                f[h] = (is_piv || h * LG + l >= NP) ? 0.0 : a[L][h][k] * inv;
+                f[L][h] = (is_piv || h * LG + l >= NP) ? 0.0 : a[L][h][k] * inv;
+                a[L][h][k + 1] -= f[L][h] * x1;
+                key[L][h] = (h * LG + l < NP && mycol[L][h] < 0) ? fabs(a[L][h][k + 1]) : -1.0;
             }
+        EHDG_END_LANES
+        if (k + 1 < NP) rw = gc.template argmax_row<R>(key);
+        EHDG_FOR_LANES(l, L)
 #pragma unroll
-            for (int jp = (k + 1) >> 1; jp <= (NC - 1) >> 1; ++jp) {
+            for (int jp = (k + 2) >> 1; jp <= (NC - 1) >> 1; ++jp) {
                 double x0, x1;
                 ld2(prow + 2 * jp, x0, x1);
 #pragma unroll
                 for (int h = 0; h < R; ++h) {
-                    if (2 * jp >= k + 1) a[L][h][2 * jp] -= f[h] * x0;
-                    if (2 * jp + 1 < NC) a[L][h][2 * jp + 1] -= f[h] * x1;
+                    if (2 * jp >= k + 2) a[L][h][2 * jp] -= f[L][h] * x0;
+                    if (2 * jp + 1 < NC) a[L][h][2 * jp + 1] -= f[L][h] * x1;
                 }
             }
         EHDG_END_LANES
@@ -468,6 +506,47 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
                     st2(Xs + c * NXS + 2 * jp, a[L][h][NP + 2 * jp], (2 * jp + 1 <= NF) ? a[L][h][NP + 2 * jp + 1] : 0.0);
             }
     EHDG_END_LANES
+
+    // ---- rows of A_FV and the diagonal of A_FF, r = (s, k) in the sorted frame.  Built only now, from a geometry that
+    // is recomputed behind an optimisation barrier: nothing of it stays live across the elimination, which is what
+    // lets the kernel run four CTAs per SM.
+    double afv[NLS][R][NP];
+    double aff[NLS][R];
+    {
+        const int* tri2 = tri;
+#ifdef __CUDA_ARCH__
+        asm volatile("" : "+l"(tri2));
+#endif
+        sorted_geom(verts, tri2, pb.bx, pb.by, sg);
+        double cfv[3], cff[3], fg0[3], fg1[3];
+        for (int s = 0; s < 3; ++s) {
+            const double bn = sg.bn[s];
+            const double pos = bn > 0.0 ? 1.0 : 0.0, neg = 1.0 - pos;
+            const double tau = pb.eps * (20.0 * lam) * (double)(P * P) * sg.ih[s];
+            cfv[s] = sg.len[s] * (-tau - pos * bn - pos);
+            cff[s] = sg.len[s] * (tau - neg * bn + pos);
+            fg0[s] = sg.len[s] * pb.eps * sg.ga0[s];
+            fg1[s] = sg.len[s] * pb.eps * sg.ga1[s];
+        }
+        EHDG_FOR_LANES(l, L)
+#pragma unroll
+        for (int h = 0; h < R; ++h) {
+            const int row = h * LG + l;
+            const int r = row < NF ? row : NF - 1;
+            const int s = r / NFL, k = r % NFL;
+            const double* tf = tab + TL.offFT + r;              // [t][j][(s,k)]: unit stride across the lanes
+            const double c_fv = sel3(cfv, s), c_g0 = sel3(fg0, s), c_g1 = sel3(fg1, s);
+#pragma unroll
+            for (int j = 0; j < NP; ++j)
+                afv[L][h][j] = c_fv * tf[j * NFS] + c_g0 * tf[(NP + j) * NFS] + c_g1 * tf[(2 * NP + j) * NFS];
+            double rk = 1.0;                                 // 1 / (2k+1) = int_0^1 mu_k^2 dt, k <= 6
+#pragma unroll
+            for (int kk = 1; kk < NFL; ++kk)
+                if (k == kk) rk = 1.0 / (2.0 * kk + 1.0);
+            aff[L][h] = sel3(cff, s) * rk;
+        }
+        EHDG_END_LANES
+    }
 
     // ---- S = A_FF - A_FV X, g = -A_FV z ; rows in the sorted frame.  W, z leave from the X scratch and S, g from a
     // staging copy with contiguous (full-sector) global stores in local edge order.

@@ -19,10 +19,12 @@ namespace ehdg {
 
 struct TensorLayout {
     int NP, NFL, nq;
+    int NFS;    // row stride of the facet tensors: 3 NFL made odd (conflict-free for a lane-per-row read)
     // offsets in doubles into `asm_tab`
     int offV;   // [5][NP][NP]    KXX, KS = KXY + KXY^T, KYY, CX, CY
     int offE;   // [3][3][NP][NP] per edge: M, DXS = DX + DX^T, DYS = DY + DY^T
-    int offF;   // [3][3][NP][NFL] per edge: MF, DXF, DYF
+    int offFT;  // [3][NP][NFS]    per edge s: MF, DXF, DYF stored as [t][i][(s,k)]: the lane that owns volume row i reads
+                //                 with the odd stride 3 NFL, the lane that owns facet row (s,k) with unit stride
     int asm_doubles;
     // offsets into `alpha_tab`
     int offAK;  // [3][NP][NP]    KXX, KS, KYY
@@ -35,10 +37,11 @@ EHDG_HD TensorLayout tensor_layout(int p, int nq) {
     L.NP = (p + 1) * (p + 2) / 2;
     L.NFL = p + 1;
     L.nq = nq;
+    L.NFS = (3 * L.NFL) | 1;
     L.offV = 0;
     L.offE = L.offV + 5 * L.NP * L.NP;
-    L.offF = L.offE + 9 * L.NP * L.NP;
-    L.asm_doubles = L.offF + 9 * L.NP * L.NFL;
+    L.offFT = L.offE + 9 * L.NP * L.NP;
+    L.asm_doubles = L.offFT + 3 * L.NP * L.NFS;
     L.offAK = 0;
     L.offAN = 3 * L.NP * L.NP;
     L.alpha_doubles = 12 * L.NP * L.NP;
@@ -98,7 +101,11 @@ inline void build_tensors(int p, int order, std::vector<double>& asm_tab, std::v
     alpha_tab.assign(L.alpha_doubles, 0.0);
     for (int i = 0; i < 5 * NP * NP; ++i) asm_tab[L.offV + i] = (double)tv[i];
     for (int i = 0; i < 9 * NP * NP; ++i) asm_tab[L.offE + i] = (double)te[i];
-    for (int i = 0; i < 9 * NP * NFL; ++i) asm_tab[L.offF + i] = (double)tf[i];
+    for (int s = 0; s < 3; ++s)
+        for (int t = 0; t < 3; ++t)
+            for (int j = 0; j < NP; ++j)
+                for (int k = 0; k < NFL; ++k)
+                    asm_tab[L.offFT + (t * NP + j) * L.NFS + s * NFL + k] = (double)tf[((s * 3 + t) * NP + j) * NFL + k];
     for (int i = 0; i < 3 * NP * NP; ++i) alpha_tab[L.offAK + i] = (double)tv[i];
     for (int i = 0; i < 9 * NP * NP; ++i) alpha_tab[L.offAN + i] = (double)tn[i];
 }
@@ -106,10 +113,17 @@ inline void build_tensors(int p, int order, std::vector<double>& asm_tab, std::v
 // phi at the points of the triangle rule for the 9 (f0, f1) vertex-order codes (6 are valid
 // permutations); layout [f0*3+f1][q][NP].  The rule lives in LOCAL reference coordinates
 // (lam_0, lam_1), so the sorted barycentrics of a point depend on the class of the element.
+//
+// Behind it, [f0*3+f1][6][NP]: the moments  sum_q w_q m(q) phi_i(q)  of the monomials m = 1, l0, l1, l0^2, l0 l1, l1^2
+// in the LOCAL barycentrics.  Where the layer functions of `coeff` have underflowed on the whole element the
+// right-hand side coefficient is a quadratic polynomial and f_V is a combination of these six vectors (the rule
+// integrates degree p + 2 exactly, so this is the same number up to rounding).
+constexpr int EHDG_RHS_MOMENTS = 6;
 inline void build_rhs_phi(int p, int order, std::vector<double>& tab) {
     const TrigRule tr = trig_rule(order);
     const int NP = (p + 1) * (p + 2) / 2, nq = (int)tr.w.size();
-    tab.assign((size_t)9 * nq * NP, 0.0);
+    tab.assign((size_t)9 * nq * NP + (size_t)9 * EHDG_RHS_MOMENTS * NP, 0.0);
+    std::vector<long double> mom((size_t)9 * EHDG_RHS_MOMENTS * NP, 0.0L);
     double v[EHDG_MAX_NP], dX[EHDG_MAX_NP], dY[EHDG_MAX_NP];
     for (int f0 = 0; f0 < 3; ++f0)
         for (int f1 = 0; f1 < 3; ++f1) {
@@ -118,8 +132,14 @@ inline void build_rhs_phi(int p, int order, std::vector<double>& tab) {
                 const double l[3] = {tr.x[q], tr.y[q], 1.0 - tr.x[q] - tr.y[q]};
                 dubiner_eval(p, l[f0], l[f1], v, dX, dY);
                 for (int i = 0; i < NP; ++i) tab[((size_t)(f0 * 3 + f1) * nq + q) * NP + i] = v[i];
+                const long double m[EHDG_RHS_MOMENTS] = {1.0L, l[0], l[1], (long double)l[0] * l[0], (long double)l[0] * l[1],
+                                                         (long double)l[1] * l[1]};
+                for (int k = 0; k < EHDG_RHS_MOMENTS; ++k)
+                    for (int i = 0; i < NP; ++i)
+                        mom[((size_t)(f0 * 3 + f1) * EHDG_RHS_MOMENTS + k) * NP + i] += (long double)tr.w[q] * m[k] * v[i];
             }
         }
+    for (size_t i = 0; i < mom.size(); ++i) tab[(size_t)9 * nq * NP + i] = (double)mom[i];
 }
 
 }  // namespace ehdg

@@ -195,3 +195,40 @@ def test_tensor_path_all_vertex_order_classes():
         Wo = np.linalg.solve(A[np.ix_(iv, iv)], A[np.ix_(iv, jf)])
         assert rel(S, A[np.ix_(jf, jf)] - A[np.ix_(jf, iv)] @ Wo) < 1e-11
         assert rel(g, -A[np.ix_(jf, iv)] @ np.linalg.solve(A[np.ix_(iv, iv)], F[iv])) < 1e-10
+
+
+def test_tensor_path_moment_rhs_matches_quadrature_oracle():
+    """Where exp(-k d) has underflowed on the whole element the device takes f_V from six moment vectors instead of
+    the quadrature loop (csrc/ehdg_fast.h); the oracle always integrates (convection_diffusion.py:380-383)."""
+    import convectiondiffusionequation_b200.mesh as M
+    base = unit_square_mesh(4, kind="unstructured")
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(base.nv)
+    verts = np.zeros_like(base.verts)
+    verts[perm] = base.verts
+    tris = np.array([np.roll(t, r) for t, r in zip(perm[base.tris], rng.integers(0, 3, size=base.ne))])
+    old = M.normalise_triangles
+    M.normalise_triangles = lambda v, t: np.asarray(t, np.int32)
+    try:
+        mesh = M.build_topology(verts, tris, 0.25, "perm")
+    finally:
+        M.normalise_triangles = old
+    order, eps, beta = 3, 1e-6, (2.0, 1.0)
+    prob = orc.run_py_problem(beta=beta, eps=eps, enriched=False)
+    o = orc.EHDGOracle(mesh.verts, mesh.tris, mesh.el2facet, mesh.facet2el, mesh.maxh, order, prob)
+    cp = c_problem(order, prob)
+    n_p, nf = o.n_p, 3 * (order + 1)
+    dmin = (1.0 - mesh.verts[mesh.tris]).min(axis=1)                     # [ne, 2]
+    moment = (dmin[:, 0] * beta[0] / eps > 747.0) & (dmin[:, 1] * beta[1] / eps > 747.0)
+    classes = {tuple(np.argsort(t)) for t in mesh.tris[moment]}
+    assert moment.sum() >= 8 and (~moment).sum() >= 4 and len(classes) >= 4
+    for el in range(mesh.ne):
+        tri = np.ascontiguousarray(mesh.tris[el], np.int32)
+        lam_o = o.alpha_lambda(el)
+        S, g, W, z = np.zeros((nf, nf)), np.zeros(nf), np.zeros((n_p, nf)), np.zeros(n_p)
+        assert L.hc_fast_assemble(C.byref(cp), dptr(mesh.verts), iptr(tri), C.c_double(lam_o), dptr(S), dptr(g), dptr(W), dptr(z)) == 0
+        A, F = o.element_matrix(el, lam_o)
+        iv, jf = np.arange(n_p), np.arange(n_p, n_p + nf)
+        tol = max(1e-11, 1e-14 * np.linalg.cond(A[np.ix_(iv, iv)]))
+        zo = np.linalg.solve(A[np.ix_(iv, iv)], F[iv])
+        assert rel(z, zo) < 10 * tol and rel(g, -A[np.ix_(jf, iv)] @ zo) < 10 * tol, (el, bool(moment[el]))
