@@ -63,6 +63,7 @@ SYMBOLS = {
     "ehdg_kernel_times_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ehdg_mark": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, _P, _P]),
     "ehdg_plan_create": (C.c_int, [_P, C.POINTER(Mesh), _P, C.c_int, C.POINTER(_P), _P]),
+    "ehdg_plan_create_select": (C.c_int, [_P, C.POINTER(Mesh), _P, C.c_int, _P, C.POINTER(_P), _P]),
     "ehdg_plan_destroy": (C.c_int, [_P]),
     "ehdg_plan_get_sizes": (C.c_int, [_P, C.POINTER(PlanSizes)]),
     "ehdg_plan_eslot": (_P, [_P]),
@@ -70,6 +71,8 @@ SYMBOLS = {
     "ehdg_alpha": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),
     "ehdg_assemble_condense": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ehdg_csr_symbolic": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.POINTER(_P), _P]),
+    "ehdg_csr_symbolic_part": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.c_int, C.c_int, C.POINTER(_P), _P]),
+    "ehdg_csr_get_partition": (C.c_int, [_P, _P, _P]),
     "ehdg_csr_destroy": (C.c_int, [_P]),
     "ehdg_csr_get_sizes": (C.c_int, [_P, C.POINTER(CsrSizes)]),
     "ehdg_csr_rowptr": (_P, [_P]),
@@ -87,6 +90,7 @@ SYMBOLS = {
     "ehdg_spmv": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ehdg_backsolve": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
     "ehdg_l2_error": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),
+    "ehdg_l2_error_select": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
 }
 
 _lib = None

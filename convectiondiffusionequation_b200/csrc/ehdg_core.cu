@@ -74,27 +74,34 @@ __global__ void mark_facets_kernel(int nf, const int32_t* __restrict__ facet2el,
 // plan
 // -------------------------------------------------------------------------------------------
 __global__ void plan_flags_kernel(int ne, const int32_t* __restrict__ el2facet,
-                                  const uint8_t* __restrict__ facet_mask, int force, int32_t* __restrict__ flag) {
+                                  const uint8_t* __restrict__ facet_mask, int force, const uint8_t* __restrict__ select,
+                                  int32_t* __restrict__ flag_gen, int32_t* __restrict__ flag_poly) {
     const int el = blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= ne) return;
     int g = force;
     if (facet_mask)
         g |= facet_mask[el2facet[3 * el]] | facet_mask[el2facet[3 * el + 1]] | facet_mask[el2facet[3 * el + 2]];
-    flag[el] = g ? 1 : 0;
+    const int on = select ? (select[el] != 0) : 1;      // elements outside the selection get no slot on either path
+    flag_gen[el] = (on && g) ? 1 : 0;
+    flag_poly[el] = (on && !g) ? 1 : 0;
 }
 
-__global__ void plan_scatter_kernel(int ne, const int32_t* __restrict__ flag, const int32_t* __restrict__ scan,
+__global__ void plan_scatter_kernel(int ne, const int32_t* __restrict__ flag_gen, const int32_t* __restrict__ flag_poly,
+                                    const int32_t* __restrict__ scan_gen, const int32_t* __restrict__ scan_poly,
                                     int32_t* __restrict__ eslot, int32_t* __restrict__ list_poly,
                                     int32_t* __restrict__ list_gen) {
     const int el = blockIdx.x * blockDim.x + threadIdx.x;
     if (el >= ne) return;
-    const int gi = scan[el];          // general elements before el
-    if (flag[el]) {
+    if (flag_gen[el]) {
+        const int gi = scan_gen[el];
         eslot[el] = EHDG_SLOT_GEN | gi;
         list_gen[gi] = el;
+    } else if (flag_poly[el]) {
+        const int pi = scan_poly[el];
+        eslot[el] = pi;
+        list_poly[pi] = el;
     } else {
-        eslot[el] = el - gi;
-        list_poly[el - gi] = el;
+        eslot[el] = EHDG_SLOT_NONE;
     }
 }
 
@@ -320,8 +327,8 @@ static int ctx_scratch(ehdg_ctx* c, size_t bytes, void** out) {
     return EHDG_OK;
 }
 
-int ehdg_plan_create(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_mask, int force_general, ehdg_plan** out,
-                     void* stream) {
+int ehdg_plan_create_select(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_mask, int force_general,
+                            const uint8_t* elem_select, ehdg_plan** out, void* stream) {
     if (!c || !m || !out) { set_error("ehdg_plan_create: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     ehdg_plan* p = new ehdg_plan();
@@ -336,12 +343,14 @@ int ehdg_plan_create(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_mask,
     const size_t nint = (size_t)(ne + 1);
     size_t tmp_bytes = 0;
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (int32_t*)nullptr, (int32_t*)nullptr, ne + 1, st));
-    const size_t off_scan = (nint * 4 + 255) & ~(size_t)255, off_tmp = 2 * off_scan;
+    const size_t off_arr = (nint * 4 + 255) & ~(size_t)255, off_tmp = 4 * off_arr;
     void* base = nullptr;
     int rc = ctx_scratch(c, off_tmp + tmp_bytes + 256, &base);
     if (rc) return rc;
-    int32_t* flag = (int32_t*)base;
-    int32_t* scan = (int32_t*)((char*)base + off_scan);
+    int32_t* flag_gen = (int32_t*)base;
+    int32_t* flag_poly = (int32_t*)((char*)base + off_arr);
+    int32_t* scan_gen = (int32_t*)((char*)base + 2 * off_arr);
+    int32_t* scan_poly = (int32_t*)((char*)base + 3 * off_arr);
     void* tmp = (char*)base + off_tmp;
     if (c->pool_eslot && c->pool_ne == ne) {             // reuse the buffers of the last destroyed plan
         p->eslot = c->pool_eslot;
@@ -351,21 +360,29 @@ int ehdg_plan_create(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_mask,
         EHDG_CUDA(cudaMalloc(&p->eslot, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1)));
         EHDG_CUDA(cudaMalloc(&p->lists, sizeof(int32_t) * (size_t)(ne > 0 ? ne : 1)));
     }
-    EHDG_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t) * nint, st));
-    if (ne > 0) plan_flags_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, m->el2facet, c->pb.nenr ? facet_mask : nullptr, force_general ? 1 : 0, flag);
+    EHDG_CUDA(cudaMemsetAsync(flag_gen, 0, 2 * off_arr, st));
+    if (ne > 0) plan_flags_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, m->el2facet, c->pb.nenr ? facet_mask : nullptr, force_general ? 1 : 0,
+                                                                     elem_select, flag_gen, flag_poly);
     EHDG_LAUNCH_CHECK();
-    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, scan, ne + 1, st));
-    int32_t ngen = 0;
-    EHDG_CUDA(cudaMemcpyAsync(&ngen, scan + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag_gen, scan_gen, ne + 1, st));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag_poly, scan_poly, ne + 1, st));
+    int32_t ngen = 0, npoly = 0;
+    EHDG_CUDA(cudaMemcpyAsync(&ngen, scan_gen + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cudaMemcpyAsync(&npoly, scan_poly + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
     p->n_gen = ngen;
-    p->n_poly = ne - ngen;
+    p->n_poly = npoly;
     p->list_poly = p->lists;
     p->list_gen = p->lists + p->n_poly;
-    if (ne > 0) plan_scatter_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, flag, scan, p->eslot, p->list_poly, p->list_gen);
+    if (ne > 0) plan_scatter_kernel<<<(ne + 255) / 256, 256, 0, st>>>(ne, flag_gen, flag_poly, scan_gen, scan_poly, p->eslot, p->list_poly, p->list_gen);
     EHDG_LAUNCH_CHECK();
     *out = p;
     return EHDG_OK;
+}
+
+int ehdg_plan_create(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_mask, int force_general, ehdg_plan** out,
+                     void* stream) {
+    return ehdg_plan_create_select(c, m, facet_mask, force_general, nullptr, out, stream);
 }
 
 int ehdg_plan_destroy(ehdg_plan* p) {

@@ -77,6 +77,7 @@ struct ehdg_plan {
 
 #define EHDG_SLOT_GEN 0x40000000
 #define EHDG_SLOT_MASK 0x3fffffff
+#define EHDG_SLOT_NONE ((int32_t)0x80000000)     /* element outside the plan's selection (partitioned assembly) */
 
 struct ehdg_csr {
     int32_t nf;
@@ -92,6 +93,14 @@ struct ehdg_csr {
     uint8_t* strip = nullptr;       // [nf]    1 = free facet of a marked element (enriched strip), null if none
     double* dinv = nullptr;         // [n_rows * nbmax] block-Jacobi inverses (set by ehdg_gmres)
     int nb;                         // slots per facet
+    // partitioned assembly (ehdg_csr_symbolic_part): this rank holds the facets [f_lo, f_hi) = rows [row_lo, row_hi);
+    // n_rows stays the GLOBAL size (column indices are global), nnz / colind / the value array cover the own rows only
+    int windowed = 0;
+    int32_t f_lo = 0, f_hi = 0;
+    int64_t row_lo = 0, row_hi = 0;
+    int nranks = 1;
+    std::vector<int64_t> part_rows;    // [nranks+1] first row of every rank
+    std::vector<int32_t> part_facets;  // [nranks+1] first facet of every rank
 };
 
 namespace ehdg {

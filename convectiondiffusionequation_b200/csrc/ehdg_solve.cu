@@ -29,7 +29,7 @@ __global__ void csr_dofmask_kernel(int nf, int nfl, const int32_t* __restrict__ 
     if (strip) strip[f] = (m != 0 && facet_mask[f] != 0) ? 1 : 0;      // free facet of a marked element
 }
 
-__global__ void csr_nbr_kernel(int nf, const int32_t* __restrict__ facet2el, const int32_t* __restrict__ el2facet,
+__global__ void csr_nbr_kernel(int nf, int f_lo, int f_hi, const int32_t* __restrict__ facet2el, const int32_t* __restrict__ el2facet,
                                const int32_t* __restrict__ nbf, int32_t* __restrict__ nbr, int32_t* __restrict__ nbr_len,
                                int64_t* __restrict__ blk) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,10 +60,10 @@ __global__ void csr_nbr_kernel(int nf, const int32_t* __restrict__ facet2el, con
     }
     const int rows = nbf[f];
     nbr_len[f] = rows ? len : 0;
-    blk[f] = (int64_t)rows * len;
+    blk[f] = (f >= f_lo && f < f_hi) ? (int64_t)rows * len : 0;     // values are stored for the facets of the window only
 }
 
-__global__ void csr_fill_kernel(int nf, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
+__global__ void csr_fill_kernel(int nf, int f_lo, int f_hi, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
                                 const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len,
                                 int64_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t* __restrict__ row_facet) {
     // one warp per facet
@@ -72,12 +72,14 @@ __global__ void csr_fill_kernel(int nf, const int32_t* __restrict__ row_start, c
     if (f >= nf) return;
     const int r0 = row_start[f], rows = row_start[f + 1] - r0;
     if (rows == 0) return;
-    const int len = nbr_len[f];
+    const bool mine = f >= f_lo && f < f_hi;
+    const int len = mine ? nbr_len[f] : 0;          // rows outside the window are empty
     const int64_t base = blk_base[f];
     for (int i = lane; i < rows; i += 32) {
         rowptr[r0 + i] = base + (int64_t)i * len;
         row_facet[r0 + i] = f;
     }
+    if (!mine) return;
     int off = 0;
     for (int t = 0; t < 5; ++t) {
         const int g = nbr[5 * f + t];
@@ -103,13 +105,13 @@ __device__ __forceinline__ int nth_set_bit(unsigned m, int n) {
     return __ffs(m) - 1;
 }
 
-__global__ void csr_numeric_kernel(int n_rows, SLayout sl, const int32_t* __restrict__ row_facet,
+__global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int32_t* __restrict__ row_facet,
                                    const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
                                    const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask,
                                    const int32_t* __restrict__ facet2el, const int32_t* __restrict__ el2facet,
                                    const int32_t* __restrict__ eslot, const double* __restrict__ S,
                                    const double* __restrict__ gv, double* __restrict__ vals, double* __restrict__ rhs) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = row_lo + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_lo, n_rows)
     if (r >= n_rows) return;
     const int f = row_facet[r];
     const int k = nth_set_bit(dofmask[f], r - row_start[f]);        // slot of this row on its facet
@@ -143,7 +145,7 @@ __global__ void csr_numeric_kernel(int n_rows, SLayout sl, const int32_t* __rest
     double b = 0.0;
     for (int s = 0; s < ne; ++s)
         if (k < nbe[s]) b += gb[s][lef[s] * nbe[s] + k];
-    rhs[r] = b;
+    rhs[r] = b;                                                     // rhs is indexed by the global row
     int64_t pos = rowptr[r];
     for (int t = 0; t < 5; ++t) {
         const int g = nbr[5 * f + t];
@@ -193,10 +195,10 @@ spmv_kernel(int row0, int n_rows, const int64_t* __restrict__ rowptr, const int3
 // columns, x is gathered once per facet, and neither colind nor rowptr is read (8 B/nnz instead of 12 B/nnz).
 template <int NBM, int CHUNKS>
 __global__ void __launch_bounds__(256)
-spmv_facet_kernel(int nf, int row0, int row1, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
+spmv_facet_kernel(int f0, int nf, int row0, int row1, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
                   const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len, const double* __restrict__ vals,
                   const double* __restrict__ x, double* __restrict__ y) {
-    const int f = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int f = f0 + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);      // facets [f0, nf)
     const int lane = threadIdx.x & 31;
     if (f >= nf) return;
     // first level of the dependency chain: everything addressed by f alone
@@ -260,18 +262,24 @@ static bool spmv_use_csr_kernel() {
 static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, double* y, cudaStream_t st, int64_t row0 = 0,
                        int64_t row1 = -1) {
     if (row1 < 0) row1 = A->n_rows;
+    if (A->windowed) {                       // only the own rows exist
+        row0 = row0 > A->row_lo ? row0 : A->row_lo;
+        row1 = row1 < A->row_hi ? row1 : A->row_hi;
+    }
     if (row1 <= row0) return EHDG_OK;
     if (spmv_use_csr_kernel()) {
         constexpr int TPR = 8;
         const int64_t threads = (row1 - row0) * TPR;
         spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)row0, (int)row1, A->rowptr, A->colind, vals, x, y);
     } else {
-        const int64_t threads = (int64_t)A->nf * 32;
+        const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
+        if (fb <= fa) return EHDG_OK;
+        const int64_t threads = (int64_t)(fb - fa) * 32;
         const unsigned gb = (unsigned)((threads + 255) / 256);
         if (A->nb <= 6)      // rows <= 6, row length <= 30: one column per lane
-            spmv_facet_kernel<6, 1><<<gb, 256, 0, st>>>(A->nf, (int)row0, (int)row1, A->row_start, A->blk_base, A->nbr, A->nbr_len, vals, x, y);
+            spmv_facet_kernel<6, 1><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base, A->nbr, A->nbr_len, vals, x, y);
         else
-            spmv_facet_kernel<EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH, 2><<<gb, 256, 0, st>>>(A->nf, (int)row0, (int)row1, A->row_start, A->blk_base,
+            spmv_facet_kernel<EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH, 2><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base,
                                                                                             A->nbr, A->nbr_len, vals, x, y);
     }
     EHDG_LAUNCH_CHECK();
@@ -283,10 +291,10 @@ static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, d
 // ---------------------------------------------------------------------------------------------
 constexpr int NBMAX = EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH;
 
-__global__ void bj_invert_kernel(int nf, int nbs, const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
+__global__ void bj_invert_kernel(int f0, int nf, int nbs, const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ nbr, const double* __restrict__ vals, double* __restrict__ dinv,
                                  int* __restrict__ fail, uint8_t* __restrict__ rowdrop) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = f0 + blockIdx.x * blockDim.x + threadIdx.x;       // facets [f0, nf)
     if (f >= nf) return;
     const int r0 = row_start[f], n = row_start[f + 1] - r0;
     if (n == 0) return;
@@ -376,12 +384,12 @@ __global__ void bj_invert_kernel(int nf, int nbs, const int32_t* __restrict__ ro
         for (int j = 0; j < nk; ++j) dinv[(size_t)(r0 + keep[i]) * nbs + keep[j]] = a[i][nk + j];
 }
 
-__global__ void bj_fold_kernel(int n_rows, int nbs, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
+__global__ void bj_fold_kernel(int row_lo, int n_rows, int nbs, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
                                const int64_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
                                const double* __restrict__ dinv, const uint8_t* __restrict__ strip, double* __restrict__ vals) {
     // one thread per (row, neighbour block): segment <- segment * Dinv_g
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = (int)(t / 5), nb_i = (int)(t % 5);
+    const int r = row_lo + (int)(t / 5), nb_i = (int)(t % 5);       // rows [row_lo, n_rows)
     if (r >= n_rows) return;
     const int f = row_facet[r];
     int off = 0, g = -1;
@@ -701,6 +709,7 @@ __global__ void backsolve_kernel(int ne, SLayout sl, int n_p, int nvmax, const i
     const int lane = threadIdx.x & 31;
     if (el >= ne) return;
     const int s = eslot[el];
+    if (s == EHDG_SLOT_NONE) return;                    // element of another rank (partitioned assembly)
     const int idx = s & EHDG_SLOT_MASK;
     const bool gen = (s & EHDG_SLOT_GEN) != 0;
     const int nv = gen ? nvmax : n_p, nf = gen ? sl.nfg : sl.nfp, nbe = gen ? sl.nb : sl.nfl;
@@ -728,12 +737,13 @@ __global__ void backsolve_kernel(int ne, SLayout sl, int n_p, int nvmax, const i
 __global__ void __launch_bounds__(128)
 l2_error_kernel(Problem pb, RuleSet rs, int ne, int n_poly, const int32_t* __restrict__ eslot,
                 const double* __restrict__ verts, const int32_t* __restrict__ tris,
-                const uint8_t* __restrict__ elem_active, const double* __restrict__ u, double* __restrict__ block_out) {
+                const uint8_t* __restrict__ elem_active, const uint8_t* __restrict__ elem_select, const double* __restrict__ u,
+                double* __restrict__ block_out) {
     // one warp per element, lanes over quadrature points (order 50 + bonus, conv_diff.py:393-394)
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int el = blockIdx.x * 4 + wid;
     double e2 = 0.0, h2 = 0.0;
-    if (el < ne) {
+    if (el < ne && eslot[el] != EHDG_SLOT_NONE && !(elem_select && !elem_select[el])) {
         ElemGeom g;
         elem_geom(verts, tris + 3 * el, g);
         const int s = eslot[el];
@@ -792,16 +802,28 @@ static SLayout make_slayout(const ehdg_ctx* c, const ehdg_plan* p) {
     return sl;
 }
 
-extern "C" {
+// first facet of each of nranks nearly equal row ranges that never cut a facet block (lower bound of k n / nranks in row_start)
+__global__ void csr_partition_kernel(int nf, int nranks, const int32_t* __restrict__ row_start, int32_t* __restrict__ facet_begin) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nranks) return;
+    const int64_t n = row_start[nf];
+    const int64_t target = (n * k) / nranks;
+    int lo = 0, hi = nf;                      // smallest f with row_start[f] >= target
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (row_start[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    facet_begin[k] = k == nranks ? nf : lo;
+}
 
-int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_active, const uint8_t* facet_mask, ehdg_csr** out,
-                      void* stream) {
-    if (!c || !m || !out) { set_error("ehdg_csr_symbolic: null argument"); return EHDG_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
+static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_active, const uint8_t* facet_mask, int nranks, int rank,
+                             ehdg_csr** out, cudaStream_t st) {
     const int nf = m->nf;
+    const bool windowed = nranks > 1;
     ehdg_csr* A = new ehdg_csr();
     A->nf = nf;
     A->nb = c->pb.nb;
+    A->nranks = nranks;
     int32_t* nbf = nullptr;
     int64_t* blk = nullptr;
     void* tmp = nullptr;
@@ -819,12 +841,34 @@ int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_acti
     csr_dofmask_kernel<<<gb, 256, 0, st>>>(nf, c->pb.nfl, m->facet2el, c->pb.nenr ? facet_active : nullptr, facet_mask, A->dofmask, nbf,
                                            want_strip ? A->strip : nullptr);
     EHDG_LAUNCH_CHECK();
-    csr_nbr_kernel<<<gb, 256, 0, st>>>(nf, m->facet2el, m->el2facet, nbf, A->nbr, A->nbr_len, blk);
-    EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb1, nbf, A->row_start, nf + 1, st));
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, blk, A->blk_base, nf + 1, st));
     EHDG_CUDA(cudaMalloc(&tmp, (tb1 > tb2 ? tb1 : tb2) + 8));
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb1, nbf, A->row_start, nf + 1, st));
+    // the row partition (every rank computes the same one from the same replicated masks)
+    A->part_facets.assign((size_t)nranks + 1, 0);
+    A->part_rows.assign((size_t)nranks + 1, 0);
+    {
+        int32_t* fb = nullptr;
+        EHDG_CUDA(cudaMalloc(&fb, sizeof(int32_t) * (size_t)(2 * (nranks + 1))));
+        csr_partition_kernel<<<(nranks + 1 + 63) / 64, 64, 0, st>>>(nf, nranks, A->row_start, fb);
+        EHDG_LAUNCH_CHECK();
+        EHDG_CUDA(cudaMemcpyAsync(A->part_facets.data(), fb, sizeof(int32_t) * (size_t)(nranks + 1), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        std::vector<int32_t> rs((size_t)nranks + 1);
+        for (int k = 0; k <= nranks; ++k)
+            EHDG_CUDA(cudaMemcpyAsync(&rs[k], A->row_start + A->part_facets[k], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k <= nranks; ++k) A->part_rows[k] = rs[k];
+        cudaFree(fb);
+    }
+    A->windowed = windowed ? 1 : 0;
+    A->f_lo = windowed ? A->part_facets[rank] : 0;
+    A->f_hi = windowed ? A->part_facets[rank + 1] : nf;
+    A->row_lo = windowed ? A->part_rows[rank] : 0;
+    A->row_hi = windowed ? A->part_rows[rank + 1] : A->part_rows[nranks];
+    csr_nbr_kernel<<<gb, 256, 0, st>>>(nf, A->f_lo, A->f_hi, m->facet2el, m->el2facet, nbf, A->nbr, A->nbr_len, blk);
+    EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb2, blk, A->blk_base, nf + 1, st));
     int32_t nrows = 0;
     int64_t nnz = 0;
@@ -837,7 +881,7 @@ int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_acti
     EHDG_CUDA(cudaMalloc(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
     int32_t* row_facet = nullptr;
     EHDG_CUDA(cudaMalloc(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1)));
-    if (nf > 0) csr_fill_kernel<<<(unsigned)(((int64_t)nf * 32 + 255) / 256), 256, 0, st>>>(nf, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
+    if (nf > 0) csr_fill_kernel<<<(unsigned)(((int64_t)nf * 32 + 255) / 256), 256, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
     EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
@@ -847,6 +891,29 @@ int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_acti
     cudaFree(tmp);
     A->row_facet = row_facet;
     *out = A;
+    return EHDG_OK;
+}
+
+extern "C" {
+
+int ehdg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_active, const uint8_t* facet_mask, ehdg_csr** out,
+                      void* stream) {
+    if (!c || !m || !out) { set_error("ehdg_csr_symbolic: null argument"); return EHDG_ERR_ARG; }
+    return csr_symbolic_impl(c, m, facet_active, facet_mask, 1, 0, out, (cudaStream_t)stream);
+}
+
+int ehdg_csr_symbolic_part(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet_active, const uint8_t* facet_mask, int nranks, int rank,
+                           ehdg_csr** out, void* stream) {
+    if (!c || !m || !out || nranks < 1 || rank < 0 || rank >= nranks) { set_error("ehdg_csr_symbolic_part: bad argument"); return EHDG_ERR_ARG; }
+    return csr_symbolic_impl(c, m, facet_active, facet_mask, nranks, rank, out, (cudaStream_t)stream);
+}
+
+int ehdg_csr_get_partition(const ehdg_csr* A, int64_t* row_begin, int32_t* facet_begin) {
+    if (!A || !row_begin || !facet_begin) { set_error("ehdg_csr_get_partition: null argument"); return EHDG_ERR_ARG; }
+    for (int k = 0; k <= A->nranks; ++k) {
+        row_begin[k] = A->part_rows[k];
+        facet_begin[k] = A->part_facets[k];
+    }
     return EHDG_OK;
 }
 
@@ -882,7 +949,9 @@ int ehdg_csr_numeric(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const e
     if (!c || !p || !A || !m || !S || !g || !vals || !rhs) { set_error("ehdg_csr_numeric: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     if (A->n_rows == 0) return EHDG_OK;
-    csr_numeric_kernel<<<(unsigned)((A->n_rows + 127) / 128), 128, 0, st>>>((int)A->n_rows, make_slayout(c, p), A->row_facet, A->row_start,
+    const int64_t rlo = A->windowed ? A->row_lo : 0, rhi = A->windowed ? A->row_hi : A->n_rows;
+    if (rhi <= rlo) return EHDG_OK;
+    csr_numeric_kernel<<<(unsigned)((rhi - rlo + 127) / 128), 128, 0, st>>>((int)rlo, (int)rhi, make_slayout(c, p), A->row_facet, A->row_start,
                                                                             A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,
                                                                             p->eslot, S, g, vals, rhs);
     EHDG_LAUNCH_CHECK();
@@ -905,7 +974,14 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     const int64_t n = r1 - r0;                                      // rows this rank iterates on
     if (dc) {
         if (info->use_strip_block) { set_error("ehdg_gmres: the strip block is not available in the distributed solve"); return EHDG_ERR_ARG; }
+        if (A->windowed && (A->row_lo != r0 || A->row_hi != r1)) {
+            set_error("ehdg_gmres: the communicator's partition differs from the rows this rank assembled");
+            return EHDG_ERR_ARG;
+        }
         rhs += r0;
+    } else if (A->windowed) {
+        set_error("ehdg_gmres: a partitioned matrix needs the communicator and its partition (ehdg_comm_init / _set_partition)");
+        return EHDG_ERR_ARG;
     }
     const int m = info->restart > 0 ? info->restart : 30;
     const int max_iters = info->max_iters > 0 ? info->max_iters : 1000;
@@ -928,8 +1004,18 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     EHDG_CUDA(cudaMemsetAsync(fail, 0, 2 * sizeof(int), st));
     uint8_t* rowdrop = nullptr;
     EHDG_CUDA(cudaMalloc(&rowdrop, (size_t)ng));
-    bj_invert_kernel<<<(A->nf + 127) / 128, 128, 0, st>>>(A->nf, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop);
-    EHDG_LAUNCH_CHECK();
+    {
+        // replicated matrix: every rank inverts all facet blocks; partitioned matrix: the own facets, and the inverses of
+        // the halo facets (the right preconditioner scales COLUMNS) come from the neighbouring ranks
+        const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
+        if (A->windowed) EHDG_CUDA(cudaMemsetAsync(A->dinv, 0, sizeof(double) * (size_t)ng * nbs, st));
+        if (fb > fa) bj_invert_kernel<<<(fb - fa + 127) / 128, 128, 0, st>>>(fa, fb, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop);
+        EHDG_LAUNCH_CHECK();
+        if (A->windowed) {
+            const int rh = dc->halo_exchange(A->dinv, st, nbs);
+            if (rh) return rh;
+        }
+    }
     // strip of marked elements: one exactly solved block (needs the unscaled matrix values)
     StripSolver* strip = nullptr;
     if (info->use_strip_block) {
@@ -938,8 +1024,12 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     }
     info->strip_dofs = strip ? strip->n_dofs : 0;
     info->strip_blocks = strip ? strip->n_blocks : 0;
-    bj_fold_kernel<<<(unsigned)((ng * 5 + 255) / 256), 256, 0, st>>>((int)ng, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr, A->dinv,
-                                                                     strip ? A->strip : nullptr, vals);
+    {
+        const int64_t fl = A->windowed ? A->row_lo : 0, fh = A->windowed ? A->row_hi : ng;
+        if (fh > fl)
+            bj_fold_kernel<<<(unsigned)(((fh - fl) * 5 + 255) / 256), 256, 0, st>>>((int)fl, (int)fh, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr,
+                                                                                    A->dinv, strip ? A->strip : nullptr, vals);
+    }
     EHDG_LAUNCH_CHECK();
     // ---- workspace
     double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr, *tvec = nullptr, *xg = nullptr;
@@ -1016,6 +1106,17 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     int fail_h2[2] = {0, 0};
     EHDG_CUDA(cudaMemcpy(fail_h2, fail, 2 * sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(fail);
+    if (dc && A->windowed) {
+        // every rank inverted its own facet blocks: failure and drop counts are collective (all ranks leave together)
+        hbuf[0] = fail_h2[0];
+        hbuf[1] = fail_h2[1];
+        EHDG_CUDA(cudaMemcpyAsync(d_nrm, hbuf, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        if ((rc = dc->allreduce_sum(d_nrm, 2, st))) return rc;
+        EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        fail_h2[0] = (int)hbuf[0];
+        fail_h2[1] = (int)hbuf[1];
+    }
     const int fail_h = fail_h2[0];
     info->dropped_dofs = fail_h2[1];
     if (fail_h) { set_error("ehdg_gmres: singular facet diagonal block"); return EHDG_ERR_SINGULAR; }
@@ -1333,8 +1434,8 @@ int ehdg_backsolve(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehd
     return EHDG_OK;
 }
 
-int ehdg_l2_error(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, const double* u, double* err2,
-                  void* stream) {
+int ehdg_l2_error_select(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, const uint8_t* elem_select,
+                         const double* u, double* err2, void* stream) {
     if (!c || !p || !m || !u || !err2) { set_error("ehdg_l2_error: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int nblocks = (m->ne + 3) / 4;
@@ -1342,13 +1443,18 @@ int ehdg_l2_error(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uin
     double* partial = nullptr;
     EHDG_CUDA(cudaMalloc(&partial, sizeof(double) * (size_t)nblocks * KT));
     l2_error_kernel<<<nblocks, 128, 0, st>>>(c->pb, c->rerr.rs, m->ne, (int)p->n_poly, p->eslot, m->verts, m->tris,
-                                             c->pb.nenr ? elem_active : nullptr, u, partial);
+                                             c->pb.nenr ? elem_active : nullptr, elem_select, u, partial);
     EHDG_LAUNCH_CHECK();
     reduce_partials_kernel<<<2, 256, 0, st>>>(nblocks, 2, partial, err2, 0);
     EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cudaStreamSynchronize(st));
     cudaFree(partial);
     return EHDG_OK;
+}
+
+int ehdg_l2_error(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, const double* u, double* err2,
+                  void* stream) {
+    return ehdg_l2_error_select(c, p, m, elem_active, nullptr, u, err2, stream);
 }
 
 }  // extern "C"

@@ -108,11 +108,16 @@ class EHDGPipeline:
                 self.vert_flags = torch.from_numpy(vf).to(self.dev)
             _lib.check(self.lib.ehdg_mark(self.ctx, C.byref(self.cmesh), _ptr(self.vert_flags), _ptr(self.elem_mask),
                                           _ptr(self.facet_mask), self._stream()), "ehdg_mark")
+        return self.make_plan(None)
+
+    def make_plan(self, elem_select=None):
+        """(re)builds the plan; elem_select (u8 [ne] device tensor or None): partitioned assembly keeps only these elements"""
         if self.plan is not None:
             self.lib.ehdg_plan_destroy(self.plan)
         self.plan = C.c_void_p()
-        _lib.check(self.lib.ehdg_plan_create(self.ctx, C.byref(self.cmesh), _ptr(self.facet_mask), int(self.force_general),
-                                             C.byref(self.plan), self._stream()), "ehdg_plan_create")
+        self.elem_select = elem_select
+        _lib.check(self.lib.ehdg_plan_create_select(self.ctx, C.byref(self.cmesh), _ptr(self.facet_mask), int(self.force_general),
+                                                    _ptr(elem_select), C.byref(self.plan), self._stream()), "ehdg_plan_create_select")
         self.plan_sizes = _lib.PlanSizes()
         _lib.check(self.lib.ehdg_plan_get_sizes(self.plan, C.byref(self.plan_sizes)), "ehdg_plan_get_sizes")
         return self
@@ -166,6 +171,29 @@ class EHDGPipeline:
         return self
 
     # ------------------------------------------------------------------ a8
+    def csr_symbolic(self, nranks=1, rank=0):
+        """pattern of the condensed system; nranks > 1: only the rows of this rank's facet range (partitioned assembly)"""
+        if self.csr is not None:
+            self.lib.ehdg_csr_destroy(self.csr)
+        self.csr = C.c_void_p()
+        _lib.check(self.lib.ehdg_csr_symbolic_part(self.ctx, C.byref(self.cmesh), _ptr(self.facet_active) if self.nenr else None,
+                                                   _ptr(self.facet_mask) if self.nenr else None, int(nranks), int(rank),
+                                                   C.byref(self.csr), self._stream()), "ehdg_csr_symbolic_part")
+        self.csr_sizes = _lib.CsrSizes()
+        _lib.check(self.lib.ehdg_csr_get_sizes(self.csr, C.byref(self.csr_sizes)), "ehdg_csr_get_sizes")
+        rb = np.zeros(nranks + 1, dtype=np.int64)
+        fb = np.zeros(nranks + 1, dtype=np.int32)
+        _lib.check(self.lib.ehdg_csr_get_partition(self.csr, rb.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.c_void_p)),
+                   "ehdg_csr_get_partition")
+        self.row_begin, self.facet_begin = rb, fb
+        return self
+
+    def csr_alloc_values(self):
+        n, nnz = self.csr_sizes.n_rows, self.csr_sizes.nnz
+        self.vals = torch.empty(max(nnz, 1), dtype=torch.float64, device=self.dev)
+        self.rhs = torch.zeros(max(n, 1), dtype=torch.float64, device=self.dev)
+        return self
+
     def csr_build(self):
         if self.csr is not None:
             self.lib.ehdg_csr_destroy(self.csr)
@@ -222,11 +250,15 @@ class EHDGPipeline:
 
     def errors(self):
         """(L2 error, H1-seminorm error) against spec.exact with the order 50+bonus rule."""
-        err2 = torch.zeros(2, dtype=torch.float64, device=self.dev)
-        _lib.check(self.lib.ehdg_l2_error(self.ctx, self.plan, C.byref(self.cmesh), _ptr(self.elem_active), _ptr(self.u),
-                                          _ptr(err2), self._stream()), "ehdg_l2_error")
-        e = err2.cpu().numpy()
+        e = self.error_sums().cpu().numpy()
         return float(np.sqrt(e[0])), float(np.sqrt(e[1]))
+
+    def error_sums(self, elem_select=None):
+        """f64[2] device tensor: squared L2 and H1-seminorm errors summed over the plan's elements (or elem_select of them)"""
+        err2 = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ehdg_l2_error_select(self.ctx, self.plan, C.byref(self.cmesh), _ptr(self.elem_active), _ptr(elem_select),
+                                                 _ptr(self.u), _ptr(err2), self._stream()), "ehdg_l2_error_select")
+        return err2
 
     def kernel_timing(self, enable=True):
         _lib.check(self.lib.ehdg_kernel_timing(self.ctx, int(enable)), "ehdg_kernel_timing")

@@ -1,4 +1,10 @@
-"""Row partition of the condensed facet system for the multi-GPU solve (one process per GPU).
+"""Row partition of the condensed facet system for the multi-GPU path (one process per GPU).
+
+Partitioned assembly: a rank owns a contiguous facet range = a contiguous row range of the condensed
+system.  It assembles and condenses the elements that touch its facets (its own elements plus one layer of
+redundantly computed ghosts, so no S_K crosses GPUs), fills its own CSR rows, and iterates on them; the halo of x
+travels per SpMV, the block-Jacobi inverses of the halo facets once, dot products as one all-reduce per batch.
+`partitioned_assemble` / `partitioned_solve` below drive that; `set_partition` is the older replicated-matrix mode.
 
 The facet-major numbering follows the facets' vertex pairs, so on the (jittered) lattice meshes the matrix is
 banded: a contiguous block of rows references columns of the two neighbouring blocks at most.  Each rank
@@ -88,3 +94,101 @@ def set_partition(pipe, nranks):
     rb, lo, hi = (np.ascontiguousarray(a, dtype=np.int64) for a in (row_begin, col_lo, col_hi))
     _lib.check(pipe.lib.ehdg_comm_set_partition(pipe.ctx, p64(rb), p64(lo), p64(hi)), "ehdg_comm_set_partition")
     return rb, lo, hi
+
+
+# ------------------------------------------------------------------------------------------------------------
+# partitioned assembly: element selection, ownership, halo extents
+# ------------------------------------------------------------------------------------------------------------
+def select_elements(facet2el, f_lo: int, f_hi: int, ne: int):
+    """u8 [ne]: 1 for every element adjacent to a facet of [f_lo, f_hi) (torch tensor or numpy array in, same kind out)."""
+    import torch
+    if isinstance(facet2el, np.ndarray):
+        sel = np.zeros(ne, dtype=np.uint8)
+        adj = facet2el[f_lo:f_hi].reshape(-1)
+        sel[adj[adj >= 0]] = 1
+        return sel
+    sel = torch.zeros(ne, dtype=torch.uint8, device=facet2el.device)
+    adj = facet2el[f_lo:f_hi].reshape(-1).long()
+    sel[adj[adj >= 0]] = 1
+    return sel
+
+
+def owned_elements(el2facet, f_lo: int, f_hi: int):
+    """u8 [ne]: an element belongs to the rank that owns its lowest-numbered facet (a partition of the elements; the
+    owner always has the element selected)."""
+    import torch
+    if isinstance(el2facet, np.ndarray):
+        m = el2facet.min(axis=1)
+        return ((m >= f_lo) & (m < f_hi)).astype(np.uint8)
+    m = el2facet.min(dim=1).values
+    return ((m >= f_lo) & (m < f_hi)).to(torch.uint8)
+
+
+def gather_extents(lo: int, hi: int, group=None, device="cpu"):
+    """all ranks' (col_lo, col_hi) from each rank's own pair"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    mine = torch.tensor([int(lo), int(hi)], dtype=torch.int64, device=device)
+    out = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    arr = torch.stack(out).cpu().numpy()
+    return arr[:, 0].copy(), arr[:, 1].copy()
+
+
+def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True):
+    """mark + prune (replicated: O(sqrt(ne)) work), then this rank's share: pattern of its rows, alpha + element blocks +
+    condensation of the elements that touch its facets, numeric fill of its rows, and the communicator's partition.
+    exchange=False stops before the collective part (single-process checks of one rank's share)."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .hot_path import _device_view
+    pipe.setup()                                             # a1, a3 on the full mesh
+    pipe.csr_symbolic(world, rank)
+    f_lo, f_hi = int(pipe.facet_begin[rank]), int(pipe.facet_begin[rank + 1])
+    m = pipe.mesh_host
+    sel = select_elements(pipe.facet2el, f_lo, f_hi, m.ne)
+    pipe.elem_owned = owned_elements(pipe.el2facet, f_lo, f_hi)
+    pipe.make_plan(sel)
+    pipe.assemble()                                          # a4-a7 on the selection
+    pipe.csr_alloc_values().csr_numeric()                    # a8, own rows
+    rb = pipe.row_begin
+    r0, r1 = int(rb[rank]), int(rb[rank + 1])
+    nnz = int(pipe.csr_sizes.nnz)
+    if nnz > 0:
+        ci = _device_view(pipe.lib.ehdg_csr_colind(pipe.csr), nnz, torch.int32, pipe.dev)
+        lo, hi = min(int(ci.min()), r0), max(int(ci.max()) + 1, r1)
+    else:
+        lo, hi = r0, r1
+    pipe.own_extent = (lo, hi)
+    if not exchange:
+        return pipe
+    if world > 1:
+        dev = pipe.dev if dist.get_backend(group) == "nccl" else "cpu"
+        col_lo, col_hi = gather_extents(lo, hi, group, dev)
+    else:
+        col_lo, col_hi = np.asarray([lo], dtype=np.int64), np.asarray([hi], dtype=np.int64)
+    if not check_neighbour_halo(rb, col_lo, col_hi):
+        raise _lib.EhdgError("the halo of a rank reaches beyond its neighbouring ranks: too many ranks for this mesh")
+    if world > 1:
+        p64 = lambda a: a.ctypes.data_as(C.c_void_p)
+        rbc, loc, hic = (np.ascontiguousarray(a, dtype=np.int64) for a in (rb, col_lo, col_hi))
+        _lib.check(pipe.lib.ehdg_comm_set_partition(pipe.ctx, p64(rbc), p64(loc), p64(hic)), "ehdg_comm_set_partition")
+    pipe.col_lo, pipe.col_hi = col_lo, col_hi
+    return pipe
+
+
+def partitioned_solve(pipe, group=None, **gm):
+    """Krylov solve on the partitioned system, back-solve on the rank's elements, (L2, H1) error over all ranks"""
+    import torch
+    import torch.distributed as dist
+    gm.setdefault("strip_block", False)
+    pipe.gmres(**gm).backsolve()
+    e = pipe.error_sums(pipe.elem_owned)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dist.get_backend(group) != "nccl":
+            e = e.cpu()
+        dist.all_reduce(e, group=group)
+    e = e.cpu().numpy()
+    return float(np.sqrt(e[0])), float(np.sqrt(e[1]))

@@ -116,6 +116,12 @@ typedef struct {
 } ehdg_plan_sizes;
 int ehdg_plan_create(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_mask, int force_general,
                      ehdg_plan** out, void* stream);
+/* partitioned assembly: only the elements with elem_select[el] != 0 (u8 [ne], device; null = all) get a slot;
+ * every later stage (alpha, assemble + condense, CSR numeric, back-solve, error) then works on that subset and the
+ * element stores are sized by it.  A rank selects the elements that touch its facet range, i.e. its own elements plus
+ * one layer of redundantly computed ghosts, so that no S_K crosses GPUs. */
+int ehdg_plan_create_select(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_mask, int force_general,
+                            const uint8_t* elem_select, ehdg_plan** out, void* stream);
 int ehdg_plan_destroy(ehdg_plan* plan);
 int ehdg_plan_get_sizes(const ehdg_plan* plan, ehdg_plan_sizes* out);
 /* eslot i32[ne]: bit 30 set = general path; low bits = index on that path (device pointer, plan-owned) */
@@ -163,6 +169,15 @@ typedef struct {
 } ehdg_csr_sizes;
 int ehdg_csr_symbolic(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_active, const uint8_t* facet_mask,
                       ehdg_csr** out, void* stream);
+/* Row-partitioned variant: the rows are split into nranks nearly equal contiguous ranges at facet boundaries (the same
+ * partition on every rank: it follows from the replicated dof masks) and this rank keeps the pattern of its own rows only.
+ * n_rows stays the global size and column indices stay global; nnz, colind and the value array cover the own rows; the
+ * right-hand side and the solution are indexed by the global row.  ehdg_csr_get_partition: row_begin i64[nranks+1],
+ * facet_begin i32[nranks+1] (host).  The Krylov solvers accept such a matrix once ehdg_comm_set_partition holds the
+ * same row_begin; they exchange the block-Jacobi inverses of the halo facets once and the halo of x per SpMV. */
+int ehdg_csr_symbolic_part(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_active, const uint8_t* facet_mask,
+                           int nranks, int rank, ehdg_csr** out, void* stream);
+int ehdg_csr_get_partition(const ehdg_csr* csr, int64_t* row_begin, int32_t* facet_begin);
 int ehdg_csr_destroy(ehdg_csr* csr);
 int ehdg_csr_get_sizes(const ehdg_csr* csr, ehdg_csr_sizes* out);
 const int64_t* ehdg_csr_rowptr(const ehdg_csr* csr);     /* i64 [n_rows+1] device */
@@ -223,6 +238,10 @@ int ehdg_backsolve(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_csr* csr, co
                    const double* W, const double* z, const double* xhat, double* u, void* stream);
 int ehdg_l2_error(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_active,
                   const double* u, double* err2, void* stream);
+/* same, over the elements with elem_select[el] != 0 only (u8 [ne], device; null = all): the owned elements of a rank,
+ * whose partial sums the caller adds over the ranks */
+int ehdg_l2_error_select(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_active,
+                         const uint8_t* elem_select, const double* u, double* err2, void* stream);
 
 #ifdef __cplusplus
 }
