@@ -260,6 +260,23 @@ class EHDGPipeline:
                                                  _ptr(self.u), _ptr(err2), self._stream()), "ehdg_l2_error_select")
         return err2
 
+    def moment_rhs_fraction(self) -> float:
+        """share of the polynomial-path elements on which both layer functions of `coeff` have underflowed, so that
+        fast_assemble_kernel takes f_V from the moment vectors (same test as csrc/ehdg_fast.h; used for flop accounting)"""
+        f = self.spec.coeff
+        if f is None or self.plan_sizes.n_poly == 0:
+            return 0.0
+        c, k = f.desc()
+        dmin = (1.0 - self.verts[self.tris.long()]).amin(dim=1)          # [ne, 2]
+        ok = torch.ones(dmin.shape[0], dtype=torch.bool, device=self.dev)
+        if c[1] != 0.0 or c[3] != 0.0:
+            ok &= dmin[:, 0] * k[0] > 747.0
+        if c[2] != 0.0 or c[3] != 0.0:
+            ok &= dmin[:, 1] * k[1] > 747.0
+        slot = _device_view(self.lib.ehdg_plan_eslot(self.plan), self.mesh_host.ne, torch.int32, self.dev)
+        poly = (slot >= 0) & ((slot & 0x40000000) == 0)
+        return float((ok & poly).sum().item()) / float(self.plan_sizes.n_poly)
+
     def kernel_timing(self, enable=True):
         _lib.check(self.lib.ehdg_kernel_timing(self.ctx, int(enable)), "ehdg_kernel_timing")
         return self
