@@ -49,8 +49,10 @@ fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, cons
     extern __shared__ double smem[];
     for (int i = threadIdx.x; i < tab_doubles; i += FAST_THREADS) smem[i] = tab_g[i];
     __syncthreads();
-    const int gid = threadIdx.x / LG;
-    Group<LG> gc{(int)(threadIdx.x % LG), smem + ((tab_doubles + 1) & ~1) + gid * fast_alpha_scratch_doubles<P>()};
+    // interleaved groups (ehdg_fast.h, Group::il): lane l of group g of a warp is thread l * GPW + g
+    constexpr int GPW = 32 / LG;
+    const int gid = (threadIdx.x / 32) * GPW + (threadIdx.x % GPW);
+    Group<LG> gc{(int)((threadIdx.x & 31) / GPW), smem + ((tab_doubles + 1) & ~1) + gid * fast_alpha_scratch_doubles<P>(), GPW};
     for (int base = blockIdx.x * GPC; base < n; base += gridDim.x * GPC) {
         const bool live = base + gid < n;
         const int idx = live ? base + gid : n - 1;

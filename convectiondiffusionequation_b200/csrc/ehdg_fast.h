@@ -66,6 +66,11 @@ template <int LG>
 struct Group {
     int lane;       // lane inside the group (device); unused on the host
     double* sh;     // group-private scratch
+    // Device: where the group's lanes sit in the warp.  il = 1: LG consecutive threads (group g = threads g LG ...).
+    // il = 32 / LG: interleaved, lane l of group g is thread l * il + g, so that the lanes of the same ROW of all the
+    // groups of a warp are neighbours: when one lane per group stores its row (16-byte accesses are issued per
+    // quarter warp) the warp needs one shared-memory wavefront instead of one per group.
+    int il = 1;
 
     // Row holding the largest key.  Every lane offers R candidate rows (row = h * LG + lane); keys are
     // magnitudes >= 0, or -1 for "not a candidate".  They are compared through the top 32 bits of the
@@ -113,7 +118,7 @@ struct Group {
 #ifdef __CUDA_ARCH__
         double s = x[0];
 #pragma unroll
-        for (int d = LG / 2; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d, LG);
+        for (int d = LG / 2; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d * il);
         return s;
 #else
         // same pairing as the butterfly so host and device round identically
@@ -127,17 +132,27 @@ struct Group {
         return t[0];
 #endif
     }
-    // bit l set iff flag of lane l is non-zero
-    EHDG_HD unsigned ballot(const int* flag) const {
+    // first lane of the group whose flag is non-zero, LG if none
+    EHDG_HD int first_set(const int* flag) const {
 #ifdef __CUDA_ARCH__
         const unsigned b = __ballot_sync(0xffffffffu, flag[0] != 0);
-        const int base = (threadIdx.x & 31) & ~(LG - 1);
-        return (LG == 32) ? b : ((b >> base) & ((1u << LG) - 1u));
+        const int t = threadIdx.x & 31;
+        if (il == 1) {
+            const int base = t & ~(LG - 1);
+            const unsigned m = (LG == 32) ? b : ((b >> base) & ((1u << LG) - 1u));
+            return m ? __ffs((int)m) - 1 : LG;
+        }
+        // interleaved: the group's lanes are the bits g, g + il, g + 2 il, ...
+        const int g = t % il;
+        unsigned pat = 0u;
+#pragma unroll
+        for (int l = 0; l < LG; ++l) pat |= 1u << (l * (32 / LG));
+        const unsigned m = (b >> g) & pat;
+        return m ? (__ffs((int)m) - 1) / il : LG;
 #else
-        unsigned b = 0;
         for (int l = 0; l < LG; ++l)
-            if (flag[l]) b |= 1u << l;
-        return b;
+            if (flag[l]) return l;
+        return LG;
 #endif
     }
 };
@@ -919,15 +934,7 @@ EHDG_HD double fast_alpha_element(const Group<AlphaDims<P>::LG>& gc, const doubl
             }
             below[L] = ok ? 1 : 0;
         EHDG_END_LANES
-        const unsigned b = gc.ballot(below);
-        // first lane whose abscissa is above the spectrum
-        int f = LG;
-#ifdef __CUDA_ARCH__
-        if (b) f = __ffs((int)b) - 1;
-#else
-        for (int l = 0; l < LG; ++l)
-            if ((b >> l) & 1u) { f = l; break; }
-#endif
+        const int f = gc.first_set(below);        // first lane whose abscissa is above the spectrum
         const double nlo = lo + step * (double)f;          // x_{f-1}  (f = 0 -> lo)
         const double nhi = (f < LG) ? lo + step * (double)(f + 1) : hi;
         lo = nlo;

@@ -192,66 +192,90 @@ spmv_kernel(int row0, int n_rows, const int64_t* __restrict__ rowptr, const int3
 
 // Facet-block SpMV.  All rows of a facet share one column set (the dofs of its <= 5 neighbour facets, ascending), and
 // csr_fill_kernel lays the facet's values out as a dense rows x len block at blk_base[f].  One warp per facet: lanes own
-// columns, x is gathered once per facet, and neither colind nor rowptr is read (8 B/nnz instead of 12 B/nnz).
-template <int NBM, int CHUNKS>
+// columns, x is gathered once per facet through the column indices of the block's FIRST row; rowptr is not read
+// (8 B/nnz + 4 B/column instead of 12 B/nnz).
+#ifndef EHDG_SPMV_FPW
+#define EHDG_SPMV_FPW 1     /* measured on B200: 2, 4, 8 facets per warp are slower (registers, not latency, limit the kernel) */
+#endif
+// FPW consecutive facets per warp, handled in lock step: the three dependent load levels (facet tables -> matrix block and
+// neighbour ranges -> x) are each issued for all FPW facets before the first use, which multiplies the bytes a warp keeps
+// in flight (the kernel is latency-bound: ~1 KB of matrix per facet behind a three-deep pointer chase).
+template <int NBM, int CHUNKS, int FPW>
 __global__ void __launch_bounds__(256)
 spmv_facet_kernel(int f0, int nf, int row0, int row1, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
-                  const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len, const double* __restrict__ vals,
+                  const int32_t* __restrict__ colind, const int32_t* __restrict__ nbr_len, const double* __restrict__ vals,
                   const double* __restrict__ x, double* __restrict__ y) {
-    const int f = f0 + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);      // facets [f0, nf)
+    const int fw = f0 + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * FPW;      // facets [f0, nf)
     const int lane = threadIdx.x & 31;
-    if (f >= nf) return;
+    if (fw >= nf) return;
     // first level of the dependency chain: everything addressed by f alone
-    const int g = lane < 5 ? nbr[5 * f + lane] : -1;
-    const int r0 = row_start[f], rows = row_start[f + 1] - r0;
-    const int len = nbr_len[f];
-    const int64_t base = blk_base[f];
-    if (rows == 0 || r0 + rows <= row0 || r0 >= row1) return;
-    // second level: the matrix block and the neighbours' column ranges
-    const double* __restrict__ blk = vals + base;
-    double a[CHUNKS][NBM];
+    int r0[FPW], rows[FPW], len[FPW];
+    int64_t base[FPW];
+    bool act[FPW];
 #pragma unroll
-    for (int c = 0; c < CHUNKS; ++c)
-#pragma unroll
-        for (int i = 0; i < NBM; ++i) a[c][i] = (i < rows && lane + 32 * c < len) ? blk[i * len + lane + 32 * c] : 0.0;
-    int c0 = 0, ng = 0;
-    if (g >= 0) {
-        c0 = row_start[g];
-        ng = row_start[g + 1] - c0;
+    for (int u = 0; u < FPW; ++u) {
+        const int f = fw + u < nf ? fw + u : nf - 1;
+        r0[u] = row_start[f];
+        rows[u] = row_start[f + 1] - r0[u];
+        len[u] = nbr_len[f];
+        base[u] = blk_base[f];
     }
-    int off = ng;                                          // exclusive scan over lanes 0..4
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, off, d);
-        if (lane >= d) off += t;
-    }
-    off -= ng;
-    // third level: x gathered once per facet
-    double xv[CHUNKS];
+    for (int u = 0; u < FPW; ++u) act[u] = fw + u < nf && rows[u] > 0 && r0[u] + rows[u] > row0 && r0[u] < row1;
+    // second level: the matrix block and the column indices of its first row (all rows of the facet share them: one
+    // coalesced 4-byte load per lane replaces the walk over the neighbour table and its warp shuffles)
+    double a[FPW][CHUNKS][NBM];
+    int col[FPW][CHUNKS];
 #pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) xv[c] = 0.0;
-#pragma unroll
-    for (int t = 0; t < 5; ++t) {
-        const int ot = __shfl_sync(0xffffffffu, off, t), nt = __shfl_sync(0xffffffffu, ng, t), ct = __shfl_sync(0xffffffffu, c0, t);
+    for (int u = 0; u < FPW; ++u) {
+        const double* __restrict__ blk = vals + base[u];
 #pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
-            const int l = lane + 32 * c - ot;
-            if (l >= 0 && l < nt) xv[c] = __ldg(x + ct + l);
+            const bool on = act[u] && lane + 32 * c < len[u];
+            col[u][c] = on ? __ldcs(colind + base[u] + lane + 32 * c) : -1;
+#pragma unroll
+            for (int i = 0; i < NBM; ++i)
+                a[u][c][i] = (on && i < rows[u]) ? __ldcs(blk + i * len[u] + lane + 32 * c) : 0.0;
         }
     }
-    double out = 0.0;
+    // third level: x gathered once per facet
+    double xv[FPW][CHUNKS];
 #pragma unroll
-    for (int i = 0; i < NBM; ++i) {
-        if (i < rows) {                                   // warp-uniform
-            double v = 0.0;
+    for (int u = 0; u < FPW; ++u)
 #pragma unroll
-            for (int c = 0; c < CHUNKS; ++c) v += a[c][i] * xv[c];
+        for (int c = 0; c < CHUNKS; ++c) xv[u][c] = col[u][c] >= 0 ? __ldg(x + col[u][c]) : 0.0;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            if (lane == i) out = v;
+    for (int u = 0; u < FPW; ++u) {
+        // NPAD row sums over the 32 lanes with one transposing butterfly: at every step a lane hands half of its
+        // rows to its partner and adds the partner's halves of the rows it keeps (NPAD/2 + NPAD/4 + ... shuffles instead
+        // of 5 per row; the kernel is bound by the shuffle pipe otherwise).
+        constexpr int NPAD = NBM <= 8 ? 8 : 16;
+        double v[NPAD];
+#pragma unroll
+        for (int i = 0; i < NPAD; ++i) {
+            v[i] = 0.0;
+            if (i < NBM) {
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) v[i] += a[u][c][i] * xv[u][c];
+            }
         }
+        int row = 0, d = 16;
+#pragma unroll
+        for (int half = NPAD / 2; half >= 1; half >>= 1, d >>= 1) {
+            const bool up = (lane & d) != 0;
+#pragma unroll
+            for (int k = 0; k < half; ++k) {
+                const double send = up ? v[k] : v[k + half];
+                const double recv = __shfl_xor_sync(0xffffffffu, send, d);
+                v[k] = (up ? v[k + half] : v[k]) + recv;
+            }
+            if (up) row += half;
+        }
+#pragma unroll
+        for (; d >= 1; d >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+        constexpr int LOWMASK = (32 / NPAD) - 1;              // lanes with these bits clear hold one row total each
+        if (act[u] && (lane & LOWMASK) == 0 && row < rows[u] && r0[u] + row >= row0 && r0[u] + row < row1) y[r0[u] + row] = v[0];
     }
-    if (lane < rows && r0 + lane >= row0 && r0 + lane < row1) y[r0 + lane] = out;
 }
 
 static bool spmv_use_csr_kernel() {
@@ -274,13 +298,14 @@ static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, d
     } else {
         const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
         if (fb <= fa) return EHDG_OK;
-        const int64_t threads = (int64_t)(fb - fa) * 32;
+        constexpr int FPW = EHDG_SPMV_FPW;
+        const int64_t threads = (((int64_t)(fb - fa) + FPW - 1) / FPW) * 32;
         const unsigned gb = (unsigned)((threads + 255) / 256);
         if (A->nb <= 6)      // rows <= 6, row length <= 30: one column per lane
-            spmv_facet_kernel<6, 1><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base, A->nbr, A->nbr_len, vals, x, y);
+            spmv_facet_kernel<6, 1, FPW><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base, A->colind, A->nbr_len, vals, x, y);
         else
-            spmv_facet_kernel<EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH, 2><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base,
-                                                                                            A->nbr, A->nbr_len, vals, x, y);
+            spmv_facet_kernel<EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH, 2, (FPW > 2 ? 2 : FPW)><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start,
+                                                                                                               A->blk_base, A->colind, A->nbr_len, vals, x, y);
     }
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
