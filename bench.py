@@ -178,7 +178,7 @@ def main():
     ap.add_argument("--solve-workload", default="ehdg_p4_eps1e-6_structured_1M",
                     help="mesh of the one-off solve leg ('same' = the timed workload; the 4M solve takes minutes)")
     ap.add_argument("--rtol", type=float, default=1e-8)
-    ap.add_argument("--restart", type=int, default=16)
+    ap.add_argument("--restart", type=int, default=8, help="GMRES restart / DQGMRES truncation length (tools/solve_k_scan.py: 8 is the fastest on the 1M system)")
     ap.add_argument("--sweeps", type=int, default=1, help="block-Jacobi sweeps per preconditioner application")
     ap.add_argument("--solve-type", default="hdg", choices=["hdg", "ehdg", "both"],
                     help="system of the one-off solve: plain HDG (well posed at every size) and/or the enriched one")
@@ -271,26 +271,64 @@ def main():
     # ---- e2e: host buffers in, alpha table + status out, every step
     pinned = dict(verts=torch.from_numpy(mesh.verts).pin_memory(), tris=torch.from_numpy(mesh.tris).pin_memory(),
                   el2facet=torch.from_numpy(mesh.el2facet).pin_memory(), facet2el=torch.from_numpy(mesh.facet2el).pin_memory())
-    lam_host = torch.empty(ne, dtype=torch.float64).pin_memory()
-    st_host = torch.empty(ne, dtype=torch.int32).pin_memory()
 
-    def e2e_step():
-        P.upload_mesh(pinned)
+    # Two-deep pipeline through the public API: a copy stream uploads the mesh of step i+1 and downloads the results of
+    # step i-1 while the compute stream works on step i.  Every step still moves its own inputs host->device and its own
+    # results device->host inside the timed region; only the copies overlap the kernels of the neighbouring steps.
+    copy_stream = torch.cuda.Stream(device=dev)
+    comp = torch.cuda.current_stream(dev)
+    slots = [dict(), dict()]
+    for sl_ in slots:
+        sl_["lam"] = torch.empty(ne, dtype=torch.float64, device=dev)
+        sl_["status"] = torch.zeros(ne, dtype=torch.int32, device=dev)
+        sl_["up"], sl_["done"], sl_["down"] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    lam_hosts = [torch.empty(ne, dtype=torch.float64).pin_memory() for _ in range(2)]
+    st_hosts = [torch.empty(ne, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def e2e_upload(i):
+        sl_ = slots[i % 2]
+        with torch.cuda.stream(copy_stream):
+            sl_["mesh"] = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+            sl_["up"].record(copy_stream)
+
+    def e2e_compute(i):
+        sl_ = slots[i % 2]
+        comp.wait_event(sl_["up"])
+        comp.wait_event(sl_["down"])                       # the slot's previous results have left the device
+        P.upload_mesh(sl_["mesh"])                         # device tensors: adopts them, no further copy
+        P.lam, P.status = sl_["lam"], sl_["status"]
         P.setup()
         P.alpha()
         P.assemble_condense()
-        lam_host.copy_(P.lam, non_blocking=True)
-        st_host.copy_(P.status, non_blocking=True)
+        sl_["done"].record(comp)
+
+    def e2e_download(i):
+        sl_ = slots[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(sl_["done"])
+            lam_hosts[i % 2].copy_(sl_["lam"], non_blocking=True)
+            st_hosts[i % 2].copy_(sl_["status"], non_blocking=True)
+            sl_["down"].record(copy_stream)
+
+    def e2e_run(k):
+        e2e_upload(0)
+        for i in range(k):
+            if i + 1 < k:
+                e2e_upload(i + 1)
+            e2e_compute(i)
+            e2e_download(i)
+        copy_stream.synchronize()
         torch.cuda.synchronize(dev)
 
-    e2e_step()
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_steps = max(2, min(args.steps, 6))
+    e2e_run(e2e_steps)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    lam_host = lam_hosts[(e2e_steps - 1) % 2]
+    assert bool(torch.isfinite(lam_host).all()) and float(lam_host.min()) > 0.0, "e2e: alpha table did not arrive"
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -435,7 +473,8 @@ def main():
                      "quadrature_equivalent_frac": value / world * int(sizes.flops_quad_elem) / 1e12 / fp64,
                      "hbm_gbs_of_outputs": out_bytes / (ms_step * 1e-3) / 1e9, "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src},
         "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_s * 1e3},
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "pipeline": "2 slots: the copy stream moves step i+1's mesh in and step i-1's alpha table + status out while step i computes"},
         "gpu_launches": int(args.steps * (2 + (3 if n_gen else 0))),
         "clocks": clocks.summary(),
     }

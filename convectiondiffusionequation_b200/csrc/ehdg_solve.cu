@@ -621,7 +621,12 @@ ring_dot_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring, 
 template <int K, int MODE>
 __global__ void __launch_bounds__(RED_THREADS)
 ring_axpy_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring, int s0, int kt, const double* __restrict__ h,
-                 const double* in, double* out, double* __restrict__ partial, double inv_d, double gamma, double* __restrict__ u) {
+                 const double* in, double* out, double* __restrict__ partial, double inv_d, double gamma, double* __restrict__ u,
+                 const double* __restrict__ scal = nullptr) {
+    if (MODE == 2 && scal) {            // written by dq_rotate_kernel earlier on the stream
+        inv_d = scal[1];
+        gamma = scal[2];
+    }
     double hh[K];
     const double* vp[K];
 #pragma unroll
@@ -654,6 +659,45 @@ ring_axpy_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring,
             partial[(size_t)blockIdx.x * KT] = v;
         }
     }
+}
+
+// One DQGMRES step of scalar work on the device (Saad, Alg. 6.13 lines 6-11): the new column of the band Hessenberg
+// matrix (h[0..nw) = (w, v_lo..it), ||w||^2 in nrm2) goes through the stored rotations lo-1..it-1, the new rotation is
+// formed, and the coefficients of the direction update are left in h2 / state.  Keeping this on the stream removes the
+// device-to-host round trip from every iteration (the host polls `state` every few iterations instead).
+// state: [0] gamma (in: current, out: next), [1] 1/d, [2] gamma of the solution update, [3] |gamma_next|, [4] ||w||
+constexpr int DQ_MAXK = 256;
+__global__ void dq_rotate_kernel(int it, int lo, int nw, int rring, const double* __restrict__ h, const double* __restrict__ nrm2,
+                                 double* __restrict__ cq, double* __restrict__ sq, double* __restrict__ state, double* __restrict__ h2) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double t[DQ_MAXK + 3];
+    const double hn = sqrt(nrm2[0]);
+    t[0] = 0.0;
+    for (int i = 0; i < nw; ++i) t[i + 1] = h[i];
+    t[nw + 1] = hn;
+    const int first_rot = lo - 1 >= 0 ? lo - 1 : 0;
+    for (int i = first_rot; i < it; ++i) {
+        const int j = i - (lo - 1);
+        const double c = cq[i % rring], sn = sq[i % rring];
+        const double a = c * t[j] + sn * t[j + 1];
+        t[j + 1] = -sn * t[j] + c * t[j + 1];
+        t[j] = a;
+    }
+    const int jm = it - (lo - 1);
+    const double a = t[jm], b = t[jm + 1];
+    const double d = hypot(a, b);
+    const double c = d > 0.0 ? a / d : 1.0, sn = d > 0.0 ? b / d : 0.0;
+    cq[it % rring] = c;
+    sq[it % rring] = sn;
+    const double gamma = state[0];
+    const int plo = lo - 1 >= 0 ? lo - 1 : 0;
+    const int np = it - plo;
+    for (int i = 0; i < np; ++i) h2[i] = t[(plo + i) - (lo - 1)];
+    state[0] = -sn * gamma;
+    state[1] = d > 0.0 ? 1.0 / d : 0.0;
+    state[2] = c * gamma;
+    state[3] = fabs(sn * gamma);
+    state[4] = hn;
 }
 
 struct VecOps {
@@ -692,7 +736,7 @@ struct VecOps {
     }
     // out = in - sum h_t V_t, last tile per `mode`: 1 = nrm2[0] = ||out||^2 (summed over the ranks); 2 = out *= inv_d, u += gamma out
     int ring_axpys(const double* V, int64_t ldv, int ring, int s0, int k, const double* h, const double* in, double* out, int mode,
-                   double* nrm2, double inv_d, double gamma, double* u) const {
+                   double* nrm2, double inv_d, double gamma, double* u, const double* scal = nullptr) const {
         int t0 = 0;
         do {
             const int kt = k - t0 < KT ? k - t0 : KT;
@@ -701,7 +745,7 @@ struct VecOps {
             const double* src = t0 == 0 ? in : out;
             if (!last) ring_axpy_kernel<KT, 0><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
             else if (mode == 1) ring_axpy_kernel<KT, 1><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
-            else if (mode == 2) ring_axpy_kernel<KT, 2><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, inv_d, gamma, u);
+            else if (mode == 2) ring_axpy_kernel<KT, 2><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, inv_d, gamma, u, scal);
             else ring_axpy_kernel<KT, 0><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
             t0 += kt;
         } while (t0 < k);
@@ -1221,8 +1265,11 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         double* usnap = nullptr;
         EHDG_CUDA(cudaMalloc(&usnap, sizeof(double) * (size_t)n));
         EHDG_CUDA(cudaMemsetAsync(usnap, 0, sizeof(double) * (size_t)n, st));
-        std::vector<double> cq, sq, t(k + 3);
-        double* hb[2] = {hbuf, hbuf + (m + 2) + 4};   // pinned staging, alternating per iteration
+        if (k > DQ_MAXK) { set_error("ehdg_dqgmres: truncation length above %d", DQ_MAXK); return EHDG_ERR_ARG; }
+        double *d_cq = nullptr, *d_sq = nullptr, *d_state = nullptr;
+        EHDG_CUDA(cudaMalloc(&d_cq, sizeof(double) * (size_t)(2 * (k + 2) + 8)));
+        d_sq = d_cq + (k + 2);
+        d_state = d_sq + (k + 2);
         const int check_every = 100;                  // iterations between true-residual checks
         // rel = ||b - Op u|| / ||b||, residual left in w
         auto true_residual = [&](double* out_rel) -> int {
@@ -1256,56 +1303,38 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
                 snap_rel = rel;
                 EHDG_CUDA(cudaMemcpyAsync(usnap, u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
             }
-            double gamma = rel * bnorm;
             scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, Vr);       // v_0 in slot 0
-            cq.assign(1, 1.0);
-            sq.assign(1, 0.0);
+            // scalar state of the recurrence lives on the device (dq_rotate_kernel); the host polls it every `poll` iterations
+            hbuf[0] = rel * bnorm;
+            hbuf[1] = hbuf[2] = hbuf[3] = hbuf[4] = 0.0;
+            EHDG_CUDA(cudaMemcpyAsync(d_state, hbuf, 5 * sizeof(double), cudaMemcpyHostToDevice, st));
+            EHDG_CUDA(cudaStreamSynchronize(st));                               // hbuf is reused below
             bool blown = false;
+            const int poll = 8;
             for (int it = 0; iters < max_iters; ++it, ++iters) {
                 const int lo = it - k + 1 > 0 ? it - k + 1 : 0;                 // window of Krylov vectors lo..it
                 const int nw = it - lo + 1;
                 const double* vit = Vr + (size_t)(it % ring) * n;
-                double* hcur = hb[it & 1];
                 if ((rc = apply_prec_op(vit, w))) return rc;
                 // h_i = (w, v_i), w -= h_i v_i for i = lo..it ; ||w||^2 comes out of the same pass
                 if ((rc = vo.ring_dots(Vr, n, ring, lo % ring, nw, w, d_h1))) return rc;
                 if ((rc = vo.ring_axpys(Vr, n, ring, lo % ring, nw, d_h1, w, w, 1, d_nrm, 0.0, 0.0, nullptr))) return rc;
                 scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, Vr + (size_t)((it + 1) % ring) * n);
-                EHDG_CUDA(cudaMemcpyAsync(hcur, d_h1, sizeof(double) * (size_t)nw, cudaMemcpyDeviceToHost, st));
-                EHDG_CUDA(cudaMemcpyAsync(hcur + (m + 2), d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
-                EHDG_CUDA(cudaStreamSynchronize(st));
-                const double hn = std::sqrt(hcur[m + 2]);
-                // column of the band Hessenberg matrix: rows lo-1 (fill), lo..it, it+1
-                t[0] = 0.0;
-                for (int i = 0; i < nw; ++i) t[i + 1] = hcur[i];
-                t[nw + 1] = hn;
-                const int first_rot = lo - 1 >= 0 ? lo - 1 : 0;                // rotations first_rot..it-1 touch this column
-                for (int i = first_rot; i < it; ++i) {
-                    const int j = i - (lo - 1);                                 // position of row i in t
-                    const double a = cq[i] * t[j] + sq[i] * t[j + 1];
-                    t[j + 1] = -sq[i] * t[j] + cq[i] * t[j + 1];
-                    t[j] = a;
-                }
-                const int jm = it - (lo - 1);
-                const double a = t[jm], b2 = t[jm + 1];
-                const double d = std::hypot(a, b2);
-                if ((int)cq.size() <= it) { cq.resize(it + 1); sq.resize(it + 1); }
-                cq[it] = d > 0 ? a / d : 1.0;
-                sq[it] = d > 0 ? b2 / d : 0.0;
-                const double gnext = -sq[it] * gamma;
-                gamma = cq[it] * gamma;
+                dq_rotate_kernel<<<1, 32, 0, st>>>(it, lo, nw, k + 2, d_h1, d_nrm, d_cq, d_sq, d_state, d_h2);
                 // p_it = (v_it - sum_{i=lo-1}^{it-1} t_i p_i) / d ;  u += gamma p_it   (one fused pass)
                 double* pnew = Pr + (size_t)(it % ring) * n;
                 const int plo = lo - 1 >= 0 ? lo - 1 : 0;
                 const int np_ = it - plo;
-                for (int i = 0; i < np_; ++i) hcur[i] = t[(plo + i) - (lo - 1)];
-                if (np_ > 0) EHDG_CUDA(cudaMemcpyAsync(d_h2, hcur, sizeof(double) * (size_t)np_, cudaMemcpyHostToDevice, st));
-                if ((rc = vo.ring_axpys(Pr, n, ring, plo % ring, np_, d_h2, vit, pnew, 2, nullptr, d > 0 ? 1.0 / d : 0.0, gamma, u))) return rc;
-                gamma = gnext;
-                rel = std::fabs(gamma) / bnorm;
+                if ((rc = vo.ring_axpys(Pr, n, ring, plo % ring, np_, d_h2, vit, pnew, 2, nullptr, 0.0, 0.0, u, d_state))) return rc;
+                const bool check_now = (it + 1) % check_every == 0;
+                if ((it + 1) % poll != 0 && !check_now && iters + 1 < max_iters) continue;
+                EHDG_CUDA(cudaMemcpyAsync(hbuf, d_state, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+                EHDG_CUDA(cudaStreamSynchronize(st));
+                const double hn = hbuf[4];
+                rel = hbuf[3] / bnorm;
                 if (!std::isfinite(rel)) { blown = true; ++iters; break; }
                 if (rel * std::sqrt((double)(it - lo + 2)) <= rtol || !(hn > 0.0)) { ++iters; break; }
-                if ((it + 1) % check_every == 0) {
+                if (check_now) {
                     // the quasi-residual keeps shrinking even when the truncated recurrence has broken down:
                     // measure the true residual (w is free here), snapshot on progress, roll back on a blow-up
                     double tr;
@@ -1325,6 +1354,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         }
         EHDG_CUDA(cudaStreamSynchronize(st));
         cudaFree(usnap);
+        cudaFree(d_cq);
         if (sweeps > 1) {      // yhat = P^ u
             EHDG_CUDA(cudaMemcpyAsync(w, u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
             if ((rc = poly(w, pt))) return rc;
