@@ -350,6 +350,7 @@ def main():
             if world > 1:
                 Ps = EHDGPipeline(smesh, make_spec(sorder, seps, enriched=(styp == "ehdg")), device=dev)
                 parallel.init_communicator(Ps)
+                parallel.gather_extents(0, 0, None, dev)                 # NCCL connects its all-gather channels on first use
                 barrier()
                 p0, p1 = ev(), ev()
                 p0.record()
