@@ -364,7 +364,8 @@ def main():
                 dist.all_gather(lst, cnt)
                 part = {"elements_per_rank": [int(t[0]) for t in lst], "owned_elements_per_rank": [int(t[1]) for t in lst],
                         "nnz_per_rank": [int(t[2]) for t in lst], "rows_per_rank": [int(t[3]) for t in lst],
-                        "mark_prune_assemble_condense_csr_ms_per_rank": [float(t[4]) / 1e3 for t in lst]}
+                        "mark_prune_assemble_condense_csr_ms_per_rank": [float(t[4]) / 1e3 for t in lst],
+                        "stages_ms_rank0": {k: round(v, 3) for k, v in Ps.part_timing.items()}}
                 s0 = s1 = None
             elif styp == "ehdg" and swl == args.workload:
                 Ps = P

@@ -63,6 +63,7 @@ SYMBOLS = {
     "ehdg_kernel_times_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ehdg_mark": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, _P, _P]),
     "ehdg_plan_create": (C.c_int, [_P, C.POINTER(Mesh), _P, C.c_int, C.POINTER(_P), _P]),
+    "ehdg_select_elements": (C.c_int, [_P, C.POINTER(Mesh), C.c_int32, C.c_int32, _P, _P, _P]),
     "ehdg_plan_create_select": (C.c_int, [_P, C.POINTER(Mesh), _P, C.c_int, _P, C.POINTER(_P), _P]),
     "ehdg_plan_destroy": (C.c_int, [_P]),
     "ehdg_plan_get_sizes": (C.c_int, [_P, C.POINTER(PlanSizes)]),

@@ -71,6 +71,22 @@ __global__ void mark_facets_kernel(int nf, const int32_t* __restrict__ facet2el,
 }
 
 // -------------------------------------------------------------------------------------------
+// partitioned assembly: elements that touch a facet range (own + ghost), elements owned by it
+// -------------------------------------------------------------------------------------------
+__global__ void select_elements_kernel(int ne, int nf, int f_lo, int f_hi, const int32_t* __restrict__ el2facet,
+                                       uint8_t* __restrict__ select, uint8_t* __restrict__ owned) {
+    const int el = blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= ne) return;
+    const int a = el2facet[3 * el], b = el2facet[3 * el + 1], c = el2facet[3 * el + 2];
+    const bool ia = a >= f_lo && a < f_hi, ib = b >= f_lo && b < f_hi, ic = c >= f_lo && c < f_hi;
+    select[el] = (ia || ib || ic) ? 1 : 0;
+    if (owned) {
+        const int m = min(a, min(b, c));          // the element belongs to the rank that owns its lowest-numbered facet
+        owned[el] = (m >= f_lo && m < f_hi) ? 1 : 0;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // plan
 // -------------------------------------------------------------------------------------------
 __global__ void plan_flags_kernel(int ne, const int32_t* __restrict__ el2facet,
@@ -324,6 +340,15 @@ static int ctx_scratch(ehdg_ctx* c, size_t bytes, void** out) {
         c->scratch_bytes = bytes;
     }
     *out = c->scratch;
+    return EHDG_OK;
+}
+
+int ehdg_select_elements(ehdg_ctx* c, const ehdg_mesh* m, int32_t f_lo, int32_t f_hi, uint8_t* elem_select, uint8_t* elem_owned,
+                         void* stream) {
+    if (!c || !m || !elem_select) { set_error("ehdg_select_elements: null argument"); return EHDG_ERR_ARG; }
+    if (m->ne > 0)
+        select_elements_kernel<<<(m->ne + 255) / 256, 256, 0, (cudaStream_t)stream>>>(m->ne, m->nf, f_lo, f_hi, m->el2facet, elem_select, elem_owned);
+    EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
 

@@ -194,88 +194,69 @@ spmv_kernel(int row0, int n_rows, const int64_t* __restrict__ rowptr, const int3
 // csr_fill_kernel lays the facet's values out as a dense rows x len block at blk_base[f].  One warp per facet: lanes own
 // columns, x is gathered once per facet through the column indices of the block's FIRST row; rowptr is not read
 // (8 B/nnz + 4 B/column instead of 12 B/nnz).
-#ifndef EHDG_SPMV_FPW
-#define EHDG_SPMV_FPW 1     /* measured on B200: 2, 4, 8 facets per warp are slower (registers, not latency, limit the kernel) */
-#endif
-// FPW consecutive facets per warp, handled in lock step: the three dependent load levels (facet tables -> matrix block and
-// neighbour ranges -> x) are each issued for all FPW facets before the first use, which multiplies the bytes a warp keeps
-// in flight (the kernel is latency-bound: ~1 KB of matrix per facet behind a three-deep pointer chase).
-template <int NBM, int CHUNKS, int FPW>
+// LPF lanes per facet (32, or 16 when the block has at most 16 columns: orders 1 and 2, two facets per warp); the matrix
+// block, the column indices of its first row and x are each loaded for the whole facet before the first use.  More than
+// one facet per lane group was measured slower on B200 (0.64 / 0.67 / 0.85 / 1.98 ms for 1 / 2 / 4 / 8 at p = 4: the
+// kernel was bound by the shuffle pipe and by registers, not by latency).
+template <int NBM, int CHUNKS, int LPF>
 __global__ void __launch_bounds__(256)
 spmv_facet_kernel(int f0, int nf, int row0, int row1, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
                   const int32_t* __restrict__ colind, const int32_t* __restrict__ nbr_len, const double* __restrict__ vals,
                   const double* __restrict__ x, double* __restrict__ y) {
-    const int fw = f0 + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * FPW;      // facets [f0, nf)
-    const int lane = threadIdx.x & 31;
-    if (fw >= nf) return;
+    static_assert(LPF == 32 || CHUNKS == 1, "column chunks only with a whole warp per facet");
+    const int fq = f0 + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPF);      // facets [f0, nf)
+    const int lane = threadIdx.x & (LPF - 1);
+    // no early exit: the lane groups of a warp shuffle together
+    const int f = fq < nf ? fq : nf - 1;
     // first level of the dependency chain: everything addressed by f alone
-    int r0[FPW], rows[FPW], len[FPW];
-    int64_t base[FPW];
-    bool act[FPW];
-#pragma unroll
-    for (int u = 0; u < FPW; ++u) {
-        const int f = fw + u < nf ? fw + u : nf - 1;
-        r0[u] = row_start[f];
-        rows[u] = row_start[f + 1] - r0[u];
-        len[u] = nbr_len[f];
-        base[u] = blk_base[f];
-    }
-#pragma unroll
-    for (int u = 0; u < FPW; ++u) act[u] = fw + u < nf && rows[u] > 0 && r0[u] + rows[u] > row0 && r0[u] < row1;
+    const int r0 = row_start[f], rows = row_start[f + 1] - r0, len = nbr_len[f];
+    const int64_t base = blk_base[f];
+    const bool act = fq < nf && rows > 0 && r0 + rows > row0 && r0 < row1;
     // second level: the matrix block and the column indices of its first row (all rows of the facet share them: one
     // coalesced 4-byte load per lane replaces the walk over the neighbour table and its warp shuffles)
-    double a[FPW][CHUNKS][NBM];
-    int col[FPW][CHUNKS];
+    double a[CHUNKS][NBM];
+    int col[CHUNKS];
+    const double* __restrict__ blk = vals + base;
 #pragma unroll
-    for (int u = 0; u < FPW; ++u) {
-        const double* __restrict__ blk = vals + base[u];
+    for (int c = 0; c < CHUNKS; ++c) {
+        const bool on = act && lane + LPF * c < len;
+        col[c] = on ? __ldcs(colind + base + lane + LPF * c) : -1;
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c) {
-            const bool on = act[u] && lane + 32 * c < len[u];
-            col[u][c] = on ? __ldcs(colind + base[u] + lane + 32 * c) : -1;
-#pragma unroll
-            for (int i = 0; i < NBM; ++i)
-                a[u][c][i] = (on && i < rows[u]) ? __ldcs(blk + i * len[u] + lane + 32 * c) : 0.0;
-        }
+        for (int i = 0; i < NBM; ++i) a[c][i] = (on && i < rows) ? __ldcs(blk + i * len + lane + LPF * c) : 0.0;
     }
     // third level: x gathered once per facet
-    double xv[FPW][CHUNKS];
+    double xv[CHUNKS];
 #pragma unroll
-    for (int u = 0; u < FPW; ++u)
+    for (int c = 0; c < CHUNKS; ++c) xv[c] = col[c] >= 0 ? __ldg(x + col[c]) : 0.0;
+    // NPAD row sums over the LPF lanes with one transposing butterfly: at every step a lane hands half of its rows to
+    // its partner and adds the partner's halves of the rows it keeps (NPAD/2 + NPAD/4 + ... shuffles instead of
+    // log2(LPF) per row; the kernel is bound by the shuffle pipe otherwise).
+    constexpr int NPAD = NBM <= 2 ? 2 : (NBM <= 4 ? 4 : (NBM <= 8 ? 8 : 16));
+    double v[NPAD];
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c) xv[u][c] = col[u][c] >= 0 ? __ldg(x + col[u][c]) : 0.0;
+    for (int i = 0; i < NPAD; ++i) {
+        v[i] = 0.0;
+        if (i < NBM) {
 #pragma unroll
-    for (int u = 0; u < FPW; ++u) {
-        // NPAD row sums over the 32 lanes with one transposing butterfly: at every step a lane hands half of its
-        // rows to its partner and adds the partner's halves of the rows it keeps (NPAD/2 + NPAD/4 + ... shuffles instead
-        // of 5 per row; the kernel is bound by the shuffle pipe otherwise).
-        constexpr int NPAD = NBM <= 8 ? 8 : 16;
-        double v[NPAD];
-#pragma unroll
-        for (int i = 0; i < NPAD; ++i) {
-            v[i] = 0.0;
-            if (i < NBM) {
-#pragma unroll
-                for (int c = 0; c < CHUNKS; ++c) v[i] += a[u][c][i] * xv[u][c];
-            }
+            for (int c = 0; c < CHUNKS; ++c) v[i] += a[c][i] * xv[c];
         }
-        int row = 0, d = 16;
-#pragma unroll
-        for (int half = NPAD / 2; half >= 1; half >>= 1, d >>= 1) {
-            const bool up = (lane & d) != 0;
-#pragma unroll
-            for (int k = 0; k < half; ++k) {
-                const double send = up ? v[k] : v[k + half];
-                const double recv = __shfl_xor_sync(0xffffffffu, send, d);
-                v[k] = (up ? v[k + half] : v[k]) + recv;
-            }
-            if (up) row += half;
-        }
-#pragma unroll
-        for (; d >= 1; d >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
-        constexpr int LOWMASK = (32 / NPAD) - 1;              // lanes with these bits clear hold one row total each
-        if (act[u] && (lane & LOWMASK) == 0 && row < rows[u] && r0[u] + row >= row0 && r0[u] + row < row1) y[r0[u] + row] = v[0];
     }
+    int row = 0, d = LPF / 2;
+#pragma unroll
+    for (int half = NPAD / 2; half >= 1; half >>= 1, d >>= 1) {
+        const bool up = (lane & d) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const double send = up ? v[k] : v[k + half];
+            const double recv = __shfl_xor_sync(0xffffffffu, send, d);
+            v[k] = (up ? v[k + half] : v[k]) + recv;
+        }
+        if (up) row += half;
+    }
+#pragma unroll
+    for (; d >= 1; d >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+    constexpr int LOWMASK = (LPF / NPAD) - 1;              // lanes with these bits clear hold one row total each
+    if (act && (lane & LOWMASK) == 0 && row < rows && r0 + row >= row0 && r0 + row < row1) y[r0 + row] = v[0];
 }
 
 static bool spmv_use_csr_kernel() {
@@ -298,14 +279,19 @@ static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, d
     } else {
         const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
         if (fb <= fa) return EHDG_OK;
-        constexpr int FPW = EHDG_SPMV_FPW;
-        const int64_t threads = (((int64_t)(fb - fa) + FPW - 1) / FPW) * 32;
+        // rows per facet <= nb, columns <= 5 nb
+        const int nb = A->nb;
+        const int lpf = nb <= 3 ? 16 : 32;
+        const int64_t threads = (int64_t)(fb - fa) * lpf;
         const unsigned gb = (unsigned)((threads + 255) / 256);
-        if (A->nb <= 6)      // rows <= 6, row length <= 30: one column per lane
-            spmv_facet_kernel<6, 1, FPW><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base, A->colind, A->nbr_len, vals, x, y);
-        else
-            spmv_facet_kernel<EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH, 2, (FPW > 2 ? 2 : FPW)><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start,
-                                                                                                               A->blk_base, A->colind, A->nbr_len, vals, x, y);
+#define EHDG_SPMV_LAUNCH(NBM, CH, LPF) \
+        spmv_facet_kernel<NBM, CH, LPF><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base, A->colind, A->nbr_len, vals, x, y)
+        if (nb <= 2) EHDG_SPMV_LAUNCH(2, 1, 16);
+        else if (nb <= 3) EHDG_SPMV_LAUNCH(3, 1, 16);
+        else if (nb <= 4) EHDG_SPMV_LAUNCH(4, 1, 32);
+        else if (nb <= 6) EHDG_SPMV_LAUNCH(6, 1, 32);
+        else EHDG_SPMV_LAUNCH(EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH, 2, 32);
+#undef EHDG_SPMV_LAUNCH
     }
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;

@@ -110,6 +110,15 @@ class EHDGPipeline:
                                           _ptr(self.facet_mask), self._stream()), "ehdg_mark")
         return self.make_plan(None)
 
+    def select_elements(self, f_lo: int, f_hi: int):
+        """(elem_select, elem_owned) u8 [ne] for the facet range [f_lo, f_hi) (partitioned assembly)"""
+        ne = self.mesh_host.ne
+        sel = torch.empty(ne, dtype=torch.uint8, device=self.dev)
+        own = torch.empty(ne, dtype=torch.uint8, device=self.dev)
+        _lib.check(self.lib.ehdg_select_elements(self.ctx, C.byref(self.cmesh), int(f_lo), int(f_hi), _ptr(sel), _ptr(own),
+                                                 self._stream()), "ehdg_select_elements")
+        return sel, own
+
     def make_plan(self, elem_select=None):
         """(re)builds the plan; elem_select (u8 [ne] device tensor or None): partitioned assembly keeps only these elements"""
         if self.plan is not None:

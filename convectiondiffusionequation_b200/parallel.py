@@ -144,15 +144,27 @@ def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True)
     import torch.distributed as dist
     from . import _lib
     from .hot_path import _device_view
+    import time
+    tm = {}
+
+    def lap(name, t0):
+        torch.cuda.synchronize(pipe.dev)
+        tm[name] = (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+    t0 = time.perf_counter()
     pipe.setup()                                             # a1, a3 on the full mesh
+    t0 = lap("mark_prune_ms", t0)
     pipe.csr_symbolic(world, rank)
+    t0 = lap("csr_symbolic_ms", t0)
     f_lo, f_hi = int(pipe.facet_begin[rank]), int(pipe.facet_begin[rank + 1])
-    m = pipe.mesh_host
-    sel = select_elements(pipe.facet2el, f_lo, f_hi, m.ne)
-    pipe.elem_owned = owned_elements(pipe.el2facet, f_lo, f_hi)
+    sel, pipe.elem_owned = pipe.select_elements(f_lo, f_hi)        # same rule as select_elements / owned_elements above
     pipe.make_plan(sel)
+    t0 = lap("select_plan_ms", t0)
     pipe.assemble()                                          # a4-a7 on the selection
+    t0 = lap("alpha_assemble_condense_ms", t0)
     pipe.csr_alloc_values().csr_numeric()                    # a8, own rows
+    t0 = lap("csr_numeric_ms", t0)
+    pipe.part_timing = tm
     rb = pipe.row_begin
     r0, r1 = int(rb[rank]), int(rb[rank + 1])
     nnz = int(pipe.csr_sizes.nnz)
@@ -161,6 +173,7 @@ def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True)
         lo, hi = min(int(ci.min()), r0), max(int(ci.max()) + 1, r1)
     else:
         lo, hi = r0, r1
+    t0 = lap("extent_ms", t0)
     pipe.own_extent = (lo, hi)
     if not exchange:
         return pipe

@@ -120,6 +120,10 @@ int ehdg_plan_create(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_
  * every later stage (alpha, assemble + condense, CSR numeric, back-solve, error) then works on that subset and the
  * element stores are sized by it.  A rank selects the elements that touch its facet range, i.e. its own elements plus
  * one layer of redundantly computed ghosts, so that no S_K crosses GPUs. */
+/* elem_select[el] = 1 iff element el touches a facet of [f_lo, f_hi); elem_owned[el] (may be null) = 1 iff its
+ * lowest-numbered facet lies in the range (every element has exactly one owner, and the owner has it selected) */
+int ehdg_select_elements(ehdg_ctx* ctx, const ehdg_mesh* mesh, int32_t f_lo, int32_t f_hi, uint8_t* elem_select,
+                         uint8_t* elem_owned, void* stream);
 int ehdg_plan_create_select(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_mask, int force_general,
                             const uint8_t* elem_select, ehdg_plan** out, void* stream);
 int ehdg_plan_destroy(ehdg_plan* plan);

@@ -77,3 +77,20 @@ def test_partitioned_rows_equal_the_global_assembly(enriched):
         P.close()
     assert owned_total == mesh.ne and rows_seen == n
     F.close()
+
+
+def test_device_selection_matches_host_rule():
+    import numpy as np
+    import torch
+    from convectiondiffusionequation_b200 import parallel
+    from convectiondiffusionequation_b200.hot_path import EHDGPipeline
+    from convectiondiffusionequation_b200.mesh import unit_square_mesh
+    from tests.common import make_pair
+    mesh = unit_square_mesh(9, kind="unstructured")
+    _, spec = make_pair(mesh, 1, enriched=False)
+    P = EHDGPipeline(mesh, spec)
+    for f_lo, f_hi in [(0, mesh.nf), (0, 0), (17, 120), (mesh.nf - 30, mesh.nf)]:
+        sel, own = P.select_elements(f_lo, f_hi)
+        assert np.array_equal(sel.cpu().numpy(), parallel.select_elements(mesh.facet2el, f_lo, f_hi, mesh.ne))
+        assert np.array_equal(own.cpu().numpy(), parallel.owned_elements(mesh.el2facet, f_lo, f_hi))
+    P.close()
