@@ -181,7 +181,7 @@ int64_t fast_flops_alpha(const ehdg_ctx* c) {
     const int64_t M = NP > NF ? NP : NF;
     const bool two = c->pb.p <= 4 && EHDG_ALPHA_R == 2;
     const int64_t LG = two ? (M <= 8 ? 4 : (M <= 16 ? 8 : 16)) : (M <= 8 ? 8 : (M <= 16 ? 16 : 32));
-    const int64_t rounds = LG >= 32 ? 12 : (LG == 16 ? 14 : (LG == 8 ? 18 : 24));
+    const int64_t rounds = LG >= 32 ? 10 : (LG == 16 ? 12 : (LG == 8 ? 16 : 21));
     f += rounds * LG * N * 5;
     return f;
 }

@@ -917,7 +917,8 @@ EHDG_HD double fast_alpha_element(const Group<AlphaDims<P>::LG>& gc, const doubl
         hi = hi * is + 1e-15;
     }
     // ---- multisection on "all eigenvalues below x" (signs of the Sturm sequence alternate): LG + 1 sections per round
-    constexpr int ROUNDS = LG >= 32 ? 12 : (LG == 16 ? 14 : (LG == 8 ? 18 : 24));
+    // (LG + 1)^ROUNDS >= 4e14 sections of a bracket of width <= 2 (scaled spectrum): lambda to ~5e-15 relative to the scale
+    constexpr int ROUNDS = LG >= 32 ? 10 : (LG == 16 ? 12 : (LG == 8 ? 16 : 21));
     for (int it = 0; it < ROUNDS; ++it) {
         int below[NLS];
         const double step = (hi - lo) / (double)(LG + 1);
