@@ -15,7 +15,7 @@ constexpr int FAST_THREADS = 128;
 
 template <int P>
 __global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ASM_MINBLOCKS : (P == 5 ? 2 : 1)))
-fast_assemble_kernel(Problem pb, RuleSet rs, const double* __restrict__ tab_g, int tab_doubles,
+fast_assemble_kernel(Problem pb, LayerConst cx, LayerConst cy, RuleSet rs, const double* __restrict__ tab_g, int tab_doubles,
                      const double* __restrict__ phi_rhs, int n, const int32_t* __restrict__ list,
                      const double* __restrict__ verts, const int32_t* __restrict__ tris,
                      const double* __restrict__ lam, double* __restrict__ S, double* __restrict__ g,
@@ -28,13 +28,15 @@ fast_assemble_kernel(Problem pb, RuleSet rs, const double* __restrict__ tab_g, i
     const int gid = threadIdx.x / LG;
     const int scratch = fast_asm_scratch_doubles<P>(rs.nq);
     Group<LG> gc{(int)(threadIdx.x % LG), smem + ((tab_doubles + 1) & ~1) + gid * scratch};
+    // cx, cy: constants of the two layer functions of `coeff`, formed once on the host; as kernel parameters they are
+    // constant-bank operands and cost no registers across the elimination
     for (int base = blockIdx.x * GPC; base < n; base += gridDim.x * GPC) {
         const bool live = base + gid < n;
         const int idx = base + gid < n ? base + gid : n - 1;
         const int el = list[idx];
         const int st = fast_assemble_element<P>(gc, pb, rs, smem, phi_rhs, verts, tris + 3 * el, lam[el], live,
                                                 S + (size_t)idx * D::NF * D::NF, g + (size_t)idx * D::NF,
-                                                W + (size_t)idx * D::NP * D::NF, z + (size_t)idx * D::NP);
+                                                W + (size_t)idx * D::NP * D::NF, z + (size_t)idx * D::NP, cx, cy);
         if (st && live && status) atomicOr(status + el, st);
     }
 }
@@ -103,7 +105,7 @@ static int launch_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
     const int64_t cap = (int64_t)c->sm_count * per_sm;
     const int grid = (int)(need < cap ? need : cap);
     if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[2], st));
-    fast_assemble_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->pb, c->rb.rs, c->tens.asm_tab, tabd, c->tens.rhs_phi, (int)p->n_poly,
+    fast_assemble_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->pb, layer_const(c->pb.coeff.k[0]), layer_const(c->pb.coeff.k[1]), c->rb.rs, c->tens.asm_tab, tabd, c->tens.rhs_phi, (int)p->n_poly,
                                                              p->list_poly, m->verts, m->tris, lam, S, g, W, z, status);
     if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[3], st));
     EHDG_LAUNCH_CHECK();

@@ -62,6 +62,9 @@ EHDG_HD void st2(double* p, double a, double b) {
 #endif
 }
 
+// exp(-50) = 1.9e-22: below this the exponential of a layer function is dropped next to its polynomial part
+#define EHDG_LAYER_DROP 50.0
+
 template <int LG>
 struct Group {
     int lane;       // lane inside the group (device); unused on the host
@@ -266,7 +269,7 @@ template <int P>
 EHDG_HD constexpr int fast_asm_scratch_doubles(int nq) {
     typedef FastDims<P> D;
     constexpr int xs = D::NP * D::NXS, ss = D::NF * D::NF + D::NF;      // X scratch doubles as the S/g staging area
-    return ((D::NC + 1) & ~1) + 2 + (((xs > ss ? xs : ss) + 1) & ~1) + ((nq + 1) & ~1);
+    return ((D::NC + 1) & ~1) + 2 + 12 + (((xs > ss ? xs : ss) + 1) & ~1) + ((nq + 1) & ~1);
 }
 
 // a5-a7 on one polynomial element.  Scratch `gc.sh` needs fast_asm_scratch_doubles() doubles.
@@ -275,7 +278,8 @@ EHDG_HD constexpr int fast_asm_scratch_doubles(int nq) {
 template <int P>
 EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Problem& pb, const RuleSet& rs,
                                   const double* tab, const double* phi_rhs, const double* verts, const int* tri,
-                                  double lam, bool store, double* S, double* gvec, double* W, double* z) {
+                                  double lam, bool store, double* S, double* gvec, double* W, double* z,
+                                  const LayerConst& cx, const LayerConst& cy) {
     typedef FastDims<P> D;
     constexpr int NP = D::NP, NFL = D::NFL, NF = D::NF, NC = D::NC, LG = D::LG, R = D::R, NXS = D::NXS;
     constexpr int NLS = EHDG_NLS(LG), NFS = NF | 1;     // NFS: row stride of the facet tensors
@@ -283,16 +287,19 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     SortedGeom sg;
     sorted_geom(verts, tri, pb.bx, pb.by, sg);
     double* prow = gc.sh;                       // NC (padded even) + 2: pivot row and the reciprocal of the pivot
-    double* Xs = prow + ((NC + 1) & ~1) + 2;    // NP x NXS, later the staging area of S (NF x NF) and g (NF)
+    double* geo = prow + ((NC + 1) & ~1) + 2;   // 12: per-edge coefficients of A_FV / A_FF, parked across the elimination
+    double* Xs = geo + 12;                      // NP x NXS, later the staging area of S (NF x NF) and g (NF)
     double* cw = Xs + (((NP * NXS > NF * NF + NF ? NP * NXS : NF * NF + NF) + 1) & ~1);   // nq
     // per-edge coefficients
-    double cvv[3], cvf[3], eg0[3], eg1[3];
+    double cvv[3], cvf[3], cfv[3], cff[3], eg0[3], eg1[3];
     for (int s = 0; s < 3; ++s) {
         const double bn = sg.bn[s];
         const double pos = bn > 0.0 ? 1.0 : 0.0, neg = 1.0 - pos;
         const double tau = pb.eps * (20.0 * lam) * (double)(P * P) * sg.ih[s];
         cvv[s] = sg.len[s] * (tau + pos * bn);
         cvf[s] = sg.len[s] * (-tau + neg * bn);
+        cfv[s] = sg.len[s] * (-tau - pos * bn - pos);
+        cff[s] = sg.len[s] * (tau - neg * bn + pos);
         eg0[s] = sg.len[s] * pb.eps * sg.ga0[s];
         eg1[s] = sg.len[s] * pb.eps * sg.ga1[s];
     }
@@ -304,19 +311,22 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     double myinv[NLS][R];
     int status = 0;
 
-    // ---- right-hand side.  Where both layer functions of `coeff` have underflowed on the whole element
-    // (k d > 746 at the vertex nearest to the outflow side, hence at every point) the coefficient is a quadratic
-    // polynomial in the local barycentrics: f_V comes from the six moment vectors behind the phi table.
+    // ---- right-hand side.  Where the exponentials of both layer functions of `coeff` are below 2e-22 on the whole
+    // element (k d > EHDG_LAYER_DROP at the vertex nearest to the outflow side, hence at every point) they cannot change
+    // a double next to the polynomial part of L(d) = (1 - d) + (E - e0) inv: |E inv| <= 2e-22 while 1 - d only gets
+    // that small where E - e0 ~ k e0 (1 - d) shrinks with it.  The coefficient is then a quadratic polynomial in the
+    // local barycentrics and f_V comes from the six moment vectors behind the phi table (the order 2p + bonus rule
+    // integrates that product exactly, so this is the quadrature's value up to rounding).
     // Otherwise: weights at the quadrature points, cw[q] = w_q |detJ| coeff(x_q).
-    const LayerConst cx = layer_const(pb.coeff.k[0]), cy = layer_const(pb.coeff.k[1]);
+    // cx, cy = layer_const(pb.coeff.k[0 / 1]): the same for every element, computed once by the caller
     const bool ux = pb.coeff.c[1] != 0.0 || pb.coeff.c[3] != 0.0, uy = pb.coeff.c[2] != 0.0 || pb.coeff.c[3] != 0.0;
     const double dminx = fmin(sg.omx[0], fmin(sg.omx[1], sg.omx[2])), dminy = fmin(sg.omy[0], fmin(sg.omy[1], sg.omy[2]));
 #ifdef EHDG_NO_RHS_MOMENTS
     const bool poly_rhs = false;
 #else
-    const bool poly_rhs = (!ux || cx.k * dminx > 747.0) && (!uy || cy.k * dminy > 747.0);     // uniform over the group
+    const bool poly_rhs = (!ux || cx.k * dminx > EHDG_LAYER_DROP) && (!uy || cy.k * dminy > EHDG_LAYER_DROP);     // uniform over the group
 #endif
-    const bool zx = cx.k * dminx > 747.0, zy = cy.k * dminy > 747.0;
+    const bool zx = cx.k * dminx > EHDG_LAYER_DROP, zy = cy.k * dminy > EHDG_LAYER_DROP;
     double cm[EHDG_RHS_MOMENTS];
     if (poly_rhs) {
         // L(d) = (1 - d) - e0 inv with d = d_2 + l0 (d_0 - d_2) + l1 (d_1 - d_2)
@@ -333,14 +343,23 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     } else {
         for (int m = 0; m < EHDG_RHS_MOMENTS; ++m) cm[m] = 0.0;
     }
+    const int elpack = sg.eloc[0] | (sg.eloc[1] << 2) | (sg.eloc[2] << 4);     // the one piece of geometry kept in a register
     {
         EHDG_FOR_LANES(l, L)
+            if (l == 0) {       // every lane holds the same values: one parks the A_FV / A_FF coefficients for after the elimination
+                st2(geo + 0, cfv[0], cfv[1]);
+                st2(geo + 2, cfv[2], cff[0]);
+                st2(geo + 4, cff[1], cff[2]);
+                st2(geo + 6, eg0[0], eg0[1]);
+                st2(geo + 8, eg0[2], eg1[0]);
+                st2(geo + 10, eg1[1], eg1[2]);
+            }
             if (!poly_rhs)
             for (int q = l; q < rs.nq; q += LG) {
                 const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
                 const double dx = l0 * sg.omx[0] + l1 * sg.omx[1] + l2 * sg.omx[2];
                 const double dy = l0 * sg.omy[0] + l1 * sg.omy[1] + l2 * sg.omy[2];
-                // an axis whose exponential has underflowed on the whole element (uniform over the group) skips exp()
+                // an axis whose exponential is negligible on the whole element (uniform over the group) skips exp()
                 const double lx = ux ? (zx ? (1.0 - dx) - cx.e0 * cx.inv : layer_val(cx, dx)) : 0.0;
                 const double ly = uy ? (zy ? (1.0 - dy) - cy.e0 * cy.inv : layer_val(cy, dy)) : 0.0;
                 cw[q] = rs.vw[q] * sg.adet * (pb.coeff.c[0] + pb.coeff.c[1] * lx + pb.coeff.c[2] * ly + pb.coeff.c[3] * lx * ly);
@@ -522,27 +541,16 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             }
     EHDG_END_LANES
 
-    // ---- rows of A_FV and the diagonal of A_FF, r = (s, k) in the sorted frame.  Built only now, from a geometry that
-    // is recomputed behind an optimisation barrier: nothing of it stays live across the elimination, which is what
-    // lets the kernel run four CTAs per SM.
+    // ---- rows of A_FV and the diagonal of A_FF, r = (s, k) in the sorted frame.  Built only now, from per-edge
+    // coefficients that waited in shared memory: nothing of the geometry stays live in registers across the elimination,
+    // which is what lets the kernel run four CTAs per SM.
     double afv[NLS][R][NP];
     double aff[NLS][R];
+    int eloc[3];
+    eloc[0] = elpack & 3;
+    eloc[1] = (elpack >> 2) & 3;
+    eloc[2] = (elpack >> 4) & 3;
     {
-        const int* tri2 = tri;
-#ifdef __CUDA_ARCH__
-        asm volatile("" : "+l"(tri2));
-#endif
-        sorted_geom(verts, tri2, pb.bx, pb.by, sg);
-        double cfv[3], cff[3], fg0[3], fg1[3];
-        for (int s = 0; s < 3; ++s) {
-            const double bn = sg.bn[s];
-            const double pos = bn > 0.0 ? 1.0 : 0.0, neg = 1.0 - pos;
-            const double tau = pb.eps * (20.0 * lam) * (double)(P * P) * sg.ih[s];
-            cfv[s] = sg.len[s] * (-tau - pos * bn - pos);
-            cff[s] = sg.len[s] * (tau - neg * bn + pos);
-            fg0[s] = sg.len[s] * pb.eps * sg.ga0[s];
-            fg1[s] = sg.len[s] * pb.eps * sg.ga1[s];
-        }
         EHDG_FOR_LANES(l, L)
 #pragma unroll
         for (int h = 0; h < R; ++h) {
@@ -550,7 +558,14 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             const int r = row < NF ? row : NF - 1;
             const int s = r / NFL, k = r % NFL;
             const double* tf = tab + TL.offFT + r;              // [t][j][(s,k)]: unit stride across the lanes
-            const double c_fv = sel3(cfv, s), c_g0 = sel3(fg0, s), c_g1 = sel3(fg1, s);
+            double cfv2[3], cff2[3], fg0[3], fg1[3];
+            ld2(geo + 0, cfv2[0], cfv2[1]);
+            ld2(geo + 2, cfv2[2], cff2[0]);
+            ld2(geo + 4, cff2[1], cff2[2]);
+            ld2(geo + 6, fg0[0], fg0[1]);
+            ld2(geo + 8, fg0[2], fg1[0]);
+            ld2(geo + 10, fg1[1], fg1[2]);
+            const double c_fv = sel3(cfv2, s), c_g0 = sel3(fg0, s), c_g1 = sel3(fg1, s);
 #pragma unroll
             for (int j = 0; j < NP; ++j)
                 afv[L][h][j] = c_fv * tf[j * NFS] + c_g0 * tf[(NP + j) * NFS] + c_g1 * tf[(2 * NP + j) * NFS];
@@ -558,7 +573,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 #pragma unroll
             for (int kk = 1; kk < NFL; ++kk)
                 if (k == kk) rk = 1.0 / (2.0 * kk + 1.0);
-            aff[L][h] = sel3(cff, s) * rk;
+            aff[L][h] = sel3(cff2, s) * rk;
         }
         EHDG_END_LANES
     }
@@ -566,7 +581,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     // ---- S = A_FF - A_FV X, g = -A_FV z ; rows in the sorted frame.  W, z leave from the X scratch and S, g from a
     // staging copy with contiguous (full-sector) global stores in local edge order.
     int sinv[3];                                    // sorted edge of local edge e
-    for (int s2 = 0; s2 < 3; ++s2) sinv[sg.eloc[s2]] = s2;
+    for (int s2 = 0; s2 < 3; ++s2) sinv[eloc[s2]] = s2;
     double srow[NLS][R][NF + 1];
     EHDG_FOR_LANES(l, L)
         if (store) {
@@ -608,7 +623,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             const int row = h * LG + l;
             if (row < NF) {
                 const int s = row / NFL, k = row % NFL;
-                const int orow = sel3i(sg.eloc, s) * NFL + k;
+                const int orow = sel3i(eloc, s) * NFL + k;
 #pragma unroll
                 for (int s2 = 0; s2 < 3; ++s2)
 #pragma unroll
@@ -616,7 +631,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
                         double val = srow[L][h][s2 * NFL + k2];
                         if (s2 * NFL + k2 == row) val += aff[L][h];
                         if (val != val) status |= EHDG_ST_NONFINITE;
-                        Ss[orow * NF + sg.eloc[s2] * NFL + k2] = val;
+                        Ss[orow * NF + eloc[s2] * NFL + k2] = val;
                     }
                 Ss[NF * NF + orow] = srow[L][h][NF];
             }

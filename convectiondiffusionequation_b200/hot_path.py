@@ -53,6 +53,9 @@ class ProblemSpec:
         return p
 
 
+LAYER_DROP = 50.0      # EHDG_LAYER_DROP of csrc/ehdg_fast.h
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -270,7 +273,7 @@ class EHDGPipeline:
         return err2
 
     def moment_rhs_fraction(self) -> float:
-        """share of the polynomial-path elements on which both layer functions of `coeff` have underflowed, so that
+        """share of the polynomial-path elements on which the exponentials of both layer functions of `coeff` are negligible, so that
         fast_assemble_kernel takes f_V from the moment vectors (same test as csrc/ehdg_fast.h; used for flop accounting)"""
         f = self.spec.coeff
         if f is None or self.plan_sizes.n_poly == 0:
@@ -279,9 +282,9 @@ class EHDGPipeline:
         dmin = (1.0 - self.verts[self.tris.long()]).amin(dim=1)          # [ne, 2]
         ok = torch.ones(dmin.shape[0], dtype=torch.bool, device=self.dev)
         if c[1] != 0.0 or c[3] != 0.0:
-            ok &= dmin[:, 0] * k[0] > 747.0
+            ok &= dmin[:, 0] * k[0] > LAYER_DROP
         if c[2] != 0.0 or c[3] != 0.0:
-            ok &= dmin[:, 1] * k[1] > 747.0
+            ok &= dmin[:, 1] * k[1] > LAYER_DROP
         slot = _device_view(self.lib.ehdg_plan_eslot(self.plan), self.mesh_host.ne, torch.int32, self.dev)
         poly = (slot >= 0) & ((slot & 0x40000000) == 0)
         return float((ok & poly).sum().item()) / float(self.plan_sizes.n_poly)

@@ -32,7 +32,8 @@ static int fast_assemble_host(const Problem& pb, const double* verts, const int*
     build_rhs_phi(P, 2 * P + pb.bonus, phi);
     std::vector<double> sh(fast_asm_scratch_doubles<P>(hr.rs.nq));
     Group<FastDims<P>::LG> gc{0, sh.data()};
-    return fast_assemble_element<P>(gc, pb, hr.rs, asm_tab.data(), phi.data(), verts, tri, lam, true, S, g, W, z);
+    return fast_assemble_element<P>(gc, pb, hr.rs, asm_tab.data(), phi.data(), verts, tri, lam, true, S, g, W, z,
+                                    layer_const(pb.coeff.k[0]), layer_const(pb.coeff.k[1]));
 }
 template <int P>
 static double fast_alpha_host(const double* verts, const int* tri, int bonus, int* status) {
