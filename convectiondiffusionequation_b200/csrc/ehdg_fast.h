@@ -64,6 +64,21 @@ EHDG_HD void st2(double* p, double a, double b) {
 
 // exp(-50) = 1.9e-22: below this the exponential of a layer function is dropped next to its polynomial part
 #define EHDG_LAYER_DROP 50.0
+// orders whose Gauss-Jordan broadcasts the pivot row by warp shuffle (bit p set); see fast_assemble_element
+#ifndef EHDG_GJ_SHFL_ORDERS
+#define EHDG_GJ_SHFL_ORDERS 0x60     /* p = 5, 6 */
+#endif
+#define EHDG_GJ_SHFL_FOR(p) (((EHDG_GJ_SHFL_ORDERS >> (p)) & 1) != 0)
+
+// entry j of row slot ho of a lane that keeps R rows (static register indexing)
+template <int R, int NC>
+EHDG_HD double own_row_entry(const double (*rows)[NC], int ho, int j) {
+    double v = rows[0][j];
+#pragma unroll
+    for (int h = 1; h < R; ++h)
+        if (h == ho) v = rows[h][j];
+    return v;
+}
 
 template <int LG>
 struct Group {
@@ -453,6 +468,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 #define EHDG_GJ_STEPS NP
 #endif
     constexpr int NCP = (NC + 1) & ~1;          // prow[NCP] = 1 / pivot
+    constexpr bool GJ_SHFL = EHDG_GJ_SHFL_FOR(P);
     int rw;
     {
         double key[NLS][R];
@@ -462,6 +478,61 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
         EHDG_END_LANES
         rw = gc.template argmax_row<R>(key);
     }
+    // Two ways to hand the pivot row to the other lanes, chosen per order from A/B timings on B200 (EHDG_GJ_SHFL_ORDERS):
+    // by warp shuffle straight out of the owner lane's registers (no store / barrier / load round trip and no section
+    // that only the owner executes: 4-5 % faster for p = 5, 6 where a group is a whole warp), or through the group's
+    // shared-memory scratch with 16-byte accesses (fewer instructions per broadcast value: equal at p = 1, 1-4 % faster
+    // for p = 2, 3, 4 where one load serves the two groups of a warp).
+    if (GJ_SHFL) {
+#ifdef __CUDA_ARCH__
+    const int grp_base = (int)(threadIdx.x & 31u) & ~(LG - 1);
+#define EHDG_GJ_BCAST(j) __shfl_sync(0xffffffffu, own_row_entry<R, NC>(a[0], ho, j), grp_base + lo)
+#else
+#define EHDG_GJ_BCAST(j) a[lo][ho][j]
+#endif
+#pragma unroll
+    for (int k = 0; k < EHDG_GJ_STEPS; ++k) {
+        const int lo = rw % LG, ho = rw / LG;
+        double f[NLS][R];
+        double key[NLS][R];
+        EHDG_FOR_LANES(l, L)
+            const double piv = EHDG_GJ_BCAST(k);
+            if (!(fabs(piv) > 0.0)) status |= EHDG_ST_SINGULAR;
+#ifdef __CUDA_ARCH__
+            const double inv = __drcp_rn(piv);
+#else
+            const double inv = 1.0 / piv;
+#endif
+            const double x1 = EHDG_GJ_BCAST(k + 1);
+            // multipliers: 0 for the pivot row (it stays unscaled; scaled once at the end) and for surplus rows
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const bool is_piv = (l == lo) && (h == ho);
+                if (is_piv) {
+                    mycol[L][h] = k;
+                    myinv[L][h] = inv;
+                }
+                f[L][h] = (is_piv || h * LG + l >= NP) ? 0.0 : a[L][h][k] * inv;
+            }
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                a[L][h][k + 1] -= f[L][h] * x1;
+                key[L][h] = (h * LG + l < NP && mycol[L][h] < 0) ? fabs(a[L][h][k + 1]) : -1.0;
+            }
+        EHDG_END_LANES
+        if (k + 1 < NP) rw = gc.template argmax_row<R>(key);
+        EHDG_FOR_LANES(l, L)
+#pragma unroll
+            for (int j = k + 2; j < NC; ++j) {
+                const double xj = EHDG_GJ_BCAST(j);
+#pragma unroll
+                for (int h = 0; h < R; ++h) a[L][h][j] -= f[L][h] * xj;
+            }
+        EHDG_END_LANES
+    }
+#undef EHDG_GJ_BCAST
+
+    } else {
 #pragma unroll
     for (int k = 0; k < EHDG_GJ_STEPS; ++k) {
         const int lo = rw % LG, ho = rw / LG;
@@ -526,6 +597,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
         EHDG_END_LANES
     }
 
+    }
     // ---- X = A_VV^-1 [A_VF | f_V]: row c sits where pivot column c was chosen
     EHDG_FOR_LANES(l, L)
 #pragma unroll
