@@ -181,7 +181,7 @@ int64_t fast_flops_alpha(const ehdg_ctx* c) {
     for (int64_t j = 0; j < N; ++j) f += 2 * 2 * (N - 1 - j) * N;
     for (int64_t k = 0; k + 2 < N; ++k) f += 6 * (N - 1 - k) * (N - 1 - k);
     const int64_t M = NP > NF ? NP : NF;
-    const bool two = c->pb.p <= 4 && EHDG_ALPHA_R == 2;
+    const bool two = c->pb.p <= EHDG_ALPHA_R2_MAXP && EHDG_ALPHA_R == 2;
     const int64_t LG = two ? (M <= 8 ? 4 : (M <= 16 ? 8 : 16)) : (M <= 8 ? 8 : (M <= 16 ? 16 : 32));
     const int64_t rounds = LG >= 32 ? 10 : (LG == 16 ? 12 : (LG == 8 ? 16 : 21));
     f += rounds * LG * N * 5;

@@ -267,7 +267,7 @@ struct FastDimsR {
     static constexpr int NXS = ((NF + 2) & ~1) + 2;    // row stride of the X scratch: even (16-byte rows), 2-way conflicts at most
 };
 
-// measured on B200 (tools/ab_time.py, A/B builds): two rows per lane pay off in the alpha kernel (-23 %) but not in
+// measured on B200 (tools/ab_time.py, A/B builds): two rows per lane pay off in the alpha kernel (-23 % at p = 4) but not in
 // the assembly kernel (254 registers, 2 CTAs/SM: +7 %)
 #ifndef EHDG_ASM_R
 #define EHDG_ASM_R 1
@@ -275,10 +275,13 @@ struct FastDimsR {
 #ifndef EHDG_ALPHA_R
 #define EHDG_ALPHA_R 2
 #endif
+#ifndef EHDG_ALPHA_R2_MAXP
+#define EHDG_ALPHA_R2_MAXP 5     /* A/B at 1M: p = 5 21.4 -> 15.9 ms with two rows per lane (254 registers), p = 6 40.4 -> 42.8 ms */
+#endif
 template <int P>
 using FastDims = FastDimsR<P, (EHDG_ASM_R == 2 && P <= 4) ? 2 : 1>;
 template <int P>
-using AlphaDims = FastDimsR<P, (EHDG_ALPHA_R == 2 && P <= 4) ? 2 : 1>;
+using AlphaDims = FastDimsR<P, (EHDG_ALPHA_R == 2 && P <= EHDG_ALPHA_R2_MAXP) ? 2 : 1>;
 
 template <int P>
 EHDG_HD constexpr int fast_asm_scratch_doubles(int nq) {
