@@ -26,19 +26,19 @@ int DistComm::allreduce_sum(double* buf, size_t count, cudaStream_t st) const {
     return EHDG_OK;
 }
 
-int DistComm::halo_exchange(double* xg, cudaStream_t st, int width) const {
+int DistComm::halo_exchange(double* xg, cudaStream_t st, int width, const double* own) const {
     const size_t w = (size_t)width;
     const int64_t r0 = row_begin[rank], r1 = row_begin[rank + 1];
     EHDG_NCCL(GroupStart());
     if (rank > 0) {
         // lower neighbour needs my first rows up to its col_hi; I need its last rows from my col_lo
         const int64_t send_hi = col_hi[rank - 1] < r1 ? col_hi[rank - 1] : r1;
-        if (send_hi > r0) EHDG_NCCL(Send(xg + r0 * w, (size_t)(send_hi - r0) * w, NCCL_F64, rank - 1, comm, st));
+        if (send_hi > r0) EHDG_NCCL(Send(own ? own : xg + r0 * w, (size_t)(send_hi - r0) * w, NCCL_F64, rank - 1, comm, st));
         if (col_lo[rank] < r0) EHDG_NCCL(Recv(xg + col_lo[rank] * w, (size_t)(r0 - col_lo[rank]) * w, NCCL_F64, rank - 1, comm, st));
     }
     if (rank + 1 < nranks) {
         const int64_t send_lo = col_lo[rank + 1] > r0 ? col_lo[rank + 1] : r0;
-        if (send_lo < r1) EHDG_NCCL(Send(xg + send_lo * w, (size_t)(r1 - send_lo) * w, NCCL_F64, rank + 1, comm, st));
+        if (send_lo < r1) EHDG_NCCL(Send(own ? own + (send_lo - r0) * w : xg + send_lo * w, (size_t)(r1 - send_lo) * w, NCCL_F64, rank + 1, comm, st));
         if (col_hi[rank] > r1) EHDG_NCCL(Recv(xg + r1 * w, (size_t)(col_hi[rank] - r1) * w, NCCL_F64, rank + 1, comm, st));
     }
     EHDG_NCCL(GroupEnd());

@@ -31,7 +31,8 @@ struct DistComm {
     int allreduce_sum(double* buf, size_t count, cudaStream_t st) const;
     // xg is a full-length vector whose rows [row_begin[rank], row_begin[rank+1]) are current: fetch the halo rows
     // width > 1: every row carries `width` doubles (the block-Jacobi inverses)
-    int halo_exchange(double* xg, cudaStream_t st, int width = 1) const;
+    // own (optional): the rank's own rows as a separate array (row r at own[(r - row_begin[rank]) * width]); sent from there
+    int halo_exchange(double* xg, cudaStream_t st, int width = 1, const double* own = nullptr) const;
     // every rank contributes its own row slice of x; afterwards all ranks hold the whole vector
     int allgather_rows(double* x, cudaStream_t st) const;
 };

@@ -202,7 +202,9 @@ template <int NBM, int CHUNKS, int LPF>
 __global__ void __launch_bounds__(256)
 spmv_facet_kernel(int f0, int nf, int row0, int row1, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
                   const int32_t* __restrict__ colind, const int32_t* __restrict__ nbr_len, const double* __restrict__ vals,
-                  const double* __restrict__ x, double* __restrict__ y) {
+                  const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ x_own, int own_lo, int own_hi) {
+    // x_own (distributed solve): the rank's own rows [own_lo, own_hi) are read from the Krylov vector itself, the halo from
+    // the full-length buffer x -- no copy of the own rows into that buffer per product
     static_assert(LPF == 32 || CHUNKS == 1, "column chunks only with a whole warp per facet");
     const int fq = f0 + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPF);      // facets [f0, nf)
     const int lane = threadIdx.x & (LPF - 1);
@@ -227,7 +229,8 @@ spmv_facet_kernel(int f0, int nf, int row0, int row1, const int32_t* __restrict_
     // third level: x gathered once per facet
     double xv[CHUNKS];
 #pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) xv[c] = col[c] >= 0 ? __ldg(x + col[c]) : 0.0;
+    for (int c = 0; c < CHUNKS; ++c)
+        xv[c] = col[c] < 0 ? 0.0 : ((col[c] >= own_lo && col[c] < own_hi) ? __ldg(x_own + (col[c] - own_lo)) : __ldg(x + col[c]));
     // NPAD row sums over the LPF lanes with one transposing butterfly: at every step a lane hands half of its rows to
     // its partner and adds the partner's halves of the rows it keeps (NPAD/2 + NPAD/4 + ... shuffles instead of
     // log2(LPF) per row; the kernel is bound by the shuffle pipe otherwise).
@@ -265,7 +268,8 @@ static bool spmv_use_csr_kernel() {
 }
 
 static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, double* y, cudaStream_t st, int64_t row0 = 0,
-                       int64_t row1 = -1) {
+                       int64_t row1 = -1, const double* x_own = nullptr) {
+    // x_own: values of the rows [row0, row1) (facet-block kernel only; the caller keeps x current otherwise)
     if (row1 < 0) row1 = A->n_rows;
     if (A->windowed) {                       // only the own rows exist
         row0 = row0 > A->row_lo ? row0 : A->row_lo;
@@ -285,7 +289,8 @@ static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, d
         const int64_t threads = (int64_t)(fb - fa) * lpf;
         const unsigned gb = (unsigned)((threads + 255) / 256);
 #define EHDG_SPMV_LAUNCH(NBM, CH, LPF) \
-        spmv_facet_kernel<NBM, CH, LPF><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base, A->colind, A->nbr_len, vals, x, y)
+        spmv_facet_kernel<NBM, CH, LPF><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base, A->colind, A->nbr_len, vals, x, y, \
+                                                            x_own ? x_own : x, x_own ? (int)row0 : 0, x_own ? (int)row1 : 0)
         if (nb <= 2) EHDG_SPMV_LAUNCH(2, 1, 16);
         else if (nb <= 3) EHDG_SPMV_LAUNCH(3, 1, 16);
         else if (nb <= 4) EHDG_SPMV_LAUNCH(4, 1, 32);
@@ -568,11 +573,34 @@ __global__ void residual_kernel(int64_t n, const double* __restrict__ b, double*
         r[i] = b[i] - r[i];
 }
 
+// Final reduction inside the producing kernel: the block that arrives last (atomic ticket) adds the per-block partials in
+// block order, so the result does not depend on which block that is.  Saves the separate reduce launch of every batch of dot
+// products (two per DQGMRES iteration), which matters once the vectors are short (multi-GPU).  `out[t] = sum_b partial[b][t]`.
+__device__ __forceinline__ void finish_partials(int kt, const double* __restrict__ partial, double* __restrict__ out,
+                                                unsigned int* __restrict__ ticket) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int t = warp; t < kt; t += nwarps) {
+        double v = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(partial + (size_t)b * KT + t);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) out[t] = v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
 // ---- DQGMRES ring kernels: vector t of a tile lives in slot (s0 + t) % ring of V ----
 template <int K>
 __global__ void __launch_bounds__(RED_THREADS)
 ring_dot_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring, int s0, int kt, const double* __restrict__ w,
-                double* __restrict__ partial) {
+                double* __restrict__ partial, double* __restrict__ out, unsigned int* __restrict__ ticket) {
     double acc[K];
     const double* vp[K];
 #pragma unroll
@@ -600,6 +628,7 @@ ring_dot_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring, 
         for (int wv = 0; wv < RED_THREADS / 32; ++wv) v += red[wv][threadIdx.x];
         partial[(size_t)blockIdx.x * KT + threadIdx.x] = v;
     }
+    finish_partials(kt, partial, out, ticket);
 }
 
 // out = in - sum_t h[t] V[slot t].  MODE 1: also partial[b][0] = sum of out^2 over the rows of block b.
@@ -608,7 +637,7 @@ template <int K, int MODE>
 __global__ void __launch_bounds__(RED_THREADS)
 ring_axpy_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring, int s0, int kt, const double* __restrict__ h,
                  const double* in, double* out, double* __restrict__ partial, double inv_d, double gamma, double* __restrict__ u,
-                 const double* __restrict__ scal = nullptr) {
+                 const double* __restrict__ scal = nullptr, double* __restrict__ nrm_out = nullptr, unsigned int* __restrict__ ticket = nullptr) {
     if (MODE == 2 && scal) {            // written by dq_rotate_kernel earlier on the stream
         inv_d = scal[1];
         gamma = scal[2];
@@ -644,6 +673,7 @@ ring_axpy_kernel(int64_t n, const double* __restrict__ V, int64_t ldv, int ring,
             for (int wv = 0; wv < RED_THREADS / 32; ++wv) v += red[wv];
             partial[(size_t)blockIdx.x * KT] = v;
         }
+        finish_partials(1, partial, nrm_out, ticket);
     }
 }
 
@@ -691,6 +721,7 @@ struct VecOps {
     double* partial;
     int64_t n;
     const DistComm* dc = nullptr;       // set: n is the local row count, dots are summed over the ranks
+    unsigned int* ticket = nullptr;     // device counter of finish_partials (zero between launches)
     int grid() const {
         const int64_t need = (n + RED_THREADS - 1) / RED_THREADS;
         return (int)(need < RED_BLOCKS ? (need > 0 ? need : 1) : RED_BLOCKS);
@@ -712,9 +743,8 @@ struct VecOps {
     int ring_dots(const double* V, int64_t ldv, int ring, int s0, int k, const double* w, double* out) const {
         for (int t0 = 0; t0 < k; t0 += KT) {
             const int kt = k - t0 < KT ? k - t0 : KT;
-            if (kt <= 2) ring_dot_kernel<2><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, (s0 + t0) % ring, kt, w, partial);
-            else ring_dot_kernel<KT><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, (s0 + t0) % ring, kt, w, partial);
-            reduce_partials_kernel<<<kt, 256, 0, st>>>(grid(), kt, partial, out + t0, 0);
+            if (kt <= 2) ring_dot_kernel<2><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, (s0 + t0) % ring, kt, w, partial, out + t0, ticket);
+            else ring_dot_kernel<KT><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, (s0 + t0) % ring, kt, w, partial, out + t0, ticket);
         }
         EHDG_LAUNCH_CHECK();
         if (dc) return dc->allreduce_sum(out, (size_t)k, st);
@@ -730,12 +760,11 @@ struct VecOps {
             const int sl = (s0 + t0) % ring;
             const double* src = t0 == 0 ? in : out;
             if (!last) ring_axpy_kernel<KT, 0><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
-            else if (mode == 1) ring_axpy_kernel<KT, 1><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
+            else if (mode == 1) ring_axpy_kernel<KT, 1><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr, nullptr, nrm2, ticket);
             else if (mode == 2) ring_axpy_kernel<KT, 2><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, inv_d, gamma, u, scal);
             else ring_axpy_kernel<KT, 0><<<grid(), RED_THREADS, 0, st>>>(n, V, ldv, ring, sl, kt, h + t0, src, out, partial, 0.0, 0.0, nullptr);
             t0 += kt;
         } while (t0 < k);
-        if (mode == 1) reduce_partials_kernel<<<1, 256, 0, st>>>(grid(), 1, partial, nrm2, 0);
         EHDG_LAUNCH_CHECK();
         if (mode == 1 && dc) return dc->allreduce_sum(nrm2, 1, st);
         return EHDG_OK;
@@ -1105,7 +1134,10 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     double* hbuf = nullptr;
     EHDG_CUDA(cudaMallocHost(&hbuf, sizeof(double) * (size_t)(2 * (m + 2) + 16)));
     EHDG_CUDA(cudaMemsetAsync(yhat, 0, sizeof(double) * (size_t)n, st));
-    VecOps vo{st, partial, n, dc};
+    unsigned int* d_ticket = nullptr;
+    EHDG_CUDA(cudaMalloc(&d_ticket, sizeof(unsigned int)));
+    EHDG_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st));
+    VecOps vo{st, partial, n, dc, d_ticket};
     // w = A~ P(v):  P leaves the bulk entries (their M^-1 is folded into A~) and solves the strip block
     auto apply_op = [&](const double* v, double* out) -> int {
         const double* in = v;
@@ -1117,11 +1149,13 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         }
         info->spmv_calls++;
         if (dc) {
-            // own rows into the full-length buffer, halo rows from the two neighbouring ranks, SpMV on own rows
-            EHDG_CUDA(cudaMemcpyAsync(xg + r0, in, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-            const int r3 = dc->halo_exchange(xg, st);
+            // halo rows from the two neighbouring ranks into the full-length buffer (sent straight out of the Krylov
+            // vector), SpMV on own rows; the facet-block kernel reads the own rows from the vector itself
+            const bool direct = !spmv_use_csr_kernel();
+            if (!direct) EHDG_CUDA(cudaMemcpyAsync(xg + r0, in, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            const int r3 = dc->halo_exchange(xg, st, 1, direct ? in : nullptr);
             if (r3) return r3;
-            return launch_spmv(A, vals, xg, out - r0, st, r0, r1);
+            return launch_spmv(A, vals, xg, out - r0, st, r0, r1, direct ? in : nullptr);
         }
         return launch_spmv(A, vals, in, out, st);
     };
@@ -1296,7 +1330,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
             EHDG_CUDA(cudaMemcpyAsync(d_state, hbuf, 5 * sizeof(double), cudaMemcpyHostToDevice, st));
             EHDG_CUDA(cudaStreamSynchronize(st));                               // hbuf is reused below
             bool blown = false;
-            const int poll = 8;
+            const int poll = 16;
             for (int it = 0; iters < max_iters; ++it, ++iters) {
                 const int lo = it - k + 1 > 0 ? it - k + 1 : 0;                 // window of Krylov vectors lo..it
                 const int nw = it - lo + 1;
@@ -1447,6 +1481,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     cudaFree(w);
     cudaFree(yhat);
     cudaFree(partial);
+    cudaFree(d_ticket);
     cudaFree(dsc);
     cudaFreeHost(hbuf);
     return EHDG_OK;
