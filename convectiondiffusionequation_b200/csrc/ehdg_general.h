@@ -38,6 +38,15 @@ struct Coop {
         else __syncwarp();                 // one warp per element
 #endif
     }
+    // number of lanes whose predicate holds (a barrier for all nl lanes on the device; the host runs one lane)
+    EHDG_HD int count(bool pred) const {
+#ifdef __CUDA_ARCH__
+        if (nl > 32) return __syncthreads_count(pred ? 1 : 0);
+        return __popc(__ballot_sync(0xffffffffu, pred));
+#else
+        return pred ? 1 : 0;
+#endif
+    }
 };
 
 // status bits per element
@@ -499,13 +508,12 @@ EHDG_HD double pencil_lambda_max(const Coop& co, int n, double* A, double* M, do
     const double tiny = 1e-300 + 1e-32 * scale * scale;
     hi += 1e-14 * scale;
     // (nl + 1)-section on the Sturm count: lane l tests the abscissa lo + (l + 1) step; with one lane this is
-    // plain bisection.  flags live in the v / pv scratch (2 n doubles >= nl bytes for nl <= 128, n >= 8; else serial).
-    unsigned char* flag = reinterpret_cast<unsigned char*>(v);
-    const int nsec = (co.nl > 1 && 2 * n * 8 >= co.nl) ? co.nl : 1;
+    // plain bisection.
+    const int nsec = co.nl > 1 ? co.nl : 1;
     for (int it = 0; it < 200; ++it) {
         const double step = (hi - lo) / (double)(nsec + 1);
         const double x = lo + step * (double)((nsec > 1 ? co.lane : 0) + 1);
-        if (!(x > lo) || !(lo + step * (double)nsec < hi) || !(step > 0.0)) break;     // uniform: same lo, hi on every lane
+        if (!(lo + step > lo) || !(lo + step * (double)nsec < hi) || !(step > 0.0)) break;   // lane-independent: every lane leaves together
         // all eigenvalues below x  <=>  every pivot of the LDL^T of T - x I is negative
         int nneg = 0;
         double q = dg[0] - x;
@@ -515,13 +523,11 @@ EHDG_HD double pencil_lambda_max(const Coop& co, int n, double* A, double* M, do
             q = (dg[i] - x) - of[i - 1] * of[i - 1] / q;
             if (q < 0.0) ++nneg;
         }
-        int f = nsec;                      // first abscissa above the whole spectrum
+        // first abscissa above the whole spectrum: the test is monotone in x, so it is the number of lanes still below
+        // (one barrier-reduction instead of a flag array that every lane scans)
+        int f = nsec;
         if (nsec > 1) {
-            co.sync();
-            flag[co.lane] = (nneg == n) ? 1 : 0;
-            co.sync();
-            for (int l = 0; l < nsec; ++l)
-                if (flag[l]) { f = l; break; }
+            f = co.count(nneg != n);
         } else if (nneg == n) {
             f = 0;
         }
