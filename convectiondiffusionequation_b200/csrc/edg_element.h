@@ -1,0 +1,168 @@
+// EDG (enriched interior-penalty DG) element routine -- GROUNDWORK for SURVEY.md 8(f) row 1, not wired into libehdg yet.
+//
+// Restates the forms of the reference's _solveEDG (Python/convection_diffusion.py:165-198) for ONE block row of the
+// global matrix: the diagonal block of element K and the blocks that couple K's test functions to the trial functions
+// of its (up to three) facet neighbours, plus K's right-hand side.  Every interior facet is visited from both sides,
+// each side writing its own block row: no atomics, a deterministic result.  Written in the lock-step style of
+// ehdg_general.h (lanes of a Coop stride over points and matrix entries), so the same source is checked on the host
+// against oracle/edg_oracle.py (tests/test_hostcheck_edg.py) before it meets a GPU.
+//
+// Conventions (those of the oracle; NGSolve decides them, see its header): on an interior facet the normal, the mesh
+// size h = |det J| / |e| and alpha_stab are taken from the FIRST element of the facet (facet2el[f][0]); facet points are
+// parametrised from the lower to the higher global vertex number, which both neighbours agree on.
+//   eps [ int grad u . grad v + sum_int ( pen [u][v] - {dn u}[v] - {dn v}[u] ) + sum_bnd ( pen u v - dn u v - dn v u ) ]
+//   - int (b u) . grad v + sum_int (b.n) u_up [v],        pen = 4 alpha_stab p^2 / h^2,  [w] = w_first - w_second.
+#pragma once
+#include "ehdg_general.h"
+
+namespace ehdg {
+
+// doubles of workspace edg_element_blocks needs
+EHDG_HD int edg_ws_doubles(const Problem& pb, int nq, int nqf) {
+    const int vol = 3 * pb.nvmax * pad_odd(nq) + nq;
+    const int fac = 4 * pb.nvmax * pad_odd(nqf) + nqf;
+    return ((vol > fac ? vol : fac) + 1) & ~1;
+}
+
+// barycentrics of the point at parameter t (from the lower to the higher global vertex) of local edge e of an element
+EHDG_HD void edg_facet_point(const ElemGeom& g, int e, double t, double* l) {
+    int a, b;
+    local_edge(e, a, b);
+    const int lo = g.vn[a] < g.vn[b] ? a : b, hi = g.vn[a] < g.vn[b] ? b : a;
+    l[0] = l[1] = l[2] = 0.0;
+    l[lo] = 1.0 - t;
+    l[hi] = t;
+}
+
+// D [nv x nv] (row-major, test x trial), O [3][nv x nv] (neighbour across local edge e; zero on the boundary), F [nv];
+// nv = pb.nvmax = n_p + n_enrich, enrichment rows/columns of inactive functions stay zero.
+// elem_active: u8 per element, bit k = enrichment k active on that element (after pruning); may be null.
+EHDG_HD void edg_element_blocks(const Coop& co, const Problem& pb, const RuleSet& rs, const double* verts, const int* tris,
+                                const int* el2facet, const int* facet2el, const unsigned char* elem_active,
+                                const double* alpha_stab, int el, double* ws, double* D, double* O, double* F) {
+    const int nv = pb.nvmax, nq = rs.nq, nqf = rs.nqf;
+    const int ldq = pad_odd(nq), ldf = pad_odd(nqf);
+    ElemGeom g;
+    elem_geom(verts, tris + 3 * el, g);
+    const int volmask = elem_active ? elem_active[el] : 0;
+    for (int idx = co.lane; idx < nv * nv; idx += co.nl) {
+        D[idx] = 0.0;
+        O[idx] = O[nv * nv + idx] = O[2 * nv * nv + idx] = 0.0;
+    }
+    for (int i = co.lane; i < nv; i += co.nl) F[i] = 0.0;
+    // ---- volume: eps grad u . grad v - (b u) . grad v ; rhs
+    {
+        double* Tp = ws;
+        double* Tgx = Tp + nv * ldq;
+        double* Tgy = Tgx + nv * ldq;
+        double* wq = Tgy + nv * ldq;
+        for (int q = co.lane; q < nq; q += co.nl) {
+            vol_shapes(pb, g, volmask, rs.vx[q], rs.vy[q], Tp + q, Tgx + q, Tgy + q, ldq);
+            wq[q] = rs.vw[q] * g.adet;
+        }
+        co.sync();
+        for (int idx = co.lane; idx < nv * nv; idx += co.nl) {
+            const int i = idx / nv, j = idx % nv;
+            const double *gxi = Tgx + i * ldq, *gyi = Tgy + i * ldq, *gxj = Tgx + j * ldq, *gyj = Tgy + j * ldq, *pj = Tp + j * ldq;
+            double acc = 0.0;
+            for (int q = 0; q < nq; ++q)
+                acc += wq[q] * (pb.eps * (gxi[q] * gxj[q] + gyi[q] * gyj[q]) - (pb.bx * gxi[q] + pb.by * gyi[q]) * pj[q]);
+            D[idx] += acc;
+        }
+        for (int i = co.lane; i < nv; i += co.nl) {
+            double acc = 0.0;
+            for (int q = 0; q < nq; ++q) {
+                const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
+                const double dx = l0 * g.omx[0] + l1 * g.omx[1] + l2 * g.omx[2];
+                const double dy = l0 * g.omy[0] + l1 * g.omy[1] + l2 * g.omy[2];
+                acc += wq[q] * layer_expr_eval(pb.coeff, dx, dy) * Tp[i * ldq + q];
+            }
+            F[i] = acc;
+        }
+        co.sync();
+    }
+    // ---- facets
+    for (int e = 0; e < 3; ++e) {
+        const int f = el2facet[3 * el + e];
+        const int e1 = facet2el[2 * f], e2 = facet2el[2 * f + 1];
+        const bool bnd = e2 < 0;
+        const bool first = (e1 == el);
+        const int other = bnd ? -1 : (first ? e2 : e1);
+        EdgeGeom eg;
+        edge_geom(g, e, eg);
+        // normal, h and alpha_stab of the facet's first element
+        double nx = eg.nx, ny = eg.ny, h1 = eg.h_e;
+        ElemGeom go;
+        int oe = 0, omask = 0;
+        if (!bnd) {
+            elem_geom(verts, tris + 3 * other, go);
+            omask = elem_active ? elem_active[other] : 0;
+            for (int k = 0; k < 3; ++k)
+                if (el2facet[3 * other + k] == f) oe = k;
+            if (!first) {
+                EdgeGeom ego;
+                edge_geom(go, oe, ego);
+                nx = ego.nx;
+                ny = ego.ny;
+                h1 = ego.h_e;
+            }
+        }
+        const double pen = 4.0 * alpha_stab[e1] / h1 * (double)(pb.p * pb.p) / h1;
+        const double bn = pb.bx * nx + pb.by * ny;
+        double* Up = ws;                    // own values at the facet points
+        double* Ud = Up + nv * ldf;         // own derivative along the first element's normal
+        double* Vp = Ud + nv * ldf;         // neighbour values
+        double* Vd = Vp + nv * ldf;         // neighbour normal derivative
+        double* we = Vd + nv * ldf;
+        for (int q = co.lane; q < nqf; q += co.nl) {
+            double l[3], ph[EHDG_MAX_NP + EHDG_MAX_ENRICH], gx[EHDG_MAX_NP + EHDG_MAX_ENRICH], gy[EHDG_MAX_NP + EHDG_MAX_ENRICH];
+            edg_facet_point(g, e, rs.st[q], l);
+            vol_shapes(pb, g, volmask, l[0], l[1], ph, gx, gy, 1);
+            for (int i = 0; i < nv; ++i) {
+                Up[i * ldf + q] = ph[i];
+                Ud[i * ldf + q] = gx[i] * nx + gy[i] * ny;
+            }
+            if (!bnd) {
+                edg_facet_point(go, oe, rs.st[q], l);
+                vol_shapes(pb, go, omask, l[0], l[1], ph, gx, gy, 1);
+                for (int i = 0; i < nv; ++i) {
+                    Vp[i * ldf + q] = ph[i];
+                    Vd[i * ldf + q] = gx[i] * nx + gy[i] * ny;
+                }
+            }
+            we[q] = rs.sw[q] * eg.len;
+        }
+        co.sync();
+        if (bnd) {
+            for (int idx = co.lane; idx < nv * nv; idx += co.nl) {
+                const int i = idx / nv, j = idx % nv;
+                double acc = 0.0;
+                for (int q = 0; q < nqf; ++q)
+                    acc += we[q] * (pen * Up[i * ldf + q] * Up[j * ldf + q] - Up[i * ldf + q] * Ud[j * ldf + q] - Ud[i * ldf + q] * Up[j * ldf + q]);
+                D[idx] += pb.eps * acc;
+            }
+        } else {
+            // own sign in the jump: + for the first element, - for the second
+            const double so = first ? 1.0 : -1.0;
+            const bool up_own = first ? (bn > 0.0) : !(bn > 0.0);      // u_up = first's trace iff b.n > 0
+            double* On = O + (size_t)e * nv * nv;
+            for (int idx = co.lane; idx < nv * nv; idx += co.nl) {
+                const int i = idx / nv, j = idx % nv;
+                double dd = 0.0, oo = 0.0;
+                for (int q = 0; q < nqf; ++q) {
+                    const double vi = Up[i * ldf + q], dvi = Ud[i * ldf + q];
+                    // trial = own (sign so), trial = neighbour (sign -so); test = own (sign so)
+                    const double uj = Up[j * ldf + q], duj = Ud[j * ldf + q];
+                    const double wj = Vp[j * ldf + q], dwj = Vd[j * ldf + q];
+                    dd += we[q] * (pb.eps * (pen * vi * uj - 0.5 * so * vi * duj - 0.5 * so * dvi * uj) + (up_own ? bn * so * vi * uj : 0.0));
+                    oo += we[q] * (pb.eps * (-pen * vi * wj - 0.5 * so * vi * dwj + 0.5 * so * dvi * wj) + (up_own ? 0.0 : bn * so * vi * wj));
+                }
+                D[idx] += dd;
+                On[idx] += oo;
+            }
+        }
+        co.sync();
+    }
+}
+
+}  // namespace ehdg

@@ -46,7 +46,7 @@ def build():
     so = os.path.join(HERE, "libhostcheck.so")
     srcs = [os.path.join(HERE, "hostcheck.cpp")] + [
         os.path.join(ROOT, "convectiondiffusionequation_b200", "csrc", f)
-        for f in ("ehdg_general.h", "ehdg_basis.h", "ehdg_rules.h", "ehdg_problem.h", "ehdg_tensors.h", "ehdg_fast.h")]
+        for f in ("ehdg_general.h", "ehdg_basis.h", "ehdg_rules.h", "ehdg_problem.h", "ehdg_tensors.h", "ehdg_fast.h", "edg_element.h")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so,

@@ -8,6 +8,7 @@
 #include "../../convectiondiffusionequation_b200/csrc/ehdg_rules.h"
 #include "../../convectiondiffusionequation_b200/csrc/ehdg_problem.h"
 #include "../../convectiondiffusionequation_b200/csrc/ehdg_fast.h"
+#include "../../convectiondiffusionequation_b200/csrc/edg_element.h"
 
 using namespace ehdg;
 
@@ -113,5 +114,15 @@ double hc_fast_alpha(const ehdg_problem* ep, const double* verts, const int* tri
         case 6: return fast_alpha_host<6>(verts, tri, ep->bonus_int, status);
     }
     return -1.0;
+}
+
+// EDG block row of one element (csrc/edg_element.h): D [nv x nv], O [3][nv x nv], F [nv], nv = n_p + n_enrich
+void hc_edg_element(const ehdg_problem* ep, const double* verts, const int* tris, const int* el2facet, const int* facet2el,
+                    const unsigned char* elem_active, const double* alpha_stab, int el, double* D, double* O, double* F) {
+    Problem pb = make_problem(*ep);
+    HostRules hr(2 * pb.p + pb.bonus);
+    std::vector<double> ws(edg_ws_doubles(pb, hr.rs.nq, hr.rs.nqf));
+    Coop co{0, 1};
+    edg_element_blocks(co, pb, hr.rs, verts, tris, el2facet, facet2el, elem_active, alpha_stab, el, ws.data(), D, O, F);
 }
 }

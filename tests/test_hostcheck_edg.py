@@ -1,0 +1,63 @@
+"""Host build of the EDG element routine (csrc/edg_element.h, groundwork for SURVEY.md 8(f) row 1) against the EDG oracle:
+every block row of the global matrix and the right-hand side, plain DG and enriched, all vertex orderings."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from convectiondiffusionequation_b200.mesh import unit_square_mesh
+from oracle import ehdg_oracle as orc
+from oracle.edg_oracle import EDGOracle
+from tests.hostcheck.binding import c_problem, dptr, iptr, lib
+
+L = lib()
+
+
+@pytest.mark.parametrize("order,eps,beta,enriched,kind", [(1, 1e-2, (2.0, 1.0), False, "structured"),
+                                                          (3, 1e-3, (2.0, 0.001), False, "unstructured"),
+                                                          (2, 2e-2, (2.0, 1.0), True, "structured"),
+                                                          (2, 1e-2, (-1.0, 2.0), True, "unstructured")])
+def test_edg_block_rows_match_the_oracle(order, eps, beta, enriched, kind):
+    mesh = unit_square_mesh(4, kind=kind)
+    prob = orc.run_py_problem(beta=beta, eps=eps, enriched=enriched)
+    o = EDGOracle(mesh.verts, mesh.tris, mesh.el2facet, mesh.facet2el, mesh.maxh, order, prob)
+    o.prune()
+    rng = np.random.default_rng(3)
+    alpha_stab = 5.0 + 20.0 * rng.random(mesh.ne)                      # any positive field: the forms are linear in it
+    A, F = o.assemble(alpha_stab)
+    A = A.tocsr()
+    cp = c_problem(order, prob)
+    nenr = len(prob.enrich_desc)
+    nv = o.n_p + nenr
+    # active enrichment bits per element: marked and not pruned
+    act = np.zeros(mesh.ne, dtype=np.uint8)
+    for i in range(nenr):
+        for el in np.nonzero(o.h.el_mark[i])[0]:
+            d = o.offQ[i] + o.q_num[i][el]
+            if o.active[d]:
+                act[el] |= 1 << i
+    tris = np.ascontiguousarray(mesh.tris, np.int32)
+    e2f = np.ascontiguousarray(mesh.el2facet, np.int32)
+    f2e = np.ascontiguousarray(mesh.facet2el, np.int32)
+    scale = abs(A).max()
+    for el in range(mesh.ne):
+        D, O, Fl = np.zeros((nv, nv)), np.zeros((3, nv, nv)), np.zeros(nv)
+        L.hc_edg_element(C.byref(cp), dptr(mesh.verts), iptr(tris), iptr(e2f), iptr(f2e), act.ctypes.data_as(C.c_void_p),
+                         dptr(alpha_stab), C.c_int(el), dptr(D), dptr(O), dptr(Fl))
+        d_own = o.el_dofs(el)
+        keep = np.array([bool(d >= 0 and (i < o.n_p or (act[el] >> (i - o.n_p)) & 1)) for i, d in enumerate(d_own)], dtype=bool)
+        ref = A[d_own[keep]][:, d_own[keep]].toarray()
+        assert np.abs(D[np.ix_(keep, keep)] - ref).max() < 1e-11 * scale, ("diag", el)
+        assert np.abs(Fl[keep] - F[d_own[keep]]).max() < 1e-12 * max(1.0, np.abs(F).max())
+        assert np.all(D[~keep] == 0.0) and np.all(D[:, ~keep] == 0.0)
+        for e in range(3):
+            f = mesh.el2facet[el, e]
+            nb = mesh.facet2el[f]
+            other = nb[1] if nb[0] == el else nb[0]
+            if other < 0:
+                assert np.all(O[e] == 0.0)
+                continue
+            d_nb = o.el_dofs(other)
+            keep_nb = np.array([bool(d >= 0 and (i < o.n_p or (act[other] >> (i - o.n_p)) & 1)) for i, d in enumerate(d_nb)], dtype=bool)
+            ref = A[d_own[keep]][:, d_nb[keep_nb]].toarray()
+            assert np.abs(O[e][np.ix_(keep, keep_nb)] - ref).max() < 1e-11 * scale, ("off", el, e)
