@@ -165,4 +165,60 @@ EHDG_HD void edg_element_blocks(const Coop& co, const Problem& pb, const RuleSet
     }
 }
 
+// EDG pruning of one marked element (reference :83-123): mass Gram  int u() v()  of the enriched volume shapes with the
+// bonus rule; enrichment k (local dof n_p + k, in the order of the compound space [V, Q_0, Q_1, ...]) is dropped when
+//   factor = sqrt |1 - 2 sum_j G_ij^2 / (G_ii G_jj) + sum_{j,k} G_ij G_ik G_jk / (G_ii G_jj G_kk)| <= theta
+// over the dofs j, k < i that are still kept.  Unlike the EHDG loop there is no try/except around it.
+// elmark: bits of the enrichments whose P0 dof exists on the element.  ws: edg_ws_doubles() + nv * nv doubles.
+// factors[k] (optional): the factor of enrichment k, -1 where it has no dof.  Returns the bit mask of dropped enrichments.
+EHDG_HD int edg_prune_element(const Coop& co, const Problem& pb, const RuleSet& rs, const double* verts, const int* tri,
+                              int elmark, double theta, double* ws, double* factors) {
+    const int nv = pb.nvmax, nq = rs.nq, ldq = pad_odd(nq);
+    ElemGeom g;
+    elem_geom(verts, tri, g);
+    double* Tp = ws;
+    double* wq = Tp + nv * ldq;
+    double* G = ws + edg_ws_doubles(pb, rs.nq, rs.nqf);
+    for (int q = co.lane; q < nq; q += co.nl) {
+        vol_shapes(pb, g, elmark, rs.vx[q], rs.vy[q], Tp + q, (double*)0, (double*)0, ldq);
+        wq[q] = rs.vw[q] * g.adet;
+    }
+    co.sync();
+    for (int idx = co.lane; idx < nv * nv; idx += co.nl) {
+        const int i = idx / nv, j = idx % nv;
+        double acc = 0.0;
+        for (int q = 0; q < nq; ++q) acc += wq[q] * Tp[i * ldq + q] * Tp[j * ldq + q];
+        G[idx] = acc;
+    }
+    co.sync();
+    int drop = 0;                       // every lane runs the same sequential test
+    for (int k = 0; k < pb.nenr; ++k) {
+        double fac = -1.0;
+        if ((elmark >> k) & 1) {
+            const int i = pb.n_p + k;
+            const double gii = G[i * nv + i];
+            int act[EHDG_MAX_NP + EHDG_MAX_ENRICH];
+            int na = 0;
+            for (int j = 0; j < pb.n_p; ++j) act[na++] = j;
+            for (int kk = 0; kk < k; ++kk)
+                if (((elmark >> kk) & 1) && !((drop >> kk) & 1)) act[na++] = pb.n_p + kk;
+            double s1 = 0.0, s2 = 0.0;
+            for (int a = 0; a < na; ++a) {
+                const int j = act[a];
+                s1 += G[i * nv + j] * G[i * nv + j] / gii / G[j * nv + j];
+            }
+            for (int a = 0; a < na; ++a)
+                for (int b = 0; b < na; ++b) {
+                    const int j = act[a], kk = act[b];
+                    s2 += G[i * nv + j] * G[i * nv + kk] * G[j * nv + kk] / gii / G[j * nv + j] / G[kk * nv + kk];
+                }
+            fac = sqrt(fabs(1.0 - 2.0 * s1 + s2));
+            if (fac <= theta) drop |= 1 << k;
+        }
+        if (factors && co.lane == 0) factors[k] = fac;
+    }
+    co.sync();
+    return drop;
+}
+
 }  // namespace ehdg

@@ -62,6 +62,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.hc_alpha.restype = C.c_double
+        _lib.hc_alpha_bonus.restype = C.c_double
     return _lib
 
 

@@ -125,4 +125,21 @@ void hc_edg_element(const ehdg_problem* ep, const double* verts, const int* tris
     Coop co{0, 1};
     edg_element_blocks(co, pb, hr.rs, verts, tris, el2facet, facet2el, elem_active, alpha_stab, el, ws.data(), D, O, F);
 }
+
+int hc_edg_prune(const ehdg_problem* ep, const double* verts, const int* tri, int elmark, double theta, double* factors) {
+    Problem pb = make_problem(*ep);
+    HostRules hr(2 * pb.p + pb.bonus);
+    std::vector<double> ws(edg_ws_doubles(pb, hr.rs.nq, hr.rs.nqf) + pb.nvmax * pb.nvmax);
+    Coop co{0, 1};
+    return edg_prune_element(co, pb, hr.rs, verts, tri, elmark, theta, ws.data(), factors);
+}
+// the alpha pencil with the rule of order 2p + bonus (the EDG integrators pass bonus_intorder, reference :129-134)
+double hc_alpha_bonus(const ehdg_problem* ep, const double* verts, const int* tri, int volmask, int exclude_const, int* status) {
+    Problem pb = make_problem(*ep);
+    HostRules hb(2 * pb.p + pb.bonus);
+    std::vector<double> ws(alpha_ws_doubles(pb, hb.rs.nq, hb.rs.nqf));
+    Coop co{0, 1};
+    *status = 0;
+    return alpha_general(co, pb, hb.rs, verts, tri, volmask, exclude_const, ws.data(), status);
+}
 }

@@ -61,3 +61,49 @@ def test_edg_block_rows_match_the_oracle(order, eps, beta, enriched, kind):
             keep_nb = np.array([bool(d >= 0 and (i < o.n_p or (act[other] >> (i - o.n_p)) & 1)) for i, d in enumerate(d_nb)], dtype=bool)
             ref = A[d_own[keep]][:, d_nb[keep_nb]].toarray()
             assert np.abs(O[e][np.ix_(keep, keep_nb)] - ref).max() < 1e-11 * scale, ("off", el, e)
+
+
+@pytest.mark.parametrize("order,eps,beta,theta", [(2, 2e-2, (2.0, 1.0), 1e-5), (1, 1e-2, (2.0, 0.001), 1e-5), (3, 1e-1, (2.0, 1.0), 0.2)])
+def test_edg_pruning_and_alpha_match_the_oracle(order, eps, beta, theta):
+    mesh = unit_square_mesh(4, kind="structured")
+    prob = orc.run_py_problem(beta=beta, eps=eps, enriched=True)
+    o = EDGOracle(mesh.verts, mesh.tris, mesh.el2facet, mesh.facet2el, mesh.maxh, order, prob, theta=theta)
+    o.prune()
+    cp = c_problem(order, prob)
+    nenr = len(prob.enrich_desc)
+    act = np.zeros(mesh.ne, dtype=np.int64)
+    n_marked = 0
+    for el in range(mesh.ne):
+        tri = np.ascontiguousarray(mesh.tris[el], np.int32)
+        elmark = sum(1 << i for i in range(nenr) if o.h.el_mark[i][el])
+        if not elmark:
+            continue
+        n_marked += 1
+        fac = np.zeros(nenr)
+        drop = L.hc_edg_prune(C.byref(cp), dptr(mesh.verts), iptr(tri), C.c_int(elmark), C.c_double(theta), dptr(fac))
+        got = [fac[i] for i in range(nenr) if (elmark >> i) & 1]
+        ref = o.factors[el]
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            # the factor is a difference of O(1) terms: absolute agreement, and the same side of theta unless it sits on it
+            assert abs(a - b) < 1e-6 * max(1.0, abs(b)) or abs(b - theta) < 1e-6
+        for i in range(nenr):
+            if (elmark >> i) & 1:
+                kept_ref = bool(o.active[o.offQ[i] + o.q_num[i][el]])
+                kept = not ((drop >> i) & 1)
+                assert kept == kept_ref or min(abs(f - theta) for f in ref) < 1e-6
+                if kept_ref:
+                    act[el] |= 1 << i
+    assert n_marked >= 4
+    # alpha: generalised eigenvalue of (m, a + f f^T) with the bonus rule on the kept dofs (reference :129-163)
+    lam = o.alpha_all()
+    checked = 0
+    for el in range(1, mesh.ne):            # element 0: `dof > 0` drops its constant mode (exclude_const)
+        tri = np.ascontiguousarray(mesh.tris[el], np.int32)
+        st = C.c_int(0)
+        got = L.hc_alpha_bonus(C.byref(cp), dptr(mesh.verts), iptr(tri), C.c_int(int(act[el])), C.c_int(0), C.byref(st))
+        if st.value == 0:
+            tol = 1e-10 if act[el] == 0 else 1e-5       # enriched pencils are ill-conditioned
+            assert abs(got - lam[el]) < tol * lam[el], (el, got, lam[el])
+            checked += 1
+    assert checked >= mesh.ne // 2
