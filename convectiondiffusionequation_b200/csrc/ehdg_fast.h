@@ -479,7 +479,11 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 #pragma unroll
             for (int h = 0; h < R; ++h) key[L][h] = (h * LG + l < NP) ? fabs(a[L][h][0]) : -1.0;
         EHDG_END_LANES
+#ifdef EHDG_EXP_NOPIVOT
+        rw = 0;                                 // timing experiment only: natural pivot order (wrong results)
+#else
         rw = gc.template argmax_row<R>(key);
+#endif
     }
     // Two ways to hand the pivot row to the other lanes, chosen per order from A/B timings on B200 (EHDG_GJ_SHFL_ORDERS):
     // by warp shuffle straight out of the owner lane's registers (no store / barrier / load round trip and no section
@@ -523,7 +527,11 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
                 key[L][h] = (h * LG + l < NP && mycol[L][h] < 0) ? fabs(a[L][h][k + 1]) : -1.0;
             }
         EHDG_END_LANES
+#ifdef EHDG_EXP_NOPIVOT
+        if (k + 1 < NP) rw = k + 1;
+#else
         if (k + 1 < NP) rw = gc.template argmax_row<R>(key);
+#endif
         EHDG_FOR_LANES(l, L)
 #pragma unroll
             for (int j = k + 2; j < NC; ++j) {
@@ -585,7 +593,11 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
                 key[L][h] = (h * LG + l < NP && mycol[L][h] < 0) ? fabs(a[L][h][k + 1]) : -1.0;
             }
         EHDG_END_LANES
+#ifdef EHDG_EXP_NOPIVOT
+        if (k + 1 < NP) rw = k + 1;
+#else
         if (k + 1 < NP) rw = gc.template argmax_row<R>(key);
+#endif
         EHDG_FOR_LANES(l, L)
 #pragma unroll
             for (int jp = (k + 2) >> 1; jp <= (NC - 1) >> 1; ++jp) {
