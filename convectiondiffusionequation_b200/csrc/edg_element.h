@@ -221,4 +221,49 @@ EHDG_HD int edg_prune_element(const Coop& co, const Problem& pb, const RuleSet& 
     return drop;
 }
 
+// ---- block-row layout of the DG matrix (dgjumps=True: an element couples to itself and its facet neighbours) ----
+// Rows are element-major: row of (element el, local slot k) = row_start[el] + rank of k among the ACTIVE slots of el, where
+// slot k < n_p is polynomial and slot n_p + j is enrichment j (active iff bit j of elem_active[el]).  NGSolve numbers the
+// constant modes of all elements first: a permutation of this numbering.
+
+// neighbours of el in ascending element number including el itself: nbr[0..n), edge[t] = local edge of el that leads to
+// nbr[t] (-1 for el itself).  Returns n <= 4.
+EHDG_HD int edg_block_neighbours(const int* el2facet, const int* facet2el, int el, int* nbr, int* edge) {
+    int n = 0;
+    nbr[n] = el;
+    edge[n++] = -1;
+    for (int e = 0; e < 3; ++e) {
+        const int f = el2facet[3 * el + e];
+        const int a = facet2el[2 * f], b = facet2el[2 * f + 1];
+        if (b < 0) continue;
+        nbr[n] = (a == el) ? b : a;
+        edge[n++] = e;
+    }
+    for (int i = 1; i < n; ++i) {               // insertion sort on the element number
+        const int v = nbr[i], w = edge[i];
+        int j = i - 1;
+        while (j >= 0 && nbr[j] > v) { nbr[j + 1] = nbr[j]; edge[j + 1] = edge[j]; --j; }
+        nbr[j + 1] = v;
+        edge[j + 1] = w;
+    }
+    return n;
+}
+
+EHDG_HD unsigned edg_dofmask(int n_p, int active_bits) { return ((1u << n_p) - 1u) | ((unsigned)active_bits << n_p); }
+
+// Values of one matrix row: local slot k of element el (must be active) against the active slots of its neighbours in
+// ascending element order, read from the block row (D, O) that edg_element_blocks wrote.  out needs
+// sum_t popc(mask[nbr[t]]) entries; returns that count.
+EHDG_HD int edg_fill_row(int nv, int n_p, const unsigned char* elem_active, int n_nbr, const int* nbr, const int* edge, int k,
+                         const double* D, const double* O, double* out) {
+    int pos = 0;
+    for (int t = 0; t < n_nbr; ++t) {
+        const unsigned m = edg_dofmask(n_p, elem_active ? elem_active[nbr[t]] : 0);
+        const double* B = edge[t] < 0 ? D : O + (size_t)edge[t] * nv * nv;
+        for (int l = 0; l < nv; ++l)
+            if ((m >> l) & 1u) out[pos++] = B[k * nv + l];
+    }
+    return pos;
+}
+
 }  // namespace ehdg

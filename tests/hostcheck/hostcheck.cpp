@@ -142,4 +142,56 @@ double hc_alpha_bonus(const ehdg_problem* ep, const double* verts, const int* tr
     *status = 0;
     return alpha_general(co, pb, hb.rs, verts, tri, volmask, exclude_const, ws.data(), status);
 }
+
+// Whole DG matrix in element-major block rows through edg_block_neighbours / edg_fill_row: rowptr [n_rows + 1], colind, vals
+// (caller sizes them from hc_edg_csr_sizes), rhs [n_rows]
+void hc_edg_csr_sizes(const ehdg_problem* ep, int ne, const int* el2facet, const int* facet2el, const unsigned char* elem_active,
+                      long long* n_rows, long long* nnz) {
+    Problem pb = make_problem(*ep);
+    std::vector<int> cnt(ne);
+    for (int el = 0; el < ne; ++el) cnt[el] = __builtin_popcount(edg_dofmask(pb.n_p, elem_active ? elem_active[el] : 0));
+    long long r = 0, z = 0;
+    for (int el = 0; el < ne; ++el) {
+        int nbr[4], edge[4];
+        const int n = edg_block_neighbours(el2facet, facet2el, el, nbr, edge);
+        int len = 0;
+        for (int t = 0; t < n; ++t) len += cnt[nbr[t]];
+        r += cnt[el];
+        z += (long long)cnt[el] * len;
+    }
+    *n_rows = r;
+    *nnz = z;
+}
+void hc_edg_csr(const ehdg_problem* ep, int ne, const double* verts, const int* tris, const int* el2facet, const int* facet2el,
+                const unsigned char* elem_active, const double* alpha_stab, long long* rowptr, int* colind, double* vals, double* rhs) {
+    Problem pb = make_problem(*ep);
+    HostRules hr(2 * pb.p + pb.bonus);
+    std::vector<double> ws(edg_ws_doubles(pb, hr.rs.nq, hr.rs.nqf));
+    const int nv = pb.nvmax;
+    std::vector<double> D(nv * nv), O(3 * nv * nv), F(nv);
+    std::vector<int> row_start(ne + 1, 0);
+    for (int el = 0; el < ne; ++el)
+        row_start[el + 1] = row_start[el] + __builtin_popcount(edg_dofmask(pb.n_p, elem_active ? elem_active[el] : 0));
+    Coop co{0, 1};
+    long long pos = 0;
+    int r = 0;
+    for (int el = 0; el < ne; ++el) {
+        edg_element_blocks(co, pb, hr.rs, verts, tris, el2facet, facet2el, elem_active, alpha_stab, el, ws.data(), D.data(), O.data(), F.data());
+        int nbr[4], edge[4];
+        const int n = edg_block_neighbours(el2facet, facet2el, el, nbr, edge);
+        const unsigned m = edg_dofmask(pb.n_p, elem_active ? elem_active[el] : 0);
+        for (int k = 0; k < nv; ++k) {
+            if (!((m >> k) & 1u)) continue;
+            rowptr[r] = pos;
+            rhs[r] = F[k];
+            const int cnt = edg_fill_row(nv, pb.n_p, elem_active, n, nbr, edge, k, D.data(), O.data(), vals + pos);
+            int c = 0;
+            for (int t = 0; t < n; ++t)
+                for (int l = row_start[nbr[t]]; l < row_start[nbr[t] + 1]; ++l) colind[pos + c++] = l;
+            pos += cnt;
+            ++r;
+        }
+    }
+    rowptr[r] = pos;
+}
 }

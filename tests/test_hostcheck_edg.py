@@ -107,3 +107,62 @@ def test_edg_pruning_and_alpha_match_the_oracle(order, eps, beta, theta):
             assert abs(got - lam[el]) < tol * lam[el], (el, got, lam[el])
             checked += 1
     assert checked >= mesh.ne // 2
+
+
+@pytest.mark.parametrize("order,enriched,kind", [(1, False, "unstructured"), (2, True, "structured"), (2, True, "unstructured")])
+def test_edg_block_csr_equals_the_oracle_matrix(order, enriched, kind):
+    """element-major block rows (edg_block_neighbours / edg_fill_row): the whole matrix against the oracle's, pattern bit-exact
+    under the permutation to NGSolve's numbering, values and right-hand side to round-off, and the solve reproduces the error"""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+    mesh = unit_square_mesh(4, kind=kind)
+    prob = orc.run_py_problem(beta=(2.0, 1.0), eps=2e-2, enriched=enriched)
+    o = EDGOracle(mesh.verts, mesh.tris, mesh.el2facet, mesh.facet2el, mesh.maxh, order, prob)
+    o.prune()
+    alpha_stab = o.alpha_all()
+    A, F = o.assemble(alpha_stab)
+    nenr = len(prob.enrich_desc)
+    act = np.zeros(mesh.ne, dtype=np.uint8)
+    for i in range(nenr):
+        for el in np.nonzero(o.h.el_mark[i])[0]:
+            if o.active[o.offQ[i] + o.q_num[i][el]]:
+                act[el] |= 1 << i
+    cp = c_problem(order, prob)
+    tris = np.ascontiguousarray(mesh.tris, np.int32)
+    e2f = np.ascontiguousarray(mesh.el2facet, np.int32)
+    f2e = np.ascontiguousarray(mesh.facet2el, np.int32)
+    nr, nz = C.c_longlong(0), C.c_longlong(0)
+    actp = act.ctypes.data_as(C.c_void_p)
+    L.hc_edg_csr_sizes(C.byref(cp), C.c_int(mesh.ne), iptr(e2f), iptr(f2e), actp, C.byref(nr), C.byref(nz))
+    n, nnz = nr.value, nz.value
+    assert n == int(o.active.sum())
+    rowptr, colind = np.zeros(n + 1, np.int64), np.zeros(nnz, np.int32)
+    vals, rhs = np.zeros(nnz), np.zeros(n)
+    L.hc_edg_csr(C.byref(cp), C.c_int(mesh.ne), dptr(mesh.verts), iptr(tris), iptr(e2f), iptr(f2e), actp, dptr(alpha_stab),
+                 rowptr.ctypes.data_as(C.c_void_p), iptr(colind), dptr(vals), dptr(rhs))
+    assert rowptr[-1] == nnz
+    B = sps.csr_matrix((vals, colind, rowptr), shape=(n, n))
+    for r in range(n):
+        assert np.all(np.diff(colind[rowptr[r]:rowptr[r + 1]]) > 0)       # columns ascending in every row
+    # our row -> NGSolve dof: element-major over the active local slots
+    ng = []
+    for el in range(mesh.ne):
+        d = o.el_dofs(el)
+        for k, dof in enumerate(d):
+            if dof >= 0 and (k < o.n_p or (act[el] >> (k - o.n_p)) & 1):
+                ng.append(dof)
+    ng = np.array(ng)
+    assert len(ng) == n and np.array_equal(np.sort(ng), np.nonzero(o.active)[0])
+    perm = np.argsort(ng)
+    Bp = B[perm][:, perm].tocsr()
+    Bp.sort_indices()
+    actd = np.nonzero(o.active)[0]
+    Ao = A[actd][:, actd].tocsr()
+    Ao.sort_indices()
+    assert np.array_equal(Bp.indptr, Ao.indptr) and np.array_equal(Bp.indices, Ao.indices)      # pattern: bit-exact
+    assert np.abs(Bp.data - Ao.data).max() < 1e-11 * np.abs(Ao.data).max()
+    assert np.abs(rhs[perm] - F[actd]).max() < 1e-12 * max(1.0, np.abs(F).max())
+    x = np.zeros(o.ndof)
+    x[ng] = spla.spsolve(B.tocsc(), rhs)
+    e_ref = o.l2_error(o.solve(alpha_stab))
+    assert abs(o.l2_error(x) - e_ref) < 1e-8 * e_ref
