@@ -48,7 +48,9 @@ class GmresInfo(C.Structure):
                 ("converged", C.c_int32), ("rel_residual", C.c_double), ("total_seconds", C.c_double),
                 ("spmv_calls", C.c_int64), ("dropped_dofs", C.c_int32),
                 ("use_strip_block", C.c_int32), ("strip_dofs", C.c_int32), ("strip_blocks", C.c_int32),
-                ("jacobi_sweeps", C.c_int32), ("reserved", C.c_int32)]
+                ("jacobi_sweeps", C.c_int32), ("use_line_block", C.c_int32), ("line_target_dofs", C.c_int32),
+                ("line_chains", C.c_int32), ("line_blocks", C.c_int32), ("line_max_block", C.c_int32),
+                ("setup_seconds", C.c_double), ("precond_bytes", C.c_double)]
 
 
 # every symbol include/ehdg.h declares: name -> (restype, argtypes)
@@ -74,6 +76,9 @@ SYMBOLS = {
     "ehdg_csr_symbolic": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.POINTER(_P), _P]),
     "ehdg_csr_symbolic_part": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.c_int, C.c_int, C.POINTER(_P), _P]),
     "ehdg_csr_get_partition": (C.c_int, [_P, _P, _P]),
+    "ehdg_csr_set_lines": (C.c_int, [_P, _P, _P]),
+    "ehdg_csr_auto_lines": (C.c_int, [_P, _P, C.POINTER(Mesh), C.c_double, C.c_double, C.c_double, C.c_double, _P]),
+    "ehdg_csr_lines": (_P, [_P]),
     "ehdg_csr_destroy": (C.c_int, [_P]),
     "ehdg_csr_get_sizes": (C.c_int, [_P, C.POINTER(CsrSizes)]),
     "ehdg_csr_rowptr": (_P, [_P]),
@@ -88,6 +93,8 @@ SYMBOLS = {
     "ehdg_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int]),
     "ehdg_comm_set_partition": (C.c_int, [_P, _P, _P, _P]),
     "ehdg_comm_destroy": (C.c_int, [_P]),
+    "ehdg_krylov_workspace_bytes": (C.c_int, [_P, _P, C.POINTER(GmresInfo), C.c_int, C.POINTER(C.c_int64)]),
+    "ehdg_set_workspace": (C.c_int, [_P, _P, C.c_int64]),
     "ehdg_spmv": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "ehdg_backsolve": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
     "ehdg_l2_error": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),

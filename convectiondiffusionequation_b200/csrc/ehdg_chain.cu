@@ -1,0 +1,605 @@
+// Line-block Jacobi: the preconditioner of the condensed facet system (a9).
+//
+// The facets are partitioned into CHAINS: streamline-aligned lines of the mesh (one chain per line of width ~h across
+// the flow, ehdg_csr_auto_lines / ehdg_csr_set_lines) and, for enriched problems, the strip of marked elements, whose
+// penalties tau ~ eps * 20 lambda_K p^2 / h are orders of magnitude above the bulk (conv_diff.py:349).  Every chain is
+// one diagonal block of a block-Jacobi preconditioner and is solved EXACTLY: the facets of a chain are ordered by the
+// BFS levels of the chain's facet graph (any graph is block tridiagonal in its BFS levels), consecutive levels are
+// merged into blocks of at most CHAIN_MAXB dofs, and the block-tridiagonal matrix is factorised once (block Thomas with
+// rank-revealing pivots) by one CTA per chain.  An application is one forward and one backward sweep of small dense
+// mat-vecs per chain: ONE WARP PER CHAIN, lanes own the rows of a block, the factor blocks arrive through a ring of
+// TMA bulk copies (cp.async.bulk + mbarrier) that runs ahead of the recurrence, so the sequential chain only ever waits
+// for shared memory.  Facet block-Jacobi is the special case "every facet its own chain".
+//
+// Measured on the 64^2 .. 128^2 order-4 systems (host study, tools/precond_study.py): 7-13x fewer GMRES iterations than
+// facet block-Jacobi; the count is insensitive to the restart length.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "ehdg_chain.h"
+#include "ehdg_internal.h"
+
+namespace ehdg {
+
+constexpr int CHAIN_MAXB = 64;       // largest block (two rows per lane in the sweep kernel)
+
+// ---------------------------------------------------------------------------------------------
+// set-up kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void chain_pos_kernel(int nd, const int32_t* __restrict__ dof_rows, const int32_t* __restrict__ dof_blk,
+                                 const ChainBlock* __restrict__ blocks, int32_t* __restrict__ sblk, int32_t* __restrict__ sloc) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nd) return;
+    const int b = dof_blk[s];
+    sblk[dof_rows[s]] = b;
+    sloc[dof_rows[s]] = s - blocks[b].s0;
+}
+
+// dense blocks (column major) from the CSR rows: D_b (n x n) and U_b = A[b, b+1] (n x n_next) into DH, L_b = A[b, b-1]
+// (n x n_prev) into G.  Couplings that leave the chain or skip a block do not belong to the preconditioner.
+__global__ void chain_extract_kernel(int nd, const int32_t* __restrict__ dof_rows, const int32_t* __restrict__ dof_blk,
+                                     const ChainBlock* __restrict__ blocks, const int32_t* __restrict__ blk_chain,
+                                     const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                     const double* __restrict__ vals, const int32_t* __restrict__ sblk, const int32_t* __restrict__ sloc,
+                                     double* __restrict__ DH, double* __restrict__ G, int* __restrict__ skipped) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nd) return;
+    const int b = dof_blk[s], r = dof_rows[s];
+    const ChainBlock B = blocks[b];
+    const int i = s - B.s0, n = B.n, ch = blk_chain[b];
+    int nskip = 0;
+    for (int64_t q = rowptr[r]; q < rowptr[r + 1]; ++q) {
+        const int c = colind[q];
+        const int cb = sblk[c];
+        if (cb < 0 || blk_chain[cb] != ch) continue;
+        const int j = sloc[c];
+        if (cb == b) DH[B.offDH + (int64_t)j * n + i] = vals[q];
+        else if (cb == b - 1) G[B.offG + (int64_t)j * n + i] = vals[q];
+        else if (cb == b + 1) DH[B.offDH + (int64_t)n * n + (int64_t)j * n + i] = vals[q];
+        else if (vals[q] != 0.0) ++nskip;     // cannot happen for BFS levels
+    }
+    if (nskip) atomicAdd(skipped, nskip);
+}
+
+// Block LU of one chain per CTA.  On exit: DH holds [Delta_b^-1 | H_b = Delta_b^-1 U_b] (rank-revealing: dependent dofs
+// get zero rows / columns), G holds G_b = L_b Delta_{b-1}^-1.
+__global__ void __launch_bounds__(128)
+chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __restrict__ blocks, const int32_t* __restrict__ dof_rows,
+                    const uint8_t* __restrict__ rowdrop, double* DH, double* G, int* dropped) {
+    extern __shared__ double sm[];
+    double* Aw = sm;                                   // n x 2n augmented [Delta | I], row major
+    __shared__ int s_piv;
+    __shared__ double s_best, s_scale;
+    __shared__ unsigned char s_drop[CHAIN_MAXB];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int b0 = chain_ptr[blockIdx.x], b1 = chain_ptr[blockIdx.x + 1];
+    for (int b = b0; b < b1; ++b) {
+        const ChainBlock B = blocks[b];
+        const int n = B.n;
+        double* Db = DH + B.offDH;                     // column major
+        const int np_ = b > b0 ? blocks[b - 1].n : 0;
+        double* Uprev = b > b0 ? DH + blocks[b - 1].offDH + (int64_t)np_ * np_ : nullptr;   // np_ x n, still the original U_{b-1}
+        // Delta_b = D_b - G_b U_{b-1}   (G_b was completed at the end of step b-1)
+        if (b > b0) {
+            const double* Gb = G + B.offG;             // n x np_
+            for (int idx = tid; idx < n * n; idx += nt) {
+                const int i = idx % n, j = idx / n;
+                double acc = Db[idx];
+                for (int k = 0; k < np_; ++k) acc -= Gb[k * n + i] * Uprev[j * np_ + k];
+                Aw[i * 2 * n + j] = acc;
+            }
+        } else {
+            for (int idx = tid; idx < n * n; idx += nt) Aw[(idx % n) * 2 * n + idx / n] = Db[idx];
+        }
+        for (int idx = tid; idx < n * n; idx += nt) Aw[(idx / n) * 2 * n + n + idx % n] = (idx / n == idx % n) ? 1.0 : 0.0;
+        if (tid < n) s_drop[tid] = rowdrop ? rowdrop[dof_rows[B.s0 + tid]] : 0;
+        __syncthreads();
+        // H_{b-1} = Delta_{b-1}^-1 U_{b-1}: the original U_{b-1} is not needed any more
+        if (b > b0) {
+            const double* Dp = DH + blocks[b - 1].offDH;
+            double* tmp = Aw + 2 * n * n;              // scratch behind the augmented matrix (sized at set-up)
+            for (int idx = tid; idx < np_ * n; idx += nt) {
+                const int i = idx % np_, j = idx / np_;
+                double acc = 0.0;
+                for (int k = 0; k < np_; ++k) acc += Dp[k * np_ + i] * Uprev[j * np_ + k];
+                tmp[idx] = acc;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < np_ * n; idx += nt) Uprev[idx] = tmp[idx];
+        }
+        // dofs already known to be dependent inside their facet block: decouple
+        for (int idx = tid; idx < n * n; idx += nt) {
+            const int i = idx / n, j = idx % n;
+            if (s_drop[i] || s_drop[j]) Aw[i * 2 * n + j] = (i == j) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double mx = 0.0;
+            for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(Aw[i * 2 * n + i]));
+            s_scale = mx;
+        }
+        __syncthreads();
+        // Gauss-Jordan with partial pivoting; a pivot below 1e-12 of the largest diagonal entry = dependent dof
+        for (int k = 0; k < n; ++k) {
+            if (tid < 32) {
+                int piv = -1;
+                double best = -1.0;
+                for (int i = k + tid; i < n; i += 32) {
+                    const double a = fabs(Aw[i * 2 * n + k]);
+                    if (a > best) { best = a; piv = i; }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+                    const int op = __shfl_xor_sync(0xffffffffu, piv, d);
+                    if (ob > best || (ob == best && op >= 0 && (piv < 0 || op < piv))) { best = ob; piv = op; }
+                }
+                if (tid == 0) { s_piv = piv; s_best = best; }
+            }
+            __syncthreads();
+            if (!(s_best > 1e-12 * s_scale)) {
+                // decouple dof k: column k := e_k, row k := e_k, right part row k := 0
+                for (int i = tid; i < n; i += nt) Aw[i * 2 * n + k] = (i == k) ? 1.0 : 0.0;
+                __syncthreads();
+                for (int j = tid; j < 2 * n; j += nt) Aw[k * 2 * n + j] = (j == k) ? 1.0 : 0.0;
+                if (tid == 0) { s_drop[k] = 1; atomicAdd(dropped, 1); }
+                __syncthreads();
+                continue;
+            }
+            const int piv = s_piv;
+            if (piv != k) {
+                for (int j = tid; j < 2 * n; j += nt) {
+                    const double t = Aw[k * 2 * n + j];
+                    Aw[k * 2 * n + j] = Aw[piv * 2 * n + j];
+                    Aw[piv * 2 * n + j] = t;
+                }
+                __syncthreads();
+            }
+            const double inv = 1.0 / Aw[k * 2 * n + k];
+            __syncthreads();
+            for (int j = tid; j < 2 * n; j += nt) Aw[k * 2 * n + j] *= inv;
+            __syncthreads();
+            for (int idx = tid; idx < n * 2 * n; idx += nt) {
+                const int i = idx / (2 * n), j = idx % (2 * n);
+                if (i == k || j == k) continue;
+                Aw[idx] -= Aw[i * 2 * n + k] * Aw[k * 2 * n + j];
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += nt)
+                if (i != k) Aw[i * 2 * n + k] = 0.0;
+            __syncthreads();
+        }
+        // Delta_b^-1 with dropped rows / columns zeroed, column major
+        for (int idx = tid; idx < n * n; idx += nt) {
+            const int i = idx % n, j = idx / n;
+            Db[idx] = (s_drop[i] || s_drop[j]) ? 0.0 : Aw[i * 2 * n + n + j];
+        }
+        __syncthreads();
+        if (b + 1 < b1) {
+            // G_{b+1} = L_{b+1} Delta_b^-1  (in place via the scratch)
+            const int nn = blocks[b + 1].n;
+            double* Lb = G + blocks[b + 1].offG;       // nn x n column major
+            for (int idx = tid; idx < nn * n; idx += nt) {
+                const int i = idx % nn, j = idx / nn;
+                double acc = 0.0;
+                for (int k = 0; k < n; ++k) acc += Lb[k * nn + i] * Db[j * n + k];
+                Aw[idx] = acc;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nn * n; idx += nt) Lb[idx] = Aw[idx];
+            __syncthreads();
+        } else if (n > 0) {
+            // the last block of a chain has no upper coupling: its (padding) H region stays zero
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// application: one warp per chain, factor blocks through a TMA ring
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(32)
+chain_sweep_kernel(int nchains, const int32_t* __restrict__ chain_ptr, const ChainBlock* __restrict__ blocks,
+                   const int32_t* __restrict__ dof_rows, const double* __restrict__ G, const double* __restrict__ DH,
+                   const double* __restrict__ v, double* __restrict__ c, double* __restrict__ t, int64_t row0, int stage_doubles) {
+    extern __shared__ __align__(16) double ring[];              // STAGES x stage_doubles
+    __shared__ __align__(8) uint64_t bar[STAGES];
+    const int chain = blockIdx.x, lane = threadIdx.x;
+    if (chain >= nchains) return;
+    const int b0 = chain_ptr[chain], b1 = chain_ptr[chain + 1], nblk = b1 - b0;
+    if (nblk <= 0) return;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // G region of block b: [offG[b], offG[b+1]); DH region: [offDH[b], offDH[b+1])  (blocks[] has a sentinel entry)
+    auto issue_fwd = [&](int k) {          // k-th block of the chain into stage k % STAGES
+        const int b = b0 + k;
+        const uint32_t bytes = (uint32_t)((blocks[b + 1].offG - blocks[b].offG) * 8);
+        uint64_t* br = &bar[k % STAGES];
+        mbar_expect_tx(br, bytes);
+        bulk_g2s(ring + (size_t)(k % STAGES) * stage_doubles, G + blocks[b].offG, bytes, br);
+    };
+    auto issue_bwd = [&](int k, int it) {  // k-th block of the chain, it = position in the ring sequence
+        const int b = b0 + k;
+        const uint32_t bytes = (uint32_t)((blocks[b + 1].offDH - blocks[b].offDH) * 8);
+        uint64_t* br = &bar[it % STAGES];
+        mbar_expect_tx(br, bytes);
+        bulk_g2s(ring + (size_t)(it % STAGES) * stage_doubles, DH + blocks[b].offDH, bytes, br);
+    };
+    if (lane == 0)
+        for (int k = 0; k < STAGES && k < nblk; ++k) issue_fwd(k);
+    // ---- forward: c_b = v_b - G_b c_{b-1}
+    double cp0 = 0.0, cp1 = 0.0;           // c of the previous block: rows lane, lane + 32
+    int np_ = 0;
+    ChainBlock B = blocks[b0];
+    double v0 = lane < B.n ? v[dof_rows[B.s0 + lane] - row0] : 0.0;
+    double v1 = lane + 32 < B.n ? v[dof_rows[B.s0 + lane + 32] - row0] : 0.0;
+    for (int k = 0; k < nblk; ++k) {
+        const int n = B.n, s0 = B.s0;
+        // one step ahead of the recurrence: metadata and right-hand side of the next block
+        ChainBlock Bn = B;
+        double vn0 = 0.0, vn1 = 0.0;
+        if (k + 1 < nblk) {
+            Bn = blocks[b0 + k + 1];
+            vn0 = lane < Bn.n ? v[dof_rows[Bn.s0 + lane] - row0] : 0.0;
+            vn1 = lane + 32 < Bn.n ? v[dof_rows[Bn.s0 + lane + 32] - row0] : 0.0;
+        }
+        const double* Gs = ring + (size_t)(k % STAGES) * stage_doubles;
+        mbar_wait(&bar[k % STAGES], (k / STAGES) & 1);
+        double a0 = v0, a1 = v1, e0 = 0.0, e1 = 0.0;
+        const bool r0 = lane < n, r1 = lane + 32 < n;
+        int j = 0;
+        for (; j + 1 < np_; j += 2) {
+            const double x0 = j < 32 ? __shfl_sync(0xffffffffu, cp0, j) : __shfl_sync(0xffffffffu, cp1, j - 32);
+            const double x1 = j + 1 < 32 ? __shfl_sync(0xffffffffu, cp0, j + 1) : __shfl_sync(0xffffffffu, cp1, j + 1 - 32);
+            if (r0) { a0 -= Gs[j * n + lane] * x0; e0 -= Gs[(j + 1) * n + lane] * x1; }
+            if (r1) { a1 -= Gs[j * n + lane + 32] * x0; e1 -= Gs[(j + 1) * n + lane + 32] * x1; }
+        }
+        if (j < np_) {
+            const double x0 = j < 32 ? __shfl_sync(0xffffffffu, cp0, j) : __shfl_sync(0xffffffffu, cp1, j - 32);
+            if (r0) a0 -= Gs[j * n + lane] * x0;
+            if (r1) a1 -= Gs[j * n + lane + 32] * x0;
+        }
+        a0 += e0;
+        a1 += e1;
+        __syncwarp();                       // every lane is done with this stage
+        if (lane == 0 && k + STAGES < nblk) issue_fwd(k + STAGES);
+        if (r0) c[s0 + lane] = a0;
+        if (r1) c[s0 + lane + 32] = a1;
+        cp0 = r0 ? a0 : 0.0;
+        cp1 = r1 ? a1 : 0.0;
+        np_ = n;
+        B = Bn;
+        v0 = vn0;
+        v1 = vn1;
+    }
+    // ---- backward: x_b = Dinv_b c_b - H_b x_{b+1}; the ring sequence continues at it = nblk
+    if (lane == 0)
+        for (int q = 0; q < STAGES && q < nblk; ++q) issue_bwd(nblk - 1 - q, nblk + q);
+    double xn0 = 0.0, xn1 = 0.0;           // x of the block after this one
+    int nn = 0;
+    B = blocks[b1 - 1];
+    double c0 = cp0, c1 = cp1;              // c of the last block is still in registers
+    for (int q = 0; q < nblk; ++q) {
+        const int k = nblk - 1 - q, it = nblk + q;
+        const int n = B.n, s0 = B.s0;
+        ChainBlock Bn = B;
+        double cn0 = 0.0, cn1 = 0.0;
+        if (k > 0) {
+            Bn = blocks[b0 + k - 1];
+            cn0 = lane < Bn.n ? c[Bn.s0 + lane] : 0.0;
+            cn1 = lane + 32 < Bn.n ? c[Bn.s0 + lane + 32] : 0.0;
+        }
+        const double* Ds = ring + (size_t)(it % STAGES) * stage_doubles;
+        const double* Hs = Ds + (size_t)n * n;
+        mbar_wait(&bar[it % STAGES], (it / STAGES) & 1);
+        double a0 = 0.0, a1 = 0.0, e0 = 0.0, e1 = 0.0;
+        const bool r0 = lane < n, r1 = lane + 32 < n;
+        for (int j = 0; j < n; ++j) {
+            const double x0 = j < 32 ? __shfl_sync(0xffffffffu, c0, j) : __shfl_sync(0xffffffffu, c1, j - 32);
+            if (r0) a0 += Ds[j * n + lane] * x0;
+            if (r1) a1 += Ds[j * n + lane + 32] * x0;
+        }
+        for (int j = 0; j < nn; ++j) {
+            const double x0 = j < 32 ? __shfl_sync(0xffffffffu, xn0, j) : __shfl_sync(0xffffffffu, xn1, j - 32);
+            if (r0) e0 -= Hs[j * n + lane] * x0;
+            if (r1) e1 -= Hs[j * n + lane + 32] * x0;
+        }
+        a0 += e0;
+        a1 += e1;
+        __syncwarp();
+        if (lane == 0 && q + STAGES < nblk) issue_bwd(nblk - 1 - (q + STAGES), it + STAGES);
+        if (r0) t[dof_rows[s0 + lane] - row0] = a0;
+        if (r1) t[dof_rows[s0 + lane + 32] - row0] = a1;
+        xn0 = r0 ? a0 : 0.0;
+        xn1 = r1 ? a1 : 0.0;
+        nn = n;
+        B = Bn;
+        c0 = cn0;
+        c1 = cn1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DevFree {
+    std::vector<void*> p;
+    ~DevFree() { for (void* q : p) cudaFree(q); }
+    template <class T> T* keep(T* q) { p.push_back((void*)q); return q; }
+};
+}  // namespace
+
+int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const int32_t* line_dev, int use_strip, int target_dofs,
+                cudaStream_t st, ChainSolver** out) {
+    *out = nullptr;
+    const int nf = A->nf;
+    const bool strip = use_strip && A->strip != nullptr;
+    if ((!line_dev && !strip) || nf == 0) return EHDG_OK;
+    if (target_dofs <= 0) target_dofs = 1;
+    const int f_lo = A->windowed ? A->f_lo : 0, f_hi = A->windowed ? A->f_hi : nf;
+    // ---- topology to the host: neighbour lists, rows per facet, chain ids
+    std::vector<int32_t> nbr(5 * (size_t)nf), row_start((size_t)nf + 1), line((size_t)nf, -1);
+    std::vector<uint8_t> stripf;
+    EHDG_CUDA(cudaMemcpyAsync(nbr.data(), A->nbr, sizeof(int32_t) * 5 * (size_t)nf, cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cudaMemcpyAsync(row_start.data(), A->row_start, sizeof(int32_t) * ((size_t)nf + 1), cudaMemcpyDeviceToHost, st));
+    if (line_dev) EHDG_CUDA(cudaMemcpyAsync(line.data(), line_dev, sizeof(int32_t) * (size_t)nf, cudaMemcpyDeviceToHost, st));
+    if (strip) {
+        stripf.resize(nf);
+        EHDG_CUDA(cudaMemcpyAsync(stripf.data(), A->strip, (size_t)nf, cudaMemcpyDeviceToHost, st));
+    }
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    // ---- chain of every participating facet (dense ids, ascending in the order of first appearance of the key)
+    //      key: strip facets share one key; line >= 0: that line; otherwise (lines given) a chain of its own
+    std::vector<int64_t> key((size_t)nf, -1);
+    const int64_t KEY_STRIP = (int64_t)1 << 40, KEY_SINGLE = (int64_t)1 << 41;
+    size_t n_part = 0;
+    for (int f = f_lo; f < f_hi; ++f) {
+        if (row_start[f + 1] == row_start[f]) continue;
+        if (strip && stripf[f]) key[f] = KEY_STRIP;
+        else if (!line_dev) continue;
+        else key[f] = line[f] >= 0 ? (int64_t)line[f] : KEY_SINGLE + f;
+        ++n_part;
+    }
+    if (n_part == 0) return EHDG_OK;
+    std::vector<int32_t> part;                 // participating facets sorted by (key, facet)
+    part.reserve(n_part);
+    for (int f = f_lo; f < f_hi; ++f)
+        if (key[f] >= 0) part.push_back(f);
+    std::stable_sort(part.begin(), part.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::vector<int32_t> chain_first;          // index into `part` of the first facet of every chain
+    for (size_t i = 0; i < part.size(); ++i)
+        if (i == 0 || key[part[i]] != key[part[i - 1]]) chain_first.push_back((int32_t)i);
+    const int nchains = (int)chain_first.size();
+    chain_first.push_back((int32_t)part.size());
+    std::vector<int32_t> chain_of((size_t)nf, -1);
+    for (int ch = 0; ch < nchains; ++ch)
+        for (int i = chain_first[ch]; i < chain_first[ch + 1]; ++i) chain_of[part[i]] = ch;
+    // ---- per chain: BFS levels from a pseudo-peripheral facet, levels merged into blocks
+    std::vector<int32_t> level((size_t)nf, -1), order, lev_of_order, queue;
+    order.reserve(part.size());
+    lev_of_order.reserve(part.size());
+    std::vector<ChainBlock> blocks;
+    std::vector<int32_t> chain_ptr{0}, dof_rows, dof_blk, blk_chain;
+    int nmax = 0;
+    auto bfs = [&](int seed, int ch, int lev0, std::vector<int32_t>& visit) -> int {      // returns the last level used
+        visit.clear();
+        level[seed] = lev0;
+        visit.push_back(seed);
+        int maxlev = lev0;
+        for (size_t h = 0; h < visit.size(); ++h) {
+            const int u = visit[h];
+            maxlev = std::max(maxlev, (int)level[u]);
+            for (int t2 = 0; t2 < 5; ++t2) {
+                const int g = nbr[5 * (size_t)u + t2];
+                if (g < 0 || chain_of[g] != ch || level[g] >= 0) continue;
+                level[g] = level[u] + 1;
+                visit.push_back(g);
+            }
+        }
+        return maxlev;
+    };
+    std::vector<int32_t> visit, visit2;
+    for (int ch = 0; ch < nchains; ++ch) {
+        const size_t o0 = order.size();
+        int lev_base = 0;
+        for (int i = chain_first[ch]; i < chain_first[ch + 1]; ++i) {
+            const int seed0 = part[i];
+            if (level[seed0] >= 0) continue;
+            // pseudo-peripheral start: the facet found last by a BFS from the component's first facet
+            bfs(seed0, ch, 0, visit);
+            const int far = visit.back();
+            for (int u : visit) level[u] = -1;
+            const int maxlev = bfs(far, ch, lev_base, visit2);
+            // BFS order is level order
+            for (int u : visit2) { order.push_back(u); lev_of_order.push_back(level[u]); }
+            lev_base = maxlev + 2;          // gap: components never share a block boundary coupling
+        }
+        // merge consecutive levels into blocks
+        size_t i = o0;
+        while (i < order.size()) {
+            int dofs = 0;
+            size_t j = i;
+            int last_level = lev_of_order[i];
+            while (j < order.size()) {
+                size_t k = j;
+                int ld = 0;
+                const int lv = lev_of_order[j];
+                while (k < order.size() && lev_of_order[k] == lv) { ld += row_start[order[k] + 1] - row_start[order[k]]; ++k; }
+                if (ld > CHAIN_MAXB) { set_error("line preconditioner: a BFS level with %d dofs exceeds %d", ld, CHAIN_MAXB); return EHDG_ERR_ARG; }
+                if (j > i && (dofs + ld > target_dofs || lv != last_level + 1)) break;
+                dofs += ld;
+                last_level = lv;
+                j = k;
+            }
+            ChainBlock B{};
+            B.s0 = (int32_t)dof_rows.size();
+            const int b = (int)blocks.size();
+            for (size_t k = i; k < j; ++k) {
+                const int u = order[k];
+                for (int d = row_start[u]; d < row_start[u + 1]; ++d) { dof_rows.push_back(d); dof_blk.push_back(b); }
+            }
+            B.n = (int32_t)dof_rows.size() - B.s0;
+            nmax = std::max(nmax, (int)B.n);
+            blocks.push_back(B);
+            blk_chain.push_back(ch);
+            i = j;
+        }
+        chain_ptr.push_back((int32_t)blocks.size());
+    }
+    const int nblk = (int)blocks.size(), nd = (int)dof_rows.size();
+    if (nd == 0) return EHDG_OK;
+    // ---- factor storage: G_b (n x n_prev), [Dinv_b | H_b] (n x n, n x n_next); every region padded to 16 bytes, never empty
+    int64_t tG = 0, tDH = 0, stage = 0;
+    auto pad2 = [](int64_t x) { return std::max<int64_t>(2, (x + 1) & ~(int64_t)1); };
+    for (int b = 0; b < nblk; ++b) {
+        const int ch = blk_chain[b];
+        const int64_t n = blocks[b].n;
+        const int64_t np_ = (b > 0 && blk_chain[b - 1] == ch) ? blocks[b - 1].n : 0;
+        const int64_t nn = (b + 1 < nblk && blk_chain[b + 1] == ch) ? blocks[b + 1].n : 0;
+        blocks[b].offG = tG;
+        blocks[b].offDH = tDH;
+        const int64_t g = pad2(n * np_), dh = pad2(n * n + n * nn);
+        tG += g;
+        tDH += dh;
+        stage = std::max(stage, std::max(g, dh));
+    }
+    ChainBlock sentinel{};
+    sentinel.s0 = nd;
+    sentinel.offG = tG;
+    sentinel.offDH = tDH;
+    blocks.push_back(sentinel);
+    ChainSolver* S = new ChainSolver();
+    S->n_dofs = nd;
+    S->n_blocks = nblk;
+    S->n_chains = nchains;
+    S->n_rows = A->n_rows;
+    S->nmax = nmax;
+    S->factor_bytes = (tG + tDH) * 8;
+    S->stage_bytes = (int)(stage * 8);
+    {
+        const int64_t own_rows = A->windowed ? A->row_hi - A->row_lo : A->n_rows;
+        S->all_rows = nd == own_rows ? 1 : 0;
+    }
+    auto fail = [&](int rc) { chain_free(S); return rc; };
+    auto up = [&](auto** dptr, const auto& h) -> int {
+        using T = typename std::remove_reference<decltype(h)>::type::value_type;
+        EHDG_CUDA(cudaMalloc(dptr, sizeof(T) * std::max<size_t>(h.size(), 1)));
+        EHDG_CUDA(cudaMemcpyAsync(*dptr, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, st));
+        return EHDG_OK;
+    };
+    int rc;
+    if ((rc = up(&S->chain_ptr, chain_ptr))) return fail(rc);
+    if ((rc = up(&S->blocks, blocks))) return fail(rc);
+    if ((rc = up(&S->dof_rows, dof_rows))) return fail(rc);
+    if ((rc = up(&S->dof_blk, dof_blk))) return fail(rc);
+    if ((rc = up(&S->blk_chain, blk_chain))) return fail(rc);
+    auto dev_alloc = [&]() -> int {
+        EHDG_CUDA(cudaMalloc(&S->sblk, sizeof(int32_t) * (size_t)A->n_rows));
+        EHDG_CUDA(cudaMalloc(&S->sloc, sizeof(int32_t) * (size_t)A->n_rows));
+        EHDG_CUDA(cudaMemsetAsync(S->sblk, 0xff, sizeof(int32_t) * (size_t)A->n_rows, st));
+        EHDG_CUDA(cudaMalloc(&S->G, sizeof(double) * (size_t)tG));
+        EHDG_CUDA(cudaMalloc(&S->DH, sizeof(double) * (size_t)tDH));
+        EHDG_CUDA(cudaMalloc(&S->c, sizeof(double) * (size_t)nd));
+        EHDG_CUDA(cudaMemsetAsync(S->G, 0, sizeof(double) * (size_t)tG, st));
+        EHDG_CUDA(cudaMemsetAsync(S->DH, 0, sizeof(double) * (size_t)tDH, st));
+        return EHDG_OK;
+    };
+    if ((rc = dev_alloc())) return fail(rc);
+    int* d_flags = nullptr;
+    auto run = [&]() -> int {
+        EHDG_CUDA(cudaMalloc(&d_flags, 2 * sizeof(int)));
+        EHDG_CUDA(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
+        chain_pos_kernel<<<(nd + 127) / 128, 128, 0, st>>>(nd, S->dof_rows, S->dof_blk, S->blocks, S->sblk, S->sloc);
+        EHDG_LAUNCH_CHECK();
+        chain_extract_kernel<<<(nd + 127) / 128, 128, 0, st>>>(nd, S->dof_rows, S->dof_blk, S->blocks, S->blk_chain, A->rowptr, A->colind,
+                                                              vals, S->sblk, S->sloc, S->DH, S->G, d_flags);
+        EHDG_LAUNCH_CHECK();
+        const int smem = (2 * nmax * nmax + nmax * nmax) * 8;      // augmented matrix + scratch
+        EHDG_CUDA(cudaFuncSetAttribute(chain_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        chain_factor_kernel<<<nchains, 128, smem, st>>>(S->chain_ptr, S->blocks, S->dof_rows, rowdrop, S->DH, S->G, d_flags + 1);
+        EHDG_LAUNCH_CHECK();
+        int flags[2] = {0, 0};
+        EHDG_CUDA(cudaMemcpyAsync(flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        if (flags[0]) { set_error("line preconditioner: matrix is not block tridiagonal in the BFS blocks"); return EHDG_ERR_ARG; }
+        S->dropped = flags[1];
+        return EHDG_OK;
+    };
+    rc = run();
+    cudaFree(d_flags);
+    if (rc) return fail(rc);
+    // ring of the sweep kernel: as many stages as fit 24 KB per warp, between 2 and 8
+    int stages = (int)std::min<int64_t>(8, std::max<int64_t>(2, (24 * 1024) / std::max(1, S->stage_bytes)));
+    stages = stages >= 8 ? 8 : (stages >= 4 ? 4 : 2);
+    S->stages = stages;
+    *out = S;
+    return EHDG_OK;
+}
+
+int chain_apply(const ChainSolver* S, const double* v, double* t, int64_t row0, cudaStream_t st) {
+    if (!S) return EHDG_OK;
+    const int sd = S->stage_bytes / 8;
+    const size_t smem = (size_t)S->stages * S->stage_bytes;
+#define EHDG_SWEEP(ST)                                                                                                          \
+    do {                                                                                                                        \
+        static size_t set_##ST = 0;                                                                                             \
+        if (smem > 48 * 1024 && smem > set_##ST) {                                                                              \
+            EHDG_CUDA(cudaFuncSetAttribute(chain_sweep_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+            set_##ST = smem;                                                                                                    \
+        }                                                                                                                       \
+        chain_sweep_kernel<ST><<<S->n_chains, 32, smem, st>>>(S->n_chains, S->chain_ptr, S->blocks, S->dof_rows, S->G, S->DH, v, \
+                                                              S->c, t, row0, sd);                                               \
+    } while (0)
+    if (S->stages == 8) EHDG_SWEEP(8);
+    else if (S->stages == 4) EHDG_SWEEP(4);
+    else EHDG_SWEEP(2);
+#undef EHDG_SWEEP
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+void chain_free(ChainSolver* S) {
+    if (!S) return;
+    cudaFree(S->chain_ptr);
+    cudaFree(S->blocks);
+    cudaFree(S->dof_rows);
+    cudaFree(S->dof_blk);
+    cudaFree(S->blk_chain);
+    cudaFree(S->sblk);
+    cudaFree(S->sloc);
+    cudaFree(S->G);
+    cudaFree(S->DH);
+    cudaFree(S->U0);
+    cudaFree(S->c);
+    delete S;
+}
+
+}  // namespace ehdg

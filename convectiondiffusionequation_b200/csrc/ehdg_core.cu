@@ -238,6 +238,8 @@ int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out) {
         return EHDG_ERR_CUDA;
     }
     ehdg_ctx* c = new ehdg_ctx();
+    // an error below releases whatever the context already owns
+    struct Guard { ehdg_ctx* c; bool ok = false; ~Guard() { if (!ok) ehdg_destroy(c); } } guard{c};
     c->ep = *prob;
     c->pb = make_problem(*prob);
     EHDG_CUDA(cudaGetDevice(&c->device));
@@ -256,6 +258,7 @@ int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out) {
     EHDG_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     EHDG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     EHDG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    guard.ok = true;
     *out = c;
     return EHDG_OK;
 }

@@ -26,32 +26,54 @@ int DistComm::allreduce_sum(double* buf, size_t count, cudaStream_t st) const {
     return EHDG_OK;
 }
 
+// Inside an open ncclGroupStart() every call is issued; the first failure is remembered, the group is always closed
+// (an early return would leave the thread's group nesting open and no later collective of this communicator would launch).
+#define EHDG_NCCL_IN_GROUP(call)                                                                \
+    do {                                                                                        \
+        const int r__ = (call);                                                                 \
+        if (r__ != 0 && first_err == 0) { first_err = r__; first_what = #call; }                 \
+    } while (0)
+
 int DistComm::halo_exchange(double* xg, cudaStream_t st, int width, const double* own) const {
     const size_t w = (size_t)width;
     const int64_t r0 = row_begin[rank], r1 = row_begin[rank + 1];
+    int first_err = 0;
+    const char* first_what = "";
     EHDG_NCCL(GroupStart());
     if (rank > 0) {
         // lower neighbour needs my first rows up to its col_hi; I need its last rows from my col_lo
         const int64_t send_hi = col_hi[rank - 1] < r1 ? col_hi[rank - 1] : r1;
-        if (send_hi > r0) EHDG_NCCL(Send(own ? own : xg + r0 * w, (size_t)(send_hi - r0) * w, NCCL_F64, rank - 1, comm, st));
-        if (col_lo[rank] < r0) EHDG_NCCL(Recv(xg + col_lo[rank] * w, (size_t)(r0 - col_lo[rank]) * w, NCCL_F64, rank - 1, comm, st));
+        if (send_hi > r0) EHDG_NCCL_IN_GROUP(Send(own ? own : xg + r0 * w, (size_t)(send_hi - r0) * w, NCCL_F64, rank - 1, comm, st));
+        if (col_lo[rank] < r0) EHDG_NCCL_IN_GROUP(Recv(xg + col_lo[rank] * w, (size_t)(r0 - col_lo[rank]) * w, NCCL_F64, rank - 1, comm, st));
     }
     if (rank + 1 < nranks) {
         const int64_t send_lo = col_lo[rank + 1] > r0 ? col_lo[rank + 1] : r0;
-        if (send_lo < r1) EHDG_NCCL(Send(own ? own + (send_lo - r0) * w : xg + send_lo * w, (size_t)(r1 - send_lo) * w, NCCL_F64, rank + 1, comm, st));
-        if (col_hi[rank] > r1) EHDG_NCCL(Recv(xg + r1 * w, (size_t)(col_hi[rank] - r1) * w, NCCL_F64, rank + 1, comm, st));
+        if (send_lo < r1) EHDG_NCCL_IN_GROUP(Send(own ? own + (send_lo - r0) * w : xg + send_lo * w, (size_t)(r1 - send_lo) * w, NCCL_F64, rank + 1, comm, st));
+        if (col_hi[rank] > r1) EHDG_NCCL_IN_GROUP(Recv(xg + r1 * w, (size_t)(col_hi[rank] - r1) * w, NCCL_F64, rank + 1, comm, st));
     }
-    EHDG_NCCL(GroupEnd());
+    const int rg = GroupEnd();
+    if (first_err == 0 && rg != 0) { first_err = rg; first_what = "GroupEnd()"; }
+    if (first_err) {
+        set_error("halo_exchange: %s: NCCL error %d (%s)", first_what, first_err, GetErrorString ? GetErrorString(first_err) : "?");
+        return EHDG_ERR_NCCL;
+    }
     return EHDG_OK;
 }
 
 int DistComm::allgather_rows(double* x, cudaStream_t st) const {
+    int first_err = 0;
+    const char* first_what = "";
     EHDG_NCCL(GroupStart());
     for (int r = 0; r < nranks; ++r) {
         const int64_t cnt = row_begin[r + 1] - row_begin[r];
-        if (cnt > 0) EHDG_NCCL(Broadcast(x + row_begin[r], x + row_begin[r], (size_t)cnt, NCCL_F64, r, comm, st));
+        if (cnt > 0) EHDG_NCCL_IN_GROUP(Broadcast(x + row_begin[r], x + row_begin[r], (size_t)cnt, NCCL_F64, r, comm, st));
     }
-    EHDG_NCCL(GroupEnd());
+    const int rg = GroupEnd();
+    if (first_err == 0 && rg != 0) { first_err = rg; first_what = "GroupEnd()"; }
+    if (first_err) {
+        set_error("allgather_rows: %s: NCCL error %d (%s)", first_what, first_err, GetErrorString ? GetErrorString(first_err) : "?");
+        return EHDG_ERR_NCCL;
+    }
     return EHDG_OK;
 }
 
@@ -97,6 +119,7 @@ int ehdg_comm_unique_id(char* out128) {
     if (rc) return rc;
     UniqueId id;
     const int r = tmp.GetUniqueId(&id);
+    dlclose(tmp.lib);                     // the library stays mapped through torch's own handle (and ehdg_comm_init's)
     if (r != 0) { set_error("ncclGetUniqueId failed (%d)", r); return EHDG_ERR_NCCL; }
     memcpy(out128, id.internal, 128);
     return EHDG_OK;
@@ -108,6 +131,11 @@ int ehdg_comm_init(ehdg_ctx* c, const char* id128, int nranks, int rank) {
     DistComm* d = c->dist;
     int rc = load_nccl(d);
     if (rc) return rc;
+    if (d->comm) {                        // re-initialisation: the previous communicator is released first
+        d->CommDestroy(d->comm);
+        d->comm = nullptr;
+        d->row_begin.clear();
+    }
     UniqueId id;
     memcpy(id.internal, id128, 128);
     typedef int (*init_fn)(void**, int, UniqueId, int);
@@ -140,6 +168,7 @@ int ehdg_comm_set_partition(ehdg_ctx* c, const int64_t* row_begin, const int64_t
 int ehdg_comm_destroy(ehdg_ctx* c) {
     if (!c || !c->dist) return EHDG_OK;
     if (c->dist->comm) c->dist->CommDestroy(c->dist->comm);
+    if (c->dist->lib) dlclose(c->dist->lib);
     delete c->dist;
     c->dist = nullptr;
     return EHDG_OK;

@@ -56,6 +56,8 @@ struct ehdg_ctx {
     int32_t *pool_eslot = nullptr, *pool_lists = nullptr;
     int32_t pool_ne = 0;
     ehdg::DistComm* dist = nullptr;   // NCCL communicator + row partition of the distributed facet solve
+    void* user_ws = nullptr;          // caller-provided workspace of the Krylov solvers (ehdg_set_workspace)
+    size_t user_ws_bytes = 0;
     cudaStream_t side = nullptr;      // the general (enriched) kernels run beside the polynomial ones
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // optional CUDA-event timing of the two polynomial-path kernels on their launching stream
@@ -91,6 +93,8 @@ struct ehdg_csr {
     uint16_t* dofmask = nullptr;    // [nf]    active slots of the facet
     int32_t* row_facet = nullptr;   // [n_rows] facet of each row
     uint8_t* strip = nullptr;       // [nf]    1 = free facet of a marked element (enriched strip), null if none
+    int32_t* line = nullptr;        // [nf]    chain of every facet for the line-block preconditioner, null until set
+    const double* folded_vals = nullptr;   // value array a Krylov solve has overwritten with A M^-1 (facet block-Jacobi mode)
     double* dinv = nullptr;         // [n_rows * nbmax] block-Jacobi inverses (set by ehdg_gmres)
     int nb;                         // slots per facet
     // partitioned assembly (ehdg_csr_symbolic_part): this rank holds the facets [f_lo, f_hi) = rows [row_lo, row_hi);

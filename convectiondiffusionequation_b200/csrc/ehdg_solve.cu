@@ -6,7 +6,7 @@
 
 #include "ehdg_dist.h"
 #include "ehdg_internal.h"
-#include "ehdg_strip.h"
+#include "ehdg_chain.h"
 
 namespace ehdg {
 
@@ -872,6 +872,39 @@ l2_error_kernel(Problem pb, RuleSet rs, int ne, int n_poly, const int32_t* __res
     }
 }
 
+// chain id of every facet from the position of its midpoint across the flow (ehdg_csr_auto_lines)
+__global__ void facet_line_kernel(int ne, const double* __restrict__ verts, const int32_t* __restrict__ tris,
+                                  const int32_t* __restrict__ el2facet, double nx, double ny, double inv_width, double offset,
+                                  int32_t* __restrict__ line) {
+    const int el = blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= ne) return;
+    double px[3], py[3];
+    for (int v = 0; v < 3; ++v) {
+        const int vi = tris[3 * el + v];
+        px[v] = verts[2 * vi];
+        py[v] = verts[2 * vi + 1];
+    }
+    // local edges e0 = {V2, V0}, e1 = {V1, V2}, e2 = {V0, V1}; both neighbours of a facet compute the same value
+    const int ea[3] = {2, 1, 0}, eb[3] = {0, 2, 1};
+    for (int e = 0; e < 3; ++e) {
+        const double a = nx * px[ea[e]] + ny * py[ea[e]], b = nx * px[eb[e]] + ny * py[eb[e]];
+        const double s = 0.5 * (fmin(a, b) + fmax(a, b));
+        line[el2facet[3 * el + e]] = (int32_t)floor(s * inv_width + offset) + (1 << 24);
+    }
+}
+
+__global__ void area_sum_kernel(int ne, const double* __restrict__ verts, const int32_t* __restrict__ tris, double* __restrict__ out) {
+    double a = 0.0;
+    for (int el = blockIdx.x * blockDim.x + threadIdx.x; el < ne; el += gridDim.x * blockDim.x) {
+        const int v0 = tris[3 * el], v1 = tris[3 * el + 1], v2 = tris[3 * el + 2];
+        a += 0.5 * fabs((verts[2 * v0] - verts[2 * v2]) * (verts[2 * v1 + 1] - verts[2 * v2 + 1])
+                        - (verts[2 * v1] - verts[2 * v2]) * (verts[2 * v0 + 1] - verts[2 * v2 + 1]));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, a);       // only sizes the default line width: order-insensitive use
+}
+
 }  // namespace ehdg
 
 using namespace ehdg;
@@ -911,7 +944,18 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     int32_t* nbf = nullptr;
     int64_t* blk = nullptr;
     void* tmp = nullptr;
+    int32_t* row_facet = nullptr;
     size_t tb1 = 0, tb2 = 0;
+    // every error return below releases the temporaries and the half-built matrix
+    struct Guard {
+        ehdg_csr*& A; int32_t*& nbf; int64_t*& blk; void*& tmp; int32_t*& row_facet; bool ok = false;
+        ~Guard() {
+            cudaFree(nbf);
+            cudaFree(blk);
+            cudaFree(tmp);
+            if (!ok) { cudaFree(row_facet); ehdg_csr_destroy(A); }
+        }
+    } guard{A, nbf, blk, tmp, row_facet};
     EHDG_CUDA(cudaMalloc(&nbf, sizeof(int32_t) * (size_t)(nf + 1)));
     EHDG_CUDA(cudaMalloc(&blk, sizeof(int64_t) * (size_t)(nf + 1)));
     EHDG_CUDA(cudaMalloc(&A->dofmask, sizeof(uint16_t) * (size_t)(nf + 1)));
@@ -935,6 +979,7 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     {
         int32_t* fb = nullptr;
         EHDG_CUDA(cudaMalloc(&fb, sizeof(int32_t) * (size_t)(2 * (nranks + 1))));
+        struct FreeFb { int32_t* p; ~FreeFb() { cudaFree(p); } } free_fb{fb};
         csr_partition_kernel<<<(nranks + 1 + 63) / 64, 64, 0, st>>>(nf, nranks, A->row_start, fb);
         EHDG_LAUNCH_CHECK();
         EHDG_CUDA(cudaMemcpyAsync(A->part_facets.data(), fb, sizeof(int32_t) * (size_t)(nranks + 1), cudaMemcpyDeviceToHost, st));
@@ -944,7 +989,6 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
             EHDG_CUDA(cudaMemcpyAsync(&rs[k], A->row_start + A->part_facets[k], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         EHDG_CUDA(cudaStreamSynchronize(st));
         for (int k = 0; k <= nranks; ++k) A->part_rows[k] = rs[k];
-        cudaFree(fb);
     }
     A->windowed = windowed ? 1 : 0;
     A->f_lo = windowed ? A->part_facets[rank] : 0;
@@ -963,20 +1007,70 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     A->nnz = nnz;
     EHDG_CUDA(cudaMalloc(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1)));
     EHDG_CUDA(cudaMalloc(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
-    int32_t* row_facet = nullptr;
     EHDG_CUDA(cudaMalloc(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1)));
     if (nf > 0) csr_fill_kernel<<<(unsigned)(((int64_t)nf * 32 + 255) / 256), 256, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
     EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
     A->dinv = nullptr;
-    cudaFree(nbf);
-    cudaFree(blk);
-    cudaFree(tmp);
     A->row_facet = row_facet;
+    guard.ok = true;
     *out = A;
     return EHDG_OK;
 }
+
+// Device / pinned buffers of one Krylov solve: carved from the caller's workspace (ehdg_set_workspace) while it lasts,
+// allocated otherwise; everything is released when the solve returns, on every path.
+namespace {
+struct SolveWorkspace {
+    char* arena = nullptr;
+    size_t arena_bytes = 0, used = 0;
+    std::vector<void*> dev, host;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    ChainSolver* chain = nullptr;
+    ~SolveWorkspace() {
+        for (void* p : dev) cudaFree(p);
+        for (void* p : host) cudaFreeHost(p);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (ev2) cudaEventDestroy(ev2);
+        chain_free(chain);
+    }
+    template <class T>
+    int get(T** out, size_t count) {
+        const size_t bytes = ((count > 0 ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (arena && used + bytes <= arena_bytes) {
+            *out = (T*)(arena + used);
+            used += bytes;
+            return EHDG_OK;
+        }
+        void* p = nullptr;
+        EHDG_CUDA(cudaMalloc(&p, bytes));
+        dev.push_back(p);
+        *out = (T*)p;
+        return EHDG_OK;
+    }
+    template <class T>
+    int get_pinned(T** out, size_t count) {
+        void* p = nullptr;
+        EHDG_CUDA(cudaMallocHost(&p, count * sizeof(T)));
+        host.push_back(p);
+        *out = (T*)p;
+        return EHDG_OK;
+    }
+};
+
+// number of n-vectors a solve keeps (Krylov basis / directions + work vectors), see krylov_solve
+int64_t krylov_vector_count(int method, int m, bool chain, bool sweeps, bool dist) {
+    int64_t v = method == 0 ? (m + 1) : (method == 1 ? 6 : 2 * (m + 1));
+    v += 2;                          // w, yhat
+    if (chain) v += 1;               // preconditioned vector
+    if (sweeps) v += 2;
+    if (method == 2) v += 1;         // snapshot
+    (void)dist;
+    return v;
+}
+}  // namespace
 
 extern "C" {
 
@@ -1001,6 +1095,68 @@ int ehdg_csr_get_partition(const ehdg_csr* A, int64_t* row_begin, int32_t* facet
     return EHDG_OK;
 }
 
+int ehdg_csr_set_lines(ehdg_csr* A, const int32_t* facet_line, void* stream) {
+    if (!A || !facet_line) { set_error("ehdg_csr_set_lines: null argument"); return EHDG_ERR_ARG; }
+    if (!A->line) EHDG_CUDA(cudaMalloc(&A->line, sizeof(int32_t) * (size_t)(A->nf > 0 ? A->nf : 1)));
+    EHDG_CUDA(cudaMemcpyAsync(A->line, facet_line, sizeof(int32_t) * (size_t)A->nf, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return EHDG_OK;
+}
+
+int ehdg_csr_auto_lines(ehdg_ctx* c, ehdg_csr* A, const ehdg_mesh* m, double dir_x, double dir_y, double width, double offset,
+                        void* stream) {
+    if (!c || !A || !m) { set_error("ehdg_csr_auto_lines: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dir_x == 0.0 && dir_y == 0.0) {
+        // across the flow; within 1:10 of a coordinate axis the lines follow that axis (lattice rows stay whole)
+        const double bx = c->pb.bx, by = c->pb.by;
+        if (fabs(by) <= 0.1 * fabs(bx)) { dir_x = 0.0; dir_y = 1.0; }
+        else if (fabs(bx) <= 0.1 * fabs(by)) { dir_x = 1.0; dir_y = 0.0; }
+        else { const double nb = hypot(bx, by); dir_x = -by / nb; dir_y = bx / nb; }
+    }
+    if (m->ne == 0 || A->nf == 0) return EHDG_OK;
+    if (!(width > 0.0)) {
+        double* d_area = nullptr;
+        EHDG_CUDA(cudaMalloc(&d_area, sizeof(double)));
+        EHDG_CUDA(cudaMemsetAsync(d_area, 0, sizeof(double), st));
+        area_sum_kernel<<<256, 256, 0, st>>>(m->ne, m->verts, m->tris, d_area);
+        double area = 0.0;
+        const cudaError_t e1 = cudaMemcpyAsync(&area, d_area, sizeof(double), cudaMemcpyDeviceToHost, st);
+        const cudaError_t e2 = cudaStreamSynchronize(st);
+        cudaFree(d_area);
+        EHDG_CUDA(e1);
+        EHDG_CUDA(e2);
+        width = sqrt(2.0 * area / m->ne);
+    }
+    if (!A->line) EHDG_CUDA(cudaMalloc(&A->line, sizeof(int32_t) * (size_t)A->nf));
+    facet_line_kernel<<<(m->ne + 255) / 256, 256, 0, st>>>(m->ne, m->verts, m->tris, m->el2facet, dir_x, dir_y, 1.0 / width, offset, A->line);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+const int32_t* ehdg_csr_lines(const ehdg_csr* A) { return A ? A->line : nullptr; }
+
+int ehdg_krylov_workspace_bytes(const ehdg_ctx* c, const ehdg_csr* A, const ehdg_gmres_info* info, int method, int64_t* bytes) {
+    if (!c || !A || !info || !bytes || method < 0 || method > 2) { set_error("ehdg_krylov_workspace_bytes: bad argument"); return EHDG_ERR_ARG; }
+    const DistComm* dc = (c->dist && c->dist->active()) ? c->dist : nullptr;
+    const int64_t ng = A->n_rows;
+    const int64_t n = dc ? dc->row_begin[dc->rank + 1] - dc->row_begin[dc->rank] : ng;
+    const int m = info->restart > 0 ? info->restart : 30;
+    const bool chain = info->use_line_block || info->use_strip_block;
+    auto pad = [](int64_t b) { return (b + 255) & ~(int64_t)255; };
+    int64_t total = krylov_vector_count(method, m, chain, info->jacobi_sweeps > 1, dc != nullptr) * pad(n * 8);
+    total += pad(ng) + (dc ? pad(ng * 8) : 0);                       // dependent-dof flags, full-length SpMV input
+    total += pad((int64_t)RED_BLOCKS * KT * 8) + 8 * 256 + pad((3 * (m + 2) + 8) * 8) + pad((2 * (m + 2) + 8) * 8);
+    *bytes = total;
+    return EHDG_OK;
+}
+
+int ehdg_set_workspace(ehdg_ctx* c, void* device_ptr, int64_t bytes) {
+    if (!c || bytes < 0) { set_error("ehdg_set_workspace: bad argument"); return EHDG_ERR_ARG; }
+    c->user_ws = device_ptr;
+    c->user_ws_bytes = device_ptr ? (size_t)bytes : 0;
+    return EHDG_OK;
+}
+
 int ehdg_csr_destroy(ehdg_csr* A) {
     if (!A) return EHDG_OK;
     cudaFree(A->row_start);
@@ -1013,6 +1169,7 @@ int ehdg_csr_destroy(ehdg_csr* A) {
     cudaFree(A->dinv);
     cudaFree(A->row_facet);
     cudaFree(A->strip);
+    cudaFree(A->line);
     delete A;
     return EHDG_OK;
 }
@@ -1035,6 +1192,7 @@ int ehdg_csr_numeric(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const e
     if (A->n_rows == 0) return EHDG_OK;
     const int64_t rlo = A->windowed ? A->row_lo : 0, rhi = A->windowed ? A->row_hi : A->n_rows;
     if (rhi <= rlo) return EHDG_OK;
+    if (A->folded_vals == vals) const_cast<ehdg_csr*>(A)->folded_vals = nullptr;     // fresh values: a Krylov solve may fold them again
     csr_numeric_kernel<<<(unsigned)((rhi - rlo + 127) / 128), 128, 0, st>>>((int)rlo, (int)rhi, make_slayout(c, p), A->row_facet, A->row_start,
                                                                             A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,
                                                                             p->eslot, S, g, vals, rhs);
@@ -1056,8 +1214,13 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     if (dc && dc->row_begin[dc->nranks] != ng) { set_error("ehdg_gmres: partition does not match the system size"); return EHDG_ERR_ARG; }
     const int64_t r0 = dc ? dc->row_begin[dc->rank] : 0, r1 = dc ? dc->row_begin[dc->rank + 1] : ng;
     const int64_t n = r1 - r0;                                      // rows this rank iterates on
+    const bool line_mode = info->use_line_block != 0;
+    if (line_mode && !A->line) { set_error("ehdg_gmres: use_line_block needs ehdg_csr_auto_lines / ehdg_csr_set_lines first"); return EHDG_ERR_ARG; }
     if (dc) {
-        if (info->use_strip_block) { set_error("ehdg_gmres: the strip block is not available in the distributed solve"); return EHDG_ERR_ARG; }
+        if ((info->use_strip_block || line_mode) && !A->windowed) {
+            set_error("ehdg_gmres: the line / strip blocks of the distributed solve need the partitioned matrix (ehdg_csr_symbolic_part)");
+            return EHDG_ERR_ARG;
+        }
         if (A->windowed && (A->row_lo != r0 || A->row_hi != r1)) {
             set_error("ehdg_gmres: the communicator's partition differs from the rows this rank assembled");
             return EHDG_ERR_ARG;
@@ -1065,6 +1228,10 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         rhs += r0;
     } else if (A->windowed) {
         set_error("ehdg_gmres: a partitioned matrix needs the communicator and its partition (ehdg_comm_init / _set_partition)");
+        return EHDG_ERR_ARG;
+    }
+    if (A->folded_vals == vals) {
+        set_error("ehdg_gmres: this value array already holds A M^-1 from an earlier solve; refill it with ehdg_csr_numeric");
         return EHDG_ERR_ARG;
     }
     const int m = info->restart > 0 ? info->restart : 30;
@@ -1075,75 +1242,96 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     info->rel_residual = 0.0;
     info->spmv_calls = 0;
     info->total_seconds = 0.0;
+    info->setup_seconds = 0.0;
+    info->precond_bytes = 0.0;
+    info->strip_dofs = info->strip_blocks = 0;
+    info->line_chains = info->line_blocks = info->line_max_block = 0;
+    info->dropped_dofs = 0;
     if (ng == 0) { info->converged = 1; return EHDG_OK; }
-    cudaEvent_t ev0, ev1;
-    EHDG_CUDA(cudaEventCreate(&ev0));
-    EHDG_CUDA(cudaEventCreate(&ev1));
-    EHDG_CUDA(cudaEventRecord(ev0, st));
+    if (method == 2 && m > DQ_MAXK) { set_error("ehdg_dqgmres: truncation length above %d", DQ_MAXK); return EHDG_ERR_ARG; }
+    SolveWorkspace ws;
+    ws.arena = (char*)c->user_ws;
+    ws.arena_bytes = c->user_ws_bytes;
+    int rc;
+    EHDG_CUDA(cudaEventCreate(&ws.ev0));
+    EHDG_CUDA(cudaEventCreate(&ws.ev1));
+    EHDG_CUDA(cudaEventCreate(&ws.ev2));
+    EHDG_CUDA(cudaEventRecord(ws.ev0, st));
     const int nbs = A->nb;
-    // ---- preconditioner: Dinv, then A <- A M^-1 in place
+    // ---- preconditioner.  Facet blocks: Dinv, then A <- A M^-1 in place.  Line blocks: the chains are factorised, A stays.
     if (!A->dinv) EHDG_CUDA(cudaMalloc(&A->dinv, sizeof(double) * (size_t)ng * nbs));
     int* fail = nullptr;
-    EHDG_CUDA(cudaMalloc(&fail, 2 * sizeof(int)));
-    EHDG_CUDA(cudaMemsetAsync(fail, 0, 2 * sizeof(int), st));
     uint8_t* rowdrop = nullptr;
-    EHDG_CUDA(cudaMalloc(&rowdrop, (size_t)ng));
+    if ((rc = ws.get(&fail, 2))) return rc;
+    if ((rc = ws.get(&rowdrop, (size_t)ng))) return rc;
+    EHDG_CUDA(cudaMemsetAsync(fail, 0, 2 * sizeof(int), st));
+    EHDG_CUDA(cudaMemsetAsync(rowdrop, 0, (size_t)ng, st));
+    int setup_rc = EHDG_OK;
     {
         // replicated matrix: every rank inverts all facet blocks; partitioned matrix: the own facets, and the inverses of
         // the halo facets (the right preconditioner scales COLUMNS) come from the neighbouring ranks
         const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
-        if (A->windowed) EHDG_CUDA(cudaMemsetAsync(A->dinv, 0, sizeof(double) * (size_t)ng * nbs, st));
+        if (A->windowed && !line_mode) EHDG_CUDA(cudaMemsetAsync(A->dinv, 0, sizeof(double) * (size_t)ng * nbs, st));
         if (fb > fa) bj_invert_kernel<<<(fb - fa + 127) / 128, 128, 0, st>>>(fa, fb, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop);
         EHDG_LAUNCH_CHECK();
-        if (A->windowed) {
+        if (A->windowed && !line_mode) {
             const int rh = dc->halo_exchange(A->dinv, st, nbs);
             if (rh) return rh;
         }
     }
-    // strip of marked elements: one exactly solved block (needs the unscaled matrix values)
-    StripSolver* strip = nullptr;
-    if (info->use_strip_block) {
-        const int rcs = strip_setup(A, vals, rowdrop, st, &strip);
-        if (rcs) return rcs;
+    // chains: the lines of the mesh (line mode) and / or the strip of marked elements, from the unscaled matrix values
+    if (line_mode || info->use_strip_block)
+        setup_rc = chain_setup(A, vals, rowdrop, line_mode ? A->line : nullptr, info->use_strip_block, info->line_target_dofs, st, &ws.chain);
+    ChainSolver* chain = ws.chain;
+    if (line_mode && setup_rc == EHDG_OK && n > 0 && !(chain && chain->all_rows)) {
+        set_error("ehdg_gmres: the line preconditioner does not cover every row");
+        setup_rc = EHDG_ERR_ARG;
     }
-    info->strip_dofs = strip ? strip->n_dofs : 0;
-    info->strip_blocks = strip ? strip->n_blocks : 0;
-    {
+    if (chain) {
+        info->line_chains = chain->n_chains;
+        info->line_blocks = chain->n_blocks;
+        info->line_max_block = chain->nmax;
+        info->precond_bytes = (double)chain->factor_bytes;
+        if (!line_mode) { info->strip_dofs = chain->n_dofs; info->strip_blocks = chain->n_blocks; }
+    }
+    if (!line_mode && setup_rc == EHDG_OK) {
         const int64_t fl = A->windowed ? A->row_lo : 0, fh = A->windowed ? A->row_hi : ng;
         if (fh > fl)
             bj_fold_kernel<<<(unsigned)(((fh - fl) * 5 + 255) / 256), 256, 0, st>>>((int)fl, (int)fh, nbs, A->row_facet, A->row_start, A->rowptr, A->nbr,
-                                                                                    A->dinv, strip ? A->strip : nullptr, vals);
+                                                                                    A->dinv, info->use_strip_block ? A->strip : nullptr, vals);
+        EHDG_LAUNCH_CHECK();
+        A->folded_vals = vals;
     }
-    EHDG_LAUNCH_CHECK();
     // ---- workspace
     double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr, *tvec = nullptr, *xg = nullptr;
-    if (strip) EHDG_CUDA(cudaMalloc(&tvec, sizeof(double) * (size_t)n));
+    if (chain && (rc = ws.get(&tvec, (size_t)n))) return rc;
     if (dc) {
-        EHDG_CUDA(cudaMalloc(&xg, sizeof(double) * (size_t)ng));          // full-length SpMV input: own rows + halo
+        if ((rc = ws.get(&xg, (size_t)ng))) return rc;                    // full-length SpMV input: own rows + halo
         EHDG_CUDA(cudaMemsetAsync(xg, 0, sizeof(double) * (size_t)ng, st));
     }
-    EHDG_CUDA(cudaMalloc(&V, sizeof(double) * (size_t)n * (method == 0 ? (m + 1) : (method == 1 ? 6 : 2 * (m + 1)))));
-    EHDG_CUDA(cudaMalloc(&w, sizeof(double) * (size_t)n));
-    EHDG_CUDA(cudaMalloc(&yhat, sizeof(double) * (size_t)n));
-    EHDG_CUDA(cudaMalloc(&partial, sizeof(double) * (size_t)RED_BLOCKS * KT));
-    EHDG_CUDA(cudaMalloc(&dsc, sizeof(double) * (size_t)(3 * (m + 2) + 8)));
+    if ((rc = ws.get(&V, (size_t)n * (method == 0 ? (m + 1) : (method == 1 ? 6 : 2 * (m + 1)))))) return rc;
+    if ((rc = ws.get(&w, (size_t)n))) return rc;
+    if ((rc = ws.get(&yhat, (size_t)n))) return rc;
+    if ((rc = ws.get(&partial, (size_t)RED_BLOCKS * KT))) return rc;
+    if ((rc = ws.get(&dsc, (size_t)(3 * (m + 2) + 8)))) return rc;
     double* d_h1 = dsc;                 // m+1
     double* d_h2 = dsc + (m + 2);       // m+1
     double* d_nrm = dsc + 2 * (m + 2);  // 1
     double* d_y = d_nrm + 4;            // m
     double* hbuf = nullptr;
-    EHDG_CUDA(cudaMallocHost(&hbuf, sizeof(double) * (size_t)(2 * (m + 2) + 16)));
+    if ((rc = ws.get_pinned(&hbuf, (size_t)(2 * (m + 2) + 16)))) return rc;
     EHDG_CUDA(cudaMemsetAsync(yhat, 0, sizeof(double) * (size_t)n, st));
     unsigned int* d_ticket = nullptr;
-    EHDG_CUDA(cudaMalloc(&d_ticket, sizeof(unsigned int)));
+    if ((rc = ws.get(&d_ticket, 1))) return rc;
     EHDG_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), st));
     VecOps vo{st, partial, n, dc, d_ticket};
-    // w = A~ P(v):  P leaves the bulk entries (their M^-1 is folded into A~) and solves the strip block
+    // w = A P(v).  Facet mode: P leaves the bulk entries (their M^-1 is folded into A) and solves the strip chain;
+    // line mode: P = M_line^-1, every row lies in a chain.
     auto apply_op = [&](const double* v, double* out) -> int {
         const double* in = v;
-        if (strip) {
-            EHDG_CUDA(cudaMemcpyAsync(tvec, v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-            const int r2 = strip_apply(strip, v, tvec, st);
+        if (chain) {
+            if (!chain->all_rows) EHDG_CUDA(cudaMemcpyAsync(tvec, v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            const int r2 = chain_apply(chain, v, tvec, r0, st);
             if (r2) return r2;
             in = tvec;
         }
@@ -1166,8 +1354,8 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     const int sweeps = info->jacobi_sweeps > 1 ? info->jacobi_sweeps : 1;
     double *pt = nullptr, *pw = nullptr;
     if (sweeps > 1) {
-        EHDG_CUDA(cudaMalloc(&pt, sizeof(double) * (size_t)n));
-        EHDG_CUDA(cudaMalloc(&pw, sizeof(double) * (size_t)n));
+        if ((rc = ws.get(&pt, (size_t)n))) return rc;
+        if ((rc = ws.get(&pw, (size_t)n))) return rc;
     }
     const int vgrid0 = vo.grid();
     auto poly = [&](const double* v, double* t) -> int {          // t = P^ v  (t != v)
@@ -1186,29 +1374,42 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         return apply_op(pt, out);
     };
     const int vgrid = vo.grid();
-    int rc;
     // ||b||
     if ((rc = vo.dots(rhs, n, 1, rhs, d_nrm))) return rc;
     EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, sizeof(double), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
     const double bnorm = std::sqrt(hbuf[0]);
-    int fail_h2[2] = {0, 0};
+    int fail_h2[3] = {0, 0, setup_rc != EHDG_OK ? 1 : 0};
     EHDG_CUDA(cudaMemcpy(fail_h2, fail, 2 * sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(fail);
+    if (line_mode) fail_h2[0] = 0;       // a facet block of rank 0 is the chain factorisation's business in line mode
+    if (chain) fail_h2[1] = line_mode ? chain->dropped : fail_h2[1] + chain->dropped;
     if (dc && A->windowed) {
-        // every rank inverted its own facet blocks: failure and drop counts are collective (all ranks leave together)
+        // every rank inverted its own facet blocks / factorised its own chains: failure and drop counts are collective
+        // (all ranks leave together)
         hbuf[0] = fail_h2[0];
         hbuf[1] = fail_h2[1];
-        EHDG_CUDA(cudaMemcpyAsync(d_nrm, hbuf, 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-        if ((rc = dc->allreduce_sum(d_nrm, 2, st))) return rc;
-        EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        hbuf[2] = fail_h2[2];
+        EHDG_CUDA(cudaMemcpyAsync(d_nrm, hbuf, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        if ((rc = dc->allreduce_sum(d_nrm, 3, st))) return rc;
+        EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
         EHDG_CUDA(cudaStreamSynchronize(st));
         fail_h2[0] = (int)hbuf[0];
         fail_h2[1] = (int)hbuf[1];
+        fail_h2[2] = (int)hbuf[2];
     }
-    const int fail_h = fail_h2[0];
     info->dropped_dofs = fail_h2[1];
-    if (fail_h) { set_error("ehdg_gmres: singular facet diagonal block"); return EHDG_ERR_SINGULAR; }
+    if (fail_h2[2]) {
+        if (setup_rc == EHDG_OK) set_error("ehdg_gmres: the preconditioner set-up failed on another rank");
+        return setup_rc != EHDG_OK ? setup_rc : EHDG_ERR_ARG;
+    }
+    if (fail_h2[0]) { set_error("ehdg_gmres: singular facet diagonal block"); return EHDG_ERR_SINGULAR; }
+    {
+        EHDG_CUDA(cudaEventRecord(ws.ev2, st));
+        EHDG_CUDA(cudaEventSynchronize(ws.ev2));
+        float ms0 = 0.f;
+        cudaEventElapsedTime(&ms0, ws.ev0, ws.ev2);
+        info->setup_seconds = ms0 * 1e-3;
+    }
     std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), gvec(m + 1), yv(m);
     double rel = 1.0;
     int iters = 0;
@@ -1283,11 +1484,10 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         double* Pr = V + (size_t)ring * n;           // ring of k+1 direction vectors
         double* u = yhat;
         double* usnap = nullptr;
-        EHDG_CUDA(cudaMalloc(&usnap, sizeof(double) * (size_t)n));
+        if ((rc = ws.get(&usnap, (size_t)n))) return rc;
         EHDG_CUDA(cudaMemsetAsync(usnap, 0, sizeof(double) * (size_t)n, st));
-        if (k > DQ_MAXK) { set_error("ehdg_dqgmres: truncation length above %d", DQ_MAXK); return EHDG_ERR_ARG; }
         double *d_cq = nullptr, *d_sq = nullptr, *d_state = nullptr;
-        EHDG_CUDA(cudaMalloc(&d_cq, sizeof(double) * (size_t)(2 * (k + 2) + 8)));
+        if ((rc = ws.get(&d_cq, (size_t)(2 * (k + 2) + 8)))) return rc;
         d_sq = d_cq + (k + 2);
         d_state = d_sq + (k + 2);
         const int check_every = 100;                  // iterations between true-residual checks
@@ -1373,8 +1573,6 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
             // the next cycle measures the true residual of u: leaves when it meets rtol, otherwise iterates on
         }
         EHDG_CUDA(cudaStreamSynchronize(st));
-        cudaFree(usnap);
-        cudaFree(d_cq);
         if (sweeps > 1) {      // yhat = P^ u
             EHDG_CUDA(cudaMemcpyAsync(w, u, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
             if ((rc = poly(w, pt))) return rc;
@@ -1456,34 +1654,22 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         conv = rel <= rtol * 10.0;
     }
     // x = M^-1 yhat
-    bj_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)r0, (int)r1, nbs, A->row_facet, A->row_start, A->dinv, yhat - r0, x);
-    EHDG_LAUNCH_CHECK();
-    if (strip && (rc = strip_apply(strip, yhat, x, st))) return rc;
+    if (line_mode) {
+        if ((rc = chain_apply(chain, yhat, x + r0, r0, st))) return rc;
+    } else {
+        bj_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)r0, (int)r1, nbs, A->row_facet, A->row_start, A->dinv, yhat - r0, x);
+        EHDG_LAUNCH_CHECK();
+        if (chain && (rc = chain_apply(chain, yhat, x + r0, r0, st))) return rc;
+    }
     if (dc && (rc = dc->allgather_rows(x, st))) return rc;
-    EHDG_CUDA(cudaEventRecord(ev1, st));
-    EHDG_CUDA(cudaEventSynchronize(ev1));
+    EHDG_CUDA(cudaEventRecord(ws.ev1, st));
+    EHDG_CUDA(cudaEventSynchronize(ws.ev1));
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
+    cudaEventElapsedTime(&ms, ws.ev0, ws.ev1);
     info->iters = iters;
     info->converged = conv ? 1 : 0;
     info->rel_residual = rel;
     info->total_seconds = ms * 1e-3;
-    info->dropped_dofs += strip ? strip->dropped : 0;
-    strip_free(strip);
-    cudaFree(rowdrop);
-    cudaFree(tvec);
-    cudaFree(xg);
-    cudaFree(pt);
-    cudaFree(pw);
-    cudaFree(V);
-    cudaFree(w);
-    cudaFree(yhat);
-    cudaFree(partial);
-    cudaFree(d_ticket);
-    cudaFree(dsc);
-    cudaFreeHost(hbuf);
     return EHDG_OK;
 }
 

@@ -188,6 +188,7 @@ class EHDGPipeline:
         if self.csr is not None:
             self.lib.ehdg_csr_destroy(self.csr)
         self.csr = C.c_void_p()
+        self._lines_csr = None
         _lib.check(self.lib.ehdg_csr_symbolic_part(self.ctx, C.byref(self.cmesh), _ptr(self.facet_active) if self.nenr else None,
                                                    _ptr(self.facet_mask) if self.nenr else None, int(nranks), int(rank),
                                                    C.byref(self.csr), self._stream()), "ehdg_csr_symbolic_part")
@@ -210,6 +211,7 @@ class EHDGPipeline:
         if self.csr is not None:
             self.lib.ehdg_csr_destroy(self.csr)
         self.csr = C.c_void_p()
+        self._lines_csr = None
         _lib.check(self.lib.ehdg_csr_symbolic(self.ctx, C.byref(self.cmesh), _ptr(self.facet_active) if self.nenr else None,
                                               _ptr(self.facet_mask) if self.nenr else None, C.byref(self.csr), self._stream()), "ehdg_csr_symbolic")
         self.csr_sizes = _lib.CsrSizes()
@@ -221,6 +223,7 @@ class EHDGPipeline:
         return self
 
     def csr_numeric(self):
+        self.vals_folded = False
         _lib.check(self.lib.ehdg_csr_numeric(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.S), _ptr(self.g),
                                              _ptr(self.vals), _ptr(self.rhs), self._stream()), "ehdg_csr_numeric")
         return self
@@ -236,18 +239,65 @@ class EHDGPipeline:
 
     # ------------------------------------------------------------------ a9
     def spmv(self, x, y=None):
+        if getattr(self, "vals_folded", False):
+            self.csr_numeric()                      # a facet-mode solve left A M^-1 in vals
         y = torch.empty_like(x) if y is None else y
         _lib.check(self.lib.ehdg_spmv(self.ctx, self.csr, _ptr(self.vals), _ptr(x), _ptr(y), self._stream()), "ehdg_spmv")
         return y
 
-    def gmres(self, restart=30, max_iters=20000, rtol=1e-12, strip_block=True, jacobi_sweeps=1, method="gmres"):
+    def set_lines(self, facet_line=None, direction=(0.0, 0.0), width=None, offset=0.25):
+        """chains of the line-block preconditioner: facet_line (i32 [nf] device tensor: any user partition of the facets into
+        chains) or, by default, lines of width `width` (default: the mesh size) across the flow direction (ehdg_csr_auto_lines)"""
+        if facet_line is not None:
+            fl = facet_line.to(self.dev, torch.int32).contiguous()
+            _lib.check(self.lib.ehdg_csr_set_lines(self.csr, _ptr(fl), self._stream()), "ehdg_csr_set_lines")
+        else:
+            w = float(self.mesh_host.maxh if width is None else width)
+            _lib.check(self.lib.ehdg_csr_auto_lines(self.ctx, self.csr, C.byref(self.cmesh), float(direction[0]), float(direction[1]),
+                                                    w, float(offset), self._stream()), "ehdg_csr_auto_lines")
+        self._lines_csr = self.csr.value
+        return self
+
+    def lines(self) -> torch.Tensor:
+        return _device_view(self.lib.ehdg_csr_lines(self.csr), self.mesh_host.nf, torch.int32, self.dev).clone()
+
+    def krylov_workspace_bytes(self, restart, method="dqgmres", precond="line", jacobi_sweeps=1) -> int:
+        info = _lib.GmresInfo()
+        info.restart, info.jacobi_sweeps = int(restart), int(jacobi_sweeps)
+        info.use_line_block = int(precond == "line")
+        info.use_strip_block = int(self.nenr > 0)
+        out = C.c_int64(0)
+        _lib.check(self.lib.ehdg_krylov_workspace_bytes(self.ctx, self.csr, C.byref(info), {"gmres": 0, "bicgstab": 1, "dqgmres": 2}[method],
+                                                        C.byref(out)), "ehdg_krylov_workspace_bytes")
+        return int(out.value)
+
+    def set_workspace(self, nbytes: int):
+        """hands the library a caller-owned device buffer for the Krylov vectors (no allocation inside the solve while it fits)"""
+        self.workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev) if nbytes else None
+        _lib.check(self.lib.ehdg_set_workspace(self.ctx, _ptr(self.workspace), int(nbytes)), "ehdg_set_workspace")
+        return self
+
+    def gmres(self, restart=30, max_iters=20000, rtol=1e-12, strip_block=True, jacobi_sweeps=1, method="gmres", precond="line",
+              line_target_dofs=0):
+        """Krylov solve of the condensed system.  precond = 'line' (line-block Jacobi: every chain of facets solved exactly; the
+        matrix values stay untouched) or 'facet' (facet block-Jacobi folded into the matrix values: they hold A M^-1 afterwards and
+        are refilled by csr_numeric before the next use)."""
+        if precond not in ("line", "facet"):
+            raise ValueError("precond must be 'line' or 'facet'")
         n = self.csr_sizes.n_rows
+        if getattr(self, "vals_folded", False):
+            self.csr_numeric()                      # an earlier facet-mode solve left A M^-1 in vals
+        if precond == "line" and getattr(self, "_lines_csr", None) != self.csr.value:
+            self.set_lines()
         self.xhat = torch.zeros(max(n, 1), dtype=torch.float64, device=self.dev)
         info = _lib.GmresInfo()
         info.restart, info.max_iters, info.rtol = int(restart), int(max_iters), float(rtol)
         info.use_strip_block = int(bool(strip_block) and self.nenr > 0)
         info.jacobi_sweeps = int(jacobi_sweeps)
+        info.use_line_block = int(precond == "line")
+        info.line_target_dofs = int(line_target_dofs)
         fn = {"gmres": self.lib.ehdg_gmres, "bicgstab": self.lib.ehdg_bicgstab, "dqgmres": self.lib.ehdg_dqgmres}[method]
+        self.vals_folded = precond == "facet"       # set before the call: an error inside may leave vals half folded
         _lib.check(fn(self.ctx, self.csr, _ptr(self.vals), _ptr(self.rhs), _ptr(self.xhat), C.byref(info), self._stream()),
                    "ehdg_" + method)
         self.gmres_info = info

@@ -182,6 +182,17 @@ int ehdg_csr_symbolic(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet
 int ehdg_csr_symbolic_part(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_active, const uint8_t* facet_mask,
                            int nranks, int rank, ehdg_csr** out, void* stream);
 int ehdg_csr_get_partition(const ehdg_csr* csr, int64_t* row_begin, int32_t* facet_begin);
+/* Chains of the line-block Jacobi preconditioner.  facet_line i32[nf] (device): chain id of every facet, any non-negative
+ * integers; a negative entry makes the facet a chain of its own (= facet block-Jacobi for it).  The array is copied.
+ * ehdg_csr_auto_lines fills it from the geometry: chain of facet f = floor(n . c_f / width + offset) with c_f the facet
+ * midpoint and n = (dir_x, dir_y) a direction ACROSS the flow; dir = (0,0) picks n from beta (snapped to a coordinate
+ * axis when beta is within 1:10 of it, so that lattice rows stay whole); width <= 0: sqrt(2 |Omega| / ne).
+ * These replace nothing in the reference (it calls a direct solver, convection_diffusion.py:385-387); they parameterise
+ * the preconditioner of ehdg_gmres / ehdg_dqgmres / ehdg_bicgstab. */
+int ehdg_csr_set_lines(ehdg_csr* csr, const int32_t* facet_line, void* stream);
+int ehdg_csr_auto_lines(ehdg_ctx* ctx, ehdg_csr* csr, const ehdg_mesh* mesh, double dir_x, double dir_y, double width,
+                        double offset, void* stream);
+const int32_t* ehdg_csr_lines(const ehdg_csr* csr);      /* i32 [nf] device, null until set */
 int ehdg_csr_destroy(ehdg_csr* csr);
 int ehdg_csr_get_sizes(const ehdg_csr* csr, ehdg_csr_sizes* out);
 const int64_t* ehdg_csr_rowptr(const ehdg_csr* csr);     /* i64 [n_rows+1] device */
@@ -210,9 +221,17 @@ typedef struct {
     int32_t strip_blocks;   /* out */
     int32_t jacobi_sweeps;  /* in : s >= 1 block-Jacobi Richardson sweeps per preconditioner application (polynomial
                              *      block-Jacobi); s * restart should exceed the number of facet layers along a streamline */
-    int32_t reserved;
+    int32_t use_line_block; /* in : 1 = line-block Jacobi: the chains of ehdg_csr_auto_lines / ehdg_csr_set_lines are the
+                             *      diagonal blocks of the preconditioner, each solved exactly (block-tridiagonal LU);
+                             *      the matrix values are NOT overwritten in this mode */
+    int32_t line_target_dofs; /* in : BFS levels of a chain are merged into blocks of at most this many dofs (0: one level per block) */
+    int32_t line_chains;    /* out: chains of the line preconditioner (incl. the strip chain) */
+    int32_t line_blocks;    /* out: blocks over all chains */
+    int32_t line_max_block; /* out: dofs of the largest block */
+    double setup_seconds;   /* out: device + host time of the preconditioner set-up (inside total_seconds) */
+    double precond_bytes;   /* out: bytes of factor data one preconditioner application streams */
 } ehdg_gmres_info;
-int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^-1 */,
+int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^-1 unless use_line_block */,
                const double* rhs, double* x, ehdg_gmres_info* info, void* stream);
 /* Same preconditioner (block-Jacobi, strip block, optional sweeps) with BiCGStab: short recurrence, no restart.
  * GMRES(m) stalls on the penalty-dominated facet systems of fine meshes; `restart` is ignored here. */
@@ -221,6 +240,12 @@ int ehdg_bicgstab(ehdg_ctx* ctx, ehdg_csr* csr, double* vals, const double* rhs,
  * progressively updated solution -- no restart, per-iteration cost of GMRES(k).  The method of choice for the
  * large facet systems, where information has to cross the mesh and restarted GMRES stagnates. */
 int ehdg_dqgmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals, const double* rhs, double* x, ehdg_gmres_info* info, void* stream);
+/* Caller-provided workspace of the Krylov solvers: ehdg_krylov_workspace_bytes gives the bytes the solver named
+ * by `method` (0 gmres, 1 bicgstab, 2 dqgmres) needs for its vectors with the settings in `info`; ehdg_set_workspace hands
+ * the context a device buffer (kept until replaced; ptr = null: back to per-call allocation).  Whatever does not fit is
+ * allocated and freed inside the call.  The factors of the line / strip preconditioner are library-owned. */
+int ehdg_krylov_workspace_bytes(const ehdg_ctx* ctx, const ehdg_csr* csr, const ehdg_gmres_info* info, int method, int64_t* bytes);
+int ehdg_set_workspace(ehdg_ctx* ctx, void* device_ptr, int64_t bytes);
 /* y = A x with the CSR SpMV kernel used inside GMRES (for tests and the bandwidth bench) */
 int ehdg_spmv(ehdg_ctx* ctx, const ehdg_csr* csr, const double* vals, const double* x, double* y, void* stream);
 
