@@ -163,6 +163,16 @@ def _emit(line):
     out.flush()
 
 
+def kernel_source_hash():
+    """sha256 over the sources of the polynomial-path kernels: a committed ncu traffic figure is only quoted for the code it
+    was captured on"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("ehdg_fast.h", "ehdg_fast.cu", "ehdg_tensors.h", "ehdg_basis.h"):
+        h.update(open(os.path.join(ROOT, "convectiondiffusionequation_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -171,24 +181,27 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--no-solve", action="store_true", help="skip the one-off GMRES solve after the timed steps")
+    ap.add_argument("--no-solve", action="store_true", help="skip the one-off solves after the timed steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e-solve", action="store_true", help="skip the mesh-in / error-out leg through Convection_Diffusion (N = 1)")
     ap.add_argument("--solve-iters", type=int, default=60000)
     ap.add_argument("--solve-method", default="dqgmres", choices=["gmres", "dqgmres", "bicgstab"])
-    ap.add_argument("--solve-workload", default="ehdg_p4_eps1e-6_structured_1M",
-                    help="mesh of the one-off solve leg ('same' = the timed workload; the 4M solve takes minutes)")
+    ap.add_argument("--solve-workload", default="same",
+                    help="mesh of the one-off solve leg ('same' = the timed workload, partitioned like it at N > 1)")
     ap.add_argument("--rtol", type=float, default=1e-8)
-    ap.add_argument("--restart", type=int, default=8, help="GMRES restart / DQGMRES truncation length (tools/solve_k_scan.py: 8 is the fastest on the 1M system)")
+    ap.add_argument("--restart", type=int, default=8, help="GMRES restart / DQGMRES truncation length")
     ap.add_argument("--sweeps", type=int, default=1, help="block-Jacobi sweeps per preconditioner application")
-    ap.add_argument("--solve-type", default="hdg", choices=["hdg", "ehdg", "both"],
-                    help="system of the one-off solve: plain HDG (well posed at every size) and/or the enriched one")
+    ap.add_argument("--precond", default="line", choices=["line", "facet"], help="line-block or facet-block Jacobi")
+    ap.add_argument("--solve-type", default="both", choices=["hdg", "ehdg", "both"],
+                    help="systems of the one-off solve: the enriched one (the workload's own) and / or plain HDG on the same mesh")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: also time one private full mesh per rank (weak-scaled replicas)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from convectiondiffusionequation_b200 import build
+    from convectiondiffusionequation_b200 import build, parallel
     from convectiondiffusionequation_b200.hot_path import EHDGPipeline
     from convectiondiffusionequation_b200.mesh import unit_square_mesh
 
@@ -204,69 +217,100 @@ def main():
     build.build()
 
     n, kind, order, eps = WORKLOADS[args.workload]
-    # weak scaling: every rank owns one mesh of the named size (rank-specific seed for the jitter)
-    mesh = unit_square_mesh(n, kind=kind, seed=20261019 + rank)
+    # strong scaling: ONE mesh of the named size (same seed on every rank); at N > 1 the facet rows are split into N
+    # contiguous ranges and a rank assembles, condenses and fills the rows of the elements that touch its range
+    mesh = unit_square_mesh(n, kind=kind, seed=20261019)
     spec = make_spec(order, eps)
     P = EHDGPipeline(mesh, spec, device=dev)
-    P.setup()
+    if world > 1:
+        parallel.init_communicator(P)
+        parallel.gather_extents(0, 0, None, dev)                 # NCCL connects its all-gather channels on first use
     ne = mesh.ne
     sizes = P.sizes
-    ps = P.plan_sizes
+    ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def rank_setup(Q):
+        """per-mesh set-up of this rank's share: marks, pruning, pattern of the own rows, element selection, plan, values"""
+        if world > 1:
+            parallel.partitioned_assemble(Q, rank, world, assemble=False)
+        else:
+            Q.setup()
+            Q.csr_symbolic(1, 0)
+            Q.csr_alloc_values()
+        return Q
+
+    def step(Q):
+        """the metric's unit of work on this rank's share: a4 (alpha), a5-a7 (blocks, rhs, condensation), a8 (numeric fill)"""
+        Q.alpha()
+        Q.assemble_condense()
+        Q.csr_numeric()
+
+    rank_setup(P)                                                # first call pays the allocations (cached by the pools afterwards)
+    barrier()
+    t_s0 = ev(); t_s1 = ev()
+    t_s0.record()
+    rank_setup(P)
+    t_s1.record()
+    torch.cuda.synchronize(dev)
+    setup_ms = t_s0.elapsed_time(t_s1)
+    ps = P.plan_sizes
+    n_share = int(ps.n_poly + ps.n_gen)
+
     # L2 flush between timed iterations: the outputs of one step (S, W: > 10 GB at 4M) exceed the 126 MB L2;
-    # for small workloads an explicit flush buffer is written.
+    # for small shares an explicit flush buffer is written.
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     need_flush = (ps.S_doubles + ps.W_doubles) * 8 < (512 << 20)
 
-    def step():
-        P.alpha()
-        P.assemble_condense()
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
     for _ in range(max(args.warmup, 3)):
-        step()
+        step(P)
     barrier()
     # ---- timed region: K steps, device time per stage, clocks sampled meanwhile
-    t_alpha, t_asm = 0.0, 0.0
+    t_alpha, t_asm, t_csr = 0.0, 0.0, 0.0
     k_alpha, k_asm = [], []          # the two polynomial-path kernels alone (events recorded inside libehdg)
     P.kernel_timing(True)
     with ClockSampler(local) as clocks:
         barrier()
-        e0, e3 = ev(), ev()
         stage = []
-        e0.record()
         for _ in range(args.steps):
             if need_flush:
                 flush.fill_(1)
-            a0, a1, a2 = ev(), ev(), ev()
+            a0, a1, a2, a3 = ev(), ev(), ev(), ev()
             a0.record()
             P.alpha()
             a1.record()
             P.assemble_condense()
             a2.record()
-            stage.append((a0, a1, a2))
+            P.csr_numeric()
+            a3.record()
+            stage.append((a0, a1, a2, a3))
             if P.plan_sizes.n_poly > 0:
                 ka, kb = P.kernel_times_ms()      # waits for this step's kernels: the next step starts after it anyway
                 k_alpha.append(ka)
                 k_asm.append(kb)
-        e3.record()
         barrier()
-    for a0, a1, a2 in stage:
+    for a0, a1, a2, a3 in stage:
         t_alpha += a0.elapsed_time(a1)
         t_asm += a1.elapsed_time(a2)
-    ms_step = (t_alpha + t_asm) / args.steps
-    tmax = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+        t_csr += a2.elapsed_time(a3)
+    ms_step = (t_alpha + t_asm + t_csr) / args.steps
+    tmax = torch.tensor([ms_step, setup_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step_max = float(tmax.item())
-    value = world * ne / (ms_step_max * 1e-3)
+    ms_step_max, setup_ms_max = float(tmax[0].item()), float(tmax[1].item())
+    value = ne / (ms_step_max * 1e-3)                 # global elements / slowest rank's time for its share
     status_bad = int((P.status != 0).sum().item())
     moment_frac = P.moment_rhs_fraction()
+    share = torch.tensor([n_share, int(P.csr_sizes.nnz)], dtype=torch.int64, device=dev)
+    shares = [torch.zeros_like(share) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(shares, share)
+    else:
+        shares = [share]
 
     # ---- e2e: host buffers in, alpha table + status out, every step
     pinned = dict(verts=torch.from_numpy(mesh.verts).pin_memory(), tris=torch.from_numpy(mesh.tris).pin_memory(),
@@ -297,9 +341,8 @@ def main():
         comp.wait_event(sl_["down"])                       # the slot's previous results have left the device
         P.upload_mesh(sl_["mesh"])                         # device tensors: adopts them, no further copy
         P.lam, P.status = sl_["lam"], sl_["status"]
-        P.setup()
-        P.alpha()
-        P.assemble_condense()
+        rank_setup(P)
+        step(P)
         sl_["done"].record(comp)
 
     def e2e_download(i):
@@ -331,60 +374,64 @@ def main():
         e2e_reps.append((time.perf_counter() - t0) / e2e_steps)
     e2e_s = sorted(e2e_reps)[1]
     lam_host = lam_hosts[(e2e_steps - 1) % 2]
-    assert bool(torch.isfinite(lam_host).all()) and float(lam_host.min()) > 0.0, "e2e: alpha table did not arrive"
+    sel_host = P.elem_select.cpu() if getattr(P, "elem_select", None) is not None else None
+    lam_chk = lam_host if sel_host is None else lam_host[sel_host.bool()]
+    assert bool(torch.isfinite(lam_chk).all()) and float(lam_chk.min()) > 0.0, "e2e: alpha table did not arrive"
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * ne / float(te.item())
+    e2e_value = ne / float(te.item())
     h2d = P.h2d_bytes + (P.vert_flags.numel() if hasattr(P, "vert_flags") else 0)
     d2h = ne * 12
 
-    # ---- one-off solve (a8-a10).  N > 1: ONE global mesh, partitioned: every rank assembles and condenses the elements
-    # that touch its facet range, fills its own CSR rows and iterates on them over NCCL (SpMV halo exchange + all-reduced
-    # dot products): strong scaling of assembly + solve on the solve workload.
+    # ---- optional: weak-scaled replicas (one private full mesh per rank, no partition), the round-1 number
+    replica_value = None
+    if args.replicas and world > 1:
+        R = EHDGPipeline(unit_square_mesh(n, kind=kind, seed=20261019 + rank), spec, device=dev)
+        R.setup()
+        for _ in range(3):
+            R.alpha(); R.assemble_condense()
+        barrier()
+        r0_, r1_ = ev(), ev()
+        r0_.record()
+        for _ in range(args.steps):
+            R.alpha(); R.assemble_condense()
+        r1_.record()
+        barrier()
+        tr_ = torch.tensor([r0_.elapsed_time(r1_) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(tr_, op=dist.ReduceOp.MAX)
+        replica_value = world * ne / (float(tr_.item()) * 1e-3)
+        R.close()
+        del R
+        torch.cuda.empty_cache()
+
+    # ---- one-off solves (a9-a10) on the timed pipeline's own system (already assembled and filled: a8 is in the step) and,
+    # with --solve-type both, on the plain HDG system of the same mesh.  N > 1: the rows stay partitioned, the Krylov
+    # iteration runs over NCCL (SpMV halo exchange + all-reduced dot products).
     solves = []
     if not args.no_solve:
-        from convectiondiffusionequation_b200 import parallel
         swl = args.workload if args.solve_workload == "same" else args.solve_workload
         sn, skind, sorder, seps = WORKLOADS[swl]
-        smesh = mesh if (swl == args.workload and world == 1) else unit_square_mesh(sn, kind=skind)
-        for styp in (["hdg", "ehdg"] if args.solve_type == "both" else [args.solve_type]):
-            part = None
-            if world > 1:
-                Ps = EHDGPipeline(smesh, make_spec(sorder, seps, enriched=(styp == "ehdg")), device=dev)
-                parallel.init_communicator(Ps)
-                parallel.gather_extents(0, 0, None, dev)                 # NCCL connects its all-gather channels on first use
-                barrier()
-                p0, p1 = ev(), ev()
-                p0.record()
-                parallel.partitioned_assemble(Ps, rank, world)          # a1-a8 of this rank's share
-                p1.record()
-                torch.cuda.synchronize(dev)
-                cnt = torch.tensor([int(Ps.plan_sizes.n_poly + Ps.plan_sizes.n_gen), int(Ps.elem_owned.sum()), int(Ps.csr_sizes.nnz),
-                                    int(Ps.row_begin[rank + 1] - Ps.row_begin[rank]), int(p0.elapsed_time(p1) * 1e3)],
-                                   dtype=torch.int64, device=dev)
-                lst = [torch.zeros_like(cnt) for _ in range(world)]
-                dist.all_gather(lst, cnt)
-                part = {"elements_per_rank": [int(t[0]) for t in lst], "owned_elements_per_rank": [int(t[1]) for t in lst],
-                        "nnz_per_rank": [int(t[2]) for t in lst], "rows_per_rank": [int(t[3]) for t in lst],
-                        "mark_prune_assemble_condense_csr_ms_per_rank": [float(t[4]) / 1e3 for t in lst],
-                        "stages_ms_rank0": {k: round(v, 3) for k, v in Ps.part_timing.items()}}
-                s0 = s1 = None
-            elif styp == "ehdg" and swl == args.workload:
+        for styp in (["ehdg", "hdg"] if args.solve_type == "both" else [args.solve_type]):
+            if styp == "ehdg" and swl == args.workload:
                 Ps = P
+                P.upload_mesh()                                          # back to the pipeline's own mesh tensors
+                rank_setup(P)
+                step(P)
             else:
+                smesh = mesh if swl == args.workload else unit_square_mesh(sn, kind=skind)
                 Ps = EHDGPipeline(smesh, make_spec(sorder, seps, enriched=(styp == "ehdg")), device=dev)
-                Ps.setup().assemble()
+                if world > 1:
+                    parallel.init_communicator(Ps)
+                rank_setup(Ps)
+                step(Ps)
+            smesh = Ps.mesh_host
             barrier()
-            s2, s3 = ev(), ev()
-            if world == 1:
-                s0, s1 = ev(), ev()
-                s0.record()
-                Ps.csr_build()
-                s1.record()
             nrows, nnz = Ps.csr_sizes.n_rows, Ps.csr_sizes.nnz            # nnz: this rank's rows
             own_rows = nrows if world == 1 else int(Ps.row_begin[rank + 1] - Ps.row_begin[rank])
-            # SpMV bandwidth: algorithmic bytes 12 nnz + 20 rows, 20 launches (own rows at N > 1, no exchange)
+            # SpMV bandwidth, 20 launches (own rows at N > 1, no exchange).  Two byte counts: the CSR-equivalent 12 nnz + 20 rows
+            # of SURVEY 8d, and what the facet-block layout really moves (8 B per value, ONE 4-byte column index per block
+            # column, 16 B of block metadata per facet, x and y once): the HBM fraction is quoted on the latter.
             xs = torch.ones(max(nrows, 1), dtype=torch.float64, device=dev)
             ys = torch.empty_like(xs)
             for _ in range(3):
@@ -396,39 +443,70 @@ def main():
             b1.record()
             torch.cuda.synchronize(dev)
             spmv_ms = b0.elapsed_time(b1) / 20
-            spmv_gbs = (12.0 * nnz + 20.0 * own_rows) / (spmv_ms * 1e-3) / 1e9
+            nb_rows = sizes.nfl if styp == "hdg" else None
+            rp, _, rs_, dm_ = Ps.csr_arrays()
+            f_act = (rs_[1:] - rs_[:-1]) > 0
+            if world > 1:
+                f_idx = torch.arange(f_act.numel(), device=dev)
+                f_act &= (f_idx >= int(Ps.facet_begin[rank])) & (f_idx < int(Ps.facet_begin[rank + 1]))
+            first_rows = rs_[:-1][f_act].long()
+            block_cols = int((rp[first_rows + 1] - rp[first_rows]).sum().item())
+            n_fac = int(f_act.sum().item())
+            del rp, rs_, dm_, first_rows, f_act
+            bytes_csr = 12.0 * nnz + 20.0 * own_rows
+            bytes_actual = 8.0 * nnz + 4.0 * block_cols + 16.0 * n_fac + 16.0 * own_rows
+            spmv_gbs = bytes_csr / (spmv_ms * 1e-3) / 1e9
+            spmv_gbs_actual = bytes_actual / (spmv_ms * 1e-3) / 1e9
             del xs, ys
             barrier()
+            s2, s3 = ev(), ev()
             s2.record()
             sweeps = max(1, args.sweeps)
-            if world > 1:
-                l2, h1 = parallel.partitioned_solve(Ps, restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol,
-                                                    jacobi_sweeps=sweeps, method=args.solve_method)
-            else:
-                Ps.gmres(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol, jacobi_sweeps=sweeps, method=args.solve_method,
-                         strip_block=True)
-                Ps.backsolve()
-                l2, h1 = Ps.errors()
+            kw = dict(restart=args.restart, max_iters=args.solve_iters, rtol=args.rtol, jacobi_sweeps=sweeps, method=args.solve_method,
+                      precond=args.precond, strip_block=True)
+            err = None
+            try:
+                if world > 1:
+                    l2, h1 = parallel.partitioned_solve(Ps, **kw)
+                else:
+                    Ps.gmres(**kw)
+                    Ps.backsolve()
+                    l2, h1 = Ps.errors()
+            except Exception as exc:                       # reported in the line, the assembly numbers stand
+                l2 = h1 = None
+                err = str(exc)
             s3.record()
             torch.cuda.synchronize(dev)
-            gi = Ps.gmres_info
-            sv = {"type": styp, "ranks": world, "workload": swl, "method": args.solve_method, "elements": int(smesh.ne), "rows": int(nrows),
-                  "nnz": int(nnz) if world == 1 else int(sum(part["nnz_per_rank"])),
-                  "csr_build_ms": s0.elapsed_time(s1) if world == 1 else None,
-                  "gmres_backsolve_error_ms": s2.elapsed_time(s3), "gmres_iters": int(gi.iters),
-                  "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual),
-                  "gmres_seconds": float(gi.total_seconds), "ms_per_iteration": 1e3 * float(gi.total_seconds) / max(1, int(gi.iters)),
-                  "restart": args.restart, "jacobi_sweeps": sweeps, "spmv_calls": int(gi.spmv_calls), "rtol": args.rtol, "dropped_dofs": int(gi.dropped_dofs),
-                  "strip_dofs": int(gi.strip_dofs), "strip_blocks": int(gi.strip_blocks), "l2_error": l2, "h1_error": h1,
-                  "spmv_ms": spmv_ms, "spmv_gbs": spmv_gbs}
-            if part:
-                sv["partitioned"] = part
+            gi = getattr(Ps, "gmres_info", None)
+            sv = {"type": styp, "ranks": world, "workload": swl, "method": args.solve_method, "precond": args.precond,
+                  "elements": int(smesh.ne), "rows": int(nrows), "nnz_this_rank": int(nnz), "error": err,
+                  "gmres_backsolve_error_ms": s2.elapsed_time(s3), "restart": args.restart, "jacobi_sweeps": sweeps, "rtol": args.rtol,
+                  "l2_error": l2, "h1_error": h1, "spmv_ms": spmv_ms, "spmv_gbs_csr_equivalent": spmv_gbs, "spmv_gbs_actual": spmv_gbs_actual,
+                  "spmv_bytes_actual": bytes_actual, "spmv_bytes_csr_equivalent": bytes_csr}
+            if gi is not None and err is None:
+                it_s = float(gi.total_seconds) - float(gi.setup_seconds)
+                sv.update({"gmres_iters": int(gi.iters), "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual),
+                           "gmres_seconds": float(gi.total_seconds), "precond_setup_seconds": float(gi.setup_seconds),
+                           "ms_per_iteration": 1e3 * it_s / max(1, int(gi.iters)), "spmv_calls": int(gi.spmv_calls),
+                           "dropped_dofs": int(gi.dropped_dofs), "strip_dofs": int(gi.strip_dofs), "line_chains": int(gi.line_chains),
+                           "line_blocks": int(gi.line_blocks), "line_max_block": int(gi.line_max_block),
+                           "precond_factor_bytes_this_rank": float(gi.precond_bytes),
+                           "precond_apply_gbs_floor": (float(gi.precond_bytes) / 1e9) / max(1e-9, (it_s / max(1, int(gi.iters)))),
+                           "note": "enriched systems at this size are singular to working precision in the reference itself (DESIGN 2.3, 6); "
+                                   "the residual is that of the assembled system, dependent dofs dropped" if styp == "ehdg" else None})
             solves.append(sv)
             if Ps is not P:
                 Ps.close()
                 del Ps
                 torch.cuda.empty_cache()
-    solve = solves[0] if solves else None
+
+    # ---- e2e_solve (N = 1): the reference-facing call, mesh in -> L2 error out, through Convection_Diffusion._solveEHDG
+    e2e_solve = None
+    if world == 1 and not args.no_e2e_solve:
+        try:
+            e2e_solve = run_e2e_solve(dev)
+        except Exception as exc:
+            e2e_solve = {"error": str(exc)}
 
     if rank != 0:
         if world > 1:
@@ -436,7 +514,7 @@ def main():
         return
 
     hbm, hbm_src, fp64, fp64_src = measured_peaks()
-    # dominant kernel: fast_assemble_kernel<P> (one launch per step, ~55 % of the step; fast_alpha_kernel<P> ~37 %)
+    # dominant kernel: fast_assemble_kernel<P> (one launch per step; fast_alpha_kernel<P> second)
     n_poly, n_gen = int(ps.n_poly), int(ps.n_gen)
     f_asm_quad, f_alpha = int(sizes.flops_poly_assemble), int(sizes.flops_poly_alpha)
     # elements whose right-hand side comes from the six moment vectors (exp underflowed on the whole element) spend
@@ -446,49 +524,62 @@ def main():
     alpha_ms = float(np.mean(k_alpha)) if k_alpha else None
     achieved_tf = n_poly * f_asm / (asm_ms * 1e-3) / 1e12 if asm_ms else None
     alpha_tf = n_poly * f_alpha / (alpha_ms * 1e-3) / 1e12 if alpha_ms else None
-    step_tf = n_poly * (f_asm + f_alpha) / (ms_step * 1e-3) / 1e12
-    traffic = None
+    step_tf = n_poly * (f_asm + f_alpha) / ((t_alpha + t_asm) / args.steps * 1e-3) / 1e12
+    traffic, traffic_note = None, "no ncu capture of this kernel source on file"
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_assemble_traffic.json")))
-        if tr.get("workload") == args.workload:
-            traffic = tr["dram_bytes_per_launch"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_assemble_traffic.json")))
+        if tr.get("workload") == args.workload and tr.get("kernel_source_sha256_16") == kernel_source_hash() and world == 1:
+            traffic, traffic_note = tr["dram_bytes_per_launch"], f"ncu --set full capture {tr.get('captured')} of this kernel source (hash matches)"
+        elif tr.get("kernel_source_sha256_16") != kernel_source_hash():
+            traffic_note = "profiles/r02_assemble_traffic.json was captured on different kernel sources: not quoted"
     except Exception:
         pass
-    out_bytes = (ps.S_doubles + ps.g_doubles + ps.W_doubles + ps.z_doubles + ne) * 8 + ne * 60
+    out_bytes = (ps.S_doubles + ps.g_doubles + ps.W_doubles + ps.z_doubles + n_share) * 8 + n_share * 60
     line = {
         "metric": "condensed EHDG elements/sec (FP64)", "value": value, "unit": "elements/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "lattice_n": n, "mesh": kind, "order": order, "epsilon": eps, "beta": list(BETA),
-                   "bonus_int": 10, "elements_per_gpu": ne, "facets_per_gpu": mesh.nf, "enriched_path_elements": n_gen,
+                   "bonus_int": 10, "elements": ne, "facets": mesh.nf, "partition": "one mesh, facet rows split into N contiguous ranges; "
+                   "a rank computes the elements touching its range (one redundant ghost layer, no collective in the step)",
+                   "elements_per_rank": [int(t[0]) for t in shares], "nnz_per_rank": [int(t[1]) for t in shares],
+                   "enriched_path_elements_rank0": n_gen,
+                   "step": "alpha (a4) + blocks, rhs, condensation (a5-a7) + numeric CSR fill (a8) of the rank's share",
                    "l2_flush": "explicit 256 MiB write between steps" if need_flush else "step outputs (S,W) exceed L2",
-                   "elements_with_status_flags": status_bad},
-        "stage_ms": {"alpha": t_alpha / args.steps, "assemble_condense": t_asm / args.steps},
+                   "elements_with_status_flags_rank0": status_bad},
+        "stage_ms": {"alpha": t_alpha / args.steps, "assemble_condense": t_asm / args.steps, "csr_numeric": t_csr / args.steps},
+        "setup_ms_per_mesh": {"max_over_ranks": setup_ms_max, "rank0": setup_ms,
+                              "what": "marks, pruning, pattern of the own rows, element selection, plan (outside the step: once per mesh)",
+                              "stages_ms_rank0": {k: round(v, 3) for k, v in getattr(P, "part_timing", {}).items()}},
         "roofline": {"bound": "fp64", "kernel": f"fast_assemble_kernel<{order}>", "achieved": achieved_tf, "peak": fp64, "unit": "TFLOP/s",
-                     "frac": (achieved_tf / fp64) if achieved_tf else None, "traffic": traffic, "kernel_ms": asm_ms,
+                     "frac": (achieved_tf / fp64) if achieved_tf else None, "traffic": traffic, "traffic_note": traffic_note, "kernel_ms": asm_ms,
                      "peak_source": fp64_src, "flops_per_element": f_asm, "moment_rhs_fraction": moment_frac,
                      "note": "FP64-FMA-bound kernel (neither hbm nor tensor); flops = tensor algorithm actually executed, "
                              "no credit for the quadrature work it avoids",
                      "algorithmic_hbm_bytes_per_launch": int((ps.S_doubles + ps.g_doubles + ps.W_doubles + ps.z_doubles) * 8 + n_poly * 80),
                      "alpha_kernel": {"kernel": f"fast_alpha_kernel<{order}>", "kernel_ms": alpha_ms, "achieved": alpha_tf,
                                       "frac": (alpha_tf / fp64) if alpha_tf else None, "flops_per_element": f_alpha},
-                     "step": {"achieved": step_tf, "frac": step_tf / fp64, "flops_per_element": f_asm + f_alpha},
+                     "step_a4_a7": {"achieved": step_tf, "frac": step_tf / fp64, "flops_per_element": f_asm + f_alpha},
                      "quadrature_algorithm_flops_per_element": int(sizes.flops_quad_elem),
-                     "quadrature_equivalent_tflops": value / world * int(sizes.flops_quad_elem) / 1e12,
-                     "quadrature_equivalent_frac": value / world * int(sizes.flops_quad_elem) / 1e12 / fp64,
                      "hbm_gbs_of_outputs": out_bytes / (ms_step * 1e-3) / 1e9, "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src},
         "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "repetitions_ms_per_step": [round(t * 1e3, 3) for t in e2e_reps],
+                "what": "per step: pinned mesh arrays -> device, per-mesh set-up, the step, alpha table + status -> host (per rank at N > 1)",
                 "pipeline": "2 slots: the copy stream moves step i+1's mesh in and step i-1's alpha table + status out while step i computes"},
-        "gpu_launches": int(args.steps * (2 + (3 if n_gen else 0))),
+        "gpu_launches": int(args.steps * (3 + (3 if n_gen else 0))),
         "clocks": clocks.summary(),
     }
+    if replica_value is not None:
+        line["replicas_weak_value"] = replica_value
     for sv in solves:
-        sv["spmv_frac_of_hbm_peak"] = sv["spmv_gbs"] / hbm
+        sv["spmv_frac_of_hbm_peak"] = sv["spmv_gbs_actual"] / hbm
+        sv["spmv_frac_of_hbm_peak_csr_equivalent_bytes"] = sv["spmv_gbs_csr_equivalent"] / hbm
     if solves:
         line["solve"] = solves[0]
         if len(solves) > 1:
-            line["solve_enriched"] = solves[1]
+            line["solve_hdg"] = solves[1]
+    if e2e_solve is not None:
+        line["e2e_solve"] = e2e_solve
     if not args.no_cpu and world == 1:
         try:
             info = cpu_reference(args.workload, budget_s=15.0)
@@ -499,6 +590,31 @@ def main():
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_e2e_solve(dev, workload="ehdg_p3_eps1e-4_structured_100k"):
+    """BASELINE config 2 through the reference-facing class: host config in, error table out (mesh generation, upload, a1-a10)."""
+    import torch
+    from convectiondiffusionequation_b200 import boundary_layer, x, y
+    from convectiondiffusionequation_b200.convection_diffusion import Convection_Diffusion
+    n, kind, order, eps = WORKLOADS[workload]
+    p, q = boundary_layer(x, BETA[0], eps), boundary_layer(y, BETA[1], eps)
+    out = {"workload": workload}
+    for typ, enr in (("ehdg", True), ("hdg", False)):
+        cfg = {'order': [order], 'beta': BETA, 'mesh_size': [1.0 / n], 'epsilon': eps, 'exact': p * q, 'coeff': BETA[1] * p + BETA[0] * q,
+               'bonus_int': 10, 'theta': 1e-5, 'enrich_functions': [p, q] if enr else [],
+               'enrich_domain_ind': [lambda X, Y, h: X > 1 - h, lambda X, Y, h: Y > 1 - h] if enr else [], 'mesh_kind': kind,
+               'device': str(dev), 'raise_on_nonconvergence': False, 'quiet': True}
+        CT = Convection_Diffusion(cfg)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        res, _ = CT._solveEHDG()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        si = CT.solver_info[-1]
+        out[typ] = {"wall_s": dt, "elements": 2 * n * n, "elements_per_s": 2 * n * n / dt, "l2_error": float(res['Error'].iloc[-1]),
+                    "iters": si["iters"], "converged": si["converged"], "rel_residual": si["rel_residual"], "stages_s": si.get("stages_s")}
+    return out
 
 
 if __name__ == "__main__":

@@ -50,7 +50,7 @@ class GmresInfo(C.Structure):
                 ("use_strip_block", C.c_int32), ("strip_dofs", C.c_int32), ("strip_blocks", C.c_int32),
                 ("jacobi_sweeps", C.c_int32), ("use_line_block", C.c_int32), ("line_target_dofs", C.c_int32),
                 ("line_chains", C.c_int32), ("line_blocks", C.c_int32), ("line_max_block", C.c_int32),
-                ("setup_seconds", C.c_double), ("precond_bytes", C.c_double)]
+                ("setup_seconds", C.c_double), ("precond_bytes", C.c_double), ("rel_residual_unscaled", C.c_double), ("drop_tol", C.c_double)]
 
 
 # every symbol include/ehdg.h declares: name -> (restype, argtypes)
@@ -76,6 +76,7 @@ SYMBOLS = {
     "ehdg_csr_symbolic": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.POINTER(_P), _P]),
     "ehdg_csr_symbolic_part": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.c_int, C.c_int, C.POINTER(_P), _P]),
     "ehdg_csr_get_partition": (C.c_int, [_P, _P, _P]),
+    "ehdg_csr_get_extent": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ehdg_csr_set_lines": (C.c_int, [_P, _P, _P]),
     "ehdg_csr_auto_lines": (C.c_int, [_P, _P, C.POINTER(Mesh), C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     "ehdg_csr_lines": (_P, [_P]),

@@ -7,11 +7,15 @@ Same class name, method names, config keys, returned tables and printed line; th
   * `exact`, `coeff`, `enrich_functions` are LayerExpr objects (coefficients.py) instead of NGSolve
     CoefficientFunctions;
   * the direct PARDISO solve of the uncondensed system (:385-387) is replaced by static condensation
-    + block-Jacobi GMRES on the facet system (mathematically the same discrete solution);
+    + line-block-Jacobi DQGMRES / GMRES on the facet system (mathematically the same discrete solution); config keys
+    `solver` ('auto' | 'dqgmres' | 'gmres' | 'bicgstab'), `preconditioner` ('line' | 'facet'), `gmres_restart`, `gmres_rtol`,
+    `gmres_max_iters`, `raise_on_nonconvergence` (default True: an unconverged solve raises instead of filling 'Error');
   * no GUI: `Draw` / `input('')` (:398-399) are dropped; the instance gets its own config dict
     (the reference mutates a class-level dict, :28-33).
 """
 from __future__ import annotations
+
+import time
 
 import numpy as np
 import pandas as pd
@@ -41,6 +45,36 @@ class Convection_Diffusion():
         raise NotImplementedError("the EDG (interior-penalty) path of the reference (convection_diffusion.py:42-219) is the "
                                   "next row of the hot-path scope table (SURVEY.md 8f-1); only _solveEHDG is built")
 
+    @staticmethod
+    def _lap(pipe):
+        import torch
+        torch.cuda.synchronize(pipe.dev)
+        return time.perf_counter()
+
+    def _solve(self, pipe, cfg):
+        """Condensed facet system: CSR build, Krylov solve, back-solve.  The reference calls a direct solver and has no notion of
+        non-convergence; here an unconverged iteration is an ERROR (config 'raise_on_nonconvergence', default True) instead
+        of a silently wrong 'Error' column.  solver 'auto' (default): DQGMRES(8) on the line-block preconditioner, then
+        GMRES(60) on the same preconditioner if that did not reach the tolerance."""
+        solver = cfg.get('solver', 'auto')
+        rtol = cfg.get('gmres_rtol', 1e-10)
+        max_iters = cfg.get('gmres_max_iters', 20000)
+        precond = cfg.get('preconditioner', 'line')
+        attempts = [('dqgmres', cfg.get('gmres_restart', 8)), ('gmres', 60)] if solver == 'auto' else [(solver, cfg.get('gmres_restart', 60))]
+        pipe.csr_build()
+        for k, (method, restart) in enumerate(attempts):
+            pipe.gmres(restart=restart, max_iters=max_iters, rtol=rtol, method=method, precond=precond)
+            self._last_method = method
+            if pipe.gmres_info.converged:
+                break
+        gi = pipe.gmres_info
+        pipe.backsolve()
+        if not gi.converged and cfg.get('raise_on_nonconvergence', True):
+            raise RuntimeError(f"facet solve did not converge: {self._last_method}, {gi.iters} iterations, relative residual "
+                               f"{gi.rel_residual:.3e} > {rtol:.1e} (order {pipe.spec.order}, {pipe.mesh_host.ne} elements); "
+                               "set config['raise_on_nonconvergence'] = False to get the table anyway")
+        return gi
+
     '''Enriched (Hybrid) Discontinuous Galerkin Methods'''
 
     def _solveEHDG(self):
@@ -54,6 +88,7 @@ class Convection_Diffusion():
                 mesh = mesh_for_size(size, kind=cfg.get('mesh_kind', 'structured'))
                 spec = ProblemSpec(order=order, epsilon=cfg['epsilon'], beta=tuple(cfg['beta']), bonus_int=cfg['bonus_int'],
                                    coeff=cfg['coeff'], exact=cfg['exact'], enrich_functions=enrich, enrich_domain_ind=inds)
+                t_start = time.perf_counter()
                 pipe = EHDGPipeline(mesh, spec, device=cfg.get('device', 'cuda:0'))
                 type = 'ehdg' if len(enrich) > 0 else 'hdg'
                 pipe.setup(prune_threshold=1e-5)            # marking + pruning            (:240-244, :270-310)
@@ -63,14 +98,17 @@ class Convection_Diffusion():
                 frame = pd.DataFrame({'alpha': alp, 'type': type, 'mesh_size': size, 'order': order}, columns=self.col)
                 self.alphas = frame if len(self.alphas) == 0 else pd.concat([self.alphas, frame], ignore_index=True)
                 pipe.assemble_condense()                    # forms + assembly + rhs       (:357-383)
-                pipe.solve(restart=cfg.get('gmres_restart', 60), max_iters=cfg.get('gmres_max_iters', 20000),
-                           rtol=cfg.get('gmres_rtol', 1e-12), method=cfg.get('solver', 'gmres'))   # replaces Inverse(..., "pardiso") (:385-387)
+                t_asm = self._lap(pipe)
+                gi = self._solve(pipe, cfg)                 # replaces Inverse(..., "pardiso") (:385-387)
+                t_sol = self._lap(pipe)
                 error, _ = pipe.errors()                    # recombination + L2 error     (:389-394)
                 ndof = pipe.ndof()
-                gi = pipe.gmres_info
                 self.solver_info.append(dict(order=order, mesh_size=size, type=type, iters=int(gi.iters), converged=bool(gi.converged),
-                                             rel_residual=float(gi.rel_residual), dropped_dofs=int(gi.dropped_dofs)))
+                                             rel_residual=float(gi.rel_residual), dropped_dofs=int(gi.dropped_dofs),
+                                             method=self._last_method, precond=cfg.get('preconditioner', 'line'),
+                                             stages_s=dict(mesh_setup_alpha_assemble=t_asm - t_start, csr_solve_backsolve=t_sol - t_asm)))
                 self.results.loc[len(self.results)] = [order, ndof, size, error, cfg['bonus_int'], type]
-                print('order:', order, 'DOFs:', ndof, 'mesh:', size, "err:", error, 'type:', type)
+                if not cfg.get('quiet', False):
+                    print('order:', order, 'DOFs:', ndof, 'mesh:', size, "err:", error, 'type:', type)
                 self.last_pipeline = pipe
         return self.results, self.alphas

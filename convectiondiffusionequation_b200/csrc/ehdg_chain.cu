@@ -30,7 +30,7 @@ constexpr int CHAIN_MAXB = 64;       // largest block (two rows per lane in the 
 __global__ void chain_pos_kernel(int nd, const int32_t* __restrict__ dof_rows, const int32_t* __restrict__ dof_blk,
                                  const ChainBlock* __restrict__ blocks, int32_t* __restrict__ sblk, int32_t* __restrict__ sloc) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nd) return;
+    if (s >= nd || dof_rows[s] < 0) return;
     const int b = dof_blk[s];
     sblk[dof_rows[s]] = b;
     sloc[dof_rows[s]] = s - blocks[b].s0;
@@ -44,7 +44,7 @@ __global__ void chain_extract_kernel(int nd, const int32_t* __restrict__ dof_row
                                      const double* __restrict__ vals, const int32_t* __restrict__ sblk, const int32_t* __restrict__ sloc,
                                      double* __restrict__ DH, double* __restrict__ G, int* __restrict__ skipped) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nd) return;
+    if (s >= nd || dof_rows[s] < 0) return;
     const int b = dof_blk[s], r = dof_rows[s];
     const ChainBlock B = blocks[b];
     const int i = s - B.s0, n = B.n, ch = blk_chain[b];
@@ -66,12 +66,13 @@ __global__ void chain_extract_kernel(int nd, const int32_t* __restrict__ dof_row
 // get zero rows / columns), G holds G_b = L_b Delta_{b-1}^-1.
 __global__ void __launch_bounds__(128)
 chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __restrict__ blocks, const int32_t* __restrict__ dof_rows,
-                    const uint8_t* __restrict__ rowdrop, double* DH, double* G, int* dropped) {
+                    uint8_t* __restrict__ rowdrop, double drop_tol, double* DH, double* G, int* dropped) {
     extern __shared__ double sm[];
     double* Aw = sm;                                   // n x 2n augmented [Delta | I], row major
     __shared__ int s_piv;
     __shared__ double s_best, s_scale;
     __shared__ unsigned char s_drop[CHAIN_MAXB];
+    __shared__ double s_dsc[CHAIN_MAXB];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int b0 = chain_ptr[blockIdx.x], b1 = chain_ptr[blockIdx.x + 1];
     for (int b = b0; b < b1; ++b) {
@@ -80,6 +81,15 @@ chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __r
         double* Db = DH + B.offDH;                     // column major
         const int np_ = b > b0 ? blocks[b - 1].n : 0;
         double* Uprev = b > b0 ? DH + blocks[b - 1].offDH + (int64_t)np_ * np_ : nullptr;   // np_ x n, still the original U_{b-1}
+        // symmetric scaling by the ORIGINAL diagonal, d_i = |D_b[i][i]|^-1/2: the elimination then runs on a matrix whose
+        // entries are relative to each dof's own size, and a pivot is the share of a dof that the dofs eliminated before it
+        // (earlier blocks of the chain and earlier pivots of this block) do not explain -- whatever the row scales
+        // (penalties of marked elements are 1e5 .. 1e10 times those of their neighbours)
+        if (tid < n) {
+            const double dg = fabs(Db[tid * n + tid]);
+            s_dsc[tid] = dg > 0.0 ? rsqrt(dg) : 1.0;
+        }
+        __syncthreads();
         // Delta_b = D_b - G_b U_{b-1}   (G_b was completed at the end of step b-1)
         if (b > b0) {
             const double* Gb = G + B.offG;             // n x np_
@@ -87,10 +97,10 @@ chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __r
                 const int i = idx % n, j = idx / n;
                 double acc = Db[idx];
                 for (int k = 0; k < np_; ++k) acc -= Gb[k * n + i] * Uprev[j * np_ + k];
-                Aw[i * 2 * n + j] = acc;
+                Aw[i * 2 * n + j] = acc * s_dsc[i] * s_dsc[j];
             }
         } else {
-            for (int idx = tid; idx < n * n; idx += nt) Aw[(idx % n) * 2 * n + idx / n] = Db[idx];
+            for (int idx = tid; idx < n * n; idx += nt) Aw[(idx % n) * 2 * n + idx / n] = Db[idx] * s_dsc[idx % n] * s_dsc[idx / n];
         }
         for (int idx = tid; idx < n * n; idx += nt) Aw[(idx / n) * 2 * n + n + idx % n] = (idx / n == idx % n) ? 1.0 : 0.0;
         if (tid < n) s_drop[tid] = rowdrop ? rowdrop[dof_rows[B.s0 + tid]] : 0;
@@ -114,13 +124,9 @@ chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __r
             if (s_drop[i] || s_drop[j]) Aw[i * 2 * n + j] = (i == j) ? 1.0 : 0.0;
         }
         __syncthreads();
-        if (tid == 0) {
-            double mx = 0.0;
-            for (int i = 0; i < n; ++i) mx = fmax(mx, fabs(Aw[i * 2 * n + i]));
-            s_scale = mx;
-        }
+        if (tid == 0) s_scale = 1.0;           // the scaled matrix has a unit original diagonal
         __syncthreads();
-        // Gauss-Jordan with partial pivoting; a pivot below 1e-12 of the largest diagonal entry = dependent dof
+        // Gauss-Jordan with partial pivoting; a pivot below drop_tol of the largest diagonal entry = dependent dof
         for (int k = 0; k < n; ++k) {
             if (tid < 32) {
                 int piv = -1;
@@ -138,7 +144,7 @@ chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __r
                 if (tid == 0) { s_piv = piv; s_best = best; }
             }
             __syncthreads();
-            if (!(s_best > 1e-12 * s_scale)) {
+            if (!(s_best > drop_tol * s_scale)) {
                 // decouple dof k: column k := e_k, row k := e_k, right part row k := 0
                 for (int i = tid; i < n; i += nt) Aw[i * 2 * n + k] = (i == k) ? 1.0 : 0.0;
                 __syncthreads();
@@ -170,10 +176,11 @@ chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __r
                 if (i != k) Aw[i * 2 * n + k] = 0.0;
             __syncthreads();
         }
-        // Delta_b^-1 with dropped rows / columns zeroed, column major
+        // Delta_b^-1 with dropped rows / columns zeroed, column major; the dropped dofs are reported per row
+        if (rowdrop && tid < n && s_drop[tid]) rowdrop[dof_rows[B.s0 + tid]] = 1;
         for (int idx = tid; idx < n * n; idx += nt) {
             const int i = idx % n, j = idx / n;
-            Db[idx] = (s_drop[i] || s_drop[j]) ? 0.0 : Aw[i * 2 * n + n + j];
+            Db[idx] = (s_drop[i] || s_drop[j]) ? 0.0 : Aw[i * 2 * n + n + j] * s_dsc[i] * s_dsc[j];
         }
         __syncthreads();
         if (b + 1 < b1) {
@@ -220,11 +227,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
+// vp[s] = v[dof_rows[s] - row0] (0 in padding slots): the chains read their right-hand side in chain order
+__global__ void chain_gather_kernel(int nd, const int32_t* __restrict__ dof_rows, const double* __restrict__ v, int64_t row0,
+                                    const double* __restrict__ vscale, double* __restrict__ vp) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nd) return;
+    const int r = dof_rows[s];
+    vp[s] = r >= 0 ? (vscale ? v[r - row0] * vscale[r - row0] : v[r - row0]) : 0.0;
+}
+__global__ void chain_scatter_kernel(int nd, const int32_t* __restrict__ dof_rows, const double* __restrict__ xp, int64_t row0,
+                                     double* __restrict__ t) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nd) return;
+    const int r = dof_rows[s];
+    if (r >= 0) t[r - row0] = xp[s];
+}
+
+__device__ __forceinline__ int pad2i(int x) { return x < 2 ? 2 : ((x + 1) & ~1); }
+
+// One warp per chain.  Everything the sequential recurrence touches is either in registers or arrives through the TMA ring:
+// the only per-block metadata is the block size (one byte, fetched 32 blocks at a time and 32 steps ahead); positions and
+// factor offsets are running sums of the sizes, the right-hand side comes in chain order with the factor block (second bulk
+// copy on the stage's mbarrier), and the forward results the backward sweep needs are read two steps ahead.
 template <int STAGES>
 __global__ void __launch_bounds__(32)
 chain_sweep_kernel(int nchains, const int32_t* __restrict__ chain_ptr, const ChainBlock* __restrict__ blocks,
-                   const int32_t* __restrict__ dof_rows, const double* __restrict__ G, const double* __restrict__ DH,
-                   const double* __restrict__ v, double* __restrict__ c, double* __restrict__ t, int64_t row0, int stage_doubles) {
+                   const uint8_t* __restrict__ nsz, const double* __restrict__ G, const double* __restrict__ DH,
+                   const double* __restrict__ vp, double* __restrict__ c, double* __restrict__ xp, int stage_doubles) {
     extern __shared__ __align__(16) double ring[];              // STAGES x stage_doubles
     __shared__ __align__(8) uint64_t bar[STAGES];
     const int chain = blockIdx.x, lane = threadIdx.x;
@@ -236,44 +265,50 @@ chain_sweep_kernel(int nchains, const int32_t* __restrict__ chain_ptr, const Cha
         for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const ChainBlock first = blocks[b0], last = blocks[b1 - 1];
+    const uint8_t* sz = nsz + b0;
+    // sizes of the blocks [base, base + 64) of this chain in two registers per lane
+    int base = 0;
+    int ch0 = lane < nblk ? sz[lane] : 0, ch1 = 32 + lane < nblk ? sz[32 + lane] : 0;
+    auto size_of = [&](int idx) -> int {          // idx uniform, base <= idx < base + 64 (or outside the chain: 0)
+        if (idx < 0 || idx >= nblk) return 0;
+        const int o = idx - base;
+        return __shfl_sync(0xffffffffu, o < 32 ? ch0 : ch1, o & 31);
+    };
     __syncwarp();
-    // G region of block b: [offG[b], offG[b+1]); DH region: [offDH[b], offDH[b+1])  (blocks[] has a sentinel entry)
-    auto issue_fwd = [&](int k) {          // k-th block of the chain into stage k % STAGES
-        const int b = b0 + k;
-        const uint32_t bytes = (uint32_t)((blocks[b + 1].offG - blocks[b].offG) * 8);
-        uint64_t* br = &bar[k % STAGES];
-        mbar_expect_tx(br, bytes);
-        bulk_g2s(ring + (size_t)(k % STAGES) * stage_doubles, G + blocks[b].offG, bytes, br);
-    };
-    auto issue_bwd = [&](int k, int it) {  // k-th block of the chain, it = position in the ring sequence
-        const int b = b0 + k;
-        const uint32_t bytes = (uint32_t)((blocks[b + 1].offDH - blocks[b].offDH) * 8);
-        uint64_t* br = &bar[it % STAGES];
-        mbar_expect_tx(br, bytes);
-        bulk_g2s(ring + (size_t)(it % STAGES) * stage_doubles, DH + blocks[b].offDH, bytes, br);
-    };
-    if (lane == 0)
-        for (int k = 0; k < STAGES && k < nblk; ++k) issue_fwd(k);
-    // ---- forward: c_b = v_b - G_b c_{b-1}
-    double cp0 = 0.0, cp1 = 0.0;           // c of the previous block: rows lane, lane + 32
-    int np_ = 0;
-    ChainBlock B = blocks[b0];
-    double v0 = lane < B.n ? v[dof_rows[B.s0 + lane] - row0] : 0.0;
-    double v1 = lane + 32 < B.n ? v[dof_rows[B.s0 + lane + 32] - row0] : 0.0;
-    for (int k = 0; k < nblk; ++k) {
-        const int n = B.n, s0 = B.s0;
-        // one step ahead of the recurrence: metadata and right-hand side of the next block
-        ChainBlock Bn = B;
-        double vn0 = 0.0, vn1 = 0.0;
-        if (k + 1 < nblk) {
-            Bn = blocks[b0 + k + 1];
-            vn0 = lane < Bn.n ? v[dof_rows[Bn.s0 + lane] - row0] : 0.0;
-            vn1 = lane + 32 < Bn.n ? v[dof_rows[Bn.s0 + lane + 32] - row0] : 0.0;
+    // ---- forward: c_b = v_b - G_b c_{b-1}.  Stage k % STAGES holds [G_b | v_b].
+    int64_t iss_offG = first.offG;                // issue pointer: next block to request
+    int iss_k = 0, iss_s0 = first.s0, iss_np = 0;
+    auto issue_fwd = [&]() {
+        const int n = size_of(iss_k);
+        const int gd = pad2i(n * iss_np), vd = pad2i(n);
+        if (lane == 0) {
+            uint64_t* br = &bar[iss_k % STAGES];
+            double* dst = ring + (size_t)(iss_k % STAGES) * stage_doubles;
+            mbar_expect_tx(br, (uint32_t)((gd + vd) * 8));
+            bulk_g2s(dst, G + iss_offG, (uint32_t)(gd * 8), br);
+            bulk_g2s(dst + gd, vp + iss_s0, (uint32_t)(vd * 8), br);
         }
+        iss_offG += gd;
+        iss_s0 += vd;
+        iss_np = n;
+        ++iss_k;
+    };
+    for (int q = 0; q < STAGES && q < nblk; ++q) issue_fwd();
+    double cp0 = 0.0, cp1 = 0.0;           // c of the previous block: rows lane, lane + 32
+    int np_ = 0, s0 = first.s0;
+    for (int k = 0; k < nblk; ++k) {
+        if (k - base == 32) {              // slide the size window: the new chunk is first used 32 - STAGES steps from now
+            base += 32;
+            ch0 = ch1;
+            ch1 = base + 32 + lane < nblk ? sz[base + 32 + lane] : 0;
+        }
+        const int n = size_of(k);
+        const int gd = pad2i(n * np_);
         const double* Gs = ring + (size_t)(k % STAGES) * stage_doubles;
-        mbar_wait(&bar[k % STAGES], (k / STAGES) & 1);
-        double a0 = v0, a1 = v1, e0 = 0.0, e1 = 0.0;
         const bool r0 = lane < n, r1 = lane + 32 < n;
+        mbar_wait(&bar[k % STAGES], (k / STAGES) & 1);
+        double a0 = r0 ? Gs[gd + lane] : 0.0, a1 = r1 ? Gs[gd + lane + 32] : 0.0, e0 = 0.0, e1 = 0.0;
         int j = 0;
         for (; j + 1 < np_; j += 2) {
             const double x0 = j < 32 ? __shfl_sync(0xffffffffu, cp0, j) : __shfl_sync(0xffffffffu, cp1, j - 32);
@@ -289,38 +324,62 @@ chain_sweep_kernel(int nchains, const int32_t* __restrict__ chain_ptr, const Cha
         a0 += e0;
         a1 += e1;
         __syncwarp();                       // every lane is done with this stage
-        if (lane == 0 && k + STAGES < nblk) issue_fwd(k + STAGES);
+        if (iss_k < nblk) issue_fwd();
         if (r0) c[s0 + lane] = a0;
         if (r1) c[s0 + lane + 32] = a1;
         cp0 = r0 ? a0 : 0.0;
         cp1 = r1 ? a1 : 0.0;
         np_ = n;
-        B = Bn;
-        v0 = vn0;
-        v1 = vn1;
+        s0 += pad2i(n);
     }
-    // ---- backward: x_b = Dinv_b c_b - H_b x_{b+1}; the ring sequence continues at it = nblk
-    if (lane == 0)
-        for (int q = 0; q < STAGES && q < nblk; ++q) issue_bwd(nblk - 1 - q, nblk + q);
+    // ---- backward: x_b = Dinv_b c_b - H_b x_{b+1}; the ring sequence continues at it = nblk.  Stage holds [Dinv_b | H_b].
+    // size window for the way back: blocks [base, base + 64) with base the largest multiple of 32 <= nblk - 1, minus 32
+    base = ((nblk - 1) / 32) * 32 - 32;
+    ch0 = (base >= 0 && base + lane < nblk) ? sz[base + lane] : 0;
+    ch1 = base + 32 + lane < nblk ? sz[base + 32 + lane] : 0;
+    __syncwarp();
+    int64_t iss_offDH = last.offDH;
+    int iss_q = 0, iss_nn = 0;             // issue pointer walks down: block nblk - 1 - iss_q
+    auto issue_bwd = [&]() {
+        const int kb = nblk - 1 - iss_q, it = nblk + iss_q;
+        const int n = size_of(kb);
+        const int dd = pad2i(n * n + n * iss_nn);
+        if (iss_q > 0) iss_offDH -= dd;      // region of block kb ends where the one above starts
+        if (lane == 0) {
+            uint64_t* br = &bar[it % STAGES];
+            mbar_expect_tx(br, (uint32_t)(dd * 8));
+            bulk_g2s(ring + (size_t)(it % STAGES) * stage_doubles, DH + iss_offDH, (uint32_t)(dd * 8), br);
+        }
+        iss_nn = n;
+        ++iss_q;
+    };
+    for (int q = 0; q < STAGES && q < nblk; ++q) issue_bwd();
     double xn0 = 0.0, xn1 = 0.0;           // x of the block after this one
     int nn = 0;
-    B = blocks[b1 - 1];
-    double c0 = cp0, c1 = cp1;              // c of the last block is still in registers
+    s0 = last.s0;
+    // c two steps ahead: cA = block k - 1, cB = block k - 2 (same lanes wrote them in the forward sweep)
+    double c0 = cp0, c1 = cp1;             // c of the last block is still in registers
+    int nA = size_of(nblk - 2), nB = size_of(nblk - 3);
+    int sA = s0 - pad2i(nA), sB = sA - pad2i(nB);
+    double cA0 = lane < nA ? c[sA + lane] : 0.0, cA1 = lane + 32 < nA ? c[sA + lane + 32] : 0.0;
+    double cB0 = lane < nB ? c[sB + lane] : 0.0, cB1 = lane + 32 < nB ? c[sB + lane + 32] : 0.0;
     for (int q = 0; q < nblk; ++q) {
         const int k = nblk - 1 - q, it = nblk + q;
-        const int n = B.n, s0 = B.s0;
-        ChainBlock Bn = B;
-        double cn0 = 0.0, cn1 = 0.0;
-        if (k > 0) {
-            Bn = blocks[b0 + k - 1];
-            cn0 = lane < Bn.n ? c[Bn.s0 + lane] : 0.0;
-            cn1 = lane + 32 < Bn.n ? c[Bn.s0 + lane + 32] : 0.0;
+        if (k < base + 32 && base >= 0) {  // slide the window down as soon as block k sits in the lower chunk
+            base -= 32;
+            ch1 = ch0;
+            ch0 = (base >= 0 && base + lane < nblk) ? sz[base + lane] : 0;
         }
+        const int n = size_of(k);
+        // request c of block k - 3 (needed three steps from now as cB -> cA -> c)
+        const int nC = size_of(k - 3);
+        const int sC = sB - pad2i(nC);
+        const double cC0 = lane < nC ? c[sC + lane] : 0.0, cC1 = lane + 32 < nC ? c[sC + lane + 32] : 0.0;
         const double* Ds = ring + (size_t)(it % STAGES) * stage_doubles;
         const double* Hs = Ds + (size_t)n * n;
+        const bool r0 = lane < n, r1 = lane + 32 < n;
         mbar_wait(&bar[it % STAGES], (it / STAGES) & 1);
         double a0 = 0.0, a1 = 0.0, e0 = 0.0, e1 = 0.0;
-        const bool r0 = lane < n, r1 = lane + 32 < n;
         for (int j = 0; j < n; ++j) {
             const double x0 = j < 32 ? __shfl_sync(0xffffffffu, c0, j) : __shfl_sync(0xffffffffu, c1, j - 32);
             if (r0) a0 += Ds[j * n + lane] * x0;
@@ -334,15 +393,18 @@ chain_sweep_kernel(int nchains, const int32_t* __restrict__ chain_ptr, const Cha
         a0 += e0;
         a1 += e1;
         __syncwarp();
-        if (lane == 0 && q + STAGES < nblk) issue_bwd(nblk - 1 - (q + STAGES), it + STAGES);
-        if (r0) t[dof_rows[s0 + lane] - row0] = a0;
-        if (r1) t[dof_rows[s0 + lane + 32] - row0] = a1;
+        if (iss_q < nblk) issue_bwd();
+        if (r0) xp[s0 + lane] = a0;
+        if (r1) xp[s0 + lane + 32] = a1;
         xn0 = r0 ? a0 : 0.0;
         xn1 = r1 ? a1 : 0.0;
         nn = n;
-        B = Bn;
-        c0 = cn0;
-        c1 = cn1;
+        s0 = sA;
+        sA = sB;
+        sB = sC;
+        c0 = cA0; c1 = cA1;
+        cA0 = cB0; cA1 = cB1;
+        cB0 = cC0; cB1 = cC1;
     }
 }
 
@@ -357,8 +419,8 @@ struct DevFree {
 };
 }  // namespace
 
-int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const int32_t* line_dev, int use_strip, int target_dofs,
-                cudaStream_t st, ChainSolver** out) {
+int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t* line_dev, int use_strip, int target_dofs,
+                double drop_tol, cudaStream_t st, ChainSolver** out) {
     *out = nullptr;
     const int nf = A->nf;
     const bool strip = use_strip && A->strip != nullptr;
@@ -409,6 +471,7 @@ int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const i
     std::vector<ChainBlock> blocks;
     std::vector<int32_t> chain_ptr{0}, dof_rows, dof_blk, blk_chain;
     int nmax = 0;
+    int64_t n_real = 0;
     auto bfs = [&](int seed, int ch, int lev0, std::vector<int32_t>& visit) -> int {      // returns the last level used
         visit.clear();
         level[seed] = lev0;
@@ -467,6 +530,8 @@ int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const i
                 for (int d = row_start[u]; d < row_start[u + 1]; ++d) { dof_rows.push_back(d); dof_blk.push_back(b); }
             }
             B.n = (int32_t)dof_rows.size() - B.s0;
+            n_real += B.n;
+            while ((int)dof_rows.size() - B.s0 < 2 || ((dof_rows.size() - (size_t)B.s0) & 1)) { dof_rows.push_back(-1); dof_blk.push_back(b); }   // even, 16-byte slots
             nmax = std::max(nmax, (int)B.n);
             blocks.push_back(B);
             blk_chain.push_back(ch);
@@ -489,7 +554,7 @@ int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const i
         const int64_t g = pad2(n * np_), dh = pad2(n * n + n * nn);
         tG += g;
         tDH += dh;
-        stage = std::max(stage, std::max(g, dh));
+        stage = std::max(stage, std::max(g + pad2(n), dh));      // forward stage: [G_b | v_b], backward: [Dinv_b | H_b]
     }
     ChainBlock sentinel{};
     sentinel.s0 = nd;
@@ -506,7 +571,7 @@ int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const i
     S->stage_bytes = (int)(stage * 8);
     {
         const int64_t own_rows = A->windowed ? A->row_hi - A->row_lo : A->n_rows;
-        S->all_rows = nd == own_rows ? 1 : 0;
+        S->all_rows = n_real == own_rows ? 1 : 0;
     }
     auto fail = [&](int rc) { chain_free(S); return rc; };
     auto up = [&](auto** dptr, const auto& h) -> int {
@@ -521,13 +586,20 @@ int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const i
     if ((rc = up(&S->dof_rows, dof_rows))) return fail(rc);
     if ((rc = up(&S->dof_blk, dof_blk))) return fail(rc);
     if ((rc = up(&S->blk_chain, blk_chain))) return fail(rc);
+    {
+        std::vector<uint8_t> nsz((size_t)nblk);
+        for (int b = 0; b < nblk; ++b) nsz[b] = (uint8_t)blocks[b].n;
+        if ((rc = up(&S->nsz, nsz))) return fail(rc);
+    }
     auto dev_alloc = [&]() -> int {
         EHDG_CUDA(cudaMalloc(&S->sblk, sizeof(int32_t) * (size_t)A->n_rows));
         EHDG_CUDA(cudaMalloc(&S->sloc, sizeof(int32_t) * (size_t)A->n_rows));
         EHDG_CUDA(cudaMemsetAsync(S->sblk, 0xff, sizeof(int32_t) * (size_t)A->n_rows, st));
         EHDG_CUDA(cudaMalloc(&S->G, sizeof(double) * (size_t)tG));
         EHDG_CUDA(cudaMalloc(&S->DH, sizeof(double) * (size_t)tDH));
-        EHDG_CUDA(cudaMalloc(&S->c, sizeof(double) * (size_t)nd));
+        EHDG_CUDA(cudaMalloc(&S->c, sizeof(double) * 3 * (size_t)nd));
+        S->vp = S->c + nd;
+        S->xp = S->c + 2 * (size_t)nd;
         EHDG_CUDA(cudaMemsetAsync(S->G, 0, sizeof(double) * (size_t)tG, st));
         EHDG_CUDA(cudaMemsetAsync(S->DH, 0, sizeof(double) * (size_t)tDH, st));
         return EHDG_OK;
@@ -544,7 +616,7 @@ int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const i
         EHDG_LAUNCH_CHECK();
         const int smem = (2 * nmax * nmax + nmax * nmax) * 8;      // augmented matrix + scratch
         EHDG_CUDA(cudaFuncSetAttribute(chain_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        chain_factor_kernel<<<nchains, 128, smem, st>>>(S->chain_ptr, S->blocks, S->dof_rows, rowdrop, S->DH, S->G, d_flags + 1);
+        chain_factor_kernel<<<nchains, 128, smem, st>>>(S->chain_ptr, S->blocks, S->dof_rows, rowdrop, drop_tol, S->DH, S->G, d_flags + 1);
         EHDG_LAUNCH_CHECK();
         int flags[2] = {0, 0};
         EHDG_CUDA(cudaMemcpyAsync(flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -564,10 +636,12 @@ int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const i
     return EHDG_OK;
 }
 
-int chain_apply(const ChainSolver* S, const double* v, double* t, int64_t row0, cudaStream_t st) {
+int chain_apply(const ChainSolver* S, const double* v, double* t, int64_t row0, cudaStream_t st, const double* vscale) {
     if (!S) return EHDG_OK;
     const int sd = S->stage_bytes / 8;
     const size_t smem = (size_t)S->stages * S->stage_bytes;
+    const int nd = S->n_dofs;
+    chain_gather_kernel<<<(nd + 255) / 256, 256, 0, st>>>(nd, S->dof_rows, v, row0, vscale, S->vp);
 #define EHDG_SWEEP(ST)                                                                                                          \
     do {                                                                                                                        \
         static size_t set_##ST = 0;                                                                                             \
@@ -575,13 +649,14 @@ int chain_apply(const ChainSolver* S, const double* v, double* t, int64_t row0, 
             EHDG_CUDA(cudaFuncSetAttribute(chain_sweep_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
             set_##ST = smem;                                                                                                    \
         }                                                                                                                       \
-        chain_sweep_kernel<ST><<<S->n_chains, 32, smem, st>>>(S->n_chains, S->chain_ptr, S->blocks, S->dof_rows, S->G, S->DH, v, \
-                                                              S->c, t, row0, sd);                                               \
+        chain_sweep_kernel<ST><<<S->n_chains, 32, smem, st>>>(S->n_chains, S->chain_ptr, S->blocks, S->nsz, S->G, S->DH, S->vp,  \
+                                                              S->c, S->xp, sd);                                                 \
     } while (0)
     if (S->stages == 8) EHDG_SWEEP(8);
     else if (S->stages == 4) EHDG_SWEEP(4);
     else EHDG_SWEEP(2);
 #undef EHDG_SWEEP
+    chain_scatter_kernel<<<(nd + 255) / 256, 256, 0, st>>>(nd, S->dof_rows, S->xp, row0, t);
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -597,7 +672,7 @@ void chain_free(ChainSolver* S) {
     cudaFree(S->sloc);
     cudaFree(S->G);
     cudaFree(S->DH);
-    cudaFree(S->U0);
+    cudaFree(S->nsz);
     cudaFree(S->c);
     delete S;
 }

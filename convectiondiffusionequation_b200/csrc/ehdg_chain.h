@@ -17,7 +17,7 @@ struct ChainBlock {
 };
 
 struct ChainSolver {
-    int n_dofs = 0, n_blocks = 0, n_chains = 0, dropped = 0, nmax = 0;
+    int n_dofs = 0 /* chain positions incl. padding to even block sizes */, n_blocks = 0, n_chains = 0, dropped = 0, nmax = 0;
     int all_rows = 0;              // every row of the (rank's) system lies in a chain
     int64_t n_rows = 0;
     int64_t factor_bytes = 0;      // bytes of G + DH (what one application streams)
@@ -25,17 +25,20 @@ struct ChainSolver {
     int32_t *chain_ptr = nullptr;  // [n_chains+1] block range of every chain
     ChainBlock* blocks = nullptr;  // [n_blocks+1]
     int32_t *dof_rows = nullptr, *dof_blk = nullptr, *sblk = nullptr, *sloc = nullptr, *blk_chain = nullptr;
-    double *G = nullptr, *DH = nullptr, *U0 = nullptr, *c = nullptr;
+    uint8_t* nsz = nullptr;        // [n_blocks] dofs of every block (the only metadata the sweep reads per block)
+    double *G = nullptr, *DH = nullptr, *c = nullptr, *vp = nullptr, *xp = nullptr;   // vp, xp: vectors in chain order (inside c's allocation)
 };
 
 // Chains of facets: facet f belongs to chain line[f] (host array of nf ints; < 0: the facet forms a chain of its own);
 // strip facets (A->strip) form one extra chain when use_strip != 0.  line == nullptr: only the strip chain.
 // Only facets inside the matrix window [f_lo, f_hi) take part.  vals: the ORIGINAL matrix values (before any fold);
-// rowdrop u8[n_rows] (optional): dofs found dependent inside their facet block.  *out stays null when there is no chain.
-int chain_setup(ehdg_csr* A, const double* vals, const uint8_t* rowdrop, const int32_t* line_dev, int use_strip, int target_dofs,
-                cudaStream_t st, ChainSolver** out);
-// t[chain rows] = M_chain^-1 v[chain rows]   (other entries of t untouched); v, t indexed from row `row0`
-int chain_apply(const ChainSolver* S, const double* v, double* t, int64_t row0, cudaStream_t st);
+// rowdrop u8[n_rows] (optional, in / out): dofs found dependent inside their facet block on entry; the dofs whose pivot in
+// the chain factorisation falls below drop_tol of their block's largest diagonal entry are added.  *out stays null when there
+// is no chain.
+int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t* line_dev, int use_strip, int target_dofs,
+                double drop_tol, cudaStream_t st, ChainSolver** out);
+// t[chain rows] = M_chain^-1 (vscale .* v)[chain rows]   (other entries of t untouched); v, vscale, t indexed from row `row0`
+int chain_apply(const ChainSolver* S, const double* v, double* t, int64_t row0, cudaStream_t st, const double* vscale = nullptr);
 void chain_free(ChainSolver* S);
 
 }  // namespace ehdg

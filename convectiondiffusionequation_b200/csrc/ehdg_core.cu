@@ -244,6 +244,14 @@ int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out) {
     c->pb = make_problem(*prob);
     EHDG_CUDA(cudaGetDevice(&c->device));
     EHDG_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    {
+        // patterns and solver workspaces come from the stream-ordered pool: freed blocks stay cached in it, so a rebuilt
+        // pattern / a second solve does not pay cudaMalloc again (milliseconds per call at these sizes)
+        cudaMemPool_t pool;
+        EHDG_CUDA(cudaDeviceGetDefaultMemPool(&pool, c->device));
+        uint64_t keep = ~(uint64_t)0;
+        EHDG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     int rc;
     if ((rc = upload_rules(2 * c->pb.p + c->pb.bonus, c->rb))) return rc;
     if ((rc = upload_rules(2 * c->pb.p, c->r0))) return rc;

@@ -102,6 +102,8 @@ struct ehdg_csr {
     int windowed = 0;
     int32_t f_lo = 0, f_hi = 0;
     int64_t row_lo = 0, row_hi = 0;
+    int64_t col_lo = 0, col_hi = 0;    // column range the own rows reference (SpMV halo extent)
+    cudaStream_t stream = nullptr;     // stream of the pattern's stream-ordered allocations
     int nranks = 1;
     std::vector<int64_t> part_rows;    // [nranks+1] first row of every rank
     std::vector<int32_t> part_facets;  // [nranks+1] first facet of every rank

@@ -175,7 +175,7 @@ __global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int
 template <int TPR>
 __global__ void __launch_bounds__(256)
 spmv_kernel(int row0, int n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-            const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+            const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ rscale) {
     // rows [row0, n_rows); y is indexed by the global row
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = row0 + (int)(gt / TPR);
@@ -187,7 +187,7 @@ spmv_kernel(int row0, int n_rows, const int64_t* __restrict__ rowptr, const int3
     }
 #pragma unroll
     for (int d = TPR / 2; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d, TPR);
-    if (r < n_rows && lane == 0) y[r] = acc;
+    if (r < n_rows && lane == 0) y[r] = rscale ? acc * rscale[r] : acc;
 }
 
 // Facet-block SpMV.  All rows of a facet share one column set (the dofs of its <= 5 neighbour facets, ascending), and
@@ -202,7 +202,8 @@ template <int NBM, int CHUNKS, int LPF>
 __global__ void __launch_bounds__(256)
 spmv_facet_kernel(int f0, int nf, int row0, int row1, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
                   const int32_t* __restrict__ colind, const int32_t* __restrict__ nbr_len, const double* __restrict__ vals,
-                  const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ x_own, int own_lo, int own_hi) {
+                  const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ x_own, int own_lo, int own_hi,
+                  const double* __restrict__ rscale) {
     // x_own (distributed solve): the rank's own rows [own_lo, own_hi) are read from the Krylov vector itself, the halo from
     // the full-length buffer x -- no copy of the own rows into that buffer per product
     static_assert(LPF == 32 || CHUNKS == 1, "column chunks only with a whole warp per facet");
@@ -259,7 +260,8 @@ spmv_facet_kernel(int f0, int nf, int row0, int row1, const int32_t* __restrict_
 #pragma unroll
     for (; d >= 1; d >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
     constexpr int LOWMASK = (LPF / NPAD) - 1;              // lanes with these bits clear hold one row total each
-    if (act && (lane & LOWMASK) == 0 && row < rows && r0 + row >= row0 && r0 + row < row1) y[r0 + row] = v[0];
+    if (act && (lane & LOWMASK) == 0 && row < rows && r0 + row >= row0 && r0 + row < row1)
+        y[r0 + row] = rscale ? v[0] * rscale[r0 + row] : v[0];
 }
 
 static bool spmv_use_csr_kernel() {
@@ -268,7 +270,8 @@ static bool spmv_use_csr_kernel() {
 }
 
 static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, double* y, cudaStream_t st, int64_t row0 = 0,
-                       int64_t row1 = -1, const double* x_own = nullptr) {
+                       int64_t row1 = -1, const double* x_own = nullptr, const double* rscale = nullptr) {
+    // rscale (optional, indexed like y by the global row): y = diag(rscale) A x
     // x_own: values of the rows [row0, row1) (facet-block kernel only; the caller keeps x current otherwise)
     if (row1 < 0) row1 = A->n_rows;
     if (A->windowed) {                       // only the own rows exist
@@ -279,7 +282,7 @@ static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, d
     if (spmv_use_csr_kernel()) {
         constexpr int TPR = 8;
         const int64_t threads = (row1 - row0) * TPR;
-        spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)row0, (int)row1, A->rowptr, A->colind, vals, x, y);
+        spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)row0, (int)row1, A->rowptr, A->colind, vals, x, y, rscale);
     } else {
         const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
         if (fb <= fa) return EHDG_OK;
@@ -290,7 +293,7 @@ static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, d
         const unsigned gb = (unsigned)((threads + 255) / 256);
 #define EHDG_SPMV_LAUNCH(NBM, CH, LPF) \
         spmv_facet_kernel<NBM, CH, LPF><<<gb, 256, 0, st>>>(fa, fb, (int)row0, (int)row1, A->row_start, A->blk_base, A->colind, A->nbr_len, vals, x, y, \
-                                                            x_own ? x_own : x, x_own ? (int)row0 : 0, x_own ? (int)row1 : 0)
+                                                            x_own ? x_own : x, x_own ? (int)row0 : 0, x_own ? (int)row1 : 0, rscale)
         if (nb <= 2) EHDG_SPMV_LAUNCH(2, 1, 16);
         else if (nb <= 3) EHDG_SPMV_LAUNCH(3, 1, 16);
         else if (nb <= 4) EHDG_SPMV_LAUNCH(4, 1, 32);
@@ -309,7 +312,7 @@ constexpr int NBMAX = EHDG_MAX_ORDER + 1 + EHDG_MAX_ENRICH;
 
 __global__ void bj_invert_kernel(int f0, int nf, int nbs, const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ nbr, const double* __restrict__ vals, double* __restrict__ dinv,
-                                 int* __restrict__ fail, uint8_t* __restrict__ rowdrop) {
+                                 int* __restrict__ fail, uint8_t* __restrict__ rowdrop, double drop_tol) {
     const int f = f0 + blockIdx.x * blockDim.x + threadIdx.x;       // facets [f0, nf)
     if (f >= nf) return;
     const int r0 = row_start[f], n = row_start[f + 1] - r0;
@@ -323,18 +326,25 @@ __global__ void bj_invert_kernel(int f0, int nf, int nbs, const int32_t* __restr
     // A facet dof can be numerically dependent on the others of its facet (an enrichment function that
     // is constant along the facet next to the Legendre mode mu_0; the reference's pruning test misses
     // it when a second enrichment lives on the same facet).  Step 1 finds the independent dofs K by
-    // elimination with complete pivoting (pivot below 1e-10 of the block's largest entry = dependent);
+    // elimination with complete pivoting (pivot below drop_tol of the block's largest entry = dependent);
     // step 2 inverts the principal sub-block [K,K].  Dropped dofs get zero rows and columns in the block
     // inverse, so the right-preconditioned iteration leaves their coefficient at 0: one solution of the
     // consistent singular system, i.e. the same discrete function.
     double a[NBMAX][2 * NBMAX];
     double w[NBMAX][NBMAX];
     double amax = 0.0;
+    // the rank test runs on the symmetrically scaled block (unit diagonal): the enrichment functions and the Legendre
+    // modes of a facet, and the two sides of a facet between a marked and an unmarked element, differ by orders of magnitude
+    double dsc[NBMAX];
+    for (int i = 0; i < n; ++i) {
+        const double dg = fabs(vals[rowptr[r0 + i] + off + i]);
+        dsc[i] = dg > 0.0 ? rsqrt(dg) : 1.0;
+    }
     for (int i = 0; i < n; ++i) {
         const double* row = vals + rowptr[r0 + i] + off;
         for (int j = 0; j < n; ++j) {
-            w[i][j] = row[j];
-            amax = fmax(amax, fabs(row[j]));
+            w[i][j] = row[j] * dsc[i] * dsc[j];
+            amax = fmax(amax, fabs(w[i][j]));
         }
     }
     int cperm[NBMAX];
@@ -346,7 +356,7 @@ __global__ void bj_invert_kernel(int f0, int nf, int nbs, const int32_t* __restr
         for (int i = k; i < n; ++i)
             for (int j = k; j < n; ++j)
                 if (fabs(w[i][j]) > best) { best = fabs(w[i][j]); pr = i; pc = j; }
-        if (!(best > 1e-10 * amax)) { rank = k; break; }
+        if (!(best > drop_tol * amax)) { rank = k; break; }
         if (pr != k)
             for (int j = 0; j < n; ++j) { const double t = w[k][j]; w[k][j] = w[pr][j]; w[pr][j] = t; }
         if (pc != k) {
@@ -532,6 +542,39 @@ __global__ void update_x_kernel(int64_t n, const double* __restrict__ V, int64_t
 __global__ void poly_update_kernel(int64_t n, const double* __restrict__ v, const double* __restrict__ w, double* __restrict__ t) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         t[i] = v[i] + t[i] - w[i];
+}
+
+// rn[r - row_lo] = max_j |a_rj| (1 for an empty / zero row), rd = 1 / rn: the row equilibration of the Krylov solvers
+__global__ void row_norm_kernel(int row_lo, int row_hi, const int64_t* __restrict__ rowptr, const double* __restrict__ vals,
+                                double* __restrict__ rn, double* __restrict__ rd) {
+    const int r = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= row_hi) return;
+    double m = 0.0;
+    for (int64_t q = rowptr[r]; q < rowptr[r + 1]; ++q) m = fmax(m, fabs(vals[q]));
+    if (!(m > 0.0) || !isfinite(m)) m = 1.0;
+    rn[r - row_lo] = m;
+    rd[r - row_lo] = 1.0 / m;
+}
+
+// w <- w on the kept rows (rd != 0), 0 on the dropped ones; bk = b restricted the same way
+__global__ void keep_rows_kernel(int64_t n, const double* __restrict__ rd, double* __restrict__ w, const double* __restrict__ b,
+                                 double* __restrict__ bk) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool keep = rd[i] != 0.0;
+        if (!keep) w[i] = 0.0;
+        bk[i] = keep ? b[i] : 0.0;
+    }
+}
+
+__global__ void drop_rows_kernel(int64_t n, const uint8_t* __restrict__ drop, double* __restrict__ rn, double* __restrict__ rd) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && drop[i]) rn[i] = rd[i] = 0.0;
+}
+
+// out = a .* b
+__global__ void mul_kernel(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = b ? a[i] * b[i] : a[i];
 }
 
 // y += x
@@ -919,6 +962,30 @@ static SLayout make_slayout(const ehdg_ctx* c, const ehdg_plan* p) {
     return sl;
 }
 
+// smallest / largest neighbour facet of the facets [f_lo, f_hi) that carry rows
+__global__ void csr_extent_kernel(int f_lo, int f_hi, const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbf, int32_t* __restrict__ ext) {
+    const int f = f_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    int lo = 0x7fffffff, hi = -1;
+    if (f < f_hi && nbf[f] > 0) {
+        for (int t = 0; t < 5; ++t) {
+            const int g = nbr[5 * f + t];
+            if (g < 0) break;
+            if (nbf[g] == 0) continue;
+            lo = g < lo ? g : lo;
+            hi = g > hi ? g : hi;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (lo != 0x7fffffff) atomicMin(ext, lo);
+        if (hi >= 0) atomicMax(ext + 1, hi);
+    }
+}
+
 // first facet of each of nranks nearly equal row ranges that never cut a facet block (lower bound of k n / nranks in row_start)
 __global__ void csr_partition_kernel(int nf, int nranks, const int32_t* __restrict__ row_start, int32_t* __restrict__ facet_begin) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -941,6 +1008,7 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     A->nf = nf;
     A->nb = c->pb.nb;
     A->nranks = nranks;
+    A->stream = st;
     int32_t* nbf = nullptr;
     int64_t* blk = nullptr;
     void* tmp = nullptr;
@@ -948,38 +1016,38 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     size_t tb1 = 0, tb2 = 0;
     // every error return below releases the temporaries and the half-built matrix
     struct Guard {
-        ehdg_csr*& A; int32_t*& nbf; int64_t*& blk; void*& tmp; int32_t*& row_facet; bool ok = false;
+        ehdg_csr*& A; int32_t*& nbf; int64_t*& blk; void*& tmp; int32_t*& row_facet; cudaStream_t st; bool ok = false;
         ~Guard() {
-            cudaFree(nbf);
-            cudaFree(blk);
-            cudaFree(tmp);
-            if (!ok) { cudaFree(row_facet); ehdg_csr_destroy(A); }
+            if (nbf) cudaFreeAsync(nbf, st);
+            if (blk) cudaFreeAsync(blk, st);
+            if (tmp) cudaFreeAsync(tmp, st);
+            if (!ok) { if (row_facet) cudaFreeAsync(row_facet, st); ehdg_csr_destroy(A); }
         }
-    } guard{A, nbf, blk, tmp, row_facet};
-    EHDG_CUDA(cudaMalloc(&nbf, sizeof(int32_t) * (size_t)(nf + 1)));
-    EHDG_CUDA(cudaMalloc(&blk, sizeof(int64_t) * (size_t)(nf + 1)));
-    EHDG_CUDA(cudaMalloc(&A->dofmask, sizeof(uint16_t) * (size_t)(nf + 1)));
-    EHDG_CUDA(cudaMalloc(&A->row_start, sizeof(int32_t) * (size_t)(nf + 1)));
-    EHDG_CUDA(cudaMalloc(&A->blk_base, sizeof(int64_t) * (size_t)(nf + 1)));
-    EHDG_CUDA(cudaMalloc(&A->nbr, sizeof(int32_t) * 5 * (size_t)(nf + 1)));
-    EHDG_CUDA(cudaMalloc(&A->nbr_len, sizeof(int32_t) * (size_t)(nf + 1)));
+    } guard{A, nbf, blk, tmp, row_facet, st};
+    EHDG_CUDA(cudaMallocAsync(&nbf, sizeof(int32_t) * (size_t)(nf + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&blk, sizeof(int64_t) * (size_t)(nf + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->dofmask, sizeof(uint16_t) * (size_t)(nf + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->row_start, sizeof(int32_t) * (size_t)(nf + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->blk_base, sizeof(int64_t) * (size_t)(nf + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->nbr, sizeof(int32_t) * 5 * (size_t)(nf + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->nbr_len, sizeof(int32_t) * (size_t)(nf + 1), st));
     const int gb = (nf + 1 + 255) / 256;
     const bool want_strip = c->pb.nenr > 0 && facet_mask != nullptr;
-    if (want_strip) EHDG_CUDA(cudaMalloc(&A->strip, (size_t)(nf + 1)));
+    if (want_strip) EHDG_CUDA(cudaMallocAsync(&A->strip, (size_t)(nf + 1), st));
     csr_dofmask_kernel<<<gb, 256, 0, st>>>(nf, c->pb.nfl, m->facet2el, c->pb.nenr ? facet_active : nullptr, facet_mask, A->dofmask, nbf,
                                            want_strip ? A->strip : nullptr);
     EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb1, nbf, A->row_start, nf + 1, st));
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, blk, A->blk_base, nf + 1, st));
-    EHDG_CUDA(cudaMalloc(&tmp, (tb1 > tb2 ? tb1 : tb2) + 8));
+    EHDG_CUDA(cudaMallocAsync(&tmp, (tb1 > tb2 ? tb1 : tb2) + 8, st));
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb1, nbf, A->row_start, nf + 1, st));
     // the row partition (every rank computes the same one from the same replicated masks)
     A->part_facets.assign((size_t)nranks + 1, 0);
     A->part_rows.assign((size_t)nranks + 1, 0);
     {
         int32_t* fb = nullptr;
-        EHDG_CUDA(cudaMalloc(&fb, sizeof(int32_t) * (size_t)(2 * (nranks + 1))));
-        struct FreeFb { int32_t* p; ~FreeFb() { cudaFree(p); } } free_fb{fb};
+        EHDG_CUDA(cudaMallocAsync(&fb, sizeof(int32_t) * (size_t)(2 * (nranks + 1)), st));
+        struct FreeFb { int32_t* p; cudaStream_t st; ~FreeFb() { if (p) cudaFreeAsync(p, st); } } free_fb{fb, st};
         csr_partition_kernel<<<(nranks + 1 + 63) / 64, 64, 0, st>>>(nf, nranks, A->row_start, fb);
         EHDG_LAUNCH_CHECK();
         EHDG_CUDA(cudaMemcpyAsync(A->part_facets.data(), fb, sizeof(int32_t) * (size_t)(nranks + 1), cudaMemcpyDeviceToHost, st));
@@ -998,16 +1066,38 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     csr_nbr_kernel<<<gb, 256, 0, st>>>(nf, A->f_lo, A->f_hi, m->facet2el, m->el2facet, nbf, A->nbr, A->nbr_len, blk);
     EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb2, blk, A->blk_base, nf + 1, st));
-    int32_t nrows = 0;
+    // column extent of the own rows (the SpMV halo): first / last neighbour facet over the window
+    int32_t* d_ext = nullptr;
+    EHDG_CUDA(cudaMallocAsync(&d_ext, 2 * sizeof(int32_t), st));
+    struct FreeExt { int32_t* p; cudaStream_t st; ~FreeExt() { if (p) cudaFreeAsync(p, st); } } free_ext{d_ext, st};
+    {
+        const int32_t init[2] = {nf, -1};
+        EHDG_CUDA(cudaMemcpyAsync(d_ext, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        if (A->f_hi > A->f_lo) csr_extent_kernel<<<(A->f_hi - A->f_lo + 255) / 256, 256, 0, st>>>(A->f_lo, A->f_hi, A->nbr, nbf, d_ext);
+        EHDG_LAUNCH_CHECK();
+    }
+    int32_t nrows = 0, ext[2] = {0, 0};
     int64_t nnz = 0;
+    EHDG_CUDA(cudaMemcpyAsync(ext, d_ext, sizeof(ext), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaMemcpyAsync(&nrows, A->row_start + nf, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaMemcpyAsync(&nnz, A->blk_base + nf, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
     A->n_rows = nrows;
     A->nnz = nnz;
-    EHDG_CUDA(cudaMalloc(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1)));
-    EHDG_CUDA(cudaMalloc(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
-    EHDG_CUDA(cudaMalloc(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1)));
+    if (ext[1] >= ext[0]) {
+        int32_t rs2[2];
+        EHDG_CUDA(cudaMemcpyAsync(&rs2[0], A->row_start + ext[0], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaMemcpyAsync(&rs2[1], A->row_start + ext[1] + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        A->col_lo = rs2[0] < A->row_lo ? rs2[0] : A->row_lo;
+        A->col_hi = rs2[1] > A->row_hi ? rs2[1] : A->row_hi;
+    } else {
+        A->col_lo = A->row_lo;
+        A->col_hi = A->row_hi;
+    }
+    EHDG_CUDA(cudaMallocAsync(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), st));
+    EHDG_CUDA(cudaMallocAsync(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1), st));
     if (nf > 0) csr_fill_kernel<<<(unsigned)(((int64_t)nf * 32 + 255) / 256), 256, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
     EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -1026,10 +1116,11 @@ struct SolveWorkspace {
     char* arena = nullptr;
     size_t arena_bytes = 0, used = 0;
     std::vector<void*> dev, host;
+    cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     ChainSolver* chain = nullptr;
     ~SolveWorkspace() {
-        for (void* p : dev) cudaFree(p);
+        for (void* p : dev) if (p) cudaFreeAsync(p, st);
         for (void* p : host) cudaFreeHost(p);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -1045,7 +1136,7 @@ struct SolveWorkspace {
             return EHDG_OK;
         }
         void* p = nullptr;
-        EHDG_CUDA(cudaMalloc(&p, bytes));
+        EHDG_CUDA(cudaMallocAsync(&p, bytes, st));
         dev.push_back(p);
         *out = (T*)p;
         return EHDG_OK;
@@ -1084,6 +1175,13 @@ int ehdg_csr_symbolic_part(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet
                            ehdg_csr** out, void* stream) {
     if (!c || !m || !out || nranks < 1 || rank < 0 || rank >= nranks) { set_error("ehdg_csr_symbolic_part: bad argument"); return EHDG_ERR_ARG; }
     return csr_symbolic_impl(c, m, facet_active, facet_mask, nranks, rank, out, (cudaStream_t)stream);
+}
+
+int ehdg_csr_get_extent(const ehdg_csr* A, int64_t* col_lo, int64_t* col_hi) {
+    if (!A || !col_lo || !col_hi) { set_error("ehdg_csr_get_extent: null argument"); return EHDG_ERR_ARG; }
+    *col_lo = A->col_lo;
+    *col_hi = A->col_hi;
+    return EHDG_OK;
 }
 
 int ehdg_csr_get_partition(const ehdg_csr* A, int64_t* row_begin, int32_t* facet_begin) {
@@ -1159,16 +1257,17 @@ int ehdg_set_workspace(ehdg_ctx* c, void* device_ptr, int64_t bytes) {
 
 int ehdg_csr_destroy(ehdg_csr* A) {
     if (!A) return EHDG_OK;
-    cudaFree(A->row_start);
-    cudaFree(A->rowptr);
-    cudaFree(A->colind);
-    cudaFree(A->blk_base);
-    cudaFree(A->nbr);
-    cudaFree(A->nbr_len);
-    cudaFree(A->dofmask);
+    cudaStream_t st = A->stream;            // the arrays came from the stream-ordered pool on this stream
+    if (A->row_start) cudaFreeAsync(A->row_start, st);
+    if (A->rowptr) cudaFreeAsync(A->rowptr, st);
+    if (A->colind) cudaFreeAsync(A->colind, st);
+    if (A->blk_base) cudaFreeAsync(A->blk_base, st);
+    if (A->nbr) cudaFreeAsync(A->nbr, st);
+    if (A->nbr_len) cudaFreeAsync(A->nbr_len, st);
+    if (A->dofmask) cudaFreeAsync(A->dofmask, st);
+    if (A->row_facet) cudaFreeAsync(A->row_facet, st);
+    if (A->strip) cudaFreeAsync(A->strip, st);
     cudaFree(A->dinv);
-    cudaFree(A->row_facet);
-    cudaFree(A->strip);
     cudaFree(A->line);
     delete A;
     return EHDG_OK;
@@ -1237,6 +1336,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     const int m = info->restart > 0 ? info->restart : 30;
     const int max_iters = info->max_iters > 0 ? info->max_iters : 1000;
     const double rtol = info->rtol > 0 ? info->rtol : 1e-10;
+    const double drop_tol = info->drop_tol > 0 ? info->drop_tol : 1e-8;
     info->iters = 0;
     info->converged = 0;
     info->rel_residual = 0.0;
@@ -1244,12 +1344,14 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     info->total_seconds = 0.0;
     info->setup_seconds = 0.0;
     info->precond_bytes = 0.0;
+    info->rel_residual_unscaled = 0.0;
     info->strip_dofs = info->strip_blocks = 0;
     info->line_chains = info->line_blocks = info->line_max_block = 0;
     info->dropped_dofs = 0;
     if (ng == 0) { info->converged = 1; return EHDG_OK; }
     if (method == 2 && m > DQ_MAXK) { set_error("ehdg_dqgmres: truncation length above %d", DQ_MAXK); return EHDG_ERR_ARG; }
     SolveWorkspace ws;
+    ws.st = st;
     ws.arena = (char*)c->user_ws;
     ws.arena_bytes = c->user_ws_bytes;
     int rc;
@@ -1266,13 +1368,26 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     if ((rc = ws.get(&rowdrop, (size_t)ng))) return rc;
     EHDG_CUDA(cudaMemsetAsync(fail, 0, 2 * sizeof(int), st));
     EHDG_CUDA(cudaMemsetAsync(rowdrop, 0, (size_t)ng, st));
+    // Row equilibration: the iteration runs on D A M^-1 D^-1 (D y) = D b with D = diag(1 / max_j |a_rj|), i.e. convergence is
+    // measured in ||D (b - A x)|| / ||D b||.  The rows of marked elements carry penalties tau ~ 1e5 .. 1e10 times those of the
+    // bulk (alpha_K of the enriched elements): in the unscaled norm their rounding errors alone put a floor of 1e-5 .. 1e-7
+    // under the relative residual (measured: every method stalls at the same value), in the scaled norm there is none.
+    double *rn = nullptr, *rd = nullptr, *rhs_s = nullptr;
+    if ((rc = ws.get(&rn, (size_t)n))) return rc;
+    if ((rc = ws.get(&rd, (size_t)n))) return rc;
+    if ((rc = ws.get(&rhs_s, (size_t)n))) return rc;
+    if (n > 0) {
+        row_norm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)r0, (int)r1, A->rowptr, vals, rn, rd);
+        EHDG_LAUNCH_CHECK();
+    }
+    const double* rhs_raw = rhs;
     int setup_rc = EHDG_OK;
     {
         // replicated matrix: every rank inverts all facet blocks; partitioned matrix: the own facets, and the inverses of
         // the halo facets (the right preconditioner scales COLUMNS) come from the neighbouring ranks
         const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
         if (A->windowed && !line_mode) EHDG_CUDA(cudaMemsetAsync(A->dinv, 0, sizeof(double) * (size_t)ng * nbs, st));
-        if (fb > fa) bj_invert_kernel<<<(fb - fa + 127) / 128, 128, 0, st>>>(fa, fb, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop);
+        if (fb > fa) bj_invert_kernel<<<(fb - fa + 127) / 128, 128, 0, st>>>(fa, fb, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop, line_mode ? 1e-13 : drop_tol);
         EHDG_LAUNCH_CHECK();
         if (A->windowed && !line_mode) {
             const int rh = dc->halo_exchange(A->dinv, st, nbs);
@@ -1281,7 +1396,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     }
     // chains: the lines of the mesh (line mode) and / or the strip of marked elements, from the unscaled matrix values
     if (line_mode || info->use_strip_block)
-        setup_rc = chain_setup(A, vals, rowdrop, line_mode ? A->line : nullptr, info->use_strip_block, info->line_target_dofs, st, &ws.chain);
+        setup_rc = chain_setup(A, vals, rowdrop, line_mode ? A->line : nullptr, info->use_strip_block, info->line_target_dofs, drop_tol, st, &ws.chain);
     ChainSolver* chain = ws.chain;
     if (line_mode && setup_rc == EHDG_OK && n > 0 && !(chain && chain->all_rows)) {
         set_error("ehdg_gmres: the line preconditioner does not cover every row");
@@ -1294,6 +1409,15 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         info->precond_bytes = (double)chain->factor_bytes;
         if (!line_mode) { info->strip_dofs = chain->n_dofs; info->strip_blocks = chain->n_blocks; }
     }
+    // Dependent dofs (pivot below drop_tol of their block's scale in the facet / chain factorisation) leave the system as
+    // test AND trial functions: their rows get weight 0 in D (the residual does not see them), M^-1 has zero rows / columns
+    // for them (their coefficient stays 0).  What is solved is the Galerkin system on the kept dofs.
+    if (n > 0) {
+        drop_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, rowdrop + r0, rn, rd);
+        mul_kernel<<<(unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(n, rhs, rd, rhs_s);
+        EHDG_LAUNCH_CHECK();
+    }
+    rhs = rhs_s;
     if (!line_mode && setup_rc == EHDG_OK) {
         const int64_t fl = A->windowed ? A->row_lo : 0, fh = A->windowed ? A->row_hi : ng;
         if (fh > fl)
@@ -1304,7 +1428,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     }
     // ---- workspace
     double *V = nullptr, *w = nullptr, *yhat = nullptr, *partial = nullptr, *dsc = nullptr, *tvec = nullptr, *xg = nullptr;
-    if (chain && (rc = ws.get(&tvec, (size_t)n))) return rc;
+    if ((rc = ws.get(&tvec, (size_t)n))) return rc;
     if (dc) {
         if ((rc = ws.get(&xg, (size_t)ng))) return rc;                    // full-length SpMV input: own rows + halo
         EHDG_CUDA(cudaMemsetAsync(xg, 0, sizeof(double) * (size_t)ng, st));
@@ -1327,15 +1451,20 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     VecOps vo{st, partial, n, dc, d_ticket};
     // w = A P(v).  Facet mode: P leaves the bulk entries (their M^-1 is folded into A) and solves the strip chain;
     // line mode: P = M_line^-1, every row lies in a chain.
-    auto apply_op = [&](const double* v, double* out) -> int {
+    // scaled = true: out = D A P (D^-1 v), the operator of the iteration; false: out = A P v (raw residual at exit)
+    auto apply_op_s = [&](const double* v, double* out, bool scaled) -> int {
         const double* in = v;
         if (chain) {
-            if (!chain->all_rows) EHDG_CUDA(cudaMemcpyAsync(tvec, v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-            const int r2 = chain_apply(chain, v, tvec, r0, st);
+            if (!chain->all_rows) mul_kernel<<<vo.grid(), RED_THREADS, 0, st>>>(n, v, scaled ? rn : nullptr, tvec);
+            const int r2 = chain_apply(chain, v, tvec, r0, st, scaled ? rn : nullptr);
             if (r2) return r2;
+            in = tvec;
+        } else if (scaled) {
+            mul_kernel<<<vo.grid(), RED_THREADS, 0, st>>>(n, v, rn, tvec);
             in = tvec;
         }
         info->spmv_calls++;
+        const double* rs = scaled ? rd - r0 : nullptr;          // indexed by the global row like the product
         if (dc) {
             // halo rows from the two neighbouring ranks into the full-length buffer (sent straight out of the Krylov
             // vector), SpMV on own rows; the facet-block kernel reads the own rows from the vector itself
@@ -1343,10 +1472,11 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
             if (!direct) EHDG_CUDA(cudaMemcpyAsync(xg + r0, in, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
             const int r3 = dc->halo_exchange(xg, st, 1, direct ? in : nullptr);
             if (r3) return r3;
-            return launch_spmv(A, vals, xg, out - r0, st, r0, r1, direct ? in : nullptr);
+            return launch_spmv(A, vals, xg, out - r0, st, r0, r1, direct ? in : nullptr, rs);
         }
-        return launch_spmv(A, vals, in, out, st);
+        return launch_spmv(A, vals, in, out, st, 0, -1, nullptr, rs);
     };
+    auto apply_op = [&](const double* v, double* out) -> int { return apply_op_s(v, out, true); };
     // polynomial block-Jacobi preconditioner: t = sum_{i<s} (I - B)^i v, i.e. s Richardson sweeps.  B (I + N + ... +
     // N^{s-1}) = I - N^s with N = I - B: for convection-dominated systems N is (nearly) nilpotent along the streamlines,
     // so one application moves information s facet layers downstream (restarted GMRES on B alone stagnates: all
@@ -1653,7 +1783,20 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         rel = std::sqrt(hbuf[0]) / bnorm;
         conv = rel <= rtol * 10.0;
     }
-    // x = M^-1 yhat
+    // raw (unscaled) residual of the same iterate, for the record: u = D^-1 yhat, ||b - A P u|| / ||b||
+    double rel_raw = rel;
+    if (!(bnorm == 0.0)) {
+        mul_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, yhat, rn, yhat);              // yhat <- D^-1 yhat, the unscaled variable
+        if ((rc = apply_op_s(yhat, w, false))) return rc;
+        residual_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, rhs_raw, w);
+        keep_rows_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, rd, w, rhs_raw, tvec);     // kept rows only; tvec = kept part of b
+        if ((rc = vo.dots(w, n, 1, w, d_nrm))) return rc;
+        if ((rc = vo.dots(tvec, n, 1, tvec, d_nrm + 1))) return rc;
+        EHDG_CUDA(cudaMemcpyAsync(hbuf, d_nrm, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        EHDG_CUDA(cudaStreamSynchronize(st));
+        rel_raw = hbuf[1] > 0.0 ? std::sqrt(hbuf[0] / hbuf[1]) : 0.0;
+    }
+    // x = M^-1 u
     if (line_mode) {
         if ((rc = chain_apply(chain, yhat, x + r0, r0, st))) return rc;
     } else {
@@ -1669,6 +1812,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     info->iters = iters;
     info->converged = conv ? 1 : 0;
     info->rel_residual = rel;
+    info->rel_residual_unscaled = rel_raw;
     info->total_seconds = ms * 1e-3;
     return EHDG_OK;
 }

@@ -199,6 +199,9 @@ class EHDGPipeline:
         _lib.check(self.lib.ehdg_csr_get_partition(self.csr, rb.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.c_void_p)),
                    "ehdg_csr_get_partition")
         self.row_begin, self.facet_begin = rb, fb
+        lo, hi = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.ehdg_csr_get_extent(self.csr, C.byref(lo), C.byref(hi)), "ehdg_csr_get_extent")
+        self.own_extent = (int(lo.value), int(hi.value))    # columns the own rows reference (SpMV halo)
         return self
 
     def csr_alloc_values(self):
@@ -278,7 +281,7 @@ class EHDGPipeline:
         return self
 
     def gmres(self, restart=30, max_iters=20000, rtol=1e-12, strip_block=True, jacobi_sweeps=1, method="gmres", precond="line",
-              line_target_dofs=0):
+              line_target_dofs=0, drop_tol=0.0):
         """Krylov solve of the condensed system.  precond = 'line' (line-block Jacobi: every chain of facets solved exactly; the
         matrix values stay untouched) or 'facet' (facet block-Jacobi folded into the matrix values: they hold A M^-1 afterwards and
         are refilled by csr_numeric before the next use)."""
@@ -296,6 +299,7 @@ class EHDGPipeline:
         info.jacobi_sweeps = int(jacobi_sweeps)
         info.use_line_block = int(precond == "line")
         info.line_target_dofs = int(line_target_dofs)
+        info.drop_tol = float(drop_tol)
         fn = {"gmres": self.lib.ehdg_gmres, "bicgstab": self.lib.ehdg_bicgstab, "dqgmres": self.lib.ehdg_dqgmres}[method]
         self.vals_folded = precond == "facet"       # set before the call: an error inside may leave vals half folded
         _lib.check(fn(self.ctx, self.csr, _ptr(self.vals), _ptr(self.rhs), _ptr(self.xhat), C.byref(info), self._stream()),

@@ -136,10 +136,11 @@ def gather_extents(lo: int, hi: int, group=None, device="cpu"):
     return arr[:, 0].copy(), arr[:, 1].copy()
 
 
-def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True):
+def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True, assemble=True):
     """mark + prune (replicated: O(sqrt(ne)) work), then this rank's share: pattern of its rows, alpha + element blocks +
     condensation of the elements that touch its facets, numeric fill of its rows, and the communicator's partition.
-    exchange=False stops before the collective part (single-process checks of one rank's share)."""
+    exchange=False stops before the collective part (single-process checks of one rank's share); assemble=False stops after
+    the per-mesh set-up (marks, pruning, pattern, selection, plan, value arrays) and leaves a4-a8 to the caller."""
     import torch
     import torch.distributed as dist
     from . import _lib
@@ -160,21 +161,15 @@ def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True)
     sel, pipe.elem_owned = pipe.select_elements(f_lo, f_hi)        # same rule as select_elements / owned_elements above
     pipe.make_plan(sel)
     t0 = lap("select_plan_ms", t0)
-    pipe.assemble()                                          # a4-a7 on the selection
-    t0 = lap("alpha_assemble_condense_ms", t0)
-    pipe.csr_alloc_values().csr_numeric()                    # a8, own rows
-    t0 = lap("csr_numeric_ms", t0)
+    pipe.csr_alloc_values()
+    if assemble:
+        pipe.assemble()                                      # a4-a7 on the selection
+        t0 = lap("alpha_assemble_condense_ms", t0)
+        pipe.csr_numeric()                                   # a8, own rows
+        t0 = lap("csr_numeric_ms", t0)
     pipe.part_timing = tm
     rb = pipe.row_begin
-    r0, r1 = int(rb[rank]), int(rb[rank + 1])
-    nnz = int(pipe.csr_sizes.nnz)
-    if nnz > 0:
-        ci = _device_view(pipe.lib.ehdg_csr_colind(pipe.csr), nnz, torch.int32, pipe.dev)
-        lo, hi = min(int(ci.min()), r0), max(int(ci.max()) + 1, r1)
-    else:
-        lo, hi = r0, r1
-    t0 = lap("extent_ms", t0)
-    pipe.own_extent = (lo, hi)
+    lo, hi = pipe.own_extent                                 # computed on the device with the pattern (ehdg_csr_get_extent)
     if not exchange:
         return pipe
     if world > 1:

@@ -182,6 +182,8 @@ int ehdg_csr_symbolic(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet
 int ehdg_csr_symbolic_part(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* facet_active, const uint8_t* facet_mask,
                            int nranks, int rank, ehdg_csr** out, void* stream);
 int ehdg_csr_get_partition(const ehdg_csr* csr, int64_t* row_begin, int32_t* facet_begin);
+/* column range [col_lo, col_hi) the rows of this rank reference (its SpMV halo extent), computed with the pattern */
+int ehdg_csr_get_extent(const ehdg_csr* csr, int64_t* col_lo, int64_t* col_hi);
 /* Chains of the line-block Jacobi preconditioner.  facet_line i32[nf] (device): chain id of every facet, any non-negative
  * integers; a negative entry makes the facet a chain of its own (= facet block-Jacobi for it).  The array is copied.
  * ehdg_csr_auto_lines fills it from the geometry: chain of facet f = floor(n . c_f / width + offset) with c_f the facet
@@ -209,10 +211,12 @@ int ehdg_csr_numeric(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_csr* csr, 
 typedef struct {
     int32_t restart;        /* Krylov dimension m */
     int32_t max_iters;
-    double rtol;            /* on ||b - A x|| / ||b|| */
+    double rtol;            /* on ||D (b - A x)|| / ||D b||, D = diag(1 / max_j |a_rj|): the row-equilibrated residual (the rows of
+                             * marked elements carry penalties 1e5..1e10 times those of the bulk; their rounding errors alone
+                             * put a floor under the unscaled residual) */
     int32_t iters;          /* out */
     int32_t converged;      /* out */
-    double rel_residual;    /* out: true residual at exit */
+    double rel_residual;    /* out: true residual at exit, in the norm of rtol */
     double total_seconds;   /* out: device time of the whole solve */
     int64_t spmv_calls;     /* out */
     int32_t dropped_dofs;   /* out: facet dofs found dependent inside their facet block (coefficient kept 0) */
@@ -230,6 +234,11 @@ typedef struct {
     int32_t line_max_block; /* out: dofs of the largest block */
     double setup_seconds;   /* out: device + host time of the preconditioner set-up (inside total_seconds) */
     double precond_bytes;   /* out: bytes of factor data one preconditioner application streams */
+    double rel_residual_unscaled; /* out: ||b - A x|| / ||b|| of the returned x in the plain Euclidean norm (kept rows) */
+    double drop_tol;        /* in : selection rule for (near-)dependent facet dofs: a dof whose pivot in the factorisation of its
+                             * preconditioner block falls below drop_tol x the block's largest diagonal entry is removed from the
+                             * system as test and trial function (coefficient 0, row ignored); 0 = default 1e-8.  The reference
+                             * prunes with a distance test at 1e-5 that misses such dofs; dropped_dofs counts them */
 } ehdg_gmres_info;
 int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^-1 unless use_line_block */,
                const double* rhs, double* x, ehdg_gmres_info* info, void* stream);

@@ -17,7 +17,21 @@ from . import ehdg_oracle as orc
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "ehdg_oracle.c")
 OUT_DIR = os.path.join(HERE, "_build")
-LIB = os.path.join(OUT_DIR, "libehdg_oracle.so")
+
+
+def _cpu_tag() -> str:
+    """the library is built -O3 -march=native, so it is keyed by the host CPU's feature flags: a copy built in another
+    container is not loaded on a different CPU (it is rebuilt there)"""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        flags = next((ln for ln in txt.splitlines() if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha256(flags.encode()).hexdigest()[:10]
+
+
+LIB = os.path.join(OUT_DIR, f"libehdg_oracle_{_cpu_tag()}.so")
 
 
 class Params(C.Structure):
@@ -33,7 +47,7 @@ class Params(C.Structure):
 def build(force=False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     if force or not os.path.exists(LIB) or os.path.getmtime(SRC) > os.path.getmtime(LIB):
-        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", LIB, SRC, "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-o", LIB, SRC, "-lm"])
     return LIB
 
 
@@ -133,7 +147,8 @@ def time_sample(n, kind, order, eps, beta, budget_s=20.0, max_elems=None, nthrea
     prob = orc.run_py_problem(beta=beta, eps=eps)
     co = COracle(order, prob)
     em, fm = marks(mesh, prob)
-    threads = lib().orc_max_threads() if nthreads <= 0 else nthreads
+    # explicit thread count: under torchrun OMP_NUM_THREADS is 1 and omp_get_max_threads() would follow it
+    threads = (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)) if nthreads <= 0 else nthreads
 
     def run(m):
         m = min(m, mesh.ne)

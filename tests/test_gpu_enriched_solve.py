@@ -1,0 +1,118 @@
+"""Enriched facet solve on the device against the reference algorithm's answer (oracle fixture), where that answer is
+reproducible (tests/test_oracle_enriched_regime.py): L2 and H1 errors within 1e-8 relative (north star), through the line-block
+Jacobi Krylov solve, plus residual / convergence checks at the BASELINE parameters where only the device's own system can be
+the yardstick."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from convectiondiffusionequation_b200.hot_path import EHDGPipeline
+from convectiondiffusionequation_b200.mesh import unit_square_mesh
+from tests.common import make_pair
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = json.load(open(os.path.join(HERE, "golden", "enriched_solve_oracle.json")))
+
+
+def _rec(n, order, eps):
+    return next(r for r in FIX if r["n"] == n and r["order"] == order and abs(r["eps"] - eps) < 1e-12 * eps)
+
+
+def _true_residual(P):
+    """||b - A x|| / ||b|| recomputed from a fresh numeric fill (independent of the solver's own bookkeeping)"""
+    P.csr_numeric()
+    r = P.rhs - P.spmv(P.xhat)
+    return float(torch.linalg.norm(r) / torch.linalg.norm(P.rhs))
+
+
+@pytest.mark.parametrize("n,order,eps", [(8, 1, 1e-2), (16, 1, 1e-2), (16, 4, 1e-2), (32, 4, 1e-3)])
+@pytest.mark.parametrize("method,restart", [("gmres", 60), ("dqgmres", 16)])
+def test_enriched_solution_matches_the_reference_answer(n, order, eps, method, restart):
+    r = _rec(n, order, eps)
+    mesh = unit_square_mesh(n)
+    _, spec = make_pair(mesh, order, eps=eps, enriched=True)
+    P = EHDGPipeline(mesh, spec).setup().assemble().csr_build()
+    P.gmres(restart=restart, max_iters=40000, rtol=1e-13, method=method, precond="line").backsolve()
+    l2, h1 = P.errors()
+    tol = max(1e-8, 20 * r["rel_disagreement"])             # the oracle's own two solves bound what can be asked
+    assert abs(l2 - r["l2_full"]) < tol * r["l2_full"], (l2, r["l2_full"], P.gmres_info.iters, P.gmres_info.rel_residual)
+    assert abs(h1 - r["h1_full"]) < tol * r["h1_full"], (h1, r["h1_full"])
+    assert _true_residual(P) < 1e-9
+    P.close()
+
+
+@pytest.mark.parametrize("n,order,eps", [(32, 3, 1e-4), (32, 4, 1e-6), (64, 4, 1e-6)])
+def test_enriched_solve_converges_at_baseline_parameters(n, order, eps):
+    """BASELINE config-2 / config-3 parameters: the reference system has no reproducible answer (see the CPU regime test), so
+    the check is on the device's own assembled system: the Krylov solve converges, the residual recomputed from a fresh fill
+    agrees, and the discrete function is sane (error of the order of plain HDG's, not the 1e0..1e27 of the direct solves)."""
+    mesh = unit_square_mesh(n)
+    _, spec = make_pair(mesh, order, eps=eps, enriched=True)
+    P = EHDGPipeline(mesh, spec).setup().assemble().csr_build()
+    P.gmres(restart=60, max_iters=40000, rtol=1e-10, method="gmres", precond="line").backsolve()
+    gi = P.gmres_info
+    assert gi.converged == 1, (gi.iters, gi.rel_residual)
+    assert _true_residual(P) < 1e-8
+    l2, _ = P.errors()
+    _, spec_h = make_pair(mesh, order, eps=eps, enriched=False)
+    H = EHDGPipeline(mesh, spec_h).setup().assemble().csr_build()
+    H.gmres(restart=60, max_iters=40000, rtol=1e-10, method="gmres", precond="line").backsolve()
+    l2h, _ = H.errors()
+    assert np.isfinite(l2) and l2 < 10 * l2h, (l2, l2h)
+    P.close()
+    H.close()
+
+
+def test_second_solve_on_the_same_pipeline_gives_the_same_answer():
+    """the facet-mode solve folds M^-1 into the value array; a second solve / spmv must not see the folded values"""
+    mesh = unit_square_mesh(12, kind="unstructured")
+    _, spec = make_pair(mesh, 2, eps=1e-2, enriched=False)
+    P = EHDGPipeline(mesh, spec).setup().assemble().csr_build()
+    v0 = P.vals.clone()
+    P.gmres(restart=40, max_iters=4000, rtol=1e-12, precond="line")
+    assert torch.equal(P.vals, v0)                          # line mode leaves the matrix alone
+    x_line = P.xhat.clone()
+    P.gmres(restart=40, max_iters=8000, rtol=1e-12, precond="facet")
+    x_facet = P.xhat.clone()
+    P.gmres(restart=40, max_iters=8000, rtol=1e-12, precond="facet")     # refills the folded values first
+    assert torch.allclose(P.xhat, x_facet, rtol=0, atol=1e-12 * float(x_facet.abs().max()))
+    assert torch.allclose(x_line, x_facet, rtol=0, atol=1e-8 * float(x_facet.abs().max()))
+    y = P.spmv(P.xhat)                                      # and spmv works on A, not on A M^-1
+    assert float(torch.linalg.norm(y - P.rhs) / torch.linalg.norm(P.rhs)) < 1e-9
+    # the C ABI itself refuses a folded array
+    from convectiondiffusionequation_b200 import _lib
+    import ctypes as C
+    info = _lib.GmresInfo()
+    info.restart, info.max_iters, info.rtol = 10, 10, 1e-6
+    P.csr_numeric()
+    rc1 = P.lib.ehdg_gmres(P.ctx, P.csr, C.c_void_p(P.vals.data_ptr()), C.c_void_p(P.rhs.data_ptr()), C.c_void_p(P.xhat.data_ptr()),
+                           C.byref(info), P._stream())
+    rc2 = P.lib.ehdg_gmres(P.ctx, P.csr, C.c_void_p(P.vals.data_ptr()), C.c_void_p(P.rhs.data_ptr()), C.c_void_p(P.xhat.data_ptr()),
+                           C.byref(info), P._stream())
+    assert rc1 == 0 and rc2 == -1 and b"already holds" in P.lib.ehdg_last_error()
+    P.close()
+
+
+def test_user_lines_and_workspace():
+    """any partition of the facets into chains is a valid preconditioner (ehdg_csr_set_lines), and the Krylov vectors can live
+    in a caller-owned workspace"""
+    mesh = unit_square_mesh(10)
+    _, spec = make_pair(mesh, 2, eps=1e-2, enriched=False)
+    P = EHDGPipeline(mesh, spec).setup().assemble().csr_build()
+    P.gmres(restart=30, max_iters=4000, rtol=1e-12, precond="line")
+    x_ref, it_ref = P.xhat.clone(), P.gmres_info.iters
+    nf = mesh.nf
+    lines = torch.arange(nf, dtype=torch.int32, device=P.dev) % 7          # an arbitrary (bad) partition
+    lines[::5] = -1                                                          # some facets as chains of their own
+    P.set_lines(lines)
+    P.set_workspace(P.krylov_workspace_bytes(30, "gmres"))
+    P.gmres(restart=30, max_iters=20000, rtol=1e-12, precond="line")
+    assert P.gmres_info.converged == 1
+    assert torch.allclose(P.xhat, x_ref, rtol=0, atol=1e-8 * float(x_ref.abs().max()))
+    assert P.gmres_info.iters >= it_ref                                      # the streamline-aligned lines are the better blocks
+    P.set_workspace(0)
+    P.close()
