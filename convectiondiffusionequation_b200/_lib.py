@@ -87,9 +87,19 @@ SYMBOLS = {
     "ehdg_csr_row_start": (_P, [_P]),
     "ehdg_csr_dofmask": (_P, [_P]),
     "ehdg_csr_numeric": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
+    "ehdg_dirichlet_project": (C.c_int, [_P, C.POINTER(Mesh), _P, _P]),
+    "ehdg_csr_numeric_bc": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P, _P]),
+    "ehdg_backsolve_bc": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P, _P]),
     "ehdg_gmres": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
     "ehdg_bicgstab": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
     "ehdg_dqgmres": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(GmresInfo), _P]),
+    "ehdg_edg_prune": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, C.c_double, _P, _P, _P]),
+    "ehdg_edg_alpha": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),
+    "ehdg_edg_alpha_carry": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "ehdg_edg_csr_symbolic": (C.c_int, [_P, C.POINTER(Mesh), _P, C.POINTER(_P), _P]),
+    "ehdg_edg_assemble": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, _P, _P, _P, _P, _P]),
+    "ehdg_edg_unpack": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, _P, _P, _P]),
+    "ehdg_edg_l2_error": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, _P, _P]),
     "ehdg_comm_unique_id": (C.c_int, [C.c_char_p]),
     "ehdg_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int]),
     "ehdg_comm_set_partition": (C.c_int, [_P, _P, _P, _P]),

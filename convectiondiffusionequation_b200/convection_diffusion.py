@@ -42,8 +42,41 @@ class Convection_Diffusion():
     '''Enriched Discontinuous Galerkin Methods'''
 
     def _solveEDG(self):
-        raise NotImplementedError("the EDG (interior-penalty) path of the reference (convection_diffusion.py:42-219) is the "
-                                  "next row of the hot-path scope table (SURVEY.md 8f-1); only _solveEHDG is built")
+        """reference :42-219.  Results 'Type' is 'edg' with enrichment functions, 'dg' without (:84, :126); the alphas frame holds
+        the eigenvalue the reference tabulates and uses as alpha_stab (:163)."""
+        from .edg_path import EDGPipeline
+        cfg = self.config
+        enrich = tuple(cfg.get('enrich_functions') or ())
+        inds = tuple(cfg.get('enrich_domain_ind') or ())
+        if len(enrich) != len(inds):
+            raise ValueError("enrich_functions and enrich_domain_ind must have the same length")
+        for order in cfg['order']:
+            for size in cfg['mesh_size']:
+                t_start = time.perf_counter()
+                mesh = mesh_for_size(size, kind=cfg.get('mesh_kind', 'structured'))
+                spec = ProblemSpec(order=order, epsilon=cfg['epsilon'], beta=tuple(cfg['beta']), bonus_int=cfg['bonus_int'],
+                                   coeff=cfg['coeff'], exact=cfg['exact'], enrich_functions=enrich, enrich_domain_ind=inds)
+                pipe = EDGPipeline(mesh, spec, device=cfg.get('device', 'cuda:0'))
+                type = 'edg' if len(enrich) > 0 else 'dg'
+                pipe.setup(theta=cfg.get('theta', 1e-5))     # marking + pruning with config['theta']   (:52-54, :83-123)
+                pipe.alpha()                                # generalised eigenvalue per element         (:129-163)
+                lam = pipe.lam.cpu().numpy()
+                frame = pd.DataFrame({'alpha': lam, 'type': type, 'mesh_size': size, 'order': order}, columns=self.col)
+                self.alphas = frame if len(self.alphas) == 0 else pd.concat([self.alphas, frame], ignore_index=True)
+                t_asm = self._lap(pipe)
+                gi = self._solve(pipe, cfg)                 # forms, assembly, solve                     (:165-203)
+                t_sol = self._lap(pipe)
+                error, _ = pipe.errors()                    # recombination + L2 error, order 5 + bonus  (:205-210)
+                ndof = pipe.ndof()
+                self.solver_info.append(dict(order=order, mesh_size=size, type=type, iters=int(gi.iters), converged=bool(gi.converged),
+                                             rel_residual=float(gi.rel_residual), dropped_dofs=int(gi.dropped_dofs),
+                                             method=self._last_method, precond='line',
+                                             stages_s=dict(mesh_setup_alpha=t_asm - t_start, assemble_solve=t_sol - t_asm)))
+                self.results.loc[len(self.results)] = [order, ndof, size, error, cfg['bonus_int'], type]
+                if not cfg.get('quiet', False):
+                    print('order:', order, 'DOFs:', ndof, 'mesh:', size, "err:", error, 'type:', type)
+                self.last_pipeline = pipe
+        return self.results, self.alphas
 
     @staticmethod
     def _lap(pipe):
@@ -54,16 +87,17 @@ class Convection_Diffusion():
     def _solve(self, pipe, cfg):
         """Condensed facet system: CSR build, Krylov solve, back-solve.  The reference calls a direct solver and has no notion of
         non-convergence; here an unconverged iteration is an ERROR (config 'raise_on_nonconvergence', default True) instead
-        of a silently wrong 'Error' column.  solver 'auto' (default): DQGMRES(8) on the line-block preconditioner, then
-        GMRES(60) on the same preconditioner if that did not reach the tolerance."""
+        of a silently wrong 'Error' column.  solver 'auto' (default): GMRES(30) on the line-block preconditioner (measured: the
+        robust choice, DQGMRES(k) is erratic on these systems), then GMRES(100) if that did not reach the tolerance."""
         solver = cfg.get('solver', 'auto')
         rtol = cfg.get('gmres_rtol', 1e-10)
         max_iters = cfg.get('gmres_max_iters', 20000)
         precond = cfg.get('preconditioner', 'line')
-        attempts = [('dqgmres', cfg.get('gmres_restart', 8)), ('gmres', 60)] if solver == 'auto' else [(solver, cfg.get('gmres_restart', 60))]
+        drop_tol = cfg.get('drop_tol', 0.0)
+        attempts = [('gmres', cfg.get('gmres_restart', 30)), ('gmres', 100)] if solver == 'auto' else [(solver, cfg.get('gmres_restart', 30))]
         pipe.csr_build()
         for k, (method, restart) in enumerate(attempts):
-            pipe.gmres(restart=restart, max_iters=max_iters, rtol=rtol, method=method, precond=precond)
+            pipe.gmres(restart=restart, max_iters=max_iters, rtol=rtol, method=method, precond=precond, drop_tol=drop_tol)
             self._last_method = method
             if pipe.gmres_info.converged:
                 break

@@ -69,8 +69,7 @@ chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __r
                     uint8_t* __restrict__ rowdrop, double drop_tol, double* DH, double* G, int* dropped) {
     extern __shared__ double sm[];
     double* Aw = sm;                                   // n x 2n augmented [Delta | I], row major
-    __shared__ int s_piv;
-    __shared__ double s_best, s_scale;
+    __shared__ double s_scale;
     __shared__ unsigned char s_drop[CHAIN_MAXB];
     __shared__ double s_dsc[CHAIN_MAXB];
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -126,44 +125,22 @@ chain_factor_kernel(const int32_t* __restrict__ chain_ptr, const ChainBlock* __r
         __syncthreads();
         if (tid == 0) s_scale = 1.0;           // the scaled matrix has a unit original diagonal
         __syncthreads();
-        // Gauss-Jordan with partial pivoting; a pivot below drop_tol of the largest diagonal entry = dependent dof
+        // Gauss-Jordan on the diagonal: the condensed (E)HDG form is coercive, so every Schur complement met here has a
+        // positive-definite symmetric part and needs no row exchanges; what the diagonal pivot measures after the scaling above
+        // is the share of dof k that the dofs eliminated before it do not explain.  Below drop_tol the dof is dependent and
+        // leaves the block as test AND trial function (row k and column k), consistently with the caller's row weights.
         for (int k = 0; k < n; ++k) {
-            if (tid < 32) {
-                int piv = -1;
-                double best = -1.0;
-                for (int i = k + tid; i < n; i += 32) {
-                    const double a = fabs(Aw[i * 2 * n + k]);
-                    if (a > best) { best = a; piv = i; }
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, d);
-                    const int op = __shfl_xor_sync(0xffffffffu, piv, d);
-                    if (ob > best || (ob == best && op >= 0 && (piv < 0 || op < piv))) { best = ob; piv = op; }
-                }
-                if (tid == 0) { s_piv = piv; s_best = best; }
-            }
+            const double piv = Aw[k * 2 * n + k];
             __syncthreads();
-            if (!(s_best > drop_tol * s_scale)) {
-                // decouple dof k: column k := e_k, row k := e_k, right part row k := 0
+            if (!(fabs(piv) > drop_tol * s_scale) || s_drop[k]) {
+                if (!s_drop[k] && tid == 0) { s_drop[k] = 1; atomicAdd(dropped, 1); }
                 for (int i = tid; i < n; i += nt) Aw[i * 2 * n + k] = (i == k) ? 1.0 : 0.0;
                 __syncthreads();
                 for (int j = tid; j < 2 * n; j += nt) Aw[k * 2 * n + j] = (j == k) ? 1.0 : 0.0;
-                if (tid == 0) { s_drop[k] = 1; atomicAdd(dropped, 1); }
                 __syncthreads();
                 continue;
             }
-            const int piv = s_piv;
-            if (piv != k) {
-                for (int j = tid; j < 2 * n; j += nt) {
-                    const double t = Aw[k * 2 * n + j];
-                    Aw[k * 2 * n + j] = Aw[piv * 2 * n + j];
-                    Aw[piv * 2 * n + j] = t;
-                }
-                __syncthreads();
-            }
-            const double inv = 1.0 / Aw[k * 2 * n + k];
-            __syncthreads();
+            const double inv = 1.0 / piv;
             for (int j = tid; j < 2 * n; j += nt) Aw[k * 2 * n + j] *= inv;
             __syncthreads();
             for (int idx = tid; idx < n * 2 * n; idx += nt) {

@@ -256,9 +256,11 @@ int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out) {
     if ((rc = upload_rules(2 * c->pb.p + c->pb.bonus, c->rb))) return rc;
     if ((rc = upload_rules(2 * c->pb.p, c->r0))) return rc;
     if ((rc = upload_rules(50 + c->pb.bonus, c->rerr))) return rc;
+    if ((rc = upload_rules(5 + c->pb.bonus, c->redg))) return rc;
     c->ws_doubles = general_ws_doubles(c->pb, c->rb.rs.nq, c->rb.rs.nqf);
     const int a_ws = alpha_ws_doubles(c->pb, c->r0.rs.nq, c->r0.rs.nqf);
-    const int smem = (c->ws_doubles > a_ws ? c->ws_doubles : a_ws) * 8;
+    const int a_ws_b = alpha_ws_doubles(c->pb, c->rb.rs.nq, c->rb.rs.nqf);      // EDG: the alpha integrators take the bonus rule
+    const int smem = ((c->ws_doubles > a_ws ? c->ws_doubles : a_ws) > a_ws_b ? (c->ws_doubles > a_ws ? c->ws_doubles : a_ws) : a_ws_b) * 8;
     EHDG_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     EHDG_CUDA(cudaFuncSetAttribute(alpha_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     EHDG_CUDA(cudaFuncSetAttribute(assemble_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -276,6 +278,7 @@ int ehdg_destroy(ehdg_ctx* c) {
     cudaFree(c->rb.buf);
     cudaFree(c->r0.buf);
     cudaFree(c->rerr.buf);
+    cudaFree(c->redg.buf);
     ehdg_comm_destroy(c);
     fast_free_tensors(c);
     cudaFree(c->scratch);
@@ -468,9 +471,27 @@ int ehdg_prune(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_
     return EHDG_OK;
 }
 
+static int alpha_impl(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, double* lam,
+                      int32_t* status, void* stream, bool bonus_rule);
+
 int ehdg_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, double* lam,
                int32_t* status, void* stream) {
+    return alpha_impl(c, p, m, elem_active, lam, status, stream, false);
+}
+
+// EDG (reference :129-163): the same pencil, integrated with the bonus rule (the EDG integrators pass bonus_intorder);
+// on polynomial elements both rules are exact, so the tensor kernel serves them unchanged
+int ehdg_edg_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, double* lam,
+                   int32_t* status, void* stream) {
+    const int rc = alpha_impl(c, p, m, elem_active, lam, status, stream, true);
+    if (rc) return rc;
+    return ehdg_edg_alpha_carry(c, m->ne, lam, stream);
+}
+
+static int alpha_impl(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_t* elem_active, double* lam,
+                      int32_t* status, void* stream, bool bonus_rule) {
     if (!c || !p || !m || !lam) { set_error("ehdg_alpha: null argument"); return EHDG_ERR_ARG; }
+    const RuleSet& rsa = bonus_rule ? c->rb.rs : c->r0.rs;
     cudaStream_t st = (cudaStream_t)stream;
     // running the O(sqrt(ne)) enriched elements on a side stream beside the bulk kernel was measured slower on B200
     // (the persistent bulk CTAs already fill every SM; +0.5 ms at 1M elements), so it is opt-in
@@ -482,7 +503,7 @@ int ehdg_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const uint8_
     }
     if (p->n_gen > 0) {
         // the alpha integrators use the order-2p rule: a quarter of the assembly workspace, 3x the resident CTAs
-        alpha_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, alpha_ws_doubles(c->pb, c->r0.rs.nq, c->r0.rs.nqf) * 8, sg>>>(c->pb, c->r0.rs, (int)p->n_gen, p->list_gen, m->verts,
+        alpha_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, alpha_ws_doubles(c->pb, rsa.nq, rsa.nqf) * 8, sg>>>(c->pb, rsa, (int)p->n_gen, p->list_gen, m->verts,
                                                                                   m->tris, c->pb.nenr ? elem_active : nullptr, (c->pb.nenr && !p->forced) ? 1 : 0, lam, status);
         EHDG_LAUNCH_CHECK();
     }

@@ -44,7 +44,7 @@ struct DeviceTensors {
 struct ehdg_ctx {
     ehdg_problem ep;
     ehdg::Problem pb;
-    ehdg::DeviceRules rb, r0, rerr;   // orders 2p+bonus, 2p, 50+bonus
+    ehdg::DeviceRules rb, r0, rerr, redg;   // orders 2p+bonus, 2p, 50+bonus, 5+bonus (EDG error, reference :205-210)
     ehdg::DeviceTensors tens;
     int ws_doubles;                   // per-warp workspace of the general kernels
     int device;
@@ -94,6 +94,7 @@ struct ehdg_csr {
     int32_t* row_facet = nullptr;   // [n_rows] facet of each row
     uint8_t* strip = nullptr;       // [nf]    1 = free facet of a marked element (enriched strip), null if none
     int32_t* line = nullptr;        // [nf]    chain of every facet for the line-block preconditioner, null until set
+    int edg = 0;                    // EDG pattern: the blocks are ELEMENTS (self + facet neighbours), up to n_p + n_enrich rows each
     const double* folded_vals = nullptr;   // value array a Krylov solve has overwritten with A M^-1 (facet block-Jacobi mode)
     double* dinv = nullptr;         // [n_rows * nbmax] block-Jacobi inverses (set by ehdg_gmres)
     int nb;                         // slots per facet

@@ -110,7 +110,8 @@ __global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int
                                    const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask,
                                    const int32_t* __restrict__ facet2el, const int32_t* __restrict__ el2facet,
                                    const int32_t* __restrict__ eslot, const double* __restrict__ S,
-                                   const double* __restrict__ gv, double* __restrict__ vals, double* __restrict__ rhs) {
+                                   const double* __restrict__ gv, double* __restrict__ vals, double* __restrict__ rhs,
+                                   const double* __restrict__ ubnd, int nfl) {
     const int r = row_lo + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_lo, n_rows)
     if (r >= n_rows) return;
     const int f = row_facet[r];
@@ -145,7 +146,6 @@ __global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int
     double b = 0.0;
     for (int s = 0; s < ne; ++s)
         if (k < nbe[s]) b += gb[s][lef[s] * nbe[s] + k];
-    rhs[r] = b;                                                     // rhs is indexed by the global row
     int64_t pos = rowptr[r];
     for (int t = 0; t < 5; ++t) {
         const int g = nbr[5 * f + t];
@@ -157,6 +157,16 @@ __global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int
             for (int u = 0; u < 3; ++u)
                 if (ef[s][u] == g) leg[s] = u;
         }
+        if (ubnd && facet2el[2 * g + 1] < 0) {
+            // inhomogeneous Dirichlet data (debug_ehdg.py:210-212: f -= A gfu with gfu = projection of `exact` on the boundary
+            // facets): the prescribed polynomial dofs of a boundary facet move to the right-hand side
+            for (int l = 0; l < nfl; ++l) {
+                double v = 0.0;
+                for (int s = 0; s < ne; ++s)
+                    if (leg[s] >= 0 && k < nbe[s]) v += Sb[s][(size_t)(lef[s] * nbe[s] + k) * ld[s] + leg[s] * nbe[s] + l];
+                b -= v * ubnd[(size_t)g * nfl + l];
+            }
+        }
         while (mg) {
             const int l = __ffs(mg) - 1;
             mg &= mg - 1;
@@ -167,6 +177,7 @@ __global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int
             vals[pos++] = v;
         }
     }
+    rhs[r] = b;                                                     // rhs is indexed by the global row
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -279,7 +290,7 @@ static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, d
         row1 = row1 < A->row_hi ? row1 : A->row_hi;
     }
     if (row1 <= row0) return EHDG_OK;
-    if (spmv_use_csr_kernel()) {
+    if (spmv_use_csr_kernel() || A->edg) {          // EDG blocks have up to n_p + n_enrich rows: the plain CSR kernel
         constexpr int TPR = 8;
         const int64_t threads = (row1 - row0) * TPR;
         spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)row0, (int)row1, A->rowptr, A->colind, vals, x, y, rscale);
@@ -830,7 +841,8 @@ struct VecOps {
 __global__ void backsolve_kernel(int ne, SLayout sl, int n_p, int nvmax, const int32_t* __restrict__ eslot,
                                  const int32_t* __restrict__ el2facet, const int32_t* __restrict__ row_start,
                                  const uint16_t* __restrict__ dofmask, const double* __restrict__ W,
-                                 const double* __restrict__ z, const double* __restrict__ xhat, double* __restrict__ u) {
+                                 const double* __restrict__ z, const double* __restrict__ xhat, double* __restrict__ u,
+                                 const double* __restrict__ ubnd) {
     // one warp per element
     const int el = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -850,6 +862,7 @@ __global__ void backsolve_kernel(int ne, SLayout sl, int n_p, int nvmax, const i
         const unsigned m = dofmask[f];
         double v = 0.0;
         if ((m >> k) & 1u) v = xhat[row_start[f] + __popc(m & ((1u << k) - 1u))];
+        else if (ubnd && k < sl.nfl) v = ubnd[(size_t)f * sl.nfl + k];      // prescribed boundary value (zero on interior facets)
         xl[c] = v;
     }
     __syncwarp();
@@ -936,6 +949,44 @@ __global__ void facet_line_kernel(int ne, const double* __restrict__ verts, cons
     }
 }
 
+// ubnd[f][k] = (2k+1) int_0^1 exact(x(t)) P_k(2t - 1) dt on boundary facets (t from the lower to the higher global vertex:
+// the orientation of the facet basis), 0 on interior facets: the L2 projection that GridFunction.Set(exact, BND)
+// computes (debug_ehdg.py:210), with the bonus rule.  One thread per facet.
+__global__ void dirichlet_project_kernel(Problem pb, RuleSet rs, int nf, const double* __restrict__ verts, const int32_t* __restrict__ tris,
+                                         const int32_t* __restrict__ el2facet, const int32_t* __restrict__ facet2el,
+                                         double* __restrict__ ubnd) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int nfl = pb.nfl;
+    for (int k = 0; k < nfl; ++k) ubnd[(size_t)f * nfl + k] = 0.0;
+    if (facet2el[2 * f + 1] >= 0) return;
+    const int el = facet2el[2 * f];
+    int e = 0;
+    for (int t = 0; t < 3; ++t)
+        if (el2facet[3 * el + t] == f) e = t;
+    int a, b;
+    local_edge(e, a, b);
+    const int va = tris[3 * el + a], vb = tris[3 * el + b];
+    const int lo = va < vb ? va : vb, hi = va < vb ? vb : va;
+    const double dxl = 1.0 - verts[2 * lo], dyl = 1.0 - verts[2 * lo + 1], dxh = 1.0 - verts[2 * hi], dyh = 1.0 - verts[2 * hi + 1];
+    double c[EHDG_MAX_ORDER + 1];
+    for (int k = 0; k < nfl; ++k) c[k] = 0.0;
+    for (int q = 0; q < rs.nqf; ++q) {
+        const double t = rs.st[q], xi = 2.0 * t - 1.0;
+        const double g = layer_expr_eval(pb.exact, (1.0 - t) * dxl + t * dxh, (1.0 - t) * dyl + t * dyh) * rs.sw[q];
+        double p0 = 1.0, p1 = xi;
+        c[0] += g;
+        if (nfl > 1) c[1] += g * xi;
+        for (int k = 2; k < nfl; ++k) {
+            const double p2 = ((2 * k - 1) * xi * p1 - (k - 1) * p0) / k;
+            c[k] += g * p2;
+            p0 = p1;
+            p1 = p2;
+        }
+    }
+    for (int k = 0; k < nfl; ++k) ubnd[(size_t)f * nfl + k] = (2 * k + 1) * c[k];
+}
+
 __global__ void area_sum_kernel(int ne, const double* __restrict__ verts, const int32_t* __restrict__ tris, double* __restrict__ out) {
     double a = 0.0;
     for (int el = blockIdx.x * blockDim.x + threadIdx.x; el < ne; el += gridDim.x * blockDim.x) {
@@ -960,6 +1011,54 @@ static SLayout make_slayout(const ehdg_ctx* c, const ehdg_plan* p) {
     sl.nb = c->pb.nb;
     sl.nfg = c->pb.nfmax;
     return sl;
+}
+
+// EDG pattern: block = element; rows per block, neighbour blocks (self + facet neighbours, ascending, -1 padded)
+__global__ void edg_nbf_kernel(int ne, int n_p, const uint8_t* __restrict__ elem_active, int32_t* __restrict__ nbf) {
+    const int el = blockIdx.x * blockDim.x + threadIdx.x;
+    if (el > ne) return;
+    nbf[el] = el == ne ? 0 : n_p + (elem_active ? __popc((int)elem_active[el]) : 0);
+}
+__global__ void edg_nbr_kernel(int ne, const int32_t* __restrict__ el2facet, const int32_t* __restrict__ facet2el,
+                               const int32_t* __restrict__ nbf, int32_t* __restrict__ nbr, int32_t* __restrict__ nbr_len,
+                               int64_t* __restrict__ blk) {
+    const int el = blockIdx.x * blockDim.x + threadIdx.x;
+    if (el > ne) return;
+    if (el == ne) { blk[el] = 0; return; }
+    int c[4], n = 0;
+    c[n++] = el;
+    for (int e = 0; e < 3; ++e) {
+        const int f = el2facet[3 * el + e];
+        const int a = facet2el[2 * f], b = facet2el[2 * f + 1];
+        if (b < 0) continue;
+        c[n++] = a == el ? b : a;
+    }
+    for (int i = 1; i < n; ++i) {
+        const int v = c[i];
+        int j = i - 1;
+        while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; --j; }
+        c[j + 1] = v;
+    }
+    int len = 0;
+    for (int i = 0; i < 5; ++i) {
+        nbr[5 * el + i] = i < n ? c[i] : -1;
+        if (i < n) len += nbf[c[i]];
+    }
+    nbr_len[el] = len;
+    blk[el] = (int64_t)nbf[el] * len;
+}
+
+// chain id of every element from the position of its centroid across the flow (EDG variant of facet_line_kernel)
+__global__ void element_line_kernel(int ne, const double* __restrict__ verts, const int32_t* __restrict__ tris, double nx, double ny,
+                                    double inv_width, double offset, int32_t* __restrict__ line) {
+    const int el = blockIdx.x * blockDim.x + threadIdx.x;
+    if (el >= ne) return;
+    double s = 0.0;
+    for (int v = 0; v < 3; ++v) {
+        const int vi = tris[3 * el + v];
+        s += nx * verts[2 * vi] + ny * verts[2 * vi + 1];
+    }
+    line[el] = (int32_t)floor(s * (1.0 / 3.0) * inv_width + offset) + (1 << 24);
 }
 
 // smallest / largest neighbour facet of the facets [f_lo, f_hi) that carry rows
@@ -1177,6 +1276,74 @@ int ehdg_csr_symbolic_part(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* facet
     return csr_symbolic_impl(c, m, facet_active, facet_mask, nranks, rank, out, (cudaStream_t)stream);
 }
 
+int ehdg_edg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* elem_active, ehdg_csr** out, void* stream) {
+    if (!c || !m || !out) { set_error("ehdg_edg_csr_symbolic: null argument"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ne = m->ne;
+    ehdg_csr* A = new ehdg_csr();
+    A->nf = ne;                        // blocks = elements
+    A->nb = c->pb.nvmax;
+    A->edg = 1;
+    A->nranks = 1;
+    A->stream = st;
+    int32_t* nbf = nullptr;
+    int64_t* blk = nullptr;
+    void* tmp = nullptr;
+    int32_t* row_facet = nullptr;
+    struct Guard {
+        ehdg_csr*& A; int32_t*& nbf; int64_t*& blk; void*& tmp; int32_t*& row_facet; cudaStream_t st; bool ok = false;
+        ~Guard() {
+            if (nbf) cudaFreeAsync(nbf, st);
+            if (blk) cudaFreeAsync(blk, st);
+            if (tmp) cudaFreeAsync(tmp, st);
+            if (!ok) { if (row_facet) cudaFreeAsync(row_facet, st); ehdg_csr_destroy(A); }
+        }
+    } guard{A, nbf, blk, tmp, row_facet, st};
+    size_t tb1 = 0, tb2 = 0;
+    EHDG_CUDA(cudaMallocAsync(&nbf, sizeof(int32_t) * (size_t)(ne + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&blk, sizeof(int64_t) * (size_t)(ne + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->row_start, sizeof(int32_t) * (size_t)(ne + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->blk_base, sizeof(int64_t) * (size_t)(ne + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->nbr, sizeof(int32_t) * 5 * (size_t)(ne + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->nbr_len, sizeof(int32_t) * (size_t)(ne + 1), st));
+    const int gb = (ne + 1 + 255) / 256;
+    edg_nbf_kernel<<<gb, 256, 0, st>>>(ne, c->pb.n_p, c->pb.nenr ? elem_active : nullptr, nbf);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb1, nbf, A->row_start, ne + 1, st));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, blk, A->blk_base, ne + 1, st));
+    EHDG_CUDA(cudaMallocAsync(&tmp, (tb1 > tb2 ? tb1 : tb2) + 8, st));
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb1, nbf, A->row_start, ne + 1, st));
+    edg_nbr_kernel<<<gb, 256, 0, st>>>(ne, m->el2facet, m->facet2el, nbf, A->nbr, A->nbr_len, blk);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb2, blk, A->blk_base, ne + 1, st));
+    int32_t nrows = 0;
+    int64_t nnz = 0;
+    EHDG_CUDA(cudaMemcpyAsync(&nrows, A->row_start + ne, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cudaMemcpyAsync(&nnz, A->blk_base + ne, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    A->n_rows = nrows;
+    A->nnz = nnz;
+    A->f_lo = 0;
+    A->f_hi = ne;
+    A->row_lo = 0;
+    A->row_hi = nrows;
+    A->col_lo = 0;
+    A->col_hi = nrows;
+    A->part_facets = {0, ne};
+    A->part_rows = {0, nrows};
+    EHDG_CUDA(cudaMallocAsync(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), st));
+    EHDG_CUDA(cudaMallocAsync(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1), st));
+    if (ne > 0) csr_fill_kernel<<<(unsigned)(((int64_t)ne * 32 + 255) / 256), 256, 0, st>>>(ne, 0, ne, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
+    EHDG_LAUNCH_CHECK();
+    EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    EHDG_CUDA(cudaStreamSynchronize(st));
+    A->row_facet = row_facet;
+    guard.ok = true;
+    *out = A;
+    return EHDG_OK;
+}
+
 int ehdg_csr_get_extent(const ehdg_csr* A, int64_t* col_lo, int64_t* col_hi) {
     if (!A || !col_lo || !col_hi) { set_error("ehdg_csr_get_extent: null argument"); return EHDG_ERR_ARG; }
     *col_lo = A->col_lo;
@@ -1226,6 +1393,11 @@ int ehdg_csr_auto_lines(ehdg_ctx* c, ehdg_csr* A, const ehdg_mesh* m, double dir
         width = sqrt(2.0 * area / m->ne);
     }
     if (!A->line) EHDG_CUDA(cudaMalloc(&A->line, sizeof(int32_t) * (size_t)A->nf));
+    if (A->edg) {
+        element_line_kernel<<<(m->ne + 255) / 256, 256, 0, st>>>(m->ne, m->verts, m->tris, dir_x, dir_y, 1.0 / width, offset, A->line);
+        EHDG_LAUNCH_CHECK();
+        return EHDG_OK;
+    }
     facet_line_kernel<<<(m->ne + 255) / 256, 256, 0, st>>>(m->ne, m->verts, m->tris, m->el2facet, dir_x, dir_y, 1.0 / width, offset, A->line);
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
@@ -1284,8 +1456,22 @@ const int32_t* ehdg_csr_colind(const ehdg_csr* A) { return A ? A->colind : nullp
 const int32_t* ehdg_csr_row_start(const ehdg_csr* A) { return A ? A->row_start : nullptr; }
 const uint16_t* ehdg_csr_dofmask(const ehdg_csr* A) { return A ? A->dofmask : nullptr; }
 
+int ehdg_dirichlet_project(ehdg_ctx* c, const ehdg_mesh* m, double* ubnd, void* stream) {
+    if (!c || !m || !ubnd) { set_error("ehdg_dirichlet_project: null argument"); return EHDG_ERR_ARG; }
+    if (m->nf == 0) return EHDG_OK;
+    dirichlet_project_kernel<<<(m->nf + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c->pb, c->rb.rs, m->nf, m->verts, m->tris, m->el2facet,
+                                                                                   m->facet2el, ubnd);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
 int ehdg_csr_numeric(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehdg_mesh* m, const double* S, const double* g,
                      double* vals, double* rhs, void* stream) {
+    return ehdg_csr_numeric_bc(c, p, A, m, S, g, nullptr, vals, rhs, stream);
+}
+
+int ehdg_csr_numeric_bc(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehdg_mesh* m, const double* S, const double* g,
+                        const double* ubnd, double* vals, double* rhs, void* stream) {
     if (!c || !p || !A || !m || !S || !g || !vals || !rhs) { set_error("ehdg_csr_numeric: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     if (A->n_rows == 0) return EHDG_OK;
@@ -1294,7 +1480,7 @@ int ehdg_csr_numeric(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const e
     if (A->folded_vals == vals) const_cast<ehdg_csr*>(A)->folded_vals = nullptr;     // fresh values: a Krylov solve may fold them again
     csr_numeric_kernel<<<(unsigned)((rhi - rlo + 127) / 128), 128, 0, st>>>((int)rlo, (int)rhi, make_slayout(c, p), A->row_facet, A->row_start,
                                                                             A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,
-                                                                            p->eslot, S, g, vals, rhs);
+                                                                            p->eslot, S, g, vals, rhs, ubnd, c->pb.nfl);
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -1315,6 +1501,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     const int64_t n = r1 - r0;                                      // rows this rank iterates on
     const bool line_mode = info->use_line_block != 0;
     if (line_mode && !A->line) { set_error("ehdg_gmres: use_line_block needs ehdg_csr_auto_lines / ehdg_csr_set_lines first"); return EHDG_ERR_ARG; }
+    if (A->edg && !line_mode) { set_error("ehdg_gmres: an EDG system needs the line-block preconditioner (use_line_block)"); return EHDG_ERR_ARG; }
     if (dc) {
         if ((info->use_strip_block || line_mode) && !A->windowed) {
             set_error("ehdg_gmres: the line / strip blocks of the distributed solve need the partitioned matrix (ehdg_csr_symbolic_part)");
@@ -1336,7 +1523,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     const int m = info->restart > 0 ? info->restart : 30;
     const int max_iters = info->max_iters > 0 ? info->max_iters : 1000;
     const double rtol = info->rtol > 0 ? info->rtol : 1e-10;
-    const double drop_tol = info->drop_tol > 0 ? info->drop_tol : 1e-8;
+    const double drop_tol = info->drop_tol > 0 ? info->drop_tol : 1e-6;
     info->iters = 0;
     info->converged = 0;
     info->rel_residual = 0.0;
@@ -1361,7 +1548,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     EHDG_CUDA(cudaEventRecord(ws.ev0, st));
     const int nbs = A->nb;
     // ---- preconditioner.  Facet blocks: Dinv, then A <- A M^-1 in place.  Line blocks: the chains are factorised, A stays.
-    if (!A->dinv) EHDG_CUDA(cudaMalloc(&A->dinv, sizeof(double) * (size_t)ng * nbs));
+    if (!A->dinv && !A->edg) EHDG_CUDA(cudaMalloc(&A->dinv, sizeof(double) * (size_t)ng * nbs));
     int* fail = nullptr;
     uint8_t* rowdrop = nullptr;
     if ((rc = ws.get(&fail, 2))) return rc;
@@ -1387,7 +1574,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         // the halo facets (the right preconditioner scales COLUMNS) come from the neighbouring ranks
         const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
         if (A->windowed && !line_mode) EHDG_CUDA(cudaMemsetAsync(A->dinv, 0, sizeof(double) * (size_t)ng * nbs, st));
-        if (fb > fa) bj_invert_kernel<<<(fb - fa + 127) / 128, 128, 0, st>>>(fa, fb, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop, line_mode ? 1e-13 : drop_tol);
+        if (fb > fa && !A->edg) bj_invert_kernel<<<(fb - fa + 127) / 128, 128, 0, st>>>(fa, fb, nbs, A->row_start, A->rowptr, A->nbr, vals, A->dinv, fail, rowdrop, line_mode ? 1e-13 : drop_tol);
         EHDG_LAUNCH_CHECK();
         if (A->windowed && !line_mode) {
             const int rh = dc->halo_exchange(A->dinv, st, nbs);
@@ -1831,11 +2018,16 @@ int ehdg_dqgmres(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rhs, doub
 
 int ehdg_backsolve(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehdg_mesh* m, const double* W, const double* z,
                    const double* xhat, double* u, void* stream) {
+    return ehdg_backsolve_bc(c, p, A, m, W, z, xhat, nullptr, u, stream);
+}
+
+int ehdg_backsolve_bc(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, const ehdg_mesh* m, const double* W, const double* z,
+                      const double* xhat, const double* ubnd, double* u, void* stream) {
     if (!c || !p || !A || !m || !W || !z || !xhat || !u) { set_error("ehdg_backsolve: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     if (m->ne == 0) return EHDG_OK;
     backsolve_kernel<<<(unsigned)(((int64_t)m->ne * 32 + 255) / 256), 256, 0, st>>>(m->ne, make_slayout(c, p), c->pb.n_p, c->pb.nvmax, p->eslot,
-                                                                                    m->el2facet, A->row_start, A->dofmask, W, z, xhat, u);
+                                                                                    m->el2facet, A->row_start, A->dofmask, W, z, xhat, u, ubnd);
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }

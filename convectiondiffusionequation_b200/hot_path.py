@@ -63,7 +63,7 @@ def _ptr(t):
 class EHDGPipeline:
     """One (mesh, order) instance of the hot path on one GPU."""
 
-    def __init__(self, mesh: TriMesh, spec: ProblemSpec, device="cuda:0", force_general=False):
+    def __init__(self, mesh: TriMesh, spec: ProblemSpec, device="cuda:0", force_general=False, dirichlet_lifting=False):
         if not torch.cuda.is_available():
             raise _lib.EhdgError("no CUDA device: the (E)HDG hot path has no CPU fallback")
         self.lib = _lib.load()
@@ -72,6 +72,8 @@ class EHDGPipeline:
         self.mesh_host = mesh
         self.spec = spec
         self.force_general = bool(force_general)
+        self.dirichlet_lifting = bool(dirichlet_lifting)    # boundary facets carry the projection of `exact` (debug_ehdg.py:210-214)
+        self.ubnd = None
         self.nenr = len(spec.enrich_functions)
         self._cprob = spec.c_struct()
         self.ctx = C.c_void_p()
@@ -85,6 +87,7 @@ class EHDGPipeline:
     # ------------------------------------------------------------------ mesh
     def upload_mesh(self, pinned=None):
         m = self.mesh_host
+        self.ubnd = None
         src = pinned or dict(verts=torch.from_numpy(m.verts), tris=torch.from_numpy(m.tris),
                              el2facet=torch.from_numpy(m.el2facet), facet2el=torch.from_numpy(m.facet2el))
         self.verts = src["verts"].to(self.dev, non_blocking=True)
@@ -225,10 +228,19 @@ class EHDGPipeline:
         self.csr_numeric()
         return self
 
+    def dirichlet_values(self):
+        """ubnd f64[nf][p+1]: L2 projection of `exact` on the boundary facets, zero elsewhere"""
+        self.ubnd = torch.empty(self.mesh_host.nf * self.sizes.nfl, dtype=torch.float64, device=self.dev)
+        _lib.check(self.lib.ehdg_dirichlet_project(self.ctx, C.byref(self.cmesh), _ptr(self.ubnd), self._stream()), "ehdg_dirichlet_project")
+        return self.ubnd
+
     def csr_numeric(self):
         self.vals_folded = False
-        _lib.check(self.lib.ehdg_csr_numeric(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.S), _ptr(self.g),
-                                             _ptr(self.vals), _ptr(self.rhs), self._stream()), "ehdg_csr_numeric")
+        if self.dirichlet_lifting and self.ubnd is None:
+            self.dirichlet_values()
+        _lib.check(self.lib.ehdg_csr_numeric_bc(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.S), _ptr(self.g),
+                                                _ptr(self.ubnd) if self.dirichlet_lifting else None, _ptr(self.vals), _ptr(self.rhs),
+                                                self._stream()), "ehdg_csr_numeric_bc")
         return self
 
     def csr_arrays(self):
@@ -310,8 +322,9 @@ class EHDGPipeline:
     # ------------------------------------------------------------------ a10
     def backsolve(self):
         self.u = torch.empty(self.plan_sizes.z_doubles, dtype=torch.float64, device=self.dev)
-        _lib.check(self.lib.ehdg_backsolve(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.W), _ptr(self.z),
-                                           _ptr(self.xhat), _ptr(self.u), self._stream()), "ehdg_backsolve")
+        _lib.check(self.lib.ehdg_backsolve_bc(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.W), _ptr(self.z),
+                                              _ptr(self.xhat), _ptr(self.ubnd) if self.dirichlet_lifting else None, _ptr(self.u),
+                                              self._stream()), "ehdg_backsolve_bc")
         return self
 
     def errors(self):

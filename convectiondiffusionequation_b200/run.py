@@ -8,6 +8,7 @@ import pandas as pd
 
 from .coefficients import boundary_layer, x, y
 from .convection_diffusion import Convection_Diffusion
+from .utils import plot_error_mesh
 
 ### Problem configuration (run.py:24-30)
 beta = (2, 0.001)
@@ -32,7 +33,7 @@ config = {
 }
 
 
-def main(write_csv=True):
+def main(write_csv=True, plot=None):
     # with enrichment
     CT = Convection_Diffusion(config)
     ehdg_table, alpha_ehdg = CT._solveEHDG()
@@ -48,6 +49,8 @@ def main(write_csv=True):
         alphas.to_csv('alphas_dg.csv')
     hdg = pd.concat([hdg_table, ehdg_table])
     print(hdg.to_string(index=False))
+    if plot if plot is not None else write_csv:
+        print('error plot:', plot_error_mesh(hdg))       # run.py:71 (saved instead of shown: headless)
     return hdg, alphas
 
 

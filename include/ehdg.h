@@ -206,6 +206,16 @@ const uint16_t* ehdg_csr_dofmask(const ehdg_csr* csr);   /* u16 [nf]       devic
 int ehdg_csr_numeric(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_csr* csr, const ehdg_mesh* mesh,
                      const double* S, const double* g, double* vals, double* rhs, void* stream);
 
+/* Inhomogeneous Dirichlet data (reference Python/debug_ehdg.py:210-214: gfu.components[1].Set(exact, BND); f -= A gfu;
+ * gfu += A^-1 f).  ehdg_dirichlet_project: ubnd f64[nf][p+1] = L2 projection of `exact` onto the Legendre modes of every
+ * boundary facet (bonus rule), 0 on interior facets.  The _bc variants of a8 / a10 move the prescribed dofs to the right-hand
+ * side of the condensed system and put them back in the element back-solve; ubnd = null is the homogeneous case. */
+int ehdg_dirichlet_project(ehdg_ctx* ctx, const ehdg_mesh* mesh, double* ubnd, void* stream);
+int ehdg_csr_numeric_bc(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_csr* csr, const ehdg_mesh* mesh, const double* S,
+                        const double* g, const double* ubnd, double* vals, double* rhs, void* stream);
+int ehdg_backsolve_bc(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_csr* csr, const ehdg_mesh* mesh, const double* W,
+                      const double* z, const double* xhat, const double* ubnd, double* u, void* stream);
+
 /* a9  restarted GMRES with block-Jacobi (facet block) right preconditioning on the condensed system
  * (replaces acd.mat.Inverse(ba_active_dofs, "pardiso"), convection_diffusion.py:385-387). */
 typedef struct {
@@ -237,7 +247,7 @@ typedef struct {
     double rel_residual_unscaled; /* out: ||b - A x|| / ||b|| of the returned x in the plain Euclidean norm (kept rows) */
     double drop_tol;        /* in : selection rule for (near-)dependent facet dofs: a dof whose pivot in the factorisation of its
                              * preconditioner block falls below drop_tol x the block's largest diagonal entry is removed from the
-                             * system as test and trial function (coefficient 0, row ignored); 0 = default 1e-8.  The reference
+                             * system as test and trial function (coefficient 0, row ignored); 0 = default 1e-6.  The reference
                              * prunes with a distance test at 1e-5 that misses such dofs; dropped_dofs counts them */
 } ehdg_gmres_info;
 int ehdg_gmres(ehdg_ctx* ctx, ehdg_csr* csr, double* vals /* overwritten by A M^-1 unless use_line_block */,
@@ -257,6 +267,35 @@ int ehdg_krylov_workspace_bytes(const ehdg_ctx* ctx, const ehdg_csr* csr, const 
 int ehdg_set_workspace(ehdg_ctx* ctx, void* device_ptr, int64_t bytes);
 /* y = A x with the CSR SpMV kernel used inside GMRES (for tests and the bandwidth bench) */
 int ehdg_spmv(ehdg_ctx* ctx, const ehdg_csr* csr, const double* vals, const double* x, double* y, void* stream);
+
+/* ---- EDG path: enriched interior-penalty DG, Convection_Diffusion._solveEDG (convection_diffusion.py:42-219) ----
+ * Spaces (:48-56): V = L2(order), Q_i = one P0 dof per element marked for enrichment i; u = u_0 + sum u_i psi_i.  Marking is
+ * ehdg_mark (elem_mask), the plan is ehdg_plan_create with its facet_mask (general list = marked elements + neighbours).
+ * ehdg_edg_prune   (:83-123)  mass Gram int u v of the enriched shapes with the bonus rule; enrichment k of a marked element is
+ *                  dropped when the reference's `factor` <= theta (config['theta']).  elem_active u8[ne]; factors f64[ne][n_enrich]
+ *                  (optional): -1 where the dof does not exist.  plan may be null (every element is visited).
+ * ehdg_edg_alpha   (:129-163) lam[el] = lambda_max of (m, a + f f^T) with the bonus rule, incl. the carry-over of the previous
+ *                  element's value where the eigenvalue is exactly zero (:158-161); the value the reference tabulates and
+ *                  uses as alpha_stab.
+ * ehdg_edg_csr_symbolic: pattern of acd.mat (:189-191, dgjumps=True): block row of element K = K and its facet neighbours in
+ *                  ascending element number, rows / columns = active volume slots (polynomial modes, then surviving
+ *                  enrichments).  The result is an ehdg_csr: ehdg_csr_auto_lines, ehdg_spmv and the Krylov solvers
+ *                  (use_line_block = 1) take it as they take the condensed facet system.
+ * ehdg_edg_assemble (:165-198) values of the block rows and the right-hand side: eps [grad u . grad v + pen [u][v] - {dn u}[v]
+ *                  - {dn v}[u] (+ boundary terms)] - (b u) . grad v + (b.n) u_up [v],  pen = 4 alpha_stab p^2 / h^2.
+ * ehdg_edg_unpack / ehdg_edg_l2_error (:205-210): u f64[ne][n_p + n_enrich] from the solution vector (inactive slots 0);
+ *                  err2[2] = squared L2 and H1-seminorm errors against `exact` with the order 5 + bonus rule. */
+int ehdg_edg_prune(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_mask, double theta,
+                   uint8_t* elem_active, double* factors, void* stream);
+int ehdg_edg_alpha(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_active, double* lam,
+                   int32_t* status, void* stream);
+int ehdg_edg_alpha_carry(ehdg_ctx* ctx, int32_t ne, double* lam, void* stream);
+int ehdg_edg_csr_symbolic(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* elem_active, ehdg_csr** out, void* stream);
+int ehdg_edg_assemble(ehdg_ctx* ctx, const ehdg_mesh* mesh, const ehdg_csr* csr, const double* alpha_stab, const uint8_t* elem_active,
+                      double* vals, double* rhs, int32_t* status, void* stream);
+int ehdg_edg_unpack(ehdg_ctx* ctx, const ehdg_mesh* mesh, const ehdg_csr* csr, const uint8_t* elem_active, const double* x, double* u,
+                    void* stream);
+int ehdg_edg_l2_error(ehdg_ctx* ctx, const ehdg_mesh* mesh, const uint8_t* elem_active, const double* u, double* err2, void* stream);
 
 /* Multi-GPU facet solve (one process per GPU).  Rows of the condensed system are split into contiguous
  * ranges; every rank holds the (replicated) matrix, iterates on its own rows, exchanges the SpMV halo rows

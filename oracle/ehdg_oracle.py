@@ -537,6 +537,67 @@ class EHDGOracle:
             x[d[c["iv"]]] = c["z"] - c["W"] @ x[d[c["jf"]]]
         return x
 
+    # ------------------------------------------------------------------ inhomogeneous Dirichlet data (debug_ehdg.py:210-214)
+    def dirichlet_values(self):
+        """gfu.components[1].Set(exact, BND): L2 projection of `exact` onto the Legendre modes of every boundary facet
+        (bonus rule; facet parameter from the lower to the higher global vertex).  {facet: coefficients [p+1]}"""
+        t, w = seg_rule(2 * self.p + self.prob.bonus)
+        mu = legendre_eval(self.p, 2.0 * t - 1.0)
+        out = {}
+        for f in np.nonzero(self.facet2el[:, 1] < 0)[0]:
+            el = self.facet2el[f, 0]
+            e = int(np.nonzero(self.el2facet[el] == f)[0][0])
+            a, b = LOCAL_EDGES[e]
+            va, vb = self.tris[el][a], self.tris[el][b]
+            lo, hi = (va, vb) if va < vb else (vb, va)
+            dlo, dhi = 1.0 - self.verts[lo], 1.0 - self.verts[hi]
+            g = self.prob.exact((1.0 - t) * dlo[0] + t * dhi[0], (1.0 - t) * dlo[1] + t * dhi[1])
+            out[int(f)] = (2.0 * np.arange(self.p + 1) + 1.0) * (mu * (g * w)[None, :]).sum(axis=1)
+        return out
+
+    def solve_full_lifted(self, lams):
+        """debug_ehdg.py:210-214 literally: gfu = boundary projection; f -= A gfu; gfu += Inverse(active) f"""
+        M, rhs = self.assemble_full(lams)
+        x0 = np.zeros(self.ndof)
+        for f, c in self.dirichlet_values().items():
+            x0[self.facet_dofs(f)] = c
+        rhs = rhs - M @ x0
+        idx = np.nonzero(self.active)[0]
+        x = x0.copy()
+        x[idx] += spla.splu(M[idx][:, idx].tocsc()).solve(rhs[idx])
+        return x
+
+    def solve_condensed_lifted(self, lams):
+        """the same through static condensation: the prescribed dofs of boundary facets move to the right-hand side of the
+        facet system and return in the element back-solve"""
+        ub = self.dirichlet_values()
+        x = np.zeros(self.ndof)
+        for f, c in ub.items():
+            x[self.facet_dofs(f)] = c
+        rows, cols, vals = [], [], []
+        rhs = np.zeros(self.ndof)
+        cond = []
+        for el in range(self.ne):
+            A, F = self.element_matrix(el, lams[el])
+            iv, jf, dofs = self.local_active(el)
+            jb = [j for e in range(3) if self.facet2el[self.el2facet[el, e], 1] < 0 for j in self.loc_F(e)]
+            jall = np.array(list(jf) + jb, dtype=int)
+            W = np.linalg.solve(A[np.ix_(iv, iv)], A[np.ix_(iv, jall)])
+            z = np.linalg.solve(A[np.ix_(iv, iv)], F[iv])
+            S = A[np.ix_(jall, jall)] - A[np.ix_(jall, iv)] @ W
+            g = -A[np.ix_(jall, iv)] @ z
+            nfree = len(jf)
+            d = dofs[jf]
+            rows.append(np.repeat(d, nfree)); cols.append(np.tile(d, nfree)); vals.append(S[:nfree, :nfree].reshape(-1))
+            np.add.at(rhs, d, g[:nfree] - S[:nfree, nfree:] @ x[dofs[jb]])
+            cond.append((iv, jall, dofs, W, z))
+        Sg = sps.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(self.ndof, self.ndof)).tocsr()
+        fd = np.nonzero(np.diff(Sg.indptr) > 0)[0]
+        x[fd] = spla.splu(Sg[fd][:, fd].tocsc()).solve(rhs[fd])
+        for iv, jall, dofs, W, z in cond:
+            x[dofs[iv]] = z - W @ x[dofs[jall]]
+        return x
+
     # ------------------------------------------------------------------ a10: recombine + error
     def l2_error(self, x, order=None, h1=False):
         """:389-394  u_h = comp[0] + sum comp[2i+2] psi_i ; sqrt(Integrate((u_h-exact)^2, order=50+bonus))."""

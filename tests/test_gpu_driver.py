@@ -29,8 +29,9 @@ def test_solve_ehdg_tables_match_reference_layout_and_oracle():
         assert abs(row.Error - err) < 1e-8 * err
         a = alphas[alphas['order'] == order]['alpha'].to_numpy()
         assert np.max(np.abs(a - 0.5 * np.sqrt(1 + lams))) < 1e-12
-    with pytest.raises(NotImplementedError):
-        CT._solveEDG()
+    # the same instance also runs the reference's other method (plain DG here: no enrichment functions configured)
+    res_dg, _ = CT._solveEDG()
+    assert list(res_dg['Type'])[-2:] == ['dg', 'dg']
 
 
 def test_run_py_default_problem():
