@@ -184,12 +184,13 @@ def main():
     ap.add_argument("--no-solve", action="store_true", help="skip the one-off solves after the timed steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e-solve", action="store_true", help="skip the mesh-in / error-out leg through Convection_Diffusion (N = 1)")
-    ap.add_argument("--solve-iters", type=int, default=60000)
-    ap.add_argument("--solve-method", default="dqgmres", choices=["gmres", "dqgmres", "bicgstab"])
+    ap.add_argument("--solve-iters", type=int, default=6000)
+    ap.add_argument("--solve-method", default="auto", choices=["auto", "gmres", "dqgmres", "bicgstab"],
+                    help="auto = EHDGPipeline.solve_auto: DQGMRES(8), then GMRES(#lines / 10) if that did not converge")
     ap.add_argument("--solve-workload", default="same",
                     help="mesh of the one-off solve leg ('same' = the timed workload, partitioned like it at N > 1)")
     ap.add_argument("--rtol", type=float, default=1e-8)
-    ap.add_argument("--restart", type=int, default=8, help="GMRES restart / DQGMRES truncation length")
+    ap.add_argument("--restart", type=int, default=30, help="GMRES restart / DQGMRES truncation length (tools/line_probe.py: GMRES(30) is the robust choice)")
     ap.add_argument("--sweeps", type=int, default=1, help="block-Jacobi sweeps per preconditioner application")
     ap.add_argument("--precond", default="line", choices=["line", "facet"], help="line-block or facet-block Jacobi")
     ap.add_argument("--solve-type", default="both", choices=["hdg", "ehdg", "both"],
@@ -427,6 +428,8 @@ def main():
                 step(Ps)
             smesh = Ps.mesh_host
             barrier()
+            if rank == 0:
+                print(f"[bench] solve leg: {styp} on {swl}", file=sys.stderr, flush=True)
             nrows, nnz = Ps.csr_sizes.n_rows, Ps.csr_sizes.nnz            # nnz: this rank's rows
             own_rows = nrows if world == 1 else int(Ps.row_begin[rank + 1] - Ps.row_begin[rank])
             # SpMV bandwidth, 20 launches (own rows at N > 1, no exchange).  Two byte counts: the CSR-equivalent 12 nnz + 20 rows
@@ -469,7 +472,10 @@ def main():
                 if world > 1:
                     l2, h1 = parallel.partitioned_solve(Ps, **kw)
                 else:
-                    Ps.gmres(**kw)
+                    if args.solve_method == "auto":
+                        Ps.solve_auto(rtol=args.rtol, max_iters=args.solve_iters, precond=args.precond)
+                    else:
+                        Ps.gmres(**kw)
                     Ps.backsolve()
                     l2, h1 = Ps.errors()
             except Exception as exc:                       # reported in the line, the assembly numbers stand
@@ -485,7 +491,8 @@ def main():
                   "spmv_bytes_actual": bytes_actual, "spmv_bytes_csr_equivalent": bytes_csr}
             if gi is not None and err is None:
                 it_s = float(gi.total_seconds) - float(gi.setup_seconds)
-                sv.update({"gmres_iters": int(gi.iters), "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual),
+                sv.update({"attempts": getattr(Ps, "solve_attempts", None) if args.solve_method == "auto" else None,
+                           "gmres_iters": int(gi.iters), "gmres_converged": bool(gi.converged), "gmres_rel_residual": float(gi.rel_residual),
                            "gmres_seconds": float(gi.total_seconds), "precond_setup_seconds": float(gi.setup_seconds),
                            "ms_per_iteration": 1e3 * it_s / max(1, int(gi.iters)), "spmv_calls": int(gi.spmv_calls),
                            "dropped_dofs": int(gi.dropped_dofs), "strip_dofs": int(gi.strip_dofs), "line_chains": int(gi.line_chains),

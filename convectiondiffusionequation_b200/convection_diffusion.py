@@ -87,20 +87,20 @@ class Convection_Diffusion():
     def _solve(self, pipe, cfg):
         """Condensed facet system: CSR build, Krylov solve, back-solve.  The reference calls a direct solver and has no notion of
         non-convergence; here an unconverged iteration is an ERROR (config 'raise_on_nonconvergence', default True) instead
-        of a silently wrong 'Error' column.  solver 'auto' (default): GMRES(30) on the line-block preconditioner (measured: the
-        robust choice, DQGMRES(k) is erratic on these systems), then GMRES(100) if that did not reach the tolerance."""
+        of a silently wrong 'Error' column.  solver 'auto' (default): EHDGPipeline.solve_auto -- DQGMRES(8) on the line-block
+        preconditioner, then GMRES(m) with m sized by the number of lines if that did not reach the tolerance."""
         solver = cfg.get('solver', 'auto')
         rtol = cfg.get('gmres_rtol', 1e-10)
         max_iters = cfg.get('gmres_max_iters', 20000)
         precond = cfg.get('preconditioner', 'line')
         drop_tol = cfg.get('drop_tol', 0.0)
-        attempts = [('gmres', cfg.get('gmres_restart', 30)), ('gmres', 100)] if solver == 'auto' else [(solver, cfg.get('gmres_restart', 30))]
         pipe.csr_build()
-        for k, (method, restart) in enumerate(attempts):
-            pipe.gmres(restart=restart, max_iters=max_iters, rtol=rtol, method=method, precond=precond, drop_tol=drop_tol)
-            self._last_method = method
-            if pipe.gmres_info.converged:
-                break
+        if solver == 'auto':
+            pipe.solve_auto(rtol=rtol, max_iters=max_iters, precond=precond, drop_tol=drop_tol)
+            self._last_method = pipe.solve_attempts[-1]['method']
+        else:
+            pipe.gmres(restart=cfg.get('gmres_restart', 30), max_iters=max_iters, rtol=rtol, method=solver, precond=precond, drop_tol=drop_tol)
+            self._last_method = solver
         gi = pipe.gmres_info
         pipe.backsolve()
         if not gi.converged and cfg.get('raise_on_nonconvergence', True):

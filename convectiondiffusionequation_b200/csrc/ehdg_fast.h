@@ -69,6 +69,10 @@ EHDG_HD void st2(double* p, double a, double b) {
 #define EHDG_GJ_SHFL_ORDERS 0x60     /* p = 5, 6 */
 #endif
 #define EHDG_GJ_SHFL_FOR(p) (((EHDG_GJ_SHFL_ORDERS >> (p)) & 1) != 0)
+// Schur update of the p = 4 assemble kernel on the FP64 tensor cores (mma.sync m8n8k4); A/B in profiles/r02_kernels.md
+#ifndef EHDG_SCHUR_DMMA
+#define EHDG_SCHUR_DMMA 1
+#endif
 
 // entry j of row slot ho of a lane that keeps R rows (static register indexing)
 template <int R, int NC>
@@ -628,6 +632,104 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             }
     EHDG_END_LANES
 
+#if defined(__CUDA_ARCH__) && EHDG_SCHUR_DMMA
+    if constexpr (P == 4 && R == 1 && LG == 16) {
+        // ---- S = A_FF - A_FV X, g = -A_FV z on the FP64 tensor cores (mma.sync m8n8k4): per element a 16 x 16 x 16 product
+        // (NF = 15 rows, NP = 15 inner, NF + 1 = 16 columns: S and g together).  A_FV is formed directly in A-fragment layout
+        // from the facet tensor, X is read in B-fragment layout (one conflict-free LDS.64 per fragment instead of the 120
+        // broadcast LDS.128 per warp of the row-per-lane update), the result leaves in C-fragment layout through the
+        // staging area.  The two elements of a warp are processed one after the other by all 32 lanes.
+        const unsigned FULL = 0xffffffffu;
+        const int wl = (int)(threadIdx.x & 31u), q4 = wl >> 2, r4 = wl & 3, myg = wl >> 4;
+        const int scr = fast_asm_scratch_doubles<P>(rs.nq);
+        int eloc_[3];
+        eloc_[0] = elpack & 3;
+        eloc_[1] = (elpack >> 2) & 3;
+        eloc_[2] = (elpack >> 4) & 3;
+        if (store) {
+            int sinv_[3];
+            for (int s2 = 0; s2 < 3; ++s2) sinv_[eloc_[s2]] = s2;
+            const int l = gc.lane;
+            for (int col = l; col < NF; col += LG) {
+                const int src = sel3i(sinv_, col / NFL) * NFL + col % NFL;
+#pragma unroll
+                for (int c = 0; c < NP; ++c) W[c * NF + col] = Xs[c * NXS + src];
+            }
+            for (int c = l; c < NP; c += LG) z[c] = Xs[c * NXS + NF];
+        }
+        // B fragments of both elements before the staging area (which aliases X) is written
+        double bfr[2][4][2];
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            const double* Xe = Xs + (e2 - myg) * scr;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int tc = 0; tc < 2; ++tc) {
+                    const int c = 4 * ks + r4, j = 8 * tc + q4;
+                    bfr[e2][ks][tc] = c < NP ? Xe[c * NXS + j] : 0.0;
+                }
+        }
+        __syncwarp();
+        const double* tfb = tab + TL.offFT;
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            double* Se = Xs + (e2 - myg) * scr;
+            const double* ge = geo + (e2 - myg) * scr;
+            const int elp = __shfl_sync(FULL, elpack, e2 * 16);
+            int el3[3];
+            el3[0] = elp & 3;
+            el3[1] = (elp >> 2) & 3;
+            el3[2] = (elp >> 4) & 3;
+            int bad = 0;
+#pragma unroll
+            for (int tr = 0; tr < 2; ++tr) {
+                const int rr = 8 * tr + q4;
+                const bool rv = rr < NF;
+                const int r = rv ? rr : NF - 1;
+                const int s = r / NFL, k = r - s * NFL;
+                const double c_fv = ge[s], c_g0 = ge[6 + s], c_g1 = ge[9 + s], c_ff = ge[3 + s];
+                double af[4];
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const int jj = 4 * ks + r4;
+                    const int j = jj < NP ? jj : NP - 1;
+                    const double v = c_fv * tfb[j * NFS + r] + c_g0 * tfb[(NP + j) * NFS + r] + c_g1 * tfb[(2 * NP + j) * NFS + r];
+                    af[ks] = (rv && jj < NP) ? v : 0.0;
+                }
+                const int orow = sel3i(el3, s) * NFL + k;
+                const double dia = c_ff / (2.0 * k + 1.0);
+#pragma unroll
+                for (int tc = 0; tc < 2; ++tc) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(c0), "+d"(c1)
+                                     : "d"(af[ks]), "d"(bfr[e2][ks][tc]));
+                    if (rv) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int col = 8 * tc + 2 * r4 + u;
+                            double val = -(u == 0 ? c0 : c1);
+                            if (col == r) val += dia;
+                            if (val != val) bad = 1;
+                            if (col < NF) {
+                                const int s2 = col / NFL;
+                                Se[orow * NF + sel3i(el3, s2) * NFL + (col - s2 * NFL)] = val;
+                            } else {
+                                Se[NF * NF + orow] = val;
+                            }
+                        }
+                    }
+                }
+            }
+            if (__any_sync(FULL, bad) && myg == e2) status |= EHDG_ST_NONFINITE;
+        }
+        __syncwarp();
+    } else
+#endif
+    {
     // ---- rows of A_FV and the diagonal of A_FF, r = (s, k) in the sorted frame.  Built only now, from per-edge
     // coefficients that waited in shared memory: nothing of the geometry stays live in registers across the elimination,
     // which is what lets the kernel run four CTAs per SM.
@@ -724,6 +826,8 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             }
         }
     EHDG_END_LANES
+    }
+    double* Ss = Xs;                                // every lane is done reading X (repeated for the copy-out below)
     EHDG_FOR_LANES(l, L)
         if (store) {
             for (int col = l; col < NF; col += LG) {

@@ -180,6 +180,99 @@ __global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int
     rhs[r] = b;                                                     // rhs is indexed by the global row
 }
 
+// Same gather, one WARP per facet: the facet's values form one dense rows x len block (blk_base), so consecutive lanes write
+// consecutive entries (full-sector stores; the thread-per-row variant above strides by a row) and read runs of p + 1
+// consecutive doubles of one S_K row.  Measured at 4M elements, p = 4: see profiles/r02_kernels.md.
+__global__ void __launch_bounds__(256)
+csr_numeric_facet_kernel(int f_lo, int f_hi, SLayout sl, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
+                         const int32_t* __restrict__ nbr_len, const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask,
+                         const int32_t* __restrict__ facet2el, const int32_t* __restrict__ el2facet, const int32_t* __restrict__ eslot,
+                         const double* __restrict__ S, const double* __restrict__ gv, double* __restrict__ vals,
+                         double* __restrict__ rhs, const double* __restrict__ ubnd, int nfl) {
+    const int f = f_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= f_hi) return;
+    const int r0 = row_start[f], rows = row_start[f + 1] - r0;
+    if (rows == 0) return;
+    const int len = nbr_len[f];
+    const int64_t base = blk_base[f];
+    const unsigned mf = dofmask[f];
+    // adjacent elements (ascending id) and where their blocks live
+    const double* Sb[2];
+    const double* gb[2];
+    int ld[2], nbe[2], lef[2], ef[2][3], ne = 0;
+    for (int s = 0; s < 2; ++s) {
+        const int e = facet2el[2 * f + s];
+        if (e < 0) continue;
+        const int sl_ = eslot[e];
+        const int idx = sl_ & EHDG_SLOT_MASK;
+        if (sl_ & EHDG_SLOT_GEN) {
+            Sb[ne] = S + (size_t)sl.n_poly * sl.nfp * sl.nfp + (size_t)idx * sl.nfg * sl.nfg;
+            gb[ne] = gv + (size_t)sl.n_poly * sl.nfp + (size_t)idx * sl.nfg;
+            ld[ne] = sl.nfg;
+            nbe[ne] = sl.nb;
+        } else {
+            Sb[ne] = S + (size_t)idx * sl.nfp * sl.nfp;
+            gb[ne] = gv + (size_t)idx * sl.nfp;
+            ld[ne] = sl.nfp;
+            nbe[ne] = sl.nfl;
+        }
+        lef[ne] = 0;
+        for (int t = 0; t < 3; ++t) {
+            ef[ne][t] = el2facet[3 * e + t];
+            if (ef[ne][t] == f) lef[ne] = t;
+        }
+        ++ne;
+    }
+    // neighbour facets: column offsets, masks, local edge in either element
+    int coff[6], leg[2][5];
+    unsigned mg[5];
+    int nt = 0;
+    coff[0] = 0;
+    for (int t = 0; t < 5; ++t) {
+        const int g = nbr[5 * f + t];
+        if (g < 0) break;
+        mg[t] = dofmask[g];
+        coff[t + 1] = coff[t] + __popc(mg[t]);
+        for (int s = 0; s < ne; ++s) {
+            leg[s][t] = -1;
+            for (int u = 0; u < 3; ++u)
+                if (ef[s][u] == g) leg[s][t] = u;
+        }
+        ++nt;
+    }
+    for (int idx = lane; idx < rows * len; idx += 32) {
+        const int i = idx / len, c = idx - i * len;
+        const int k = nth_set_bit(mf, i);
+        int t = 0;
+        while (t + 1 < nt && c >= coff[t + 1]) ++t;
+        const int l = nth_set_bit(mg[t], c - coff[t]);
+        double v = 0.0;
+        for (int s = 0; s < ne; ++s)
+            if (leg[s][t] >= 0 && k < nbe[s] && l < nbe[s])
+                v += Sb[s][(size_t)(lef[s] * nbe[s] + k) * ld[s] + leg[s][t] * nbe[s] + l];
+        vals[base + idx] = v;
+    }
+    if (lane < rows) {
+        const int k = nth_set_bit(mf, lane);
+        double b = 0.0;
+        for (int s = 0; s < ne; ++s)
+            if (k < nbe[s]) b += gb[s][lef[s] * nbe[s] + k];
+        if (ubnd)
+            for (int t = 0; t < nt; ++t) {
+                const int g = nbr[5 * f + t];
+                if (facet2el[2 * g + 1] >= 0) continue;
+                for (int l = 0; l < nfl; ++l) {
+                    double v = 0.0;
+                    for (int s = 0; s < ne; ++s)
+                        if (leg[s][t] >= 0 && k < nbe[s]) v += Sb[s][(size_t)(lef[s] * nbe[s] + k) * ld[s] + leg[s][t] * nbe[s] + l];
+                    b -= v * ubnd[(size_t)g * nfl + l];
+                }
+            }
+        rhs[r0 + lane] = b;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // SpMV: CSR, TPR threads per row
 // ---------------------------------------------------------------------------------------------
@@ -1478,9 +1571,18 @@ int ehdg_csr_numeric_bc(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, cons
     const int64_t rlo = A->windowed ? A->row_lo : 0, rhi = A->windowed ? A->row_hi : A->n_rows;
     if (rhi <= rlo) return EHDG_OK;
     if (A->folded_vals == vals) const_cast<ehdg_csr*>(A)->folded_vals = nullptr;     // fresh values: a Krylov solve may fold them again
-    csr_numeric_kernel<<<(unsigned)((rhi - rlo + 127) / 128), 128, 0, st>>>((int)rlo, (int)rhi, make_slayout(c, p), A->row_facet, A->row_start,
-                                                                            A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,
-                                                                            p->eslot, S, g, vals, rhs, ubnd, c->pb.nfl);
+    static const bool row_kernel = [] { const char* e = getenv("EHDG_CSR_NUMERIC_ROW"); return e && e[0] == '1'; }();
+    if (row_kernel) {
+        csr_numeric_kernel<<<(unsigned)((rhi - rlo + 127) / 128), 128, 0, st>>>((int)rlo, (int)rhi, make_slayout(c, p), A->row_facet, A->row_start,
+                                                                                A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,
+                                                                                p->eslot, S, g, vals, rhs, ubnd, c->pb.nfl);
+    } else {
+        const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
+        if (fb > fa)
+            csr_numeric_facet_kernel<<<(unsigned)(((int64_t)(fb - fa) * 32 + 255) / 256), 256, 0, st>>>(
+                fa, fb, make_slayout(c, p), A->row_start, A->blk_base, A->nbr_len, A->nbr, A->dofmask, m->facet2el, m->el2facet, p->eslot, S, g,
+                vals, rhs, ubnd, c->pb.nfl);
+    }
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -1896,6 +1998,8 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
             EHDG_CUDA(cudaMemcpyAsync(yhat, pt, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         }
     }
+    int gm_stall = 0;
+    double gm_prev_rel = 1e300;
     while (method == 0 && !conv && iters < max_iters) {
         // r = b - A yhat  (into w), beta = ||r||
         if ((rc = apply_op(yhat, w))) return rc;
@@ -1906,6 +2010,12 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
         const double beta = std::sqrt(hbuf[0]);
         rel = beta / bnorm;
         if (rel <= rtol) { conv = true; break; }
+        // stagnation: ten restart cycles in a row that gain less than 1e-5 each (the attainable accuracy of the
+        // preconditioned operator is reached, or the system is singular beyond the selection rule): stop instead of
+        // spending max_iters on it; `converged` then reports whether 10 rtol was met.  The bar is this low on purpose: on
+        // large meshes the residual sits on a plateau (1e-4 .. 1e-3 per cycle) until the information has crossed the mesh.
+        if (rel > (1.0 - 1e-5) * gm_prev_rel) { if (++gm_stall >= 10) break; } else gm_stall = 0;
+        gm_prev_rel = rel;
         scale_kernel<<<vgrid, RED_THREADS, 0, st>>>(n, w, d_nrm, V);
         std::fill(gvec.begin(), gvec.end(), 0.0);
         gvec[0] = beta;

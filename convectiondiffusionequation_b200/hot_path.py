@@ -319,6 +319,27 @@ class EHDGPipeline:
         self.gmres_info = info
         return self
 
+    def solve_auto(self, rtol=1e-8, max_iters=8000, precond="line", drop_tol=0.0, strip_block=True):
+        """Solver portfolio of the facet system (measured on B200, tools/line_probe.py): DQGMRES(8) on the line-block
+        preconditioner is the fastest where it converges (no restart, eight vectors: 4M elements in 1 520 iterations / 15 s) but
+        erratic on some systems; GMRES(m) is robust once m covers the plateau that the residual sits on until the information
+        has crossed the mesh, m = #lines / 10 clamped to [30, 200] (4M elements: GMRES(30) stalls, GMRES(150) needs 1 937
+        iterations / 45 s).  Tries the first, falls back to the second.  self.solve_attempts records both."""
+        self.solve_attempts = []
+        for method, restart in (("dqgmres", 8), ("gmres", None)):
+            if restart is None:
+                chains = max(1, int(self.gmres_info.line_chains)) if precond == "line" else 300
+                restart = int(min(200, max(30, chains // 10)))
+            cap = min(max_iters, 2500) if method == "dqgmres" else max_iters      # where DQGMRES(8) works it is done well before
+            self.gmres(restart=restart, max_iters=cap, rtol=rtol, method=method, precond=precond, drop_tol=drop_tol,
+                       strip_block=strip_block)
+            gi = self.gmres_info
+            self.solve_attempts.append(dict(method=method, restart=restart, iters=int(gi.iters), converged=bool(gi.converged),
+                                            rel_residual=float(gi.rel_residual), seconds=float(gi.total_seconds)))
+            if gi.converged:
+                break
+        return self
+
     # ------------------------------------------------------------------ a10
     def backsolve(self):
         self.u = torch.empty(self.plan_sizes.z_doubles, dtype=torch.float64, device=self.dev)

@@ -191,8 +191,12 @@ def partitioned_solve(pipe, group=None, **gm):
     """Krylov solve on the partitioned system, back-solve on the rank's elements, (L2, H1) error over all ranks"""
     import torch
     import torch.distributed as dist
-    gm.setdefault("strip_block", False)
-    pipe.gmres(**gm).backsolve()
+    if gm.get("method") == "auto":
+        pipe.solve_auto(rtol=gm.get("rtol", 1e-8), max_iters=gm.get("max_iters", 8000), precond=gm.get("precond", "line"),
+                        drop_tol=gm.get("drop_tol", 0.0), strip_block=gm.get("strip_block", True))
+        pipe.backsolve()
+    else:
+        pipe.gmres(**gm).backsolve()
     e = pipe.error_sums(pipe.elem_owned)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         if dist.get_backend(group) != "nccl":

@@ -343,42 +343,51 @@ class EHDGOracle:
             G[np.ix_(jf, jf)] += np.einsum("in,jn,n->ij", fs, fs, w)
         return G
 
+    def prune_element(self, el, threshold=1e-5):
+        """conv_diff.py:286-310 for ONE marked element, literally (python floats => ZeroDivisionError aborts the element).
+        The loop only looks at the element's own dof list (`important` starts from dofs[i] >= 0), so its decisions do not
+        depend on what other elements removed.  Returns (dropped global dofs, [(local index, factor)])."""
+        dofs = self.el_dofs(el)
+        N = len(dofs)
+        elmat = self.boundary_gram(el).tolist()
+        important = [bool(dofs[i] >= 0) for i in range(N)]
+        factors, dropped = [], []
+        try:
+            for i in range(self.n_p, N):
+                if important[i]:
+                    if elmat[i][i] == 0.0:
+                        # psi vanishes identically on this facet (the outflow edge itself, d = 0 in the
+                        # cancellation-free form used here).  NGSolve evaluates psi from a rounded x and
+                        # gets ~1e-16 instead of 0, so the reference neither divides by zero nor prunes
+                        # this (Dirichlet) dof: skip it, and keep it out of the later `active` lists.
+                        important[i] = False
+                        factors.append((i, -3.0))
+                        continue
+                    act = [j for j in range(i) if important[j]]
+                    factor = 1 - 2 * sum([elmat[i][j] ** 2 / elmat[i][i] / elmat[j][j] for j in act])
+                    factor += sum([elmat[i][j] * elmat[i][k] * elmat[j][k] / elmat[i][i]
+                                   / elmat[j][j] / elmat[k][k] for j in act for k in act])
+                    factor = np.sqrt(abs(factor))
+                    factors.append((i, factor))
+                    if factor <= threshold:
+                        important[i] = False
+                        if dofs[i] >= 0:
+                            dropped.append(int(dofs[i]))
+        except ZeroDivisionError:
+            pass
+        return dropped, factors
+
     def prune(self, threshold=1e-5):
-        """conv_diff.py:282-310, literally (python floats => ZeroDivisionError aborts the element)."""
+        """conv_diff.py:282-310: every marked element in turn; a global dof is deactivated as soon as one element says so."""
         self.prune_factors = {}
         if self.nenr == 0:
             return self.active
         for el in range(self.ne):
             if not self.el_marked_any[el]:
                 continue
-            dofs = self.el_dofs(el)
-            N = len(dofs)
-            elmat = self.boundary_gram(el).tolist()
-            important = [bool(dofs[i] >= 0) for i in range(N)]
-            factors = []
-            try:
-                for i in range(self.n_p, N):
-                    if important[i]:
-                        if elmat[i][i] == 0.0:
-                            # psi vanishes identically on this facet (the outflow edge itself, d = 0 in the
-                            # cancellation-free form used here).  NGSolve evaluates psi from a rounded x and
-                            # gets ~1e-16 instead of 0, so the reference neither divides by zero nor prunes
-                            # this (Dirichlet) dof: skip it, and keep it out of the later `active` lists.
-                            important[i] = False
-                            factors.append((i, -3.0))
-                            continue
-                        act = [j for j in range(i) if important[j]]
-                        factor = 1 - 2 * sum([elmat[i][j] ** 2 / elmat[i][i] / elmat[j][j] for j in act])
-                        factor += sum([elmat[i][j] * elmat[i][k] * elmat[j][k] / elmat[i][i]
-                                       / elmat[j][j] / elmat[k][k] for j in act for k in act])
-                        factor = np.sqrt(abs(factor))
-                        factors.append((i, factor))
-                        if factor <= threshold:
-                            important[i] = False
-                            if dofs[i] >= 0:
-                                self.active[dofs[i]] = False
-            except ZeroDivisionError:
-                pass
+            dropped, factors = self.prune_element(el, threshold)
+            for d in dropped:
+                self.active[d] = False
             self.prune_factors[el] = factors
         return self.active
 

@@ -47,7 +47,8 @@ if __name__ == "__main__":
     elif which == "1m":
         run(708, 4, 1e-6, configs=(("line", "dqgmres", 8, 0), ("line", "dqgmres", 8, 32), ("line", "gmres", 30, 0)))
     elif which == "4m":
-        run(1414, 4, 1e-6, kind="unstructured", configs=(("line", "dqgmres", 8, 0),))
+        run(1414, 4, 1e-6, kind="unstructured", configs=(("line", "gmres", 30, 0), ("line", "gmres", 60, 0)), iters=5000)
+        run(1414, 4, 1e-6, kind="unstructured", enriched=True, configs=(("line", "gmres", 30, 0),), iters=5000)
     elif which == "one":
         run(708, 4, 1e-6, configs=(("line", "gmres", 30, 0),), iters=40)
     elif which == "enr3":
@@ -57,6 +58,17 @@ if __name__ == "__main__":
             run(n, p, eps, enriched=True, configs=(("facet", "gmres", 60, 0),), iters=4000)
             run(n, p, eps, enriched=False, configs=(("line", "gmres", 30, 0),), iters=4000)
         run(708, 4, 1e-6, enriched=True, configs=(("line", "gmres", 30, 0),), iters=4000)
+    elif which == "4m2":
+        run(1414, 4, 1e-6, kind="unstructured", configs=(("line", "dqgmres", 16, 0), ("line", "gmres", 150, 0), ("line", "dqgmres", 8, 32)), iters=8000)
+    elif which == "4m3":
+        run(1414, 4, 1e-6, kind="unstructured", configs=(("line", "dqgmres", 8, 0),), iters=8000)
+        run(1414, 4, 1e-6, kind="unstructured", enriched=True, configs=(("line", "dqgmres", 8, 0), ("line", "gmres", 150, 0)), iters=8000)
+        run(708, 4, 1e-6, enriched=True, configs=(("line", "dqgmres", 8, 0),), iters=8000)
+        run(224, 3, 1e-4, enriched=True, configs=(("line", "dqgmres", 8, 0),), iters=8000)
+    elif which == "enru":
+        for (n, p, eps) in [(64, 4, 1e-6), (64, 4, 2.2e-5), (224, 4, 1e-6), (708, 4, 1e-6)]:
+            run(n, p, eps, kind="unstructured", enriched=True, configs=(("line", "gmres", 60, 0), ("facet", "gmres", 60, 0)), iters=3000)
+            run(n, p, eps, kind="unstructured", enriched=False, configs=(("line", "gmres", 60, 0),), iters=3000)
     elif which == "enr":
         for (n, p, eps) in [(16, 2, 1e-2), (16, 4, 1e-2), (32, 4, 1e-3), (32, 3, 1e-4), (64, 4, 1.1e-5), (64, 4, 1e-6), (224, 3, 1e-4)]:
             run(n, p, eps, enriched=True, configs=(("line", "gmres", 30, 0), ("line", "gmres", 100, 0), ("facet", "gmres", 60, 0)), iters=6000)
