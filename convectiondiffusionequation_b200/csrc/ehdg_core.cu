@@ -293,6 +293,12 @@ int ehdg_destroy(ehdg_ctx* c) {
     return EHDG_OK;
 }
 
+int ehdg_set_drop_tol(ehdg_ctx* c, double vol_drop_tol) {
+    if (!c || !(vol_drop_tol >= 0.0)) { set_error("ehdg_set_drop_tol: bad argument"); return EHDG_ERR_ARG; }
+    c->pb.vol_drop_tol = vol_drop_tol;
+    return EHDG_OK;
+}
+
 int ehdg_kernel_timing(ehdg_ctx* c, int enable) {
     if (!c) { set_error("ehdg_kernel_timing: null argument"); return EHDG_ERR_ARG; }
     if (enable && !c->ev_k[0])

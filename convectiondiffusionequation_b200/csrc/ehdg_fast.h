@@ -69,9 +69,11 @@ EHDG_HD void st2(double* p, double a, double b) {
 #define EHDG_GJ_SHFL_ORDERS 0x60     /* p = 5, 6 */
 #endif
 #define EHDG_GJ_SHFL_FOR(p) (((EHDG_GJ_SHFL_ORDERS >> (p)) & 1) != 0)
-// Schur update of the p = 4 assemble kernel on the FP64 tensor cores (mma.sync m8n8k4); A/B in profiles/r02_kernels.md
+// Schur update of the p = 4 assemble kernel on the FP64 tensor cores (mma.sync m8n8k4).  A/B on B200, 4M elements
+// (profiles/r02_kernels.md): 20.26 ms with DMMA against 19.18 ms without (bit-identical S): the 32 DMMA per warp and the
+// fragment-layout A_FV build cost more than the 104 shared-memory wavefronts per element they save.  Off by default.
 #ifndef EHDG_SCHUR_DMMA
-#define EHDG_SCHUR_DMMA 1
+#define EHDG_SCHUR_DMMA 0
 #endif
 
 // entry j of row slot ho of a lane that keeps R rows (static register indexing)

@@ -19,6 +19,7 @@ namespace ehdg {
 struct Problem {
     int p, n_p, nfl, nenr, nb, nvmax, nfmax, bonus;
     double eps, bx, by;
+    double vol_drop_tol;     // selection rule for dependent VOLUME enrichment dofs in the element condensation (0 = off)
     int enr_axis[EHDG_MAX_ENRICH];
     double enr_k[EHDG_MAX_ENRICH];
     LayerExpr coeff, exact;
@@ -50,7 +51,7 @@ struct Coop {
 };
 
 // status bits per element
-enum { EHDG_ST_SINGULAR = 1, EHDG_ST_NONFINITE = 2, EHDG_ST_ALPHA_DEFICIENT = 4 };
+enum { EHDG_ST_SINGULAR = 1, EHDG_ST_NONFINITE = 2, EHDG_ST_ALPHA_DEFICIENT = 4, EHDG_ST_ENR_DROPPED = 8 };
 
 struct ElemGeom {
     double P[3][2];
@@ -336,17 +337,37 @@ EHDG_HD int assemble_condense_general(const Coop& co, const Problem& pb, const R
         co.sync();
     }
 
-    // ---- a6: Gaussian elimination with partial pivoting on [A_VV | A_VF f_V]
+    // ---- a6: Gaussian elimination on [A_VV | A_VF f_V].  Polynomial rows: partial pivoting among themselves (the polynomial
+    // block is the plain HDG element matrix).  Enrichment rows come last and are eliminated on their diagonal, which after the
+    // polynomial (and earlier enrichment) dofs have been eliminated is the share of psi_k that those dofs do not explain,
+    // relative to its own size d0: below pb.vol_drop_tol the enrichment is dependent on this element (q(y) on an element of
+    // height h with beta_y h / eps < 1 is a polynomial to 1e-6) and leaves the element space -- its coefficient is 0, its row
+    // and column do not enter S_K.  The reference keeps such dofs (its pruning factor :296-301 is a boundary-Gram distance at
+    // 1e-5) and hands PARDISO a singular block; status bit EHDG_ST_ENR_DROPPED records where the rule fired.
     const int ncol = ldA;
+    double d0[EHDG_MAX_ENRICH];
+    for (int k = 0; k < pb.nenr; ++k) d0[k] = fabs(Aug[(pb.n_p + k) * ldA + pb.n_p + k]);
+    co.sync();
     for (int k = 0; k < nv; ++k) {
+        const bool enr = k >= pb.n_p;
         int piv = k;
         double best = fabs(Aug[k * ldA + k]);
-        for (int i = k + 1; i < nv; ++i) {
-            const double a = fabs(Aug[i * ldA + k]);
-            if (a > best) { best = a; piv = i; }
-        }
+        if (!enr)
+            for (int i = k + 1; i < pb.n_p; ++i) {
+                const double a = fabs(Aug[i * ldA + k]);
+                if (a > best) { best = a; piv = i; }
+            }
         if (!(best > 0.0) || best != best) status |= EHDG_ST_SINGULAR;
+        const bool drop = enr && ((volmask >> (k - pb.n_p)) & 1) && pb.vol_drop_tol > 0.0 && !(best > pb.vol_drop_tol * d0[k - pb.n_p]);
         co.sync();                      // every lane has finished scanning column k before rows move
+        if (drop) {
+            status |= EHDG_ST_ENR_DROPPED;
+            for (int j = co.lane; j < ncol; j += co.nl) Aug[k * ldA + j] = (j == k) ? 1.0 : 0.0;     // x_k = 0
+            for (int i = co.lane; i < nv; i += co.nl)
+                if (i != k) Aug[i * ldA + k] = 0.0;                                                   // and nobody sees it
+            co.sync();
+            continue;
+        }
         if (piv != k) {
             for (int j = k + co.lane; j < ncol; j += co.nl) {
                 const double t = Aug[k * ldA + j];

@@ -28,6 +28,7 @@ inline Problem make_problem(const ehdg_problem& ep) {
     pb.eps = ep.epsilon;
     pb.bx = ep.beta[0];
     pb.by = ep.beta[1];
+    pb.vol_drop_tol = 1e-6;      // ehdg_set_drop_tol
     for (int k = 0; k < EHDG_MAX_ENRICH; ++k) {
         pb.enr_axis[k] = k < ep.n_enrich ? ep.enrich_axis[k] : 0;
         pb.enr_k[k] = k < ep.n_enrich ? ep.enrich_k[k] : 0.0;

@@ -182,7 +182,8 @@ __global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int
 
 // Same gather, one WARP per facet: the facet's values form one dense rows x len block (blk_base), so consecutive lanes write
 // consecutive entries (full-sector stores; the thread-per-row variant above strides by a row) and read runs of p + 1
-// consecutive doubles of one S_K row.  Measured at 4M elements, p = 4: see profiles/r02_kernels.md.
+// consecutive doubles of one S_K row.  Measured SLOWER than the thread-per-row kernel at 4M elements, p = 4 (13.8 against
+// 9.2 ms, tools/csr_numeric_time.py): kept behind EHDG_CSR_NUMERIC_FACET=1 for the record.
 __global__ void __launch_bounds__(256)
 csr_numeric_facet_kernel(int f_lo, int f_hi, SLayout sl, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
                          const int32_t* __restrict__ nbr_len, const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask,
@@ -1571,7 +1572,10 @@ int ehdg_csr_numeric_bc(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, cons
     const int64_t rlo = A->windowed ? A->row_lo : 0, rhi = A->windowed ? A->row_hi : A->n_rows;
     if (rhi <= rlo) return EHDG_OK;
     if (A->folded_vals == vals) const_cast<ehdg_csr*>(A)->folded_vals = nullptr;     // fresh values: a Krylov solve may fold them again
-    static const bool row_kernel = [] { const char* e = getenv("EHDG_CSR_NUMERIC_ROW"); return e && e[0] == '1'; }();
+    // A/B on B200, 4M elements, p = 4 (tools/csr_numeric_time.py): thread-per-row 9.17 ms (1.52 TB/s), warp-per-facet
+    // 13.84 ms (1.01 TB/s: the per-entry index arithmetic costs more than the coalesced stores win).  EHDG_CSR_NUMERIC_FACET=1
+    // selects the latter.
+    static const bool row_kernel = [] { const char* e = getenv("EHDG_CSR_NUMERIC_FACET"); return !(e && e[0] == '1'); }();
     if (row_kernel) {
         csr_numeric_kernel<<<(unsigned)((rhi - rlo + 127) / 128), 128, 0, st>>>((int)rlo, (int)rhi, make_slayout(c, p), A->row_facet, A->row_start,
                                                                                 A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,

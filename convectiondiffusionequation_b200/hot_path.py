@@ -28,6 +28,7 @@ class ProblemSpec:
     exact: LayerExpr | None = None
     enrich_functions: tuple = ()
     enrich_domain_ind: tuple = ()
+    vol_drop_tol: float = 1e-6      # selection rule for dependent volume enrichments (ehdg_set_drop_tol); 0 = reference-literal
 
     def c_struct(self) -> _lib.Problem:
         p = _lib.Problem()
@@ -78,6 +79,7 @@ class EHDGPipeline:
         self._cprob = spec.c_struct()
         self.ctx = C.c_void_p()
         _lib.check(self.lib.ehdg_create(C.byref(self._cprob), C.byref(self.ctx)), "ehdg_create")
+        _lib.check(self.lib.ehdg_set_drop_tol(self.ctx, float(spec.vol_drop_tol)), "ehdg_set_drop_tol")
         self.sizes = _lib.Sizes()
         _lib.check(self.lib.ehdg_get_sizes(self.ctx, C.byref(self.sizes)), "ehdg_get_sizes")
         self.plan = None

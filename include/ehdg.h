@@ -92,6 +92,12 @@ const char* ehdg_last_error(void);
 int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out);
 int ehdg_destroy(ehdg_ctx* ctx);
 int ehdg_get_sizes(const ehdg_ctx* ctx, ehdg_sizes* out);
+/* Selection rule for dependent VOLUME enrichment dofs inside the element condensation (a6): after the polynomial dofs of an
+ * element have been eliminated, an enrichment whose remaining diagonal is below vol_drop_tol x its own size is dependent on
+ * that element (e.g. q(y) where beta_y h / eps < 1) and leaves the element space: coefficient 0, no contribution to S_K;
+ * status bit 8 marks the element.  Default 1e-6; 0 restores the reference's literal behaviour (every unpruned enrichment is
+ * kept, A_VV may be singular to working precision).  The facet-level counterpart is ehdg_gmres_info.drop_tol. */
+int ehdg_set_drop_tol(ehdg_ctx* ctx, double vol_drop_tol);
 /* CUDA-event timing of the two polynomial-path kernels (recorded on the launching stream); off by default.
  * ehdg_kernel_times_ms returns the durations of the most recent launches. */
 int ehdg_kernel_timing(ehdg_ctx* ctx, int enable);

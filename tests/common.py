@@ -6,8 +6,9 @@ import numpy as np
 from oracle import ehdg_oracle as orc
 
 
-def make_pair(mesh, order, beta=(2.0, 0.001), eps=0.01, bonus=10, enriched=True):
-    """(oracle object, product ProblemSpec) for the run.py problem on `mesh`."""
+def make_pair(mesh, order, beta=(2.0, 0.001), eps=0.01, bonus=10, enriched=True, literal=False):
+    """(oracle object, product ProblemSpec) for the run.py problem on `mesh`.  literal=True switches the product's selection rule
+    for dependent volume enrichments off (block-by-block comparisons with the oracle, which keeps every unpruned dof)."""
     from convectiondiffusionequation_b200 import boundary_layer, x, y
     from convectiondiffusionequation_b200.hot_path import ProblemSpec
     prob = orc.run_py_problem(beta=beta, eps=eps, bonus_int=bonus, enriched=enriched)
@@ -15,7 +16,8 @@ def make_pair(mesh, order, beta=(2.0, 0.001), eps=0.01, bonus=10, enriched=True)
     p, q = boundary_layer(x, beta[0], eps), boundary_layer(y, beta[1], eps)
     spec = ProblemSpec(order=order, epsilon=eps, beta=beta, bonus_int=bonus, coeff=beta[1] * p + beta[0] * q, exact=p * q,
                        enrich_functions=(p, q) if enriched else (),
-                       enrich_domain_ind=(lambda X, Y, h: X > 1 - h, lambda X, Y, h: Y > 1 - h) if enriched else ())
+                       enrich_domain_ind=(lambda X, Y, h: X > 1 - h, lambda X, Y, h: Y > 1 - h) if enriched else (),
+                       vol_drop_tol=0.0 if literal else 1e-6)
     return o, spec
 
 

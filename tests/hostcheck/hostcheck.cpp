@@ -63,11 +63,13 @@ void hc_dubiner(int p, int n, const double* X, const double* Y, double* v, doubl
 }
 void hc_sizes(const ehdg_problem* ep, int* out) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     out[0] = pb.n_p; out[1] = pb.nb; out[2] = pb.nvmax; out[3] = pb.nfmax;
 }
 int hc_assemble(const ehdg_problem* ep, const double* verts, const int* tri, double lam, int volmask,
                 const int* facmask, double* S, double* g, double* W, double* z, double* Afull) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     HostRules hr(2 * pb.p + pb.bonus);
     std::vector<double> ws(general_ws_doubles(pb, hr.rs.nq, hr.rs.nqf));
     Coop co{0, 1};
@@ -76,6 +78,7 @@ int hc_assemble(const ehdg_problem* ep, const double* verts, const int* tri, dou
 double hc_alpha(const ehdg_problem* ep, const double* verts, const int* tri, int volmask, int exclude_const,
                 int* status) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     HostRules hb(2 * pb.p + pb.bonus), h0(2 * pb.p);
     std::vector<double> ws(alpha_ws_doubles(pb, h0.rs.nq, h0.rs.nqf));
     Coop co{0, 1};
@@ -85,6 +88,7 @@ double hc_alpha(const ehdg_problem* ep, const double* verts, const int* tri, int
 void hc_prune(const ehdg_problem* ep, const double* verts, const int* tri, int elmark, const int* facmask,
               double threshold, int* vol_drop, int* fac_drop, double* factors) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     HostRules hb(2 * pb.p + pb.bonus);
     std::vector<double> ws(general_ws_doubles(pb, hb.rs.nq, hb.rs.nqf));
     Coop co{0, 1};
@@ -94,6 +98,7 @@ void hc_prune(const ehdg_problem* ep, const double* verts, const int* tri, int e
 int hc_fast_assemble(const ehdg_problem* ep, const double* verts, const int* tri, double lam, double* S, double* g,
                      double* W, double* z) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     switch (pb.p) {
         case 1: return fast_assemble_host<1>(pb, verts, tri, lam, S, g, W, z);
         case 2: return fast_assemble_host<2>(pb, verts, tri, lam, S, g, W, z);
@@ -120,6 +125,7 @@ double hc_fast_alpha(const ehdg_problem* ep, const double* verts, const int* tri
 void hc_edg_element(const ehdg_problem* ep, const double* verts, const int* tris, const int* el2facet, const int* facet2el,
                     const unsigned char* elem_active, const double* alpha_stab, int el, double* D, double* O, double* F) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     HostRules hr(2 * pb.p + pb.bonus);
     std::vector<double> ws(edg_ws_doubles(pb, hr.rs.nq, hr.rs.nqf));
     Coop co{0, 1};
@@ -128,6 +134,7 @@ void hc_edg_element(const ehdg_problem* ep, const double* verts, const int* tris
 
 int hc_edg_prune(const ehdg_problem* ep, const double* verts, const int* tri, int elmark, double theta, double* factors) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     HostRules hr(2 * pb.p + pb.bonus);
     std::vector<double> ws(edg_ws_doubles(pb, hr.rs.nq, hr.rs.nqf) + pb.nvmax * pb.nvmax);
     Coop co{0, 1};
@@ -136,6 +143,7 @@ int hc_edg_prune(const ehdg_problem* ep, const double* verts, const int* tri, in
 // the alpha pencil with the rule of order 2p + bonus (the EDG integrators pass bonus_intorder, reference :129-134)
 double hc_alpha_bonus(const ehdg_problem* ep, const double* verts, const int* tri, int volmask, int exclude_const, int* status) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     HostRules hb(2 * pb.p + pb.bonus);
     std::vector<double> ws(alpha_ws_doubles(pb, hb.rs.nq, hb.rs.nqf));
     Coop co{0, 1};
@@ -148,6 +156,7 @@ double hc_alpha_bonus(const ehdg_problem* ep, const double* verts, const int* tr
 void hc_edg_csr_sizes(const ehdg_problem* ep, int ne, const int* el2facet, const int* facet2el, const unsigned char* elem_active,
                       long long* n_rows, long long* nnz) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     std::vector<int> cnt(ne);
     for (int el = 0; el < ne; ++el) cnt[el] = __builtin_popcount(edg_dofmask(pb.n_p, elem_active ? elem_active[el] : 0));
     long long r = 0, z = 0;
@@ -165,6 +174,7 @@ void hc_edg_csr_sizes(const ehdg_problem* ep, int ne, const int* el2facet, const
 void hc_edg_csr(const ehdg_problem* ep, int ne, const double* verts, const int* tris, const int* el2facet, const int* facet2el,
                 const unsigned char* elem_active, const double* alpha_stab, long long* rowptr, int* colind, double* vals, double* rhs) {
     Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = 0.0;      // host checks compare block by block with the oracle: reference-literal elimination
     HostRules hr(2 * pb.p + pb.bonus);
     std::vector<double> ws(edg_ws_doubles(pb, hr.rs.nq, hr.rs.nqf));
     const int nv = pb.nvmax;

@@ -116,7 +116,7 @@ def test_edg_solution(n, order, eps, beta, enriched, kind):
     alpha_stab = P.lam.cpu().numpy()
     x = o.solve(alpha_stab)                                                      # same stabilisation on both sides
     l2_ref = o.l2_error(x)
-    P.assemble().gmres(restart=60, max_iters=20000, rtol=1e-11, method="gmres").backsolve()
+    P.assemble().gmres(restart=60, max_iters=20000, rtol=1e-10, method="gmres").backsolve()      # floor of the line blocks: a few 1e-10 at p = 3
     assert P.gmres_info.converged == 1, (P.gmres_info.iters, P.gmres_info.rel_residual)
     l2, _ = P.errors()
     assert abs(l2 - l2_ref) < 1e-8 * l2_ref, (l2, l2_ref)

@@ -102,7 +102,7 @@ def test_alpha_known_answers():
 def test_general_path_blocks(n, order, eps, beta, kind):
     """quadrature path on every element (force_general): uncondensed blocks, alpha, S, g, W, z."""
     mesh = _mesh(n, kind)
-    o, spec = make_pair(mesh, order, beta=beta, eps=eps)
+    o, spec = make_pair(mesh, order, beta=beta, eps=eps, literal=True)
     o.prune()
     P = _pipe(mesh, spec, force_general=True).setup().alpha()
     lam_dev = P.lam.cpu().numpy()

@@ -18,7 +18,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     n = int(os.environ.get("DS_N", "64"))
     order, eps = int(os.environ.get("DS_P", "3")), float(os.environ.get("DS_EPS", "1e-6"))
-    method, k = os.environ.get("DS_METHOD", "dqgmres"), int(os.environ.get("DS_K", "40"))
+    method, k = os.environ.get("DS_METHOD", "gmres"), int(os.environ.get("DS_K", "40"))
+    precond = os.environ.get("DS_PRECOND", "line")       # of the partitioned solve; the replicated-matrix mode has facet blocks only
     iters = int(os.environ.get("DS_ITERS", "20000"))
     mesh = unit_square_mesh(n, kind=os.environ.get("DS_KIND", "unstructured"))
     spec = make_spec(order, eps, enriched=False)
@@ -26,14 +27,14 @@ def main():
     ref = None
     if os.environ.get("DS_REF", "1") == "1":
         Pr = EHDGPipeline(mesh, spec, device=dev).setup().assemble().csr_build()
-        Pr.gmres(restart=k, max_iters=iters, rtol=1e-10, method=method)
+        Pr.gmres(restart=k, max_iters=iters, rtol=1e-10, method=method, precond="facet")
         ref = (Pr.xhat.clone(), Pr.gmres_info.iters, Pr.gmres_info.total_seconds, Pr.gmres_info.rel_residual)
         Pr.close()
     P = EHDGPipeline(mesh, spec, device=dev).setup().assemble().csr_build()
     parallel.init_communicator(P)
     rb, lo, hi = parallel.set_partition(P, world)
     dist.barrier()
-    P.gmres(restart=k, max_iters=iters, rtol=1e-10, method=method, strip_block=False)
+    P.gmres(restart=k, max_iters=iters, rtol=1e-10, method=method, strip_block=False, precond="facet")
     gi = P.gmres_info
     out = dict(world=world, n=n, p=order, eps=eps, method=method, rows=int(P.csr_sizes.n_rows), iters=int(gi.iters), converged=bool(gi.converged),
                rel_residual=float(gi.rel_residual), seconds=float(gi.total_seconds), rows_per_rank=[int(b - a) for a, b in zip(rb[:-1], rb[1:])],
@@ -60,13 +61,13 @@ def main():
         dist.barrier(); t0.record()
         parallel.partitioned_assemble(P, rank, world)
         t1.record(); torch.cuda.synchronize()
-        l2p, h1p = parallel.partitioned_solve(P, restart=k, max_iters=iters, rtol=1e-10, method=method)
+        l2p, h1p = parallel.partitioned_solve(P, restart=k, max_iters=iters, rtol=1e-10, method=method, precond=precond)
         gi = P.gmres_info
         cnt = torch.tensor([int(P.plan_sizes.n_poly + P.plan_sizes.n_gen), int(P.elem_owned.sum()), int(P.csr_sizes.nnz)],
                            dtype=torch.int64, device=dev)
         lst = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(lst, cnt)
-        pa = dict(iters=int(gi.iters), converged=bool(gi.converged), rel_residual=float(gi.rel_residual), seconds=float(gi.total_seconds),
+        pa = dict(precond=precond, chains=int(gi.line_chains), iters=int(gi.iters), converged=bool(gi.converged), rel_residual=float(gi.rel_residual), seconds=float(gi.total_seconds),
                   l2_error=l2p, h1_error=h1p, setup_assemble_ms=float(t0.elapsed_time(t1)),
                   elements_per_rank=[int(t[0]) for t in lst], owned_per_rank=[int(t[1]) for t in lst], nnz_per_rank=[int(t[2]) for t in lst])
         if ref is not None:
