@@ -61,6 +61,7 @@ SYMBOLS = {
     "ehdg_create": (C.c_int, [C.POINTER(Problem), C.POINTER(_P)]),
     "ehdg_destroy": (C.c_int, [_P]),
     "ehdg_get_sizes": (C.c_int, [_P, C.POINTER(Sizes)]),
+    "ehdg_set_expression": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),
     "ehdg_set_drop_tol": (C.c_int, [_P, C.c_double]),
     "ehdg_kernel_timing": (C.c_int, [_P, C.c_int]),
     "ehdg_kernel_times_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

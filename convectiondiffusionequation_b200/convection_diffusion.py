@@ -20,6 +20,7 @@ import time
 import numpy as np
 import pandas as pd
 
+from .coefficients import LayerExpr, SymExpr
 from .hot_path import EHDGPipeline, ProblemSpec
 from .mesh import mesh_for_size
 
@@ -55,7 +56,7 @@ class Convection_Diffusion():
                 t_start = time.perf_counter()
                 mesh = mesh_for_size(size, kind=cfg.get('mesh_kind', 'structured'))
                 spec = ProblemSpec(order=order, epsilon=cfg['epsilon'], beta=tuple(cfg['beta']), bonus_int=cfg['bonus_int'],
-                                   coeff=cfg['coeff'], exact=cfg['exact'], enrich_functions=enrich, enrich_domain_ind=inds)
+                                   coeff=self._cf(cfg['coeff']), exact=self._cf(cfg['exact']), enrich_functions=enrich, enrich_domain_ind=inds)
                 pipe = EDGPipeline(mesh, spec, device=cfg.get('device', 'cuda:0'))
                 type = 'edg' if len(enrich) > 0 else 'dg'
                 pipe.setup(theta=cfg.get('theta', 1e-5))     # marking + pruning with config['theta']   (:52-54, :83-123)
@@ -77,6 +78,13 @@ class Convection_Diffusion():
                     print('order:', order, 'DOFs:', ndof, 'mesh:', size, "err:", error, 'type:', type)
                 self.last_pipeline = pipe
         return self.results, self.alphas
+
+    @staticmethod
+    def _cf(f):
+        """config['coeff'] / config['exact']: a LayerExpr (the boundary-layer family of run.py:26-30, fast path) or any expression
+        of x and y -- a sympy expression, a string sympify understands, or a SymExpr -- the stand-in for an NGSolve
+        CoefficientFunction"""
+        return f if (f is None or isinstance(f, (LayerExpr, SymExpr))) else SymExpr(f)
 
     @staticmethod
     def _lap(pipe):
@@ -121,9 +129,10 @@ class Convection_Diffusion():
             for size in cfg['mesh_size']:
                 mesh = mesh_for_size(size, kind=cfg.get('mesh_kind', 'structured'))
                 spec = ProblemSpec(order=order, epsilon=cfg['epsilon'], beta=tuple(cfg['beta']), bonus_int=cfg['bonus_int'],
-                                   coeff=cfg['coeff'], exact=cfg['exact'], enrich_functions=enrich, enrich_domain_ind=inds)
+                                   coeff=self._cf(cfg['coeff']), exact=self._cf(cfg['exact']), enrich_functions=enrich, enrich_domain_ind=inds)
                 t_start = time.perf_counter()
-                pipe = EHDGPipeline(mesh, spec, device=cfg.get('device', 'cuda:0'))
+                pipe = EHDGPipeline(mesh, spec, device=cfg.get('device', 'cuda:0'),
+                                    dirichlet_lifting=bool(cfg.get('dirichlet_lifting', False)))      # debug_ehdg.py:210-214
                 type = 'ehdg' if len(enrich) > 0 else 'hdg'
                 pipe.setup(prune_threshold=1e-5)            # marking + pruning            (:240-244, :270-310)
                 pipe.alpha()                                # lambda_K per element         (:314-351)

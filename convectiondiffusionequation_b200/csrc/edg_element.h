@@ -75,7 +75,7 @@ EHDG_HD void edg_element_blocks(const Coop& co, const Problem& pb, const RuleSet
                 const double l0 = rs.vx[q], l1 = rs.vy[q], l2 = 1.0 - l0 - l1;
                 const double dx = l0 * g.omx[0] + l1 * g.omx[1] + l2 * g.omx[2];
                 const double dy = l0 * g.omy[0] + l1 * g.omy[1] + l2 * g.omy[2];
-                acc += wq[q] * layer_expr_eval(pb.coeff, dx, dy) * Tp[i * ldq + q];
+                acc += wq[q] * problem_coeff(pb, dx, dy) * Tp[i * ldq + q];
             }
             F[i] = acc;
         }

@@ -279,6 +279,7 @@ int ehdg_destroy(ehdg_ctx* c) {
     cudaFree(c->r0.buf);
     cudaFree(c->rerr.buf);
     cudaFree(c->redg.buf);
+    for (int i = 0; i < 4; ++i) cudaFree(c->d_prog[i]);
     ehdg_comm_destroy(c);
     fast_free_tensors(c);
     cudaFree(c->scratch);
@@ -290,6 +291,34 @@ int ehdg_destroy(ehdg_ctx* c) {
     for (int i = 0; i < 4; ++i)
         if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
     delete c;
+    return EHDG_OK;
+}
+
+int ehdg_set_expression(ehdg_ctx* c, int which, const int32_t* ops, const double* args, int n) {
+    if (!c || which < 0 || which > 3 || n < 0 || n > EHDG_EXPR_MAX || (n > 0 && (!ops || !args))) {
+        set_error("ehdg_set_expression: bad argument (at most %d instructions)", EHDG_EXPR_MAX);
+        return EHDG_ERR_ARG;
+    }
+    const ExprProg** slot[4] = {&c->pb.xcoeff, &c->pb.xexact, &c->pb.xexact_dx, &c->pb.xexact_dy};
+    if (n == 0) { *slot[which] = nullptr; return EHDG_OK; }
+    // validate the stack discipline on the host: the device interpreter does not check
+    int sp = 0;
+    for (int i = 0; i < n; ++i) {
+        const int op = ops[i];
+        const int pops = (op == EX_ADD || op == EX_SUB || op == EX_MUL || op == EX_DIV || op == EX_POW) ? 2
+                         : (op == EX_CONST || op == EX_X || op == EX_Y) ? 0 : 1;
+        if (op <= EX_END || op > EX_SIGN || sp < pops) { set_error("ehdg_set_expression: malformed program at instruction %d", i); return EHDG_ERR_ARG; }
+        sp += 1 - pops;
+        if (sp > EHDG_EXPR_STACK) { set_error("ehdg_set_expression: expression needs more than %d stack slots", EHDG_EXPR_STACK); return EHDG_ERR_ARG; }
+    }
+    if (sp != 1) { set_error("ehdg_set_expression: program leaves %d values on the stack", sp); return EHDG_ERR_ARG; }
+    ExprProg h;
+    memset(&h, 0, sizeof(h));
+    h.n = n;
+    for (int i = 0; i < n; ++i) { h.op[i] = ops[i]; h.arg[i] = args[i]; }
+    if (!c->d_prog[which]) EHDG_CUDA(cudaMalloc(&c->d_prog[which], sizeof(ExprProg)));
+    EHDG_CUDA(cudaMemcpy(c->d_prog[which], &h, sizeof(ExprProg), cudaMemcpyHostToDevice));
+    *slot[which] = c->d_prog[which];
     return EHDG_OK;
 }
 

@@ -135,7 +135,7 @@ edg_error_kernel(Problem pb, RuleSet rs, int ne, const double* __restrict__ vert
             const double dx = l0 * g.omx[0] + l1 * g.omx[1] + l2 * g.omx[2];
             const double dy = l0 * g.omy[0] + l1 * g.omy[1] + l2 * g.omy[2];
             double ex, egx, egy;
-            layer_expr_grad(pb.exact, dx, dy, &ex, &egx, &egy);
+            problem_exact(pb, dx, dy, &ex, &egx, &egy);
             const double w = rs.vw[q] * g.adet;
             e2 += w * (uh - ex) * (uh - ex);
             h2 += w * ((ux - egx) * (ux - egx) + (uy - egy) * (uy - egy));

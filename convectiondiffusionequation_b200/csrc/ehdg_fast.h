@@ -348,7 +348,7 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
 #ifdef EHDG_NO_RHS_MOMENTS
     const bool poly_rhs = false;
 #else
-    const bool poly_rhs = (!ux || cx.k * dminx > EHDG_LAYER_DROP) && (!uy || cy.k * dminy > EHDG_LAYER_DROP);     // uniform over the group
+    const bool poly_rhs = !pb.xcoeff && (!ux || cx.k * dminx > EHDG_LAYER_DROP) && (!uy || cy.k * dminy > EHDG_LAYER_DROP);     // uniform over the group
 #endif
     const bool zx = cx.k * dminx > EHDG_LAYER_DROP, zy = cy.k * dminy > EHDG_LAYER_DROP;
     double cm[EHDG_RHS_MOMENTS];
@@ -386,7 +386,8 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
                 // an axis whose exponential is negligible on the whole element (uniform over the group) skips exp()
                 const double lx = ux ? (zx ? (1.0 - dx) - cx.e0 * cx.inv : layer_val(cx, dx)) : 0.0;
                 const double ly = uy ? (zy ? (1.0 - dy) - cy.e0 * cy.inv : layer_val(cy, dy)) : 0.0;
-                cw[q] = rs.vw[q] * sg.adet * (pb.coeff.c[0] + pb.coeff.c[1] * lx + pb.coeff.c[2] * ly + pb.coeff.c[3] * lx * ly);
+                cw[q] = rs.vw[q] * sg.adet * (pb.xcoeff ? expr_eval(pb.xcoeff, 1.0 - dx, 1.0 - dy)
+                                                        : pb.coeff.c[0] + pb.coeff.c[1] * lx + pb.coeff.c[2] * ly + pb.coeff.c[3] * lx * ly);
             }
         EHDG_END_LANES
     }

@@ -13,6 +13,7 @@
 // NGSolve conventions: SURVEY.md Appendix A; block formulas: SURVEY.md Appendix B.
 #pragma once
 #include "ehdg_basis.h"
+#include "ehdg_expr.h"
 
 namespace ehdg {
 
@@ -23,7 +24,23 @@ struct Problem {
     int enr_axis[EHDG_MAX_ENRICH];
     double enr_k[EHDG_MAX_ENRICH];
     LayerExpr coeff, exact;
+    // generic expression programs (device pointers, ehdg_set_expression); null = the layer family above
+    const ExprProg *xcoeff, *xexact, *xexact_dx, *xexact_dy;
 };
+
+EHDG_HD double problem_coeff(const Problem& pb, double dx, double dy) {
+    return pb.xcoeff ? expr_eval(pb.xcoeff, 1.0 - dx, 1.0 - dy) : layer_expr_eval(pb.coeff, dx, dy);
+}
+EHDG_HD void problem_exact(const Problem& pb, double dx, double dy, double* val, double* gx, double* gy) {
+    if (pb.xexact) {
+        const double x = 1.0 - dx, y = 1.0 - dy;
+        *val = expr_eval(pb.xexact, x, y);
+        *gx = pb.xexact_dx ? expr_eval(pb.xexact_dx, x, y) : 0.0;
+        *gy = pb.xexact_dy ? expr_eval(pb.xexact_dy, x, y) : 0.0;
+    } else {
+        layer_expr_grad(pb.exact, dx, dy, val, gx, gy);
+    }
+}
 
 struct RuleSet {          // pointers valid on the side (host/device) the routine runs on
     int nq, nqf;
@@ -238,7 +255,7 @@ EHDG_HD int assemble_condense_general(const Coop& co, const Problem& pb, const R
             wq[q] = rs.vw[q0 + q] * g.adet;
             const double dx = l0 * g.omx[0] + l1 * g.omx[1] + l2 * g.omx[2];
             const double dy = l0 * g.omy[0] + l1 * g.omy[1] + l2 * g.omy[2];
-            cq[q] = layer_expr_eval(pb.coeff, dx, dy);
+            cq[q] = problem_coeff(pb, dx, dy);
         }
         co.sync();
         for (int idx = co.lane; idx < nv * (nv + 1); idx += co.nl) {

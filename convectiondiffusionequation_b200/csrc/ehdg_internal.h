@@ -56,6 +56,7 @@ struct ehdg_ctx {
     int32_t *pool_eslot = nullptr, *pool_lists = nullptr;
     int32_t pool_ne = 0;
     ehdg::DistComm* dist = nullptr;   // NCCL communicator + row partition of the distributed facet solve
+    ehdg::ExprProg* d_prog[4] = {nullptr, nullptr, nullptr, nullptr};   // coeff, exact, d/dx exact, d/dy exact (ehdg_set_expression)
     void* user_ws = nullptr;          // caller-provided workspace of the Krylov solvers (ehdg_set_workspace)
     size_t user_ws_bytes = 0;
     cudaStream_t side = nullptr;      // the general (enriched) kernels run beside the polynomial ones

@@ -1002,7 +1002,7 @@ l2_error_kernel(Problem pb, RuleSet rs, int ne, int n_poly, const int32_t* __res
             const double dx = l0 * g.omx[0] + l1 * g.omx[1] + l2 * g.omx[2];
             const double dy = l0 * g.omy[0] + l1 * g.omy[1] + l2 * g.omy[2];
             double ex, egx, egy;
-            layer_expr_grad(pb.exact, dx, dy, &ex, &egx, &egy);
+            problem_exact(pb, dx, dy, &ex, &egx, &egy);
             const double w = rs.vw[q] * g.adet;
             e2 += w * (uh - ex) * (uh - ex);
             h2 += w * ((ux - egx) * (ux - egx) + (uy - egy) * (uy - egy));
@@ -1067,7 +1067,9 @@ __global__ void dirichlet_project_kernel(Problem pb, RuleSet rs, int nf, const d
     for (int k = 0; k < nfl; ++k) c[k] = 0.0;
     for (int q = 0; q < rs.nqf; ++q) {
         const double t = rs.st[q], xi = 2.0 * t - 1.0;
-        const double g = layer_expr_eval(pb.exact, (1.0 - t) * dxl + t * dxh, (1.0 - t) * dyl + t * dyh) * rs.sw[q];
+        double g, gdx_, gdy_;
+        problem_exact(pb, (1.0 - t) * dxl + t * dxh, (1.0 - t) * dyl + t * dyh, &g, &gdx_, &gdy_);
+        g *= rs.sw[q];
         double p0 = 1.0, p1 = xi;
         c[0] += g;
         if (nfl > 1) c[1] += g * xi;

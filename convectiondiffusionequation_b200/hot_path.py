@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .coefficients import LayerExpr
+from .coefficients import LayerExpr, SymExpr
 from .enrichment_proxy import vertex_flags, vertex_flags_device
 from .mesh import TriMesh
 
@@ -45,7 +45,7 @@ class ProblemSpec:
             p.enrich_k[i] = k
         for name in ("coeff", "exact"):
             f = getattr(self, name)
-            if f is not None:
+            if f is not None and not isinstance(f, SymExpr):
                 c, k = f.desc()
                 for i in range(4):
                     getattr(p, name).c[i] = c[i]
@@ -80,6 +80,16 @@ class EHDGPipeline:
         self.ctx = C.c_void_p()
         _lib.check(self.lib.ehdg_create(C.byref(self._cprob), C.byref(self.ctx)), "ehdg_create")
         _lib.check(self.lib.ehdg_set_drop_tol(self.ctx, float(spec.vol_drop_tol)), "ehdg_set_drop_tol")
+        # generic coefficient functions (run.py:29-30 as arbitrary expressions): postfix programs for the kernels
+        progs = []
+        if isinstance(spec.coeff, SymExpr):
+            progs.append((0, spec.coeff))
+        if isinstance(spec.exact, SymExpr):
+            progs += [(1, spec.exact), (2, spec.exact.diff(0)), (3, spec.exact.diff(1))]
+        for which, e in progs:
+            ops, args = e.program()
+            _lib.check(self.lib.ehdg_set_expression(self.ctx, which, ops.ctypes.data_as(C.c_void_p), args.ctypes.data_as(C.c_void_p),
+                                                    len(ops)), "ehdg_set_expression")
         self.sizes = _lib.Sizes()
         _lib.check(self.lib.ehdg_get_sizes(self.ctx, C.byref(self.sizes)), "ehdg_get_sizes")
         self.plan = None
@@ -366,7 +376,7 @@ class EHDGPipeline:
         """share of the polynomial-path elements on which the exponentials of both layer functions of `coeff` are negligible, so that
         fast_assemble_kernel takes f_V from the moment vectors (same test as csrc/ehdg_fast.h; used for flop accounting)"""
         f = self.spec.coeff
-        if f is None or self.plan_sizes.n_poly == 0:
+        if f is None or isinstance(f, SymExpr) or self.plan_sizes.n_poly == 0:
             return 0.0
         c, k = f.desc()
         dmin = (1.0 - self.verts[self.tris.long()]).amin(dim=1)          # [ne, 2]

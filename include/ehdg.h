@@ -92,6 +92,14 @@ const char* ehdg_last_error(void);
 int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out);
 int ehdg_destroy(ehdg_ctx* ctx);
 int ehdg_get_sizes(const ehdg_ctx* ctx, ehdg_sizes* out);
+/* Generic coefficient functions (reference run.py:26-30, :44: `coeff` and `exact` are arbitrary NGSolve CoefficientFunctions
+ * of x, y).  An expression is handed over as a postfix program of at most 128 instructions, ops[i] in
+ *   1 CONST(args[i]) 2 X 3 Y 4 ADD 5 SUB 6 MUL 7 DIV 8 NEG 9 EXP 10 LOG 11 SIN 12 COS 13 TAN 14 SQRT 15 POWI(int args[i]) 16 POW
+ *   17 TANH 18 ABS 19 ATAN 20 SIGN
+ * and every kernel on the path evaluates it with a register stack (csrc/ehdg_expr.h).  which: 0 = coeff, 1 = exact, 2 / 3 =
+ * d exact / dx, dy (H1 error).  n = 0 restores the built-in boundary-layer family of ehdg_problem.  The enrichment functions
+ * stay in that family. */
+int ehdg_set_expression(ehdg_ctx* ctx, int which, const int32_t* ops, const double* args, int n);
 /* Selection rule for dependent VOLUME enrichment dofs inside the element condensation (a6): after the polynomial dofs of an
  * element have been eliminated, an enrichment whose remaining diagonal is below vol_drop_tol x its own size is dependent on
  * that element (e.g. q(y) where beta_y h / eps < 1) and leaves the element space: coefficient 0, no contribution to S_K;

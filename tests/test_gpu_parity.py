@@ -201,7 +201,8 @@ def test_polynomial_path_blocks(order, eps, kind):
 def test_csr_solve_and_error(order, eps, beta, enriched, kind):
     """condensed CSR (pattern bit-exact in NGSolve numbering), SpMV, GMRES, back-solve, L2 error."""
     mesh = _mesh(5, kind)
-    o, spec = make_pair(mesh, order, beta=beta, eps=eps, enriched=enriched)
+    # literal: entry-by-entry comparison with the oracle's matrix -- the selection rules for dependent dofs are off / at round-off
+    o, spec = make_pair(mesh, order, beta=beta, eps=eps, enriched=enriched, literal=True)
     o.prune()
     lam_ref = o.alpha_all()
     P = _pipe(mesh, spec).setup().alpha()
@@ -237,7 +238,7 @@ def test_csr_solve_and_error(order, eps, beta, enriched, kind):
     y = P.spmv(x).cpu().numpy()
     assert rel(y, A @ x.cpu().numpy()) < 1e-13
     # solve + back-solve + error
-    P.gmres(restart=60, max_iters=6000, rtol=1e-11).backsolve()
+    P.gmres(restart=60, max_iters=6000, rtol=1e-11, drop_tol=1e-13).backsolve()
     if condV < 1e10:
         assert P.gmres_info.converged == 1, (P.gmres_info.iters, P.gmres_info.rel_residual)
     else:

@@ -27,6 +27,8 @@ def run(n, order, eps, kind="structured", methods=(("dqgmres", 8), ("dqgmres", 4
     for meth, k in methods:
         P.csr_build()
         P.gmres(restart=k, max_iters=iters, rtol=rtol, method=meth, strip_block=True).backsolve()
+        if dump:
+            np.savez_compressed(os.path.join(dump, f"sol_{n}_{order}_{eps}_{kind}.npz"), xhat=P.xhat.cpu().numpy(), lines=P.lines().cpu().numpy(), elem_active=P.elem_active.cpu().numpy(), status=P.status.cpu().numpy(), lam=P.lam.cpu().numpy())
         gi = P.gmres_info
         l2, h1 = P.errors()
         print(json.dumps(dict(method=meth, k=k, iters=gi.iters, conv=bool(gi.converged), res=gi.rel_residual, sec=round(gi.total_seconds, 3),
@@ -38,8 +40,8 @@ if __name__ == "__main__":
     dump = os.environ.get("EP_DUMP")
     if dump:
         os.makedirs(dump, exist_ok=True)
-    for (n, p, eps) in [(32, 3, 1e-4), (64, 4, 1.1e-5), (64, 4, 1e-6), (224, 3, 1e-4)]:
+    for (n, p, eps) in [(48, 4, 3e-5), (48, 4, 1.5e-5)]:
         try:
-            run(n, p, eps, dump=dump if n <= 64 else None)
+            run(n, p, eps, kind="unstructured", dump=dump, methods=(("gmres", 60),), iters=1500)
         except Exception as exc:
             print("FAILED", n, p, eps, exc, flush=True)
