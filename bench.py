@@ -305,7 +305,8 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step_max, setup_ms_max = float(tmax[0].item()), float(tmax[1].item())
     value = ne / (ms_step_max * 1e-3)                 # global elements / slowest rank's time for its share
-    status_bad = int((P.status != 0).sum().item())
+    status_bad = int(((P.status & ~8) != 0).sum().item())           # singular / non-finite / deficient-alpha flags
+    status_dropped = int(((P.status & 8) != 0).sum().item())         # elements where a dependent volume enrichment left the space
     moment_frac = P.moment_rhs_fraction()
     share = torch.tensor([n_share, int(P.csr_sizes.nnz)], dtype=torch.int64, device=dev)
     shares = [torch.zeros_like(share) for _ in range(world)]
@@ -562,7 +563,7 @@ def main():
                    "enriched_path_elements_rank0": n_gen,
                    "step": "alpha (a4) + blocks, rhs, condensation (a5-a7) + numeric CSR fill (a8) of the rank's share",
                    "l2_flush": "explicit 256 MiB write between steps" if need_flush else "step outputs (S,W) exceed L2",
-                   "elements_with_status_flags_rank0": status_bad},
+                   "elements_with_status_flags_rank0": status_bad, "elements_with_dropped_enrichment_rank0": status_dropped},
         "stage_ms": {"alpha": t_alpha / args.steps, "assemble_condense": t_asm / args.steps, "csr_numeric": t_csr / args.steps},
         "setup_ms_per_mesh": {"max_over_ranks": setup_ms_max, "rank0": setup_ms,
                               "what": "marks, pruning, pattern of the own rows, element selection, plan (outside the step: once per mesh)",

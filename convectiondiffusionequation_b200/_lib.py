@@ -50,7 +50,8 @@ class GmresInfo(C.Structure):
                 ("use_strip_block", C.c_int32), ("strip_dofs", C.c_int32), ("strip_blocks", C.c_int32),
                 ("jacobi_sweeps", C.c_int32), ("use_line_block", C.c_int32), ("line_target_dofs", C.c_int32),
                 ("line_chains", C.c_int32), ("line_blocks", C.c_int32), ("line_max_block", C.c_int32),
-                ("setup_seconds", C.c_double), ("precond_bytes", C.c_double), ("rel_residual_unscaled", C.c_double), ("drop_tol", C.c_double)]
+                ("setup_seconds", C.c_double), ("precond_bytes", C.c_double), ("rel_residual_unscaled", C.c_double), ("drop_tol", C.c_double),
+                ("line_max_blocks", C.c_int32), ("reserved2", C.c_int32)]
 
 
 # every symbol include/ehdg.h declares: name -> (restype, argtypes)

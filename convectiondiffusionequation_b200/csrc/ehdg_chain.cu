@@ -397,7 +397,7 @@ struct DevFree {
 }  // namespace
 
 int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t* line_dev, int use_strip, int target_dofs,
-                double drop_tol, cudaStream_t st, ChainSolver** out) {
+                double drop_tol, int max_blocks, cudaStream_t st, ChainSolver** out) {
     *out = nullptr;
     const int nf = A->nf;
     const bool strip = use_strip && A->strip != nullptr;
@@ -447,6 +447,7 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
     lev_of_order.reserve(part.size());
     std::vector<ChainBlock> blocks;
     std::vector<int32_t> chain_ptr{0}, dof_rows, dof_blk, blk_chain;
+    int nchains_out = 0;                      // chains after cutting (segments)
     int nmax = 0;
     int64_t n_real = 0;
     auto bfs = [&](int seed, int ch, int lev0, std::vector<int32_t>& visit) -> int {      // returns the last level used
@@ -511,10 +512,24 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
             while ((int)dof_rows.size() - B.s0 < 2 || ((dof_rows.size() - (size_t)B.s0) & 1)) { dof_rows.push_back(-1); dof_blk.push_back(b); }   // even, 16-byte slots
             nmax = std::max(nmax, (int)B.n);
             blocks.push_back(B);
-            blk_chain.push_back(ch);
+            blk_chain.push_back(nchains_out);
             i = j;
         }
-        chain_ptr.push_back((int32_t)blocks.size());
+        // long chains are cut into segments of at most max_blocks blocks (each solved exactly, the coupling between two
+        // segments is left to the Krylov iteration): the sweep is a sequential recurrence of one warp per chain, so its
+        // latency is the chain length, and a GPU (or a rank of a multi-GPU run) with few chains has warp slots to spare
+        {
+            const int first_blk = chain_ptr.back(), nb_ch = (int)blocks.size() - first_blk;
+            const int nseg = (max_blocks > 0 && nb_ch > max_blocks) ? (nb_ch + max_blocks - 1) / max_blocks : 1;
+            for (int sg = 1; sg <= nseg; ++sg) {
+                const int end_blk = first_blk + (int)(((int64_t)nb_ch * sg) / nseg);
+                if (sg > 1)
+                    for (int b2 = chain_ptr.back(); b2 < end_blk; ++b2) blk_chain[b2] = nchains_out;
+                chain_ptr.push_back(end_blk);
+                ++nchains_out;
+            }
+            // blocks of the first segment keep the id they were given; ids must be unique per segment
+        }
     }
     const int nblk = (int)blocks.size(), nd = (int)dof_rows.size();
     if (nd == 0) return EHDG_OK;
@@ -541,7 +556,7 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
     ChainSolver* S = new ChainSolver();
     S->n_dofs = nd;
     S->n_blocks = nblk;
-    S->n_chains = nchains;
+    S->n_chains = nchains_out;
     S->n_rows = A->n_rows;
     S->nmax = nmax;
     S->factor_bytes = (tG + tDH) * 8;
@@ -593,7 +608,7 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
         EHDG_LAUNCH_CHECK();
         const int smem = (2 * nmax * nmax + nmax * nmax) * 8;      // augmented matrix + scratch
         EHDG_CUDA(cudaFuncSetAttribute(chain_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        chain_factor_kernel<<<nchains, 128, smem, st>>>(S->chain_ptr, S->blocks, S->dof_rows, rowdrop, drop_tol, S->DH, S->G, d_flags + 1);
+        chain_factor_kernel<<<nchains_out, 128, smem, st>>>(S->chain_ptr, S->blocks, S->dof_rows, rowdrop, drop_tol, S->DH, S->G, d_flags + 1);
         EHDG_LAUNCH_CHECK();
         int flags[2] = {0, 0};
         EHDG_CUDA(cudaMemcpyAsync(flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -35,8 +35,9 @@ struct ChainSolver {
 // rowdrop u8[n_rows] (optional, in / out): dofs found dependent inside their facet block on entry; the dofs whose pivot in
 // the chain factorisation falls below drop_tol of their block's largest diagonal entry are added.  *out stays null when there
 // is no chain.
+// max_blocks > 0: chains longer than that are cut into equal segments (more, shorter recurrences).
 int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t* line_dev, int use_strip, int target_dofs,
-                double drop_tol, cudaStream_t st, ChainSolver** out);
+                double drop_tol, int max_blocks, cudaStream_t st, ChainSolver** out);
 // t[chain rows] = M_chain^-1 (vscale .* v)[chain rows]   (other entries of t untouched); v, vscale, t indexed from row `row0`
 int chain_apply(const ChainSolver* S, const double* v, double* t, int64_t row0, cudaStream_t st, const double* vscale = nullptr);
 void chain_free(ChainSolver* S);

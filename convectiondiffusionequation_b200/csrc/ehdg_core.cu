@@ -186,7 +186,7 @@ alpha_general_kernel(Problem pb, RuleSet rs0, int n_gen, const int32_t* __restri
     if (skip_unenriched && volmask == 0) return;      // polynomial alpha: done by the tensor kernel (CTA-uniform exit)
     int st = 0;
     const double l = alpha_general(co, pb, rs0, verts, tris + 3 * el, volmask, el == 0, ws, &st);
-    st = __syncthreads_or(st);
+    st = block_or_bits(st);
     if (threadIdx.x == 0) {
         lam[el] = l;
         if (status) status[el] = st;
@@ -213,7 +213,7 @@ assemble_general_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __rest
     int st = assemble_condense_general(co, pb, rs, verts, tris + 3 * el, lam[el], volmask, facmask, ws,
                                        S + (size_t)gi * nf * nf, g + (size_t)gi * nf, W + (size_t)gi * nv * nf,
                                        z + (size_t)gi * nv, Afull ? Afull + (size_t)gi * afull_sz : nullptr);
-    st = __syncthreads_or(st);
+    st = block_or_bits(st);
     if (threadIdx.x == 0 && status) status[el] |= st;
 }
 

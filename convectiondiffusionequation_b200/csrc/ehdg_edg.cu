@@ -91,7 +91,7 @@ edg_assemble_kernel(Problem pb, RuleSet rs, int ne, const double* __restrict__ v
         off += cols;
     }
     for (int i = threadIdx.x; i < rows; i += EDG_THREADS) rhs[r0 + i] = F[edg_active_slot(n_p, own_bits, i)];
-    bad = __syncthreads_or(bad);
+    bad = block_or_bits(bad);
     if (threadIdx.x == 0 && status) status[el] |= bad;
 }
 

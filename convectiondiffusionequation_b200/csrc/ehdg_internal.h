@@ -26,6 +26,18 @@ void set_error(const char* fmt, ...);
 
 #define EHDG_LAUNCH_CHECK() EHDG_CUDA(cudaGetLastError())
 
+#ifdef __CUDACC__
+// bitwise OR of a per-thread status word over the CTA (__syncthreads_or only says whether ANY bit is set anywhere)
+__device__ __forceinline__ int block_or_bits(int v) {
+    __shared__ int s_bits;
+    if (threadIdx.x == 0) s_bits = 0;
+    __syncthreads();
+    if (v) atomicOr(&s_bits, v);
+    __syncthreads();
+    return s_bits;
+}
+#endif
+
 struct DeviceRules {
     RuleSet rs;                 // device pointers
     double* buf = nullptr;

@@ -1691,7 +1691,7 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     }
     // chains: the lines of the mesh (line mode) and / or the strip of marked elements, from the unscaled matrix values
     if (line_mode || info->use_strip_block)
-        setup_rc = chain_setup(A, vals, rowdrop, line_mode ? A->line : nullptr, info->use_strip_block, info->line_target_dofs, drop_tol, st, &ws.chain);
+        setup_rc = chain_setup(A, vals, rowdrop, line_mode ? A->line : nullptr, info->use_strip_block, info->line_target_dofs, drop_tol, info->line_max_blocks, st, &ws.chain);
     ChainSolver* chain = ws.chain;
     if (line_mode && setup_rc == EHDG_OK && n > 0 && !(chain && chain->all_rows)) {
         set_error("ehdg_gmres: the line preconditioner does not cover every row");

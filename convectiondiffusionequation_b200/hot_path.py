@@ -305,7 +305,7 @@ class EHDGPipeline:
         return self
 
     def gmres(self, restart=30, max_iters=20000, rtol=1e-12, strip_block=True, jacobi_sweeps=1, method="gmres", precond="line",
-              line_target_dofs=0, drop_tol=0.0):
+              line_target_dofs=0, drop_tol=0.0, line_max_blocks=0):
         """Krylov solve of the condensed system.  precond = 'line' (line-block Jacobi: every chain of facets solved exactly; the
         matrix values stay untouched) or 'facet' (facet block-Jacobi folded into the matrix values: they hold A M^-1 afterwards and
         are refilled by csr_numeric before the next use)."""
@@ -324,6 +324,7 @@ class EHDGPipeline:
         info.use_line_block = int(precond == "line")
         info.line_target_dofs = int(line_target_dofs)
         info.drop_tol = float(drop_tol)
+        info.line_max_blocks = int(line_max_blocks)
         fn = {"gmres": self.lib.ehdg_gmres, "bicgstab": self.lib.ehdg_bicgstab, "dqgmres": self.lib.ehdg_dqgmres}[method]
         self.vals_folded = precond == "facet"       # set before the call: an error inside may leave vals half folded
         _lib.check(fn(self.ctx, self.csr, _ptr(self.vals), _ptr(self.rhs), _ptr(self.xhat), C.byref(info), self._stream()),
@@ -331,7 +332,7 @@ class EHDGPipeline:
         self.gmres_info = info
         return self
 
-    def solve_auto(self, rtol=1e-8, max_iters=8000, precond="line", drop_tol=0.0, strip_block=True):
+    def solve_auto(self, rtol=1e-8, max_iters=8000, precond="line", drop_tol=0.0, strip_block=True, line_max_blocks=0):
         """Solver portfolio of the facet system (measured on B200, tools/line_probe.py): DQGMRES(8) on the line-block
         preconditioner is the fastest where it converges (no restart, eight vectors: 4M elements in 1 520 iterations / 15 s) but
         erratic on some systems; GMRES(m) is robust once m covers the plateau that the residual sits on until the information
@@ -344,7 +345,7 @@ class EHDGPipeline:
                 restart = int(min(200, max(30, chains // 10)))
             cap = min(max_iters, 2500) if method == "dqgmres" else max_iters      # where DQGMRES(8) works it is done well before
             self.gmres(restart=restart, max_iters=cap, rtol=rtol, method=method, precond=precond, drop_tol=drop_tol,
-                       strip_block=strip_block)
+                       strip_block=strip_block, line_max_blocks=line_max_blocks)
             gi = self.gmres_info
             self.solve_attempts.append(dict(method=method, restart=restart, iters=int(gi.iters), converged=bool(gi.converged),
                                             rel_residual=float(gi.rel_residual), seconds=float(gi.total_seconds)))

@@ -75,6 +75,16 @@ int hc_assemble(const ehdg_problem* ep, const double* verts, const int* tri, dou
     Coop co{0, 1};
     return assemble_condense_general(co, pb, hr.rs, verts, tri, lam, volmask, facmask, ws.data(), S, g, W, z, Afull);
 }
+// same with the selection rule for dependent volume enrichments at a given tolerance (0 = off)
+int hc_assemble_tol(const ehdg_problem* ep, const double* verts, const int* tri, double lam, int volmask,
+                    const int* facmask, double vol_drop_tol, double* S, double* g, double* W, double* z, double* Afull) {
+    Problem pb = make_problem(*ep);
+    pb.vol_drop_tol = vol_drop_tol;
+    HostRules hr(2 * pb.p + pb.bonus);
+    std::vector<double> ws(general_ws_doubles(pb, hr.rs.nq, hr.rs.nqf));
+    Coop co{0, 1};
+    return assemble_condense_general(co, pb, hr.rs, verts, tri, lam, volmask, facmask, ws.data(), S, g, W, z, Afull);
+}
 double hc_alpha(const ehdg_problem* ep, const double* verts, const int* tri, int volmask, int exclude_const,
                 int* status) {
     Problem pb = make_problem(*ep);

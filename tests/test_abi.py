@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.LayerExpr) == 48
     assert C.sizeof(_lib.Problem) == 4 + 4 + 8 + 16 + 4 + 8 + 4 + 16 + 48 + 48      # incl. padding after n_enrich arrays
     assert C.sizeof(_lib.Mesh) == 16 + 4 * 8
-    assert C.sizeof(_lib.GmresInfo) == 120
+    assert C.sizeof(_lib.GmresInfo) == 128
 
 
 def test_no_cpu_path(libehdg_built):

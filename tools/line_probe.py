@@ -8,14 +8,14 @@ from convectiondiffusionequation_b200.mesh import unit_square_mesh
 
 
 def run(n, order, eps, kind="structured", enriched=False, configs=(("line", "dqgmres", 8, 0), ("facet", "dqgmres", 8, 0)), iters=60000, rtol=1e-8,
-        drop_tol=0.0):
+        drop_tol=0.0, max_blocks=0):
     mesh = unit_square_mesh(n, kind=kind)
     P = EHDGPipeline(mesh, make_spec(order, eps, enriched=enriched))
     P.setup().assemble()
     for prec, meth, k, tgt in configs:
         P.csr_build()
         try:
-            P.gmres(restart=k, max_iters=iters, rtol=rtol, method=meth, precond=prec, line_target_dofs=tgt, drop_tol=drop_tol).backsolve()
+            P.gmres(restart=k, max_iters=iters, rtol=rtol, method=meth, precond=prec, line_target_dofs=tgt, drop_tol=drop_tol, line_max_blocks=max_blocks).backsolve()
         except Exception as exc:
             print("FAILED", n, order, eps, prec, meth, k, exc, flush=True)
             continue
@@ -25,7 +25,7 @@ def run(n, order, eps, kind="structured", enriched=False, configs=(("line", "dqg
                               conv=bool(gi.converged), res=gi.rel_residual, res_raw=gi.rel_residual_unscaled, sec=round(gi.total_seconds, 3), setup=round(gi.setup_seconds, 3),
                               ms_per_it=round(1e3 * (gi.total_seconds - gi.setup_seconds) / max(1, gi.iters), 4), l2=l2, h1=h1,
                               chains=gi.line_chains, blocks=gi.line_blocks, maxb=gi.line_max_block, factor_GB=round(gi.precond_bytes / 1e9, 3),
-                              dropped=gi.dropped_dofs, drop_tol=drop_tol, rows=int(P.csr_sizes.n_rows))), flush=True)
+                              dropped=gi.dropped_dofs, drop_tol=drop_tol, max_blocks=max_blocks, rows=int(P.csr_sizes.n_rows))), flush=True)
     P.close()
 
 
@@ -69,6 +69,11 @@ if __name__ == "__main__":
         for (n, p, eps) in [(64, 4, 1e-6), (64, 4, 2.2e-5), (224, 4, 1e-6), (708, 4, 1e-6)]:
             run(n, p, eps, kind="unstructured", enriched=True, configs=(("line", "gmres", 60, 0), ("facet", "gmres", 60, 0)), iters=3000)
             run(n, p, eps, kind="unstructured", enriched=False, configs=(("line", "gmres", 60, 0),), iters=3000)
+    elif which == "seg":
+        for mb in (0, 708, 354, 177, 88):
+            run(708, 4, 1e-6, configs=(("line", "gmres", 30, 0),), iters=4000, max_blocks=mb)
+        for mb in (0, 1414, 707, 354, 177):
+            run(1414, 4, 1e-6, kind="unstructured", configs=(("line", "dqgmres", 8, 0),), iters=4000, max_blocks=mb)
     elif which == "enr":
         for (n, p, eps) in [(16, 2, 1e-2), (16, 4, 1e-2), (32, 4, 1e-3), (32, 3, 1e-4), (64, 4, 1.1e-5), (64, 4, 1e-6), (224, 3, 1e-4)]:
             run(n, p, eps, enriched=True, configs=(("line", "gmres", 30, 0), ("line", "gmres", 100, 0), ("facet", "gmres", 60, 0)), iters=6000)
