@@ -305,7 +305,7 @@ class EHDGPipeline:
         return self
 
     def gmres(self, restart=30, max_iters=20000, rtol=1e-12, strip_block=True, jacobi_sweeps=1, method="gmres", precond="line",
-              line_target_dofs=0, drop_tol=0.0, line_max_blocks=0):
+              line_target_dofs=0, drop_tol=0.0, line_max_blocks=-1):
         """Krylov solve of the condensed system.  precond = 'line' (line-block Jacobi: every chain of facets solved exactly; the
         matrix values stay untouched) or 'facet' (facet block-Jacobi folded into the matrix values: they hold A M^-1 afterwards and
         are refilled by csr_numeric before the next use)."""
@@ -332,18 +332,26 @@ class EHDGPipeline:
         self.gmres_info = info
         return self
 
-    def solve_auto(self, rtol=1e-8, max_iters=8000, precond="line", drop_tol=0.0, strip_block=True, line_max_blocks=0):
+    def solve_auto(self, rtol=1e-8, max_iters=8000, precond="line", drop_tol=0.0, strip_block=True, line_max_blocks=-1):
         """Solver portfolio of the facet system (measured on B200, tools/line_probe.py): DQGMRES(8) on the line-block
         preconditioner is the fastest where it converges (no restart, eight vectors: 4M elements in 1 520 iterations / 15 s) but
         erratic on some systems; GMRES(m) is robust once m covers the plateau that the residual sits on until the information
         has crossed the mesh, m = #lines / 10 clamped to [30, 200] (4M elements: GMRES(30) stalls, GMRES(150) needs 1 937
-        iterations / 45 s).  Tries the first, falls back to the second.  self.solve_attempts records both."""
+        iterations / 45 s).  Plain systems try the first and fall back to the second; enriched systems take the second directly.
+        self.solve_attempts records what ran."""
         self.solve_attempts = []
-        for method, restart in (("dqgmres", 8), ("gmres", None)):
-            if restart is None:
-                chains = max(1, int(self.gmres_info.line_chains)) if precond == "line" else 300
-                restart = int(min(200, max(30, chains // 10)))
-            cap = min(max_iters, 2500) if method == "dqgmres" else max_iters      # where DQGMRES(8) works it is done well before
+        if precond == "line":
+            if getattr(self, "_lines_csr", None) != self.csr.value:
+                self.set_lines()
+            chains = int(torch.unique(self.lines()).numel())
+        else:
+            chains = 300
+        m_auto = int(min(200, max(30, chains // 10)))
+        # enriched systems: DQGMRES is unreliable on them (config 2 does not converge with it, config 3 takes 2.5x as long as
+        # GMRES), so they go straight to GMRES; plain systems try the cheap method first
+        plan = (("dqgmres", 8), ("gmres", m_auto)) if self.nenr == 0 else (("gmres", m_auto),)
+        for method, restart in plan:
+            cap = min(max_iters, 2500) if (method == "dqgmres" and len(plan) > 1) else max_iters      # where DQGMRES(8) works it is done well before
             self.gmres(restart=restart, max_iters=cap, rtol=rtol, method=method, precond=precond, drop_tol=drop_tol,
                        strip_block=strip_block, line_max_blocks=line_max_blocks)
             gi = self.gmres_info

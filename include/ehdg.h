@@ -264,7 +264,8 @@ typedef struct {
                              * system as test and trial function (coefficient 0, row ignored); 0 = default 1e-6.  The reference
                              * prunes with a distance test at 1e-5 that misses such dofs; dropped_dofs counts them */
     int32_t line_max_blocks;/* in : chains of the line preconditioner longer than this many blocks are cut into equal segments, each
-                             *      solved exactly (0 = whole lines).  Shorter chains = more, shorter sequential sweeps (the sweep is
+                             *      solved exactly (0 = whole lines, < 0 = automatic: up to 4 segments per line while the GPU has fewer than
+                             *      ~2400 chains).  Shorter chains = more, shorter sequential sweeps (the sweep is
                              *      latency-bound) at the price of a weaker preconditioner */
     int32_t reserved2;
 } ehdg_gmres_info;

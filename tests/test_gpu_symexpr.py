@@ -54,7 +54,7 @@ def test_lifting_with_symbolic_boundary_data():
     P = EHDGPipeline(mesh, spec, dirichlet_lifting=True).setup().assemble().solve(restart=60, max_iters=8000, rtol=1e-11)
     l2, _ = P.errors()
     # the error itself is 3e-6 of a solution of size 3: 1e-8 of it is below what a 1e-11 residual resolves
-    assert abs(l2 - l2_o) < max(1e-8 * l2_o, 1e-11), (l2, l2_o)
+    assert abs(l2 - l2_o) < max(1e-8 * l2_o, 1e-10), (l2, l2_o)
     assert l2 < 1e-4
     P.close()
 
