@@ -182,8 +182,7 @@ __global__ void csr_numeric_kernel(int row_lo, int n_rows, SLayout sl, const int
 
 // Same gather, one WARP per facet: the facet's values form one dense rows x len block (blk_base), so consecutive lanes write
 // consecutive entries (full-sector stores; the thread-per-row variant above strides by a row) and read runs of p + 1
-// consecutive doubles of one S_K row.  Measured SLOWER than the thread-per-row kernel at 4M elements, p = 4 (13.8 against
-// 9.2 ms, tools/csr_numeric_time.py): kept behind EHDG_CSR_NUMERIC_FACET=1 for the record.
+// consecutive doubles of one S_K row.
 __global__ void __launch_bounds__(256)
 csr_numeric_facet_kernel(int f_lo, int f_hi, SLayout sl, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
                          const int32_t* __restrict__ nbr_len, const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask,
@@ -242,17 +241,33 @@ csr_numeric_facet_kernel(int f_lo, int f_hi, SLayout sl, const int32_t* __restri
         }
         ++nt;
     }
-    for (int idx = lane; idx < rows * len; idx += 32) {
-        const int i = idx / len, c = idx - i * len;
+    // a lane owns one COLUMN of the block (two for len > 32): where its value comes from in either element's S_K is the same
+    // for every row, so it is worked out once -- no per-entry index arithmetic in the row loop
+    int so[2][2], sk[2][2];                    // [chunk][element]: offset inside the S row, slot l (for the l < nbe test)
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const int c = lane + 32 * ch;
+        so[ch][0] = so[ch][1] = -1;
+        sk[ch][0] = sk[ch][1] = 0;
+        if (c < len) {
+            int t = 0;
+            while (t + 1 < nt && c >= coff[t + 1]) ++t;
+            const int l = nth_set_bit(mg[t], c - coff[t]);
+            for (int s = 0; s < ne; ++s)
+                if (leg[s][t] >= 0 && l < nbe[s]) { so[ch][s] = leg[s][t] * nbe[s] + l; sk[ch][s] = l; }
+        }
+    }
+    for (int i = 0; i < rows; ++i) {
         const int k = nth_set_bit(mf, i);
-        int t = 0;
-        while (t + 1 < nt && c >= coff[t + 1]) ++t;
-        const int l = nth_set_bit(mg[t], c - coff[t]);
-        double v = 0.0;
-        for (int s = 0; s < ne; ++s)
-            if (leg[s][t] >= 0 && k < nbe[s] && l < nbe[s])
-                v += Sb[s][(size_t)(lef[s] * nbe[s] + k) * ld[s] + leg[s][t] * nbe[s] + l];
-        vals[base + idx] = v;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int c = lane + 32 * ch;
+            if (c >= len) continue;
+            double v = 0.0;
+            if (ne > 0 && so[ch][0] >= 0 && k < nbe[0]) v += Sb[0][(size_t)(lef[0] * nbe[0] + k) * ld[0] + so[ch][0]];
+            if (ne > 1 && so[ch][1] >= 0 && k < nbe[1]) v += Sb[1][(size_t)(lef[1] * nbe[1] + k) * ld[1] + so[ch][1]];
+            vals[base + (int64_t)i * len + c] = v;
+        }
     }
     if (lane < rows) {
         const int k = nth_set_bit(mf, lane);
@@ -1574,10 +1589,10 @@ int ehdg_csr_numeric_bc(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, cons
     const int64_t rlo = A->windowed ? A->row_lo : 0, rhi = A->windowed ? A->row_hi : A->n_rows;
     if (rhi <= rlo) return EHDG_OK;
     if (A->folded_vals == vals) const_cast<ehdg_csr*>(A)->folded_vals = nullptr;     // fresh values: a Krylov solve may fold them again
-    // A/B on B200, 4M elements, p = 4 (tools/csr_numeric_time.py): thread-per-row 9.17 ms (1.52 TB/s), warp-per-facet
-    // 13.84 ms (1.01 TB/s: the per-entry index arithmetic costs more than the coalesced stores win).  EHDG_CSR_NUMERIC_FACET=1
-    // selects the latter.
-    static const bool row_kernel = [] { const char* e = getenv("EHDG_CSR_NUMERIC_FACET"); return !(e && e[0] == '1'); }();
+    // A/B on B200, 4M elements, p = 4 (tools/csr_numeric_time.py, profiles/r02_ab_csr_numeric.jsonl): thread-per-row 9.17 ms
+    // (1.52 TB/s); warp-per-facet with per-entry index arithmetic 13.84 ms; warp-per-facet with a lane per block column (the
+    // version below): see the profile.  EHDG_CSR_NUMERIC_ROW=1 selects the thread-per-row kernel.
+    static const bool row_kernel = [] { const char* e = getenv("EHDG_CSR_NUMERIC_ROW"); return e && e[0] == '1'; }();
     if (row_kernel) {
         csr_numeric_kernel<<<(unsigned)((rhi - rlo + 127) / 128), 128, 0, st>>>((int)rlo, (int)rhi, make_slayout(c, p), A->row_facet, A->row_start,
                                                                                 A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,

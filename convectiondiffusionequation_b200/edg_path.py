@@ -91,6 +91,11 @@ class EDGPipeline(EHDGPipeline):
         rs = _device_view(self.lib.ehdg_csr_row_start(self.csr), ne + 1, torch.int32, self.dev).clone()
         return rp, ci, rs
 
+    def lines(self):
+        """chain id of every ELEMENT (the blocks of the EDG matrix are elements)"""
+        from .hot_path import _device_view
+        return _device_view(self.lib.ehdg_csr_lines(self.csr), self.mesh_host.ne, torch.int32, self.dev).clone()
+
     def backsolve(self):
         """u [ne][n_p + n_enrich] from the solution vector (the recombination of :205-206 happens in the error kernel)"""
         s = self.sizes

@@ -141,3 +141,33 @@ def single_triangle(P) -> TriMesh:
     """One-element mesh (known-answer tests on a given triangle shape)."""
     verts = np.asarray(P, dtype=np.float64).reshape(3, 2)
     return build_topology(verts, np.array([[0, 1, 2]]), maxh=1.0, kind="single")
+
+
+def from_arrays(verts, tris, maxh: float | None = None, kind: str = "imported") -> TriMesh:
+    """Any conforming triangle mesh given as arrays (a Netgen / NGSolve mesh exported with `mesh.Coordinates()` and the vertex
+    numbers of `mesh.Elements()`): triangles are made counter-clockwise, the facet topology is built.  maxh defaults to the
+    longest edge (what the enrichment indicators of run.py:45 receive as `h`)."""
+    verts = np.ascontiguousarray(verts, dtype=np.float64)
+    tris = np.asarray(tris, dtype=np.int64)
+    if maxh is None:
+        e = verts[tris[:, [1, 2, 0]]] - verts[tris]
+        maxh = float(np.sqrt((e ** 2).sum(axis=2)).max())
+    return build_topology(verts, tris, maxh=maxh, kind=kind)
+
+
+def stripe_order(mesh: TriMesh, direction=(0.0, 1.0)) -> TriMesh:
+    """Renumbers the vertices along `direction` (default: y, across a flow in x) and rebuilds the topology.  Facets are numbered
+    by their (lower, higher) vertex pair, so the facet-major rows of the condensed system become banded along that direction
+    whatever numbering the mesh generator used: contiguous row ranges are then stripes of the domain, the SpMV halo of a stripe
+    lies in its two neighbouring stripes (what ehdg_comm_set_partition requires), and the lines of the line-block preconditioner
+    (along the flow) stay inside one rank.  This is the general-mesh route to the partitioned multi-GPU path."""
+    d = np.asarray(direction, dtype=np.float64)
+    key = mesh.verts @ (d / np.linalg.norm(d))
+    order = np.lexsort((mesh.verts[:, 0] * d[1] - mesh.verts[:, 1] * d[0], key))      # along the stripe second
+    new_id = np.empty(mesh.nv, dtype=np.int64)
+    new_id[order] = np.arange(mesh.nv)
+    verts = mesh.verts[order]
+    tris = new_id[mesh.tris]
+    # elements sorted by their lowest vertex: element-major stores follow the stripes too
+    tris = tris[np.argsort(tris.min(axis=1), kind="stable")]
+    return build_topology(verts, tris, maxh=mesh.maxh, kind=mesh.kind)
