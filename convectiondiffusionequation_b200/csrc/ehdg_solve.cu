@@ -1590,9 +1590,11 @@ int ehdg_csr_numeric_bc(ehdg_ctx* c, const ehdg_plan* p, const ehdg_csr* A, cons
     if (rhi <= rlo) return EHDG_OK;
     if (A->folded_vals == vals) const_cast<ehdg_csr*>(A)->folded_vals = nullptr;     // fresh values: a Krylov solve may fold them again
     // A/B on B200, 4M elements, p = 4 (tools/csr_numeric_time.py, profiles/r02_ab_csr_numeric.jsonl): thread-per-row 9.17 ms
-    // (1.52 TB/s); warp-per-facet with per-entry index arithmetic 13.84 ms; warp-per-facet with a lane per block column (the
-    // version below): see the profile.  EHDG_CSR_NUMERIC_ROW=1 selects the thread-per-row kernel.
-    static const bool row_kernel = [] { const char* e = getenv("EHDG_CSR_NUMERIC_ROW"); return e && e[0] == '1'; }();
+    // (1.52 TB/s); warp-per-facet with per-entry index arithmetic 13.84 ms, with a lane per block column (the version kept
+    // below) 14.41 ms; thread-per-row with the warp's rows staged in shared memory and written with full-sector stores 13.86 ms.
+    // Coalescing the stores is not what this kernel lacks (L2 merges the row-strided writes); the thread-per-row gather stays
+    // the default, EHDG_CSR_NUMERIC_FACET=1 selects the warp-per-facet variant.
+    static const bool row_kernel = [] { const char* e = getenv("EHDG_CSR_NUMERIC_FACET"); return !(e && e[0] == '1'); }();
     if (row_kernel) {
         csr_numeric_kernel<<<(unsigned)((rhi - rlo + 127) / 128), 128, 0, st>>>((int)rlo, (int)rhi, make_slayout(c, p), A->row_facet, A->row_start,
                                                                                 A->rowptr, A->nbr, A->dofmask, m->facet2el, m->el2facet,

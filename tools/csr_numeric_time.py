@@ -1,4 +1,4 @@
-"""a8 numeric fill: ms and GB/s of ehdg_csr_numeric on the named mesh (EHDG_CSR_NUMERIC_ROW=1: the thread-per-row variant)."""
+"""a8 numeric fill: ms and GB/s of ehdg_csr_numeric on the named mesh (EHDG_CSR_NUMERIC_FACET=1: the warp-per-facet variant)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,5 +20,5 @@ b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 10
 nbytes = P.S.numel() * 8 + P.g.numel() * 8 + P.csr_sizes.nnz * 8 + P.csr_sizes.n_rows * 8
-print(json.dumps(dict(variant="row" if os.environ.get("EHDG_CSR_NUMERIC_ROW") == "1" else "facet-lane-per-column", n=n, p=order, ms=ms, gbs=nbytes / ms / 1e6,
+print(json.dumps(dict(variant="facet-lane-per-column" if os.environ.get("EHDG_CSR_NUMERIC_FACET") == "1" else "row", n=n, p=order, ms=ms, gbs=nbytes / ms / 1e6,
                       bytes=nbytes, checksum=float(P.vals.abs().sum().item()), rhs=float(P.rhs.abs().sum().item()))))
