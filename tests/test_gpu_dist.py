@@ -63,7 +63,8 @@ def test_partitioned_rows_equal_the_global_assembly(enriched):
         assert torch.equal(P.vals[:z1 - z0], vals[z0:z1])                 # bit-exact: same kernels, same order of additions
         assert torch.equal(P.rhs[r0:r1], rhs[r0:r1])
         n_sel = P.plan_sizes.n_poly + P.plan_sizes.n_gen
-        assert n_sel == int(P.elem_select.sum()) and n_sel < 0.6 * mesh.ne
+        # (with enrichment the partition is by cost: ranks without strip elements take more of the cheap ones)
+        assert n_sel == int(P.elem_select.sum()) and n_sel < (0.75 if enriched else 0.6) * mesh.ne
         lo, hi = P.own_extent
         assert lo <= r0 and hi >= r1 and lo == min(int(ci[z0:z1].min()), r0)
         owned_total += int(P.elem_owned.sum())
