@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--solve-type", default="both", choices=["hdg", "ehdg", "both"],
                     help="systems of the one-off solve: the enriched one (the workload's own) and / or plain HDG on the same mesh")
     ap.add_argument("--enriched-headline-iters", type=int, default=600, help="iteration cap per attempt of the enriched 4M solve")
+    ap.add_argument("--two-pass", action="store_true", help="a8 as a separate gather over the element blocks S_K (round-2a path) instead of the fused store")
     ap.add_argument("--replicas", action="store_true", help="N > 1: also time one private full mesh per rank (weak-scaled replicas)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -249,8 +250,11 @@ def main():
     def step(Q):
         """the metric's unit of work on this rank's share: a4 (alpha), a5-a7 (blocks, rhs, condensation), a8 (numeric fill)"""
         Q.alpha()
-        Q.assemble_condense()
-        Q.csr_numeric()
+        if args.two_pass:
+            Q.assemble_condense()
+            Q.csr_numeric()
+        else:
+            Q.assemble_condense_csr()                            # the element kernels store straight into the value array
 
     rank_setup(P)                                                # first call pays the allocations (cached by the pools afterwards)
     barrier()
@@ -266,7 +270,7 @@ def main():
     # L2 flush between timed iterations: the outputs of one step (S, W: > 10 GB at 4M) exceed the 126 MB L2;
     # for small shares an explicit flush buffer is written.
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    need_flush = (ps.S_doubles + ps.W_doubles) * 8 < (512 << 20)
+    need_flush = ((ps.S_doubles if args.two_pass else int(P.csr_sizes.nnz)) + ps.W_doubles) * 8 < (512 << 20)
 
     for _ in range(max(args.warmup, 3)):
         step(P)
@@ -285,9 +289,13 @@ def main():
             a0.record()
             P.alpha()
             a1.record()
-            P.assemble_condense()
-            a2.record()
-            P.csr_numeric()
+            if args.two_pass:
+                P.assemble_condense()
+                a2.record()
+                P.csr_numeric()
+            else:
+                P.assemble_condense_csr()
+                a2.record()
             a3.record()
             stage.append((a0, a1, a2, a3))
             if P.plan_sizes.n_poly > 0:
@@ -551,7 +559,9 @@ def main():
             traffic_note = "profiles/r02_assemble_traffic.json was captured on different kernel sources: not quoted"
     except Exception:
         pass
-    out_bytes = (ps.S_doubles + ps.g_doubles + ps.W_doubles + ps.z_doubles + n_share) * 8 + n_share * 60
+    own_rows_step = int(P.csr_sizes.n_rows if world == 1 else P.row_begin[rank + 1] - P.row_begin[rank])
+    store_doubles = (ps.S_doubles + ps.g_doubles) if args.two_pass else (int(P.csr_sizes.nnz) + own_rows_step)
+    out_bytes = (store_doubles + ps.W_doubles + ps.z_doubles + n_share) * 8 + n_share * 60
     line = {
         "metric": "condensed EHDG elements/sec (FP64)", "value": value, "unit": "elements/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "strong",
@@ -562,9 +572,12 @@ def main():
                    "elements_per_rank": [int(t[0]) for t in shares], "nnz_per_rank": [int(t[1]) for t in shares],
                    "enriched_path_elements_rank0": n_gen,
                    "step": "alpha (a4) + blocks, rhs, condensation (a5-a7) + numeric CSR fill (a8) of the rank's share",
-                   "l2_flush": "explicit 256 MiB write between steps" if need_flush else "step outputs (S,W) exceed L2",
+                   "a8_store": "two passes: element blocks S_K to HBM, then the gather ehdg_csr_numeric" if args.two_pass else
+                               "fused: the element kernels write the CSR value array (ehdg_assemble_condense_csr), diagonal blocks merged first + second",
+                   "l2_flush": "explicit 256 MiB write between steps" if need_flush else "step outputs (values, W) exceed L2",
                    "elements_with_status_flags_rank0": status_bad, "elements_with_dropped_enrichment_rank0": status_dropped},
-        "stage_ms": {"alpha": t_alpha / args.steps, "assemble_condense": t_asm / args.steps, "csr_numeric": t_csr / args.steps},
+        "stage_ms": ({"alpha": t_alpha / args.steps, "assemble_condense": t_asm / args.steps, "csr_numeric": t_csr / args.steps} if args.two_pass
+                     else {"alpha": t_alpha / args.steps, "assemble_condense_csr": t_asm / args.steps}),
         "setup_ms_per_mesh": {"max_over_ranks": setup_ms_max, "rank0": setup_ms,
                               "what": "marks, pruning, pattern of the own rows, element selection, plan (outside the step: once per mesh)",
                               "stages_ms_rank0": {k: round(v, 3) for k, v in getattr(P, "part_timing", {}).items()}},
@@ -573,7 +586,7 @@ def main():
                      "peak_source": fp64_src, "flops_per_element": f_asm, "moment_rhs_fraction": moment_frac,
                      "note": "FP64-FMA-bound kernel (neither hbm nor tensor); flops = tensor algorithm actually executed, "
                              "no credit for the quadrature work it avoids",
-                     "algorithmic_hbm_bytes_per_launch": int((ps.S_doubles + ps.g_doubles + ps.W_doubles + ps.z_doubles) * 8 + n_poly * 80),
+                     "algorithmic_hbm_bytes_per_launch": int((store_doubles + ps.W_doubles + ps.z_doubles) * 8 + n_poly * (80 if args.two_pass else 144)),
                      "alpha_kernel": {"kernel": f"fast_alpha_kernel<{order}>", "kernel_ms": alpha_ms, "achieved": alpha_tf,
                                       "frac": (alpha_tf / fp64) if alpha_tf else None, "flops_per_element": f_alpha},
                      "step_a4_a7": {"achieved": step_tf, "frac": step_tf / fp64, "flops_per_element": f_asm + f_alpha},
@@ -583,7 +596,9 @@ def main():
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "repetitions_ms_per_step": [round(t * 1e3, 3) for t in e2e_reps],
                 "what": "per step: pinned mesh arrays -> device, per-mesh set-up, the step, alpha table + status -> host (per rank at N > 1)",
                 "pipeline": "2 slots: the copy stream moves step i+1's mesh in and step i-1's alpha table + status out while step i computes"},
-        "gpu_launches": int(args.steps * (3 + (3 if n_gen else 0))),
+        # two-pass: alpha, assemble, gather (+ alpha_general, alpha of the neighbours, assemble_general);
+        # fused: alpha, assemble, diagonal merge (+ the same three and the scatter of the quadrature-path blocks)
+        "gpu_launches": int(args.steps * (3 + ((3 if args.two_pass else 4) if n_gen else 0))),
         "clocks": clocks.summary(),
     }
     if replica_value is not None:

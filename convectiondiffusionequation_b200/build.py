@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, os.environ.get("EHDG_LIB_NAME", "libehdg.so"))     # variant builds for A/B timing
-SOURCES = ["ehdg_core.cu", "ehdg_fast.cu", "ehdg_solve.cu", "ehdg_chain.cu", "ehdg_dist.cu", "ehdg_edg.cu"]
+SOURCES = ["ehdg_core.cu", "ehdg_fast.cu", "ehdg_solve.cu", "ehdg_chain.cu", "ehdg_dist.cu", "ehdg_edg.cu", "ehdg_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

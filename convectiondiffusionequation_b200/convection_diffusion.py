@@ -92,7 +92,7 @@ class Convection_Diffusion():
         torch.cuda.synchronize(pipe.dev)
         return time.perf_counter()
 
-    def _solve(self, pipe, cfg):
+    def _solve(self, pipe, cfg, built=False):
         """Condensed facet system: CSR build, Krylov solve, back-solve.  The reference calls a direct solver and has no notion of
         non-convergence; here an unconverged iteration is an ERROR (config 'raise_on_nonconvergence', default True) instead
         of a silently wrong 'Error' column.  solver 'auto' (default): EHDGPipeline.solve_auto -- DQGMRES(8) on the line-block
@@ -102,7 +102,8 @@ class Convection_Diffusion():
         max_iters = cfg.get('gmres_max_iters', 20000)
         precond = cfg.get('preconditioner', 'line')
         drop_tol = cfg.get('drop_tol', 0.0)
-        pipe.csr_build()
+        if not built:
+            pipe.csr_build()
         if solver == 'auto':
             pipe.solve_auto(rtol=rtol, max_iters=max_iters, precond=precond, drop_tol=drop_tol)
             self._last_method = pipe.solve_attempts[-1]['method']
@@ -140,9 +141,13 @@ class Convection_Diffusion():
                 alp = 0.5 * np.sqrt(1.0 + lam)              # value the reference tabulates (:350-351)
                 frame = pd.DataFrame({'alpha': alp, 'type': type, 'mesh_size': size, 'order': order}, columns=self.col)
                 self.alphas = frame if len(self.alphas) == 0 else pd.concat([self.alphas, frame], ignore_index=True)
-                pipe.assemble_condense()                    # forms + assembly + rhs       (:357-383)
+                fused = not pipe.dirichlet_lifting and not cfg.get('two_pass_assembly', False)
+                if fused:
+                    pipe.assemble_condense_csr()            # forms + assembly + rhs + condensed matrix in one pass (:357-383)
+                else:
+                    pipe.assemble_condense()                # element blocks S_K; the lifted right-hand side needs them
                 t_asm = self._lap(pipe)
-                gi = self._solve(pipe, cfg)                 # replaces Inverse(..., "pardiso") (:385-387)
+                gi = self._solve(pipe, cfg, built=fused)    # replaces Inverse(..., "pardiso") (:385-387)
                 t_sol = self._lap(pipe)
                 error, _ = pipe.errors()                    # recombination + L2 error     (:389-394)
                 ndof = pipe.ndof()

@@ -470,8 +470,11 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
     // max_blocks < 0: automatic.  Measured on B200 (profiles/r02_line_segments.jsonl): with 708 lines (1M elements) cutting
     // every line in 2-4 segments takes the iteration from 3.9 to 2.3 ms for 15 % more iterations (2.6 -> 1.8 s); 16 segments
     // stop converging; with 1 414 lines (4M) the sweep is no longer the bottleneck and cutting only costs iterations.
-    // Rule: enough chains for 2 x 8 warps per SM, at most 4 segments per line.
+    // With 224 lines of ~670 blocks (100k elements) the iteration is not sweep-bound and 4 segments cost 50 % more iterations
+    // (HDG 630 -> 960) and the convergence of the enriched config-2 system (profiles/r02d_bench_1gpu_4M.json).
+    // Rule: enough chains for 2 x 8 warps per SM, at most 4 segments per line, no segment shorter than 500 blocks.
     const int auto_seg = std::max(1, std::min(4, (2 * 1184 + nchains - 1) / std::max(1, nchains)));
+    constexpr int AUTO_SEG_MIN_BLOCKS = 500;
     std::vector<int32_t> visit, visit2;
     for (int ch = 0; ch < nchains; ++ch) {
         const size_t o0 = order.size();
@@ -526,7 +529,7 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
         {
             const int first_blk = chain_ptr.back(), nb_ch = (int)blocks.size() - first_blk;
             int nseg = (max_blocks > 0 && nb_ch > max_blocks) ? (nb_ch + max_blocks - 1) / max_blocks : 1;
-            if (max_blocks < 0 && nb_ch >= 64) nseg = auto_seg;
+            if (max_blocks < 0) nseg = std::max(1, std::min(auto_seg, nb_ch / AUTO_SEG_MIN_BLOCKS));
             for (int sg = 1; sg <= nseg; ++sg) {
                 const int end_blk = first_blk + (int)(((int64_t)nb_ch * sg) / nseg);
                 if (sg > 1)

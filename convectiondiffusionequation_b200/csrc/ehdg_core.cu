@@ -217,6 +217,18 @@ assemble_general_kernel(Problem pb, RuleSet rs, int n_gen, const int32_t* __rest
     if (threadIdx.x == 0 && status) status[el] |= st;
 }
 
+// the quadrature path on the plan's general elements; Sg .. zg point at THEIR part of the element stores
+int general_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, const uint8_t* elem_active,
+                     const uint8_t* facet_mask, double* Sg, double* gg, double* Wg, double* zg, int32_t* status, double* Afull,
+                     cudaStream_t st) {
+    if (p->n_gen <= 0) return EHDG_OK;
+    assemble_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, c->ws_doubles * 8, st>>>(
+        c->pb, c->rb.rs, (int)p->n_gen, p->list_gen, m->verts, m->tris, m->el2facet, lam,
+        c->pb.nenr ? elem_active : nullptr, c->pb.nenr ? facet_mask : nullptr, Sg, gg, Wg, zg, status, Afull);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
 }  // namespace ehdg
 
 using namespace ehdg;
@@ -571,14 +583,9 @@ int ehdg_assemble_condense(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
     }
     if (p->n_gen > 0) {
         const size_t nfp = p->nf_poly, np = p->n_p;
-        double* Sg = S + (size_t)p->n_poly * nfp * nfp;
-        double* gg = g + (size_t)p->n_poly * nfp;
-        double* Wg = W + (size_t)p->n_poly * np * nfp;
-        double* zg = z + (size_t)p->n_poly * np;
-        assemble_general_kernel<<<(unsigned)p->n_gen, GEN_THREADS, c->ws_doubles * 8, sg>>>(
-            c->pb, c->rb.rs, (int)p->n_gen, p->list_gen, m->verts, m->tris, m->el2facet, lam,
-            c->pb.nenr ? elem_active : nullptr, c->pb.nenr ? facet_mask : nullptr, Sg, gg, Wg, zg, status, Afull);
-        EHDG_LAUNCH_CHECK();
+        int rc = general_assemble(c, p, m, lam, elem_active, facet_mask, S + (size_t)p->n_poly * nfp * nfp, g + (size_t)p->n_poly * nfp,
+                                  W + (size_t)p->n_poly * np * nfp, z + (size_t)p->n_poly * np, status, Afull, sg);
+        if (rc) return rc;
     }
     if (p->n_poly > 0) {
         int rc = fast_assemble(c, p, m, lam, S, g, W, z, status, st);

@@ -19,7 +19,7 @@ fast_assemble_kernel(Problem pb, LayerConst cx, LayerConst cy, RuleSet rs, const
                      const double* __restrict__ phi_rhs, int n, const int32_t* __restrict__ list,
                      const double* __restrict__ verts, const int32_t* __restrict__ tris,
                      const double* __restrict__ lam, double* __restrict__ S, double* __restrict__ g,
-                     double* __restrict__ W, double* __restrict__ z, int32_t* status) {
+                     double* __restrict__ W, double* __restrict__ z, int32_t* status, CsrOut co) {
     typedef FastDims<P> D;
     constexpr int LG = D::LG, GPC = FAST_THREADS / LG;
     extern __shared__ double smem[];
@@ -36,7 +36,8 @@ fast_assemble_kernel(Problem pb, LayerConst cx, LayerConst cy, RuleSet rs, const
         const int el = list[idx];
         const int st = fast_assemble_element<P>(gc, pb, rs, smem, phi_rhs, verts, tris + 3 * el, lam[el], live,
                                                 S + (size_t)idx * D::NF * D::NF, g + (size_t)idx * D::NF,
-                                                W + (size_t)idx * D::NP * D::NF, z + (size_t)idx * D::NP, cx, cy);
+                                                W + (size_t)idx * D::NP * D::NF, z + (size_t)idx * D::NP, cx, cy,
+                                                co.em ? co.em + el : nullptr, &co);
         if (st && live && status) atomicOr(status + el, st);
     }
 }
@@ -92,7 +93,7 @@ static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, con
 
 template <int P>
 static int launch_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, double* S, double* g,
-                           double* W, double* z, int32_t* status, cudaStream_t st) {
+                           double* W, double* z, int32_t* status, cudaStream_t st, const CsrOut& co) {
     typedef FastDims<P> D;
     constexpr int GPC = FAST_THREADS / D::LG;
     const int tabd = c->tens.asm_doubles;
@@ -106,7 +107,7 @@ static int launch_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
     const int grid = (int)(need < cap ? need : cap);
     if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[2], st));
     fast_assemble_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->pb, layer_const(c->pb.coeff.k[0]), layer_const(c->pb.coeff.k[1]), c->rb.rs, c->tens.asm_tab, tabd, c->tens.rhs_phi, (int)p->n_poly,
-                                                             p->list_poly, m->verts, m->tris, lam, S, g, W, z, status);
+                                                             p->list_poly, m->verts, m->tris, lam, S, g, W, z, status, co);
     if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[3], st));
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
@@ -154,8 +155,10 @@ int fast_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const int32_
 }
 
 int fast_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, double* S, double* g, double* W,
-                  double* z, int32_t* status, cudaStream_t st) {
-#define CALL(PP) launch_assemble<PP>(c, p, m, lam, S, g, W, z, status, st)
+                  double* z, int32_t* status, cudaStream_t st, const CsrOut* csr_out) {
+    CsrOut co{};
+    if (csr_out) co = *csr_out;
+#define CALL(PP) launch_assemble<PP>(c, p, m, lam, S, g, W, z, status, st, co)
     EHDG_DISPATCH_P(c->pb.p, CALL)
 #undef CALL
 }

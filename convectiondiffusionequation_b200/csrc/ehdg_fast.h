@@ -10,6 +10,7 @@
 // with __syncwarp) and on the host (a phase is a loop over the LG lanes, L == l); the host
 // instantiation exists only for tests/hostcheck.
 #pragma once
+#include <stdint.h>
 #include <string.h>
 #include <cmath>
 
@@ -61,6 +62,26 @@ EHDG_HD void st2(double* p, double a, double b) {
     p[1] = b;
 #endif
 }
+
+// Fused a5-a8 store (ehdg_assemble_condense_csr): where the condensed block of one element goes in the facet-major value
+// array.  Off-diagonal facet pairs (a != b) belong to exactly one element and are written in place; the diagonal block of a
+// facet has two contributors: the first element of facet2el writes it in place, the second one into a side buffer that a
+// merge kernel adds afterwards (first + second = the ascending-element order of the gather in ehdg_csr_numeric).
+struct ElMap {
+    int64_t base[3];     // first value of the row block of local facet a; -1: no rows (boundary facet / another rank's rows)
+    int32_t row0[3];     // first global row of that facet
+    int32_t len[3];      // row length
+    uint8_t coff[3][3];  // column offset of facet b's block inside a row of facet a; 255: facet b has no dofs
+    uint8_t hi;          // bit a: this element is the second one of facet a
+    uint8_t pad[2];
+};
+struct CsrOut {
+    const ElMap* em;     // [ne]; null: the condensed blocks leave element-wise (S, g)
+    double *vals, *rhs;  // value array of the pattern; right-hand side by GLOBAL row
+    double *diag2, *g2;  // second contributions: [own rows][nb] and [own rows]
+    int64_t row_lo;
+    int nb;
+};
 
 // exp(-50) = 1.9e-22: below this the exponential of a layer function is dropped next to its polynomial part
 #define EHDG_LAYER_DROP 50.0
@@ -303,7 +324,8 @@ template <int P>
 EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Problem& pb, const RuleSet& rs,
                                   const double* tab, const double* phi_rhs, const double* verts, const int* tri,
                                   double lam, bool store, double* S, double* gvec, double* W, double* z,
-                                  const LayerConst& cx, const LayerConst& cy) {
+                                  const LayerConst& cx, const LayerConst& cy, const ElMap* em = nullptr,
+                                  const CsrOut* co = nullptr) {
     typedef FastDims<P> D;
     constexpr int NP = D::NP, NFL = D::NFL, NF = D::NF, NC = D::NC, LG = D::LG, R = D::R, NXS = D::NXS;
     constexpr int NLS = EHDG_NLS(LG), NFS = NF | 1;     // NFS: row stride of the facet tensors
@@ -832,7 +854,36 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
     }
     double* Ss = Xs;                                // every lane is done reading X (repeated for the copy-out below)
     EHDG_FOR_LANES(l, L)
-        if (store) {
+        if (store && em) {
+            // straight into the pattern: lane l owns column (b, lc) of the local block; the NFL lanes of one facet write
+            // NFL consecutive doubles of a row
+            for (int col = l; col < NF; col += LG) {
+                const int b = col / NFL, lc = col - b * NFL;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const int64_t base = em->base[a];
+                    const int cf = em->coff[a][b];
+                    if (base < 0 || cf == 255) continue;
+                    double* dst;
+                    size_t stride;
+                    if (a == b && ((em->hi >> a) & 1)) {
+                        dst = co->diag2 + (size_t)(em->row0[a] - co->row_lo) * co->nb + lc;
+                        stride = (size_t)co->nb;
+                    } else {
+                        dst = co->vals + base + cf + lc;
+                        stride = (size_t)em->len[a];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NFL; ++i) dst[i * stride] = Ss[(a * NFL + i) * NF + col];
+                }
+            }
+            for (int r = l; r < NF; r += LG) {
+                const int a = r / NFL, i = r - a * NFL;
+                if (em->base[a] < 0) continue;
+                if ((em->hi >> a) & 1) co->g2[em->row0[a] - co->row_lo + i] = Ss[NF * NF + r];
+                else co->rhs[em->row0[a] + i] = Ss[NF * NF + r];
+            }
+        } else if (store) {
             for (int col = l; col < NF; col += LG) {
 #pragma unroll
                 for (int r = 0; r < NF; ++r) S[r * NF + col] = Ss[r * NF + col];

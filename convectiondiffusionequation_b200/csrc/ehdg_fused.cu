@@ -1,0 +1,167 @@
+// Fused a5-a8: the element kernels store their condensed blocks straight into the facet-major value array of the pattern.
+//
+// The separate numeric fill (ehdg_csr_numeric) reads every S_K back from HBM and writes the values: 13.9 GB and 9.2 ms at
+// 4M elements, a fifth of the step.  It is not needed: in the condensed matrix the block of a facet pair (f, g), f != g, has
+// exactly ONE contributing element (two facets share at most one triangle), so its owner can write it in place; only the
+// diagonal blocks (f, f) and the right-hand side have two contributors.  There the first element of facet2el writes in
+// place, the second one into a side buffer, and a merge kernel adds first + second -- the ascending-element order of the
+// gather, so the value array is identical to ehdg_csr_numeric's (tests/test_gpu_fused.py) and no atomics are involved.
+#include "ehdg_fast.h"
+#include "ehdg_internal.h"
+
+namespace ehdg {
+
+// one thread per element: where its block goes
+__global__ void elmap_kernel(int ne, int f_lo, int f_hi, const int32_t* __restrict__ el2facet, const int32_t* __restrict__ facet2el,
+                             const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
+                             const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len,
+                             const uint16_t* __restrict__ dofmask, ElMap* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    ElMap m;
+    int f[3];
+    for (int a = 0; a < 3; ++a) f[a] = el2facet[3 * e + a];
+    m.hi = 0;
+    m.pad[0] = m.pad[1] = 0;
+    for (int a = 0; a < 3; ++a) {
+        const int fa = f[a];
+        const int r0 = row_start[fa], rows = row_start[fa + 1] - r0;
+        const bool mine = rows > 0 && fa >= f_lo && fa < f_hi;
+        m.base[a] = mine ? blk_base[fa] : -1;
+        m.row0[a] = r0;
+        m.len[a] = mine ? nbr_len[fa] : 0;
+        if (facet2el[2 * fa + 1] == e) m.hi |= (uint8_t)(1u << a);
+        for (int b = 0; b < 3; ++b) {
+            int off = 0, found = 255;
+            for (int t = 0; t < 5; ++t) {
+                const int g = nbr[5 * fa + t];
+                if (g < 0) break;
+                if (g == f[b]) { found = dofmask[g] ? off : 255; break; }
+                off += __popc((unsigned)dofmask[g]);
+            }
+            m.coff[a][b] = (uint8_t)found;
+        }
+    }
+    out[e] = m;
+}
+
+// general-path elements: one thread per (element, local facet slot row) of the element-wise S_K the quadrature kernel wrote
+__global__ void scatter_general_kernel(int n_gen, int nb, const int32_t* __restrict__ list_gen, const int32_t* __restrict__ el2facet,
+                                       const uint16_t* __restrict__ dofmask, const ElMap* __restrict__ em,
+                                       const double* __restrict__ Sg, const double* __restrict__ gg, CsrOut co) {
+    const int nfg = 3 * nb;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_gen * nfg) return;
+    const int idx = (int)(t / nfg), rr = (int)(t - (int64_t)idx * nfg);
+    const int e = list_gen[idx];
+    const int a = rr / nb, k = rr - a * nb;
+    const ElMap m = em[e];
+    if (m.base[a] < 0) return;
+    const unsigned mf = dofmask[el2facet[3 * e + a]];
+    if (!((mf >> k) & 1u)) return;
+    const int i = __popc(mf & ((1u << k) - 1u));                    // row of slot k inside the facet's row block
+    const double* srow = Sg + (size_t)idx * nfg * nfg + (size_t)rr * nfg;
+    const bool hi = (m.hi >> a) & 1;
+    for (int b = 0; b < 3; ++b) {
+        const int cf = m.coff[a][b];
+        if (cf == 255) continue;
+        unsigned mg = dofmask[el2facet[3 * e + b]];
+        double* dst = (a == b && hi) ? co.diag2 + (size_t)(m.row0[a] + i - co.row_lo) * co.nb
+                                     : co.vals + m.base[a] + (int64_t)i * m.len[a] + cf;
+        int j = 0;
+        while (mg) {
+            const int l = __ffs(mg) - 1;
+            mg &= mg - 1;
+            dst[j++] = srow[b * nb + l];
+        }
+    }
+    const double gval = gg[(size_t)idx * nfg + rr];
+    if (hi) co.g2[m.row0[a] + i - co.row_lo] = gval;
+    else co.rhs[m.row0[a] + i] = gval;
+}
+
+// first + second contribution of the diagonal blocks and of the right-hand side; one thread per own row
+__global__ void merge_diag_kernel(int64_t row_lo, int64_t row_hi, int nb, const int32_t* __restrict__ row_facet,
+                                  const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
+                                  const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask,
+                                  const double* __restrict__ diag2, const double* __restrict__ g2, double* __restrict__ vals,
+                                  double* __restrict__ rhs) {
+    const int64_t r = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= row_hi) return;
+    const int f = row_facet[r];
+    const int rows = row_start[f + 1] - row_start[f];
+    int off = 0;
+    for (int t = 0; t < 5; ++t) {
+        const int g = nbr[5 * f + t];
+        if (g < 0 || g == f) break;
+        off += __popc((unsigned)dofmask[g]);
+    }
+    double* v = vals + rowptr[r] + off;
+    const double* d = diag2 + (size_t)(r - row_lo) * nb;
+    for (int j = 0; j < rows; ++j) v[j] += d[j];
+    rhs[r] += g2[r - row_lo];
+}
+
+int general_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, const uint8_t* elem_active,
+                     const uint8_t* facet_mask, double* Sg, double* gg, double* Wg, double* zg, int32_t* status, double* Afull,
+                     cudaStream_t st);   // ehdg_core.cu
+
+}  // namespace ehdg
+
+using namespace ehdg;
+
+extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_csr* A, const ehdg_mesh* m, const double* lam,
+                                          const uint8_t* elem_active, const uint8_t* facet_mask, double* vals, double* rhs,
+                                          double* W, double* z, int32_t* status, void* stream) {
+    if (!c || !p || !A || !m || !lam || !vals || !rhs || !W || !z) { set_error("ehdg_assemble_condense_csr: null argument"); return EHDG_ERR_ARG; }
+    if (A->edg) { set_error("ehdg_assemble_condense_csr: the pattern is an EDG pattern"); return EHDG_ERR_ARG; }
+    if (A->nf != m->nf) { set_error("ehdg_assemble_condense_csr: pattern and mesh do not match"); return EHDG_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rlo = A->windowed ? A->row_lo : 0, rhi = A->windowed ? A->row_hi : A->n_rows;
+    const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
+    if (A->folded_vals == vals) A->folded_vals = nullptr;
+    if (!A->elmap || A->elmap_ne != m->ne) {
+        if (A->elmap) EHDG_CUDA(cudaFreeAsync(A->elmap, st));
+        A->elmap = nullptr;
+        EHDG_CUDA(cudaMallocAsync(&A->elmap, sizeof(ElMap) * (size_t)(m->ne > 0 ? m->ne : 1), st));
+        A->elmap_ne = m->ne;
+        if (m->ne > 0)
+            elmap_kernel<<<(m->ne + 127) / 128, 128, 0, st>>>(m->ne, fa, fb, m->el2facet, m->facet2el, A->row_start, A->blk_base, A->nbr,
+                                                              A->nbr_len, A->dofmask, (ElMap*)A->elmap);
+        EHDG_LAUNCH_CHECK();
+    }
+    const int nb = c->pb.nb;
+    const int64_t nown = rhi > rlo ? rhi - rlo : 0;
+    double *diag2 = nullptr, *g2 = nullptr, *Sg = nullptr, *gg = nullptr;
+    EHDG_CUDA(cudaMallocAsync(&diag2, sizeof(double) * (size_t)(nown * (nb + 1) + 1), st));
+    g2 = diag2 + nown * nb;
+    EHDG_CUDA(cudaMemsetAsync(diag2, 0, sizeof(double) * (size_t)(nown * (nb + 1) + 1), st));
+    CsrOut co{(const ElMap*)A->elmap, vals, rhs, diag2, g2, rlo, nb};
+    int rc = EHDG_OK;
+    if (p->n_gen > 0) {
+        const size_t nfg = (size_t)p->nfmax;
+        if (cudaMallocAsync(&Sg, sizeof(double) * (size_t)p->n_gen * (nfg * nfg + nfg), st) != cudaSuccess) {
+            cudaFreeAsync(diag2, st);
+            set_error("ehdg_assemble_condense_csr: out of memory for the element blocks of the quadrature path");
+            return EHDG_ERR_CUDA;
+        }
+        gg = Sg + (size_t)p->n_gen * nfg * nfg;
+        rc = general_assemble(c, p, m, lam, elem_active, facet_mask, Sg, gg, W + (size_t)p->n_poly * p->n_p * p->nf_poly,
+                              z + (size_t)p->n_poly * p->n_p, status, nullptr, st);
+        if (rc == EHDG_OK) {
+            const int64_t nthr = p->n_gen * (int64_t)nfg;
+            scatter_general_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>((int)p->n_gen, nb, p->list_gen, m->el2facet, A->dofmask,
+                                                                                   (const ElMap*)A->elmap, Sg, gg, co);
+            if (cudaGetLastError() != cudaSuccess) rc = EHDG_ERR_CUDA;
+        }
+    }
+    if (rc == EHDG_OK && p->n_poly > 0) rc = fast_assemble(c, p, m, lam, nullptr, nullptr, W, z, status, st, &co);
+    if (rc == EHDG_OK && nown > 0) {
+        merge_diag_kernel<<<(unsigned)((nown + 127) / 128), 128, 0, st>>>(rlo, rhi, nb, A->row_facet, A->row_start, A->rowptr, A->nbr,
+                                                                         A->dofmask, diag2, g2, vals, rhs);
+        if (cudaGetLastError() != cudaSuccess) { set_error("ehdg_assemble_condense_csr: merge launch failed"); rc = EHDG_ERR_CUDA; }
+    }
+    if (Sg) cudaFreeAsync(Sg, st);
+    cudaFreeAsync(diag2, st);
+    return rc;
+}

@@ -106,6 +106,8 @@ struct ehdg_csr {
     uint16_t* dofmask = nullptr;    // [nf]    active slots of the facet
     int32_t* row_facet = nullptr;   // [n_rows] facet of each row
     uint8_t* strip = nullptr;       // [nf]    1 = free facet of a marked element (enriched strip), null if none
+    void* elmap = nullptr;          // [ne] ElMap: scatter table of the fused a5-a8 store, built on first use
+    int32_t elmap_ne = 0;
     int32_t* line = nullptr;        // [nf]    chain of every facet for the line-block preconditioner, null until set
     int edg = 0;                    // EDG pattern: the blocks are ELEMENTS (self + facet neighbours), up to n_p + n_enrich rows each
     const double* folded_vals = nullptr;   // value array a Krylov solve has overwritten with A M^-1 (facet block-Jacobi mode)
@@ -124,6 +126,7 @@ struct ehdg_csr {
 };
 
 namespace ehdg {
+struct CsrOut;   // ehdg_fast.h
 // polynomial-path kernels (ehdg_fast.cu)
 int fast_build_tensors(ehdg_ctx* ctx);
 void fast_free_tensors(ehdg_ctx* ctx);
@@ -131,7 +134,7 @@ void fast_free_tensors(ehdg_ctx* ctx);
 int fast_alpha(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const int32_t* list, int n, const uint8_t* skip_if_set,
                double* lam, int32_t* status, cudaStream_t st);
 int fast_assemble(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const double* lam, double* S,
-                  double* g, double* W, double* z, int32_t* status, cudaStream_t st);
+                  double* g, double* W, double* z, int32_t* status, cudaStream_t st, const CsrOut* csr_out = nullptr);
 int64_t fast_flops_per_element(const ehdg_ctx* ctx);
 int64_t fast_flops_alpha(const ehdg_ctx* ctx);
 int64_t fast_flops_assemble(const ehdg_ctx* ctx);

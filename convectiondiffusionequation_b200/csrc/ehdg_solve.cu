@@ -1565,6 +1565,7 @@ int ehdg_csr_destroy(ehdg_csr* A) {
     if (A->dofmask) cudaFreeAsync(A->dofmask, st);
     if (A->row_facet) cudaFreeAsync(A->row_facet, st);
     if (A->strip) cudaFreeAsync(A->strip, st);
+    if (A->elmap) cudaFreeAsync(A->elmap, st);
     cudaFree(A->dinv);
     cudaFree(A->line);
     delete A;

@@ -189,8 +189,9 @@ class EHDGPipeline:
         self.Afull = torch.zeros(ps.n_gen * self.afull_stride, **f64) if want_full else None
 
     def assemble_condense(self, want_full=False):
-        if not hasattr(self, "S") or self.S.numel() != self.plan_sizes.S_doubles or (want_full and self.Afull is None):
+        if getattr(self, "S", None) is None or self.S.numel() != self.plan_sizes.S_doubles or (want_full and self.Afull is None):
             self.alloc_blocks(want_full)
+        self.fused = False
         _lib.check(self.lib.ehdg_assemble_condense(self.ctx, self.plan, C.byref(self.cmesh), _ptr(self.lam), _ptr(self.elem_active),
                                                    _ptr(self.facet_mask), _ptr(self.S), _ptr(self.g), _ptr(self.W), _ptr(self.z),
                                                    _ptr(self.status), _ptr(self.Afull) if want_full else None, self._stream()),
@@ -240,6 +241,46 @@ class EHDGPipeline:
         self.csr_numeric()
         return self
 
+    def csr_pattern(self):
+        """pattern + value storage without the numeric fill (the fused a5-a8 store fills it: assemble_condense_csr)"""
+        if self.csr is not None:
+            self.lib.ehdg_csr_destroy(self.csr)
+        self.csr = C.c_void_p()
+        self._lines_csr = None
+        _lib.check(self.lib.ehdg_csr_symbolic(self.ctx, C.byref(self.cmesh), _ptr(self.facet_active) if self.nenr else None,
+                                              _ptr(self.facet_mask) if self.nenr else None, C.byref(self.csr), self._stream()), "ehdg_csr_symbolic")
+        self.csr_sizes = _lib.CsrSizes()
+        _lib.check(self.lib.ehdg_csr_get_sizes(self.csr, C.byref(self.csr_sizes)), "ehdg_csr_get_sizes")
+        return self.csr_alloc_values()
+
+    def assemble_condense_csr(self):
+        """a5-a8 in one pass: the element kernels store the condensed blocks straight into the value array of the pattern
+        (ehdg_assemble_condense_csr); no element-wise S_K store, no separate numeric fill.  Same values as
+        assemble_condense() + csr_numeric(); not available with Dirichlet lifting (the lifted right-hand side needs S_K)."""
+        if self.dirichlet_lifting:
+            raise ValueError("the fused store has no lifting variant: use assemble_condense() + csr_numeric()")
+        if self.csr is None:
+            self.csr_pattern()
+        if getattr(self, "vals", None) is None or self.vals.numel() < max(self.csr_sizes.nnz, 1):
+            self.csr_alloc_values()
+        ps = self.plan_sizes
+        if getattr(self, "W", None) is None or self.W.numel() != ps.W_doubles:
+            f64 = dict(dtype=torch.float64, device=self.dev)
+            self.W = torch.empty(ps.W_doubles, **f64)
+            self.z = torch.empty(ps.z_doubles, **f64)
+        self.S = self.g = None
+        self.fused = True
+        self.vals_folded = False
+        _lib.check(self.lib.ehdg_assemble_condense_csr(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.lam),
+                                                       _ptr(self.elem_active), _ptr(self.facet_mask), _ptr(self.vals), _ptr(self.rhs),
+                                                       _ptr(self.W), _ptr(self.z), _ptr(self.status), self._stream()),
+                   "ehdg_assemble_condense_csr")
+        return self
+
+    def assemble_csr(self):
+        """alpha + fused assembly/condensation/fill: the whole a4-a8 step"""
+        return self.alpha().assemble_condense_csr()
+
     def dirichlet_values(self):
         """ubnd f64[nf][p+1]: L2 projection of `exact` on the boundary facets, zero elsewhere"""
         self.ubnd = torch.empty(self.mesh_host.nf * self.sizes.nfl, dtype=torch.float64, device=self.dev)
@@ -248,6 +289,8 @@ class EHDGPipeline:
 
     def csr_numeric(self):
         self.vals_folded = False
+        if getattr(self, "fused", False) and getattr(self, "S", None) is None:
+            return self.assemble_condense_csr()              # fused pipeline: the values come from the element kernels
         if self.dirichlet_lifting and self.ubnd is None:
             self.dirichlet_values()
         _lib.check(self.lib.ehdg_csr_numeric_bc(self.ctx, self.plan, self.csr, C.byref(self.cmesh), _ptr(self.S), _ptr(self.g),

@@ -136,11 +136,12 @@ def gather_extents(lo: int, hi: int, group=None, device="cpu"):
     return arr[:, 0].copy(), arr[:, 1].copy()
 
 
-def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True, assemble=True):
+def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True, assemble=True, fused=True):
     """mark + prune (replicated: O(sqrt(ne)) work), then this rank's share: pattern of its rows, alpha + element blocks +
     condensation of the elements that touch its facets, numeric fill of its rows, and the communicator's partition.
     exchange=False stops before the collective part (single-process checks of one rank's share); assemble=False stops after
-    the per-mesh set-up (marks, pruning, pattern, selection, plan, value arrays) and leaves a4-a8 to the caller."""
+    the per-mesh set-up (marks, pruning, pattern, selection, plan, value arrays) and leaves a4-a8 to the caller; fused=False
+    keeps the element blocks S_K and fills the rows with the separate gather."""
     import torch
     import torch.distributed as dist
     from . import _lib
@@ -162,7 +163,10 @@ def partitioned_assemble(pipe, rank: int, world: int, group=None, exchange=True,
     pipe.make_plan(sel)
     t0 = lap("select_plan_ms", t0)
     pipe.csr_alloc_values()
-    if assemble:
+    if assemble and fused and not pipe.dirichlet_lifting:
+        pipe.assemble_csr()                                  # a4-a8 on the selection, own rows written by the element kernels
+        t0 = lap("alpha_assemble_condense_csr_ms", t0)
+    elif assemble:
         pipe.assemble()                                      # a4-a7 on the selection
         t0 = lap("alpha_assemble_condense_ms", t0)
         pipe.csr_numeric()                                   # a8, own rows

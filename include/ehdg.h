@@ -220,6 +220,16 @@ const uint16_t* ehdg_csr_dofmask(const ehdg_csr* csr);   /* u16 [nf]       devic
 int ehdg_csr_numeric(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_csr* csr, const ehdg_mesh* mesh,
                      const double* S, const double* g, double* vals, double* rhs, void* stream);
 
+/* a5-a8 fused: ehdg_assemble_condense with the condensed blocks stored straight into the value array of the pattern
+ * (convection_diffusion.py:357-383 -- what acd.Assemble() with condense=True does in one pass).  A block (f, g), f != g, has
+ * exactly one contributing element and is written in place; the diagonal blocks and the right-hand side take their second
+ * contribution through a side buffer, first + second as in ehdg_csr_numeric: vals and rhs are IDENTICAL to those of
+ * ehdg_assemble_condense + ehdg_csr_numeric, which stay for callers that want the element blocks S_K (parity tests, the
+ * Dirichlet-lifting variant).  W, z as in ehdg_assemble_condense; the pattern caches a per-element scatter table. */
+int ehdg_assemble_condense_csr(ehdg_ctx* ctx, const ehdg_plan* plan, ehdg_csr* csr, const ehdg_mesh* mesh, const double* lam,
+                               const uint8_t* elem_active, const uint8_t* facet_mask, double* vals, double* rhs, double* W,
+                               double* z, int32_t* status, void* stream);
+
 /* Inhomogeneous Dirichlet data (reference Python/debug_ehdg.py:210-214: gfu.components[1].Set(exact, BND); f -= A gfu;
  * gfu += A^-1 f).  ehdg_dirichlet_project: ubnd f64[nf][p+1] = L2 projection of `exact` onto the Legendre modes of every
  * boundary facet (bonus rule), 0 on interior facets.  The _bc variants of a8 / a10 move the prescribed dofs to the right-hand
