@@ -467,14 +467,14 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
         }
         return maxlev;
     };
-    // max_blocks < 0: automatic.  Measured on B200 (profiles/r02_line_segments.jsonl): with 708 lines (1M elements) cutting
-    // every line in 2-4 segments takes the iteration from 3.9 to 2.3 ms for 15 % more iterations (2.6 -> 1.8 s); 16 segments
-    // stop converging; with 1 414 lines (4M) the sweep is no longer the bottleneck and cutting only costs iterations.
-    // With 224 lines of ~670 blocks (100k elements) the iteration is not sweep-bound and 4 segments cost 50 % more iterations
-    // (HDG 630 -> 960) and the convergence of the enriched config-2 system (profiles/r02d_bench_1gpu_4M.json).
-    // Rule: enough chains for 2 x 8 warps per SM, at most 4 segments per line, no segment shorter than 500 blocks.
-    const int auto_seg = std::max(1, std::min(4, (2 * 1184 + nchains - 1) / std::max(1, nchains)));
-    constexpr int AUTO_SEG_MIN_BLOCKS = 500;
+    // max_blocks < 0: automatic.  Measured on B200 (profiles/r02_line_segments.jsonl, r02d_bench_1gpu_4M.json): with 708 lines
+    // (1M elements, 4.8 chains per SM) the sweep is latency-bound and cutting every line in 4 takes the iteration from 3.9 to
+    // 2.3 ms for 15 % more iterations (2.6 -> 1.8 s); 16 segments stop converging.  With 1 414 lines (4M) the iteration is not
+    // sweep-bound: 2 segments leave it at 8.3 ms and cost 50 % more iterations (13.6 -> 19.5 s).  With 224 lines of ~670 blocks
+    // (100k) 4 segments cost 50 % more iterations and the convergence of the enriched config-2 system.
+    // Rule: cut only while there are fewer chains than 8 warps per SM, into at most 4 segments of at least 350 blocks.
+    const int auto_seg = nchains >= 1184 ? 1 : std::max(1, std::min(4, 2832 / std::max(1, nchains)));
+    constexpr int AUTO_SEG_MIN_BLOCKS = 350;
     std::vector<int32_t> visit, visit2;
     for (int ch = 0; ch < nchains; ++ch) {
         const size_t o0 = order.size();

@@ -124,7 +124,14 @@ __global__ void plan_scatter_kernel(int ne, const int32_t* __restrict__ flag_gen
 // -------------------------------------------------------------------------------------------
 // general kernels: one CTA of GEN_THREADS threads per element, workspace in dynamic smem
 // -------------------------------------------------------------------------------------------
-constexpr int GEN_THREADS = 128;
+// A/B on B200, 4M headline mesh, 12 183 elements on this path (profiles/r02_ab_gen_threads*.txt), step in ms:
+// 256 threads 41.5, 128: 39.2, 96: 39.0, 64: 38.4, 32: 38.2.  The kernels need 128 registers per thread and 26 KB of shared
+// memory per element (p = 4): smaller CTAs mean more elements resident per SM and cheaper barriers, and the per-element
+// phases have too little parallelism for more than two warps anyway.  64 keeps 8 warps per SM at p = 6 as well (50 KB).
+#ifndef EHDG_GEN_THREADS
+#define EHDG_GEN_THREADS 64
+#endif
+constexpr int GEN_THREADS = EHDG_GEN_THREADS;
 
 __device__ __forceinline__ int fac_bits(const uint8_t* fm, const int32_t* el2facet, int el, int e) {
     return fm ? (int)fm[el2facet[3 * el + e]] : 0;
@@ -277,7 +284,22 @@ int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out) {
     EHDG_CUDA(cudaFuncSetAttribute(alpha_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     EHDG_CUDA(cudaFuncSetAttribute(assemble_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if ((rc = fast_build_tensors(c))) return rc;
-    EHDG_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    {
+        // the quadrature-path kernels (O(sqrt(ne)) elements, latency-bound: one CTA per element) can run on a high-priority side
+        // stream beside the polynomial-path kernels, which then draw their work from a counter (see fast_assemble_kernel)
+        int lo = 0, hi = 0;
+        EHDG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        EHDG_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+        EHDG_CUDA(cudaMalloc(&c->work_counters, 2 * sizeof(int)));
+        const char* e = getenv("EHDG_OVERLAP");
+        c->overlap_general = (e && e[0] == '1') ? 1 : 0;
+        // A/B on B200, 4M elements (profiles/r02_ab_overlap.txt): drawn work makes the assemble kernel 1.0 ms faster (18.57 ->
+        // 17.57 ms: no tail) and the alpha kernel 0.4 ms slower (uniform work, the atomics only cost); the overlap itself buys
+        // nothing on top (both polynomial kernels fill the register file, the quadrature CTAs do not become co-resident).
+        // Default: assemble draws (bit 0), alpha keeps its static partition (bit 1 off), no overlap.
+        const char* d = getenv("EHDG_DYNAMIC");
+        c->dynamic_work = d ? atoi(d) : (c->overlap_general ? 3 : 1);
+    }
     EHDG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     EHDG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     guard.ok = true;
@@ -295,6 +317,7 @@ int ehdg_destroy(ehdg_ctx* c) {
     ehdg_comm_destroy(c);
     fast_free_tensors(c);
     cudaFree(c->scratch);
+    cudaFree(c->work_counters);
     cudaFree(c->pool_eslot);
     cudaFree(c->pool_lists);
     if (c->side) cudaStreamDestroy(c->side);
@@ -542,7 +565,7 @@ static int alpha_impl(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const
     cudaStream_t st = (cudaStream_t)stream;
     // running the O(sqrt(ne)) enriched elements on a side stream beside the bulk kernel was measured slower on B200
     // (the persistent bulk CTAs already fill every SM; +0.5 ms at 1M elements), so it is opt-in
-    const bool fork = p->n_gen > 0 && p->n_poly > 0 && getenv("EHDG_FORK");
+    const bool fork = p->n_gen > 0 && p->n_poly > 0 && c->overlap_general;
     cudaStream_t sg = fork ? c->side : st;
     if (fork) {
         EHDG_CUDA(cudaEventRecord(c->ev_fork, st));
@@ -575,7 +598,7 @@ int ehdg_assemble_condense(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
                            double* z, int32_t* status, double* Afull, void* stream) {
     if (!c || !p || !m || !lam || !S || !g || !W || !z) { set_error("ehdg_assemble_condense: null argument"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fork = p->n_gen > 0 && p->n_poly > 0 && getenv("EHDG_FORK");
+    const bool fork = p->n_gen > 0 && p->n_poly > 0 && c->overlap_general;
     cudaStream_t sg = fork ? c->side : st;
     if (fork) {
         EHDG_CUDA(cudaEventRecord(c->ev_fork, st));

@@ -13,15 +13,22 @@ constexpr int FAST_THREADS = 128;
 #define EHDG_ALPHA_MINBLOCKS (EHDG_ALPHA_R == 2 ? 3 : 4)
 #endif
 
+// lane 0 of the warp draws `step` consecutive work items, all lanes get the first one
+__device__ __forceinline__ int next_work(int* counter, int step) {
+    int b = 0;
+    if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, step);
+    return __shfl_sync(0xffffffffu, b, 0);
+}
+
 template <int P>
 __global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ASM_MINBLOCKS : (P == 5 ? 2 : 1)))
 fast_assemble_kernel(Problem pb, LayerConst cx, LayerConst cy, RuleSet rs, const double* __restrict__ tab_g, int tab_doubles,
                      const double* __restrict__ phi_rhs, int n, const int32_t* __restrict__ list,
                      const double* __restrict__ verts, const int32_t* __restrict__ tris,
                      const double* __restrict__ lam, double* __restrict__ S, double* __restrict__ g,
-                     double* __restrict__ W, double* __restrict__ z, int32_t* status, CsrOut co) {
+                     double* __restrict__ W, double* __restrict__ z, int32_t* status, CsrOut co, int* __restrict__ work) {
     typedef FastDims<P> D;
-    constexpr int LG = D::LG, GPC = FAST_THREADS / LG;
+    constexpr int LG = D::LG, GPC = FAST_THREADS / LG, GPW = 32 / LG;
     extern __shared__ double smem[];
     for (int i = threadIdx.x; i < tab_doubles; i += FAST_THREADS) smem[i] = tab_g[i];
     __syncthreads();
@@ -30,9 +37,15 @@ fast_assemble_kernel(Problem pb, LayerConst cx, LayerConst cy, RuleSet rs, const
     Group<LG> gc{(int)(threadIdx.x % LG), smem + ((tab_doubles + 1) & ~1) + gid * scratch};
     // cx, cy: constants of the two layer functions of `coeff`, formed once on the host; as kernel parameters they are
     // constant-bank operands and cost no registers across the elimination
-    for (int base = blockIdx.x * GPC; base < n; base += gridDim.x * GPC) {
-        const bool live = base + gid < n;
-        const int idx = base + gid < n ? base + gid : n - 1;
+    // work: every warp draws its next GPW elements from a global counter (null: static grid-stride partition).  With the
+    // quadrature-path kernel running beside this one on another stream, CTAs of this kernel become resident at different
+    // times; drawn work keeps them all busy to the end, a static share would make the late ones the tail.
+    const int gw = gid % GPW;
+    for (int base = work ? next_work(work, GPW) : blockIdx.x * GPC; base < n;
+         base = work ? next_work(work, GPW) : base + gridDim.x * GPC) {
+        const int mine = work ? base + gw : base + gid;
+        const bool live = mine < n;
+        const int idx = live ? mine : n - 1;
         const int el = list[idx];
         const int st = fast_assemble_element<P>(gc, pb, rs, smem, phi_rhs, verts, tris + 3 * el, lam[el], live,
                                                 S + (size_t)idx * D::NF * D::NF, g + (size_t)idx * D::NF,
@@ -46,7 +59,7 @@ template <int P>
 __global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ALPHA_MINBLOCKS : 2))
 fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, const int32_t* __restrict__ list,
                   const uint8_t* __restrict__ skip_if_set, const double* __restrict__ verts, const int32_t* __restrict__ tris,
-                  double* __restrict__ lam, int32_t* status) {
+                  double* __restrict__ lam, int32_t* status, int* __restrict__ work) {
     typedef AlphaDims<P> D;
     constexpr int LG = D::LG, GPC = FAST_THREADS / LG;
     extern __shared__ double smem[];
@@ -56,9 +69,12 @@ fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, cons
     constexpr int GPW = 32 / LG;
     const int gid = (threadIdx.x / 32) * GPW + (threadIdx.x % GPW);
     Group<LG> gc{(int)((threadIdx.x & 31) / GPW), smem + ((tab_doubles + 1) & ~1) + gid * fast_alpha_scratch_doubles<P>(), GPW};
-    for (int base = blockIdx.x * GPC; base < n; base += gridDim.x * GPC) {
-        const bool live = base + gid < n;
-        const int idx = live ? base + gid : n - 1;
+    const int gw = threadIdx.x % GPW;
+    for (int base = work ? next_work(work, GPW) : blockIdx.x * GPC; base < n;
+         base = work ? next_work(work, GPW) : base + gridDim.x * GPC) {
+        const int mine = work ? base + gw : base + gid;
+        const bool live = mine < n;
+        const int idx = live ? mine : n - 1;
         const int el = list[idx];
         int st = 0;
         const double l = fast_alpha_element<P>(gc, smem, verts, tris + 3 * el, &st);
@@ -85,7 +101,12 @@ static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, con
     const int grid = (int)(need < cap ? need : cap);
     const bool timed = c->time_kernels && list == p->list_poly;
     if (timed) EHDG_CUDA(cudaEventRecord(c->ev_k[0], st));
-    fast_alpha_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->tens.alpha_tab, tabd, n, list, skip_if_set, m->verts, m->tris, lam, status);
+    int* work = nullptr;
+    if ((c->dynamic_work & 2) && list == p->list_poly) {
+        work = c->work_counters;
+        EHDG_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));
+    }
+    fast_alpha_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->tens.alpha_tab, tabd, n, list, skip_if_set, m->verts, m->tris, lam, status, work);
     if (timed) EHDG_CUDA(cudaEventRecord(c->ev_k[1], st));
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
@@ -105,9 +126,14 @@ static int launch_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
     const int64_t need = (p->n_poly + GPC - 1) / GPC;
     const int64_t cap = (int64_t)c->sm_count * per_sm;
     const int grid = (int)(need < cap ? need : cap);
+    int* work = nullptr;
+    if (c->dynamic_work & 1) {
+        work = c->work_counters + 1;
+        EHDG_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));
+    }
     if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[2], st));
     fast_assemble_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->pb, layer_const(c->pb.coeff.k[0]), layer_const(c->pb.coeff.k[1]), c->rb.rs, c->tens.asm_tab, tabd, c->tens.rhs_phi, (int)p->n_poly,
-                                                             p->list_poly, m->verts, m->tris, lam, S, g, W, z, status, co);
+                                                             p->list_poly, m->verts, m->tris, lam, S, g, W, z, status, co, work);
     if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[3], st));
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;

@@ -80,26 +80,32 @@ __global__ void scatter_general_kernel(int n_gen, int nb, const int32_t* __restr
     else co.rhs[m.row0[a] + i] = gval;
 }
 
-// first + second contribution of the diagonal blocks and of the right-hand side; one thread per own row
-__global__ void merge_diag_kernel(int64_t row_lo, int64_t row_hi, int nb, const int32_t* __restrict__ row_facet,
-                                  const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
-                                  const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask,
-                                  const double* __restrict__ diag2, const double* __restrict__ g2, double* __restrict__ vals,
-                                  double* __restrict__ rhs) {
-    const int64_t r = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= row_hi) return;
-    const int f = row_facet[r];
-    const int rows = row_start[f + 1] - row_start[f];
+// column offset of a facet's own (diagonal) block inside its rows; one thread per facet
+__global__ void diag_off_kernel(int nf, const int32_t* __restrict__ nbr, const uint16_t* __restrict__ dofmask, int32_t* __restrict__ doff) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
     int off = 0;
     for (int t = 0; t < 5; ++t) {
         const int g = nbr[5 * f + t];
         if (g < 0 || g == f) break;
         off += __popc((unsigned)dofmask[g]);
     }
-    double* v = vals + rowptr[r] + off;
-    const double* d = diag2 + (size_t)(r - row_lo) * nb;
-    for (int j = 0; j < rows; ++j) v[j] += d[j];
-    rhs[r] += g2[r - row_lo];
+    doff[f] = off;
+}
+
+// first + second contribution of the diagonal blocks and of the right-hand side; one thread per (own row, block column):
+// the side buffer is read contiguously, the value array in runs of one block row
+__global__ void merge_diag_kernel(int64_t row_lo, int64_t row_hi, int nb, const int32_t* __restrict__ row_facet,
+                                  const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
+                                  const int32_t* __restrict__ doff, const double* __restrict__ diag2,
+                                  const double* __restrict__ g2, double* __restrict__ vals, double* __restrict__ rhs) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = row_lo + t / nb;
+    const int l = (int)(t % nb);
+    if (r >= row_hi) return;
+    const int f = row_facet[r];
+    if (l < row_start[f + 1] - row_start[f]) vals[rowptr[r] + doff[f] + l] += diag2[t];
+    if (l == 0) rhs[r] += g2[r - row_lo];
 }
 
 int general_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, const uint8_t* elem_active,
@@ -129,6 +135,11 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
             elmap_kernel<<<(m->ne + 127) / 128, 128, 0, st>>>(m->ne, fa, fb, m->el2facet, m->facet2el, A->row_start, A->blk_base, A->nbr,
                                                               A->nbr_len, A->dofmask, (ElMap*)A->elmap);
         EHDG_LAUNCH_CHECK();
+        if (A->diag_off) EHDG_CUDA(cudaFreeAsync(A->diag_off, st));
+        A->diag_off = nullptr;
+        EHDG_CUDA(cudaMallocAsync(&A->diag_off, sizeof(int32_t) * (size_t)(A->nf > 0 ? A->nf : 1), st));
+        if (A->nf > 0) diag_off_kernel<<<(A->nf + 255) / 256, 256, 0, st>>>(A->nf, A->nbr, A->dofmask, A->diag_off);
+        EHDG_LAUNCH_CHECK();
     }
     const int nb = c->pb.nb;
     const int64_t nown = rhi > rlo ? rhi - rlo : 0;
@@ -138,6 +149,12 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
     EHDG_CUDA(cudaMemsetAsync(diag2, 0, sizeof(double) * (size_t)(nown * (nb + 1) + 1), st));
     CsrOut co{(const ElMap*)A->elmap, vals, rhs, diag2, g2, rlo, nb};
     int rc = EHDG_OK;
+    const bool fork = p->n_gen > 0 && p->n_poly > 0 && c->overlap_general;
+    cudaStream_t sg = fork ? c->side : st;
+    if (fork) {
+        EHDG_CUDA(cudaEventRecord(c->ev_fork, st));
+        EHDG_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    }
     if (p->n_gen > 0) {
         const size_t nfg = (size_t)p->nfmax;
         if (cudaMallocAsync(&Sg, sizeof(double) * (size_t)p->n_gen * (nfg * nfg + nfg), st) != cudaSuccess) {
@@ -147,18 +164,22 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
         }
         gg = Sg + (size_t)p->n_gen * nfg * nfg;
         rc = general_assemble(c, p, m, lam, elem_active, facet_mask, Sg, gg, W + (size_t)p->n_poly * p->n_p * p->nf_poly,
-                              z + (size_t)p->n_poly * p->n_p, status, nullptr, st);
+                              z + (size_t)p->n_poly * p->n_p, status, nullptr, sg);
         if (rc == EHDG_OK) {
             const int64_t nthr = p->n_gen * (int64_t)nfg;
-            scatter_general_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, st>>>((int)p->n_gen, nb, p->list_gen, m->el2facet, A->dofmask,
+            scatter_general_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, sg>>>((int)p->n_gen, nb, p->list_gen, m->el2facet, A->dofmask,
                                                                                    (const ElMap*)A->elmap, Sg, gg, co);
             if (cudaGetLastError() != cudaSuccess) rc = EHDG_ERR_CUDA;
         }
     }
     if (rc == EHDG_OK && p->n_poly > 0) rc = fast_assemble(c, p, m, lam, nullptr, nullptr, W, z, status, st, &co);
+    if (fork) {
+        cudaEventRecord(c->ev_join, c->side);
+        cudaStreamWaitEvent(st, c->ev_join, 0);
+    }
     if (rc == EHDG_OK && nown > 0) {
-        merge_diag_kernel<<<(unsigned)((nown + 127) / 128), 128, 0, st>>>(rlo, rhi, nb, A->row_facet, A->row_start, A->rowptr, A->nbr,
-                                                                         A->dofmask, diag2, g2, vals, rhs);
+        merge_diag_kernel<<<(unsigned)((nown * nb + 255) / 256), 256, 0, st>>>(rlo, rhi, nb, A->row_facet, A->row_start, A->rowptr,
+                                                                              A->diag_off, diag2, g2, vals, rhs);
         if (cudaGetLastError() != cudaSuccess) { set_error("ehdg_assemble_condense_csr: merge launch failed"); rc = EHDG_ERR_CUDA; }
     }
     if (Sg) cudaFreeAsync(Sg, st);

@@ -72,6 +72,9 @@ struct ehdg_ctx {
     void* user_ws = nullptr;          // caller-provided workspace of the Krylov solvers (ehdg_set_workspace)
     size_t user_ws_bytes = 0;
     cudaStream_t side = nullptr;      // the general (enriched) kernels run beside the polynomial ones
+    int overlap_general = 0;          // 1: quadrature-path kernels on `side`, concurrently with the polynomial-path kernels
+    int dynamic_work = 1;             // bit 0: the assemble kernel draws its elements from a counter (work_counters), bit 1: alpha too
+    int* work_counters = nullptr;     // [2] device: alpha, assemble
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // optional CUDA-event timing of the two polynomial-path kernels on their launching stream
     int time_kernels = 0;
@@ -108,6 +111,7 @@ struct ehdg_csr {
     uint8_t* strip = nullptr;       // [nf]    1 = free facet of a marked element (enriched strip), null if none
     void* elmap = nullptr;          // [ne] ElMap: scatter table of the fused a5-a8 store, built on first use
     int32_t elmap_ne = 0;
+    int32_t* diag_off = nullptr;    // [nf]    column offset of the facet's own block inside its rows (with elmap)
     int32_t* line = nullptr;        // [nf]    chain of every facet for the line-block preconditioner, null until set
     int edg = 0;                    // EDG pattern: the blocks are ELEMENTS (self + facet neighbours), up to n_p + n_enrich rows each
     const double* folded_vals = nullptr;   // value array a Krylov solve has overwritten with A M^-1 (facet block-Jacobi mode)

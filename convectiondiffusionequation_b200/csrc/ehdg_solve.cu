@@ -666,12 +666,12 @@ __global__ void poly_update_kernel(int64_t n, const double* __restrict__ v, cons
 
 // rn[r - row_lo] = max_j |a_rj| (1 for an empty / zero row), rd = 1 / rn: the row equilibration of the Krylov solvers
 __global__ void row_norm_kernel(int row_lo, int row_hi, const int64_t* __restrict__ rowptr, const double* __restrict__ vals,
-                                double* __restrict__ rn, double* __restrict__ rd) {
+                                double* __restrict__ rn, double* __restrict__ rd, int unit) {
     const int r = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= row_hi) return;
     double m = 0.0;
     for (int64_t q = rowptr[r]; q < rowptr[r + 1]; ++q) m = fmax(m, fabs(vals[q]));
-    if (!(m > 0.0) || !isfinite(m)) m = 1.0;
+    if (!(m > 0.0) || !isfinite(m) || unit) m = 1.0;
     rn[r - row_lo] = m;
     rd[r - row_lo] = 1.0 / m;
 }
@@ -1566,6 +1566,7 @@ int ehdg_csr_destroy(ehdg_csr* A) {
     if (A->row_facet) cudaFreeAsync(A->row_facet, st);
     if (A->strip) cudaFreeAsync(A->strip, st);
     if (A->elmap) cudaFreeAsync(A->elmap, st);
+    if (A->diag_off) cudaFreeAsync(A->diag_off, st);
     cudaFree(A->dinv);
     cudaFree(A->line);
     delete A;
@@ -1705,7 +1706,8 @@ static int krylov_solve(ehdg_ctx* c, ehdg_csr* A, double* vals, const double* rh
     if ((rc = ws.get(&rd, (size_t)n))) return rc;
     if ((rc = ws.get(&rhs_s, (size_t)n))) return rc;
     if (n > 0) {
-        row_norm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)r0, (int)r1, A->rowptr, vals, rn, rd);
+        static const bool no_eq = [] { const char* e = getenv("EHDG_NO_EQUILIBRATE"); return e && e[0] == '1'; }();   // A/B switch
+        row_norm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int)r0, (int)r1, A->rowptr, vals, rn, rd, no_eq ? 1 : 0);
         EHDG_LAUNCH_CHECK();
     }
     const double* rhs_raw = rhs;

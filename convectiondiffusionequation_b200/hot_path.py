@@ -221,9 +221,14 @@ class EHDGPipeline:
         return self
 
     def csr_alloc_values(self):
+        """value array + right-hand side of the current pattern; storage of the right size is kept (a rebuilt pattern of the same
+        mesh family must not pay a multi-GB allocation per mesh)"""
         n, nnz = self.csr_sizes.n_rows, self.csr_sizes.nnz
-        self.vals = torch.empty(max(nnz, 1), dtype=torch.float64, device=self.dev)
-        self.rhs = torch.zeros(max(n, 1), dtype=torch.float64, device=self.dev)
+        if getattr(self, "vals", None) is None or self.vals.numel() != max(nnz, 1):
+            self.vals = None
+            self.vals = torch.empty(max(nnz, 1), dtype=torch.float64, device=self.dev)
+        if getattr(self, "rhs", None) is None or self.rhs.numel() != max(n, 1):
+            self.rhs = torch.zeros(max(n, 1), dtype=torch.float64, device=self.dev)
         return self
 
     def csr_build(self):

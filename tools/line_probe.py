@@ -49,6 +49,10 @@ if __name__ == "__main__":
     elif which == "4m":
         run(1414, 4, 1e-6, kind="unstructured", configs=(("line", "gmres", 30, 0), ("line", "gmres", 60, 0)), iters=5000)
         run(1414, 4, 1e-6, kind="unstructured", enriched=True, configs=(("line", "gmres", 30, 0),), iters=5000)
+    elif which == "4mh":        # plain HDG at 4M, DQGMRES(8): A/B of the row equilibration (EHDG_NO_EQUILIBRATE=1)
+        run(1414, 4, 1e-6, kind="unstructured", configs=(("line", "dqgmres", 8, 0),), iters=5000)
+    elif which == "1mh":
+        run(708, 4, 1e-6, configs=(("line", "dqgmres", 8, 0), ("line", "gmres", 30, 0)), iters=5000, max_blocks=-1)
     elif which == "one":
         run(708, 4, 1e-6, configs=(("line", "gmres", 30, 0),), iters=40)
     elif which == "enr3":
