@@ -93,19 +93,26 @@ __global__ void diag_off_kernel(int nf, const int32_t* __restrict__ nbr, const u
     doff[f] = off;
 }
 
-// first + second contribution of the diagonal blocks and of the right-hand side; one thread per (own row, block column):
-// the side buffer is read contiguously, the value array in runs of one block row
-__global__ void merge_diag_kernel(int64_t row_lo, int64_t row_hi, int nb, const int32_t* __restrict__ row_facet,
-                                  const int32_t* __restrict__ row_start, const int64_t* __restrict__ rowptr,
-                                  const int32_t* __restrict__ doff, const double* __restrict__ diag2,
-                                  const double* __restrict__ g2, double* __restrict__ vals, double* __restrict__ rhs) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t r = row_lo + t / nb;
-    const int l = (int)(t % nb);
-    if (r >= row_hi) return;
-    const int f = row_facet[r];
-    if (l < row_start[f + 1] - row_start[f]) vals[rowptr[r] + doff[f] + l] += diag2[t];
-    if (l == 0) rhs[r] += g2[r - row_lo];
+// first + second contribution of the diagonal blocks and of the right-hand side; one warp per own facet: the index loads
+// happen once per facet, lane (i, l) owns entry l of row i of the facet's rows x rows diagonal block
+__global__ void __launch_bounds__(256)
+merge_diag_kernel(int f_lo, int f_hi, int64_t row_lo, int nb, const int32_t* __restrict__ row_start,
+                  const int64_t* __restrict__ blk_base, const int32_t* __restrict__ nbr_len, const int32_t* __restrict__ doff,
+                  const double* __restrict__ diag2, const double* __restrict__ g2, double* __restrict__ vals,
+                  double* __restrict__ rhs) {
+    const int f = f_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= f_hi) return;
+    const int r0 = row_start[f], rows = row_start[f + 1] - r0;
+    if (rows == 0) return;
+    const int len = nbr_len[f];
+    double* v = vals + blk_base[f] + doff[f];
+    const double* d = diag2 + (size_t)(r0 - row_lo) * nb;
+    for (int e = lane; e < rows * rows; e += 32) {
+        const int i = e / rows, l = e - i * rows;
+        v[(int64_t)i * len + l] += d[i * nb + l];
+    }
+    if (lane < rows) rhs[r0 + lane] += g2[r0 - row_lo + lane];
 }
 
 int general_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, const uint8_t* elem_active,
@@ -178,8 +185,8 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
         cudaStreamWaitEvent(st, c->ev_join, 0);
     }
     if (rc == EHDG_OK && nown > 0) {
-        merge_diag_kernel<<<(unsigned)((nown * nb + 255) / 256), 256, 0, st>>>(rlo, rhi, nb, A->row_facet, A->row_start, A->rowptr,
-                                                                              A->diag_off, diag2, g2, vals, rhs);
+        merge_diag_kernel<<<(unsigned)(((int64_t)(fb - fa) * 32 + 255) / 256), 256, 0, st>>>(fa, fb, rlo, nb, A->row_start, A->blk_base, A->nbr_len,
+                                                                                            A->diag_off, diag2, g2, vals, rhs);
         if (cudaGetLastError() != cudaSuccess) { set_error("ehdg_assemble_condense_csr: merge launch failed"); rc = EHDG_ERR_CUDA; }
     }
     if (Sg) cudaFreeAsync(Sg, st);
