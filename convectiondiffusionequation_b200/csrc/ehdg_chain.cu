@@ -612,6 +612,8 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
         EHDG_CUDA(cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
         chain_pos_kernel<<<(nd + 127) / 128, 128, 0, st>>>(nd, S->dof_rows, S->dof_blk, S->blocks, S->sblk, S->sloc);
         EHDG_LAUNCH_CHECK();
+        const int rce = ensure_colind(A, st);
+        if (rce) return rce;
         chain_extract_kernel<<<(nd + 127) / 128, 128, 0, st>>>(nd, S->dof_rows, S->dof_blk, S->blocks, S->blk_chain, A->rowptr, A->colind,
                                                               vals, S->sblk, S->sloc, S->DH, S->G, d_flags);
         EHDG_LAUNCH_CHECK();

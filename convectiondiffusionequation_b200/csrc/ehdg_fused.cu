@@ -115,6 +115,25 @@ merge_diag_kernel(int f_lo, int f_hi, int64_t row_lo, int nb, const int32_t* __r
     if (lane < rows) rhs[r0 + lane] += g2[r0 - row_lo + lane];
 }
 
+// scatter table + diagonal offsets of a pattern (built with the pattern by ehdg_csr_symbolic, on the pattern's stream)
+int build_elmap(ehdg_csr* A, const ehdg_mesh* m, cudaStream_t st) {
+    const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
+    if (A->elmap) EHDG_CUDA(cudaFreeAsync(A->elmap, st));
+    if (A->diag_off) EHDG_CUDA(cudaFreeAsync(A->diag_off, st));
+    A->elmap = nullptr;
+    A->diag_off = nullptr;
+    EHDG_CUDA(cudaMallocAsync(&A->elmap, sizeof(ElMap) * (size_t)(m->ne > 0 ? m->ne : 1), st));
+    EHDG_CUDA(cudaMallocAsync(&A->diag_off, sizeof(int32_t) * (size_t)(A->nf > 0 ? A->nf : 1), st));
+    A->elmap_ne = m->ne;
+    if (m->ne > 0)
+        elmap_kernel<<<(m->ne + 127) / 128, 128, 0, st>>>(m->ne, fa, fb, m->el2facet, m->facet2el, A->row_start, A->blk_base, A->nbr,
+                                                          A->nbr_len, A->dofmask, (ElMap*)A->elmap);
+    EHDG_LAUNCH_CHECK();
+    if (A->nf > 0) diag_off_kernel<<<(A->nf + 255) / 256, 256, 0, st>>>(A->nf, A->nbr, A->dofmask, A->diag_off);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
 int general_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, const uint8_t* elem_active,
                      const uint8_t* facet_mask, double* Sg, double* gg, double* Wg, double* zg, int32_t* status, double* Afull,
                      cudaStream_t st);   // ehdg_core.cu
@@ -134,19 +153,8 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
     const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
     if (A->folded_vals == vals) A->folded_vals = nullptr;
     if (!A->elmap || A->elmap_ne != m->ne) {
-        if (A->elmap) EHDG_CUDA(cudaFreeAsync(A->elmap, st));
-        A->elmap = nullptr;
-        EHDG_CUDA(cudaMallocAsync(&A->elmap, sizeof(ElMap) * (size_t)(m->ne > 0 ? m->ne : 1), st));
-        A->elmap_ne = m->ne;
-        if (m->ne > 0)
-            elmap_kernel<<<(m->ne + 127) / 128, 128, 0, st>>>(m->ne, fa, fb, m->el2facet, m->facet2el, A->row_start, A->blk_base, A->nbr,
-                                                              A->nbr_len, A->dofmask, (ElMap*)A->elmap);
-        EHDG_LAUNCH_CHECK();
-        if (A->diag_off) EHDG_CUDA(cudaFreeAsync(A->diag_off, st));
-        A->diag_off = nullptr;
-        EHDG_CUDA(cudaMallocAsync(&A->diag_off, sizeof(int32_t) * (size_t)(A->nf > 0 ? A->nf : 1), st));
-        if (A->nf > 0) diag_off_kernel<<<(A->nf + 255) / 256, 256, 0, st>>>(A->nf, A->nbr, A->dofmask, A->diag_off);
-        EHDG_LAUNCH_CHECK();
+        const int rcm = build_elmap(A, m, st);
+        if (rcm) return rcm;
     }
     const int nb = c->pb.nb;
     const int64_t nown = rhi > rlo ? rhi - rlo : 0;

@@ -102,6 +102,7 @@ struct ehdg_csr {
     int64_t n_rows, nnz;
     int32_t* row_start = nullptr;   // [nf+1]  first row of facet f
     int64_t* rowptr = nullptr;      // [n_rows+1]
+    int colind_full = 1;            // 0: only the first row of every facet holds its column indices yet (ensure_colind)
     int32_t* colind = nullptr;      // [nnz]
     int64_t* blk_base = nullptr;    // [nf+1]  first nnz of the row block of facet f
     int32_t* nbr = nullptr;         // [nf][5] neighbour facets ascending, -1 padded
@@ -130,6 +131,8 @@ struct ehdg_csr {
 };
 
 namespace ehdg {
+int ensure_colind(const ehdg_csr* A, cudaStream_t st);   // ehdg_solve.cu
+int build_elmap(ehdg_csr* A, const ehdg_mesh* m, cudaStream_t st);   // ehdg_fused.cu
 struct CsrOut;   // ehdg_fast.h
 // polynomial-path kernels (ehdg_fast.cu)
 int fast_build_tensors(ehdg_ctx* ctx);

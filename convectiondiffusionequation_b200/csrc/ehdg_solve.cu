@@ -65,8 +65,9 @@ __global__ void csr_nbr_kernel(int nf, int f_lo, int f_hi, const int32_t* __rest
 
 __global__ void csr_fill_kernel(int nf, int f_lo, int f_hi, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
                                 const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len,
-                                int64_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t* __restrict__ row_facet) {
-    // one warp per facet
+                                int64_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t* __restrict__ row_facet, int mode) {
+    // one warp per facet.  mode 0: everything; 1: rowptr, row_facet and the column indices of the FIRST row of every facet
+    // (all the facet-block SpMV reads); 2: the column indices of the remaining rows (ensure_colind)
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (f >= nf) return;
@@ -75,22 +76,36 @@ __global__ void csr_fill_kernel(int nf, int f_lo, int f_hi, const int32_t* __res
     const bool mine = f >= f_lo && f < f_hi;
     const int len = mine ? nbr_len[f] : 0;          // rows outside the window are empty
     const int64_t base = blk_base[f];
-    for (int i = lane; i < rows; i += 32) {
-        rowptr[r0 + i] = base + (int64_t)i * len;
-        row_facet[r0 + i] = f;
-    }
+    if (mode != 2)
+        for (int i = lane; i < rows; i += 32) {
+            rowptr[r0 + i] = base + (int64_t)i * len;
+            row_facet[r0 + i] = f;
+        }
     if (!mine) return;
+    const int i_lo = mode == 2 ? 1 : 0, i_hi = mode == 1 ? 1 : rows;
     int off = 0;
     for (int t = 0; t < 5; ++t) {
         const int g = nbr[5 * f + t];
         if (g < 0) break;
         const int c0 = row_start[g], nbg = row_start[g + 1] - c0;
-        for (int idx = lane; idx < rows * nbg; idx += 32) {
+        for (int idx = lane + i_lo * nbg; idx < i_hi * nbg; idx += 32) {
             const int i = idx / nbg, l = idx % nbg;
             colind[base + (int64_t)i * len + off + l] = c0 + l;
         }
         off += nbg;
     }
+}
+
+// column indices of rows 2.. of every facet (ehdg_csr_symbolic writes the first rows only)
+int ensure_colind(const ehdg_csr* Ac, cudaStream_t st) {
+    ehdg_csr* A = const_cast<ehdg_csr*>(Ac);
+    if (A->colind_full || A->edg) return EHDG_OK;
+    if (A->nf > 0)
+        csr_fill_kernel<<<(unsigned)(((int64_t)A->nf * 32 + 255) / 256), 256, 0, st>>>(A->nf, A->windowed ? A->f_lo : 0, A->windowed ? A->f_hi : A->nf, A->row_start,
+                                                                                       A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, A->row_facet, 2);
+    EHDG_LAUNCH_CHECK();
+    A->colind_full = 1;
+    return EHDG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -401,6 +416,8 @@ static int launch_spmv(const ehdg_csr* A, const double* vals, const double* x, d
     if (row1 <= row0) return EHDG_OK;
     if (spmv_use_csr_kernel() || A->edg) {          // EDG blocks have up to n_p + n_enrich rows: the plain CSR kernel
         constexpr int TPR = 8;
+        const int rce = ensure_colind(A, st);
+        if (rce) return rce;
         const int64_t threads = (row1 - row0) * TPR;
         spmv_kernel<TPR><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((int)row0, (int)row1, A->rowptr, A->colind, vals, x, y, rscale);
     } else {
@@ -1323,8 +1340,14 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     EHDG_CUDA(cudaMallocAsync(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1), st));
     EHDG_CUDA(cudaMallocAsync(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), st));
     EHDG_CUDA(cudaMallocAsync(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1), st));
-    if (nf > 0) csr_fill_kernel<<<(unsigned)(((int64_t)nf * 32 + 255) / 256), 256, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
+    if (nf > 0) csr_fill_kernel<<<(unsigned)(((int64_t)nf * 32 + 255) / 256), 256, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet, 1);
     EHDG_LAUNCH_CHECK();
+    A->colind_full = 0;          // rows 2.. of every facet on first use (ensure_colind): 3 GB of index writes at 4M that a4-a9 never read
+    {
+        // scatter table of the fused a5-a8 store, on the pattern's stream like the rest of the pattern
+        const int rcm = build_elmap(A, m, st);
+        if (rcm) return rcm;
+    }
     EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
     A->dinv = nullptr;
@@ -1460,7 +1483,7 @@ int ehdg_edg_csr_symbolic(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* elem_a
     EHDG_CUDA(cudaMallocAsync(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1), st));
     EHDG_CUDA(cudaMallocAsync(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), st));
     EHDG_CUDA(cudaMallocAsync(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1), st));
-    if (ne > 0) csr_fill_kernel<<<(unsigned)(((int64_t)ne * 32 + 255) / 256), 256, 0, st>>>(ne, 0, ne, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
+    if (ne > 0) csr_fill_kernel<<<(unsigned)(((int64_t)ne * 32 + 255) / 256), 256, 0, st>>>(ne, 0, ne, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet, 0);
     EHDG_LAUNCH_CHECK();
     EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
@@ -1580,7 +1603,13 @@ int ehdg_csr_get_sizes(const ehdg_csr* A, ehdg_csr_sizes* o) {
     return EHDG_OK;
 }
 const int64_t* ehdg_csr_rowptr(const ehdg_csr* A) { return A ? A->rowptr : nullptr; }
-const int32_t* ehdg_csr_colind(const ehdg_csr* A) { return A ? A->colind : nullptr; }
+const int32_t* ehdg_csr_colind(const ehdg_csr* A) {
+    if (!A) return nullptr;
+    if (!A->colind_full && !A->edg) {            // first export of the full index array: fill the rows a4-a9 never read
+        if (ensure_colind(A, A->stream) != EHDG_OK || cudaStreamSynchronize(A->stream) != cudaSuccess) return nullptr;
+    }
+    return A->colind;
+}
 const int32_t* ehdg_csr_row_start(const ehdg_csr* A) { return A ? A->row_start : nullptr; }
 const uint16_t* ehdg_csr_dofmask(const ehdg_csr* A) { return A ? A->dofmask : nullptr; }
 
