@@ -93,26 +93,29 @@ __global__ void diag_off_kernel(int nf, const int32_t* __restrict__ nbr, const u
     doff[f] = off;
 }
 
-// first + second contribution of the diagonal blocks and of the right-hand side; one warp per own facet: the index loads
-// happen once per facet, lane (i, l) owns entry l of row i of the facet's rows x rows diagonal block
-__global__ void __launch_bounds__(256)
-merge_diag_kernel(int f_lo, int f_hi, int64_t row_lo, int nb, const int32_t* __restrict__ row_start,
-                  const int64_t* __restrict__ blk_base, const int32_t* __restrict__ nbr_len, const int32_t* __restrict__ doff,
-                  const double* __restrict__ diag2, const double* __restrict__ g2, double* __restrict__ vals,
-                  double* __restrict__ rhs) {
-    const int f = f_lo + (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (f >= f_hi) return;
-    const int r0 = row_start[f], rows = row_start[f + 1] - r0;
-    if (rows == 0) return;
-    const int len = nbr_len[f];
-    double* v = vals + blk_base[f] + doff[f];
-    const double* d = diag2 + (size_t)(r0 - row_lo) * nb;
-    for (int e = lane; e < rows * rows; e += 32) {
-        const int i = e / rows, l = e - i * rows;
-        v[(int64_t)i * len + l] += d[i * nb + l];
-    }
-    if (lane < rows) rhs[r0 + lane] += g2[r0 - row_lo + lane];
+// per own row: where its piece of the diagonal block starts in the value array, and how many entries it has (top byte)
+__global__ void diag_dst_kernel(int64_t row_lo, int64_t row_hi, const int32_t* __restrict__ row_facet, const int32_t* __restrict__ row_start,
+                                const int64_t* __restrict__ rowptr, const int32_t* __restrict__ doff, int64_t* __restrict__ dst) {
+    const int64_t r = row_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= row_hi) return;
+    const int f = row_facet[r];
+    const int64_t rows = row_start[f + 1] - row_start[f];
+    dst[r - row_lo] = (rowptr[r] + doff[f]) | (rows << 56);
+}
+
+// first + second contribution of the diagonal blocks and of the right-hand side; one thread per own row, one 8-byte index
+// load per row (diag_dst), the side buffer read contiguously
+__global__ void merge_diag_kernel(int64_t row_lo, int64_t n_own, int nb, const int64_t* __restrict__ dst,
+                                  const double* __restrict__ diag2, const double* __restrict__ g2, double* __restrict__ vals,
+                                  double* __restrict__ rhs) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_own) return;
+    const int64_t d = dst[t];
+    const int rows = (int)(d >> 56);
+    double* v = vals + (d & (((int64_t)1 << 56) - 1));
+    const double* src = diag2 + t * nb;
+    for (int l = 0; l < rows; ++l) v[l] += src[l];
+    rhs[row_lo + t] += g2[t];
 }
 
 // scatter table + diagonal offsets of a pattern (built with the pattern by ehdg_csr_symbolic, on the pattern's stream)
@@ -130,6 +133,19 @@ int build_elmap(ehdg_csr* A, const ehdg_mesh* m, cudaStream_t st) {
                                                           A->nbr_len, A->dofmask, (ElMap*)A->elmap);
     EHDG_LAUNCH_CHECK();
     if (A->nf > 0) diag_off_kernel<<<(A->nf + 255) / 256, 256, 0, st>>>(A->nf, A->nbr, A->dofmask, A->diag_off);
+    EHDG_LAUNCH_CHECK();
+    return EHDG_OK;
+}
+
+// needs rowptr / row_facet: called once the pattern is complete (first fused store)
+int build_diag_dst(ehdg_csr* A, cudaStream_t st) {
+    const int64_t rlo = A->windowed ? A->row_lo : 0, rhi = A->windowed ? A->row_hi : A->n_rows;
+    const int64_t nown = rhi > rlo ? rhi - rlo : 0;
+    if (A->diag_dst) EHDG_CUDA(cudaFreeAsync(A->diag_dst, st));
+    A->diag_dst = nullptr;
+    EHDG_CUDA(cudaMallocAsync(&A->diag_dst, sizeof(int64_t) * (size_t)(nown > 0 ? nown : 1), st));
+    if (nown > 0)
+        diag_dst_kernel<<<(unsigned)((nown + 255) / 256), 256, 0, st>>>(rlo, rhi, A->row_facet, A->row_start, A->rowptr, A->diag_off, A->diag_dst);
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
 }
@@ -155,6 +171,10 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
     if (!A->elmap || A->elmap_ne != m->ne) {
         const int rcm = build_elmap(A, m, st);
         if (rcm) return rcm;
+    }
+    if (!A->diag_dst) {
+        const int rcd = build_diag_dst(A, st);
+        if (rcd) return rcd;
     }
     const int nb = c->pb.nb;
     const int64_t nown = rhi > rlo ? rhi - rlo : 0;
@@ -193,8 +213,7 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
         cudaStreamWaitEvent(st, c->ev_join, 0);
     }
     if (rc == EHDG_OK && nown > 0) {
-        merge_diag_kernel<<<(unsigned)(((int64_t)(fb - fa) * 32 + 255) / 256), 256, 0, st>>>(fa, fb, rlo, nb, A->row_start, A->blk_base, A->nbr_len,
-                                                                                            A->diag_off, diag2, g2, vals, rhs);
+        merge_diag_kernel<<<(unsigned)((nown + 255) / 256), 256, 0, st>>>(rlo, nown, nb, A->diag_dst, diag2, g2, vals, rhs);
         if (cudaGetLastError() != cudaSuccess) { set_error("ehdg_assemble_condense_csr: merge launch failed"); rc = EHDG_ERR_CUDA; }
     }
     if (Sg) cudaFreeAsync(Sg, st);

@@ -113,6 +113,7 @@ struct ehdg_csr {
     void* elmap = nullptr;          // [ne] ElMap: scatter table of the fused a5-a8 store, built on first use
     int32_t elmap_ne = 0;
     int32_t* diag_off = nullptr;    // [nf]    column offset of the facet's own block inside its rows (with elmap)
+    int64_t* diag_dst = nullptr;    // [own rows] value index of the row's piece of the diagonal block | entries << 56 (merge of the fused store)
     int32_t* line = nullptr;        // [nf]    chain of every facet for the line-block preconditioner, null until set
     int edg = 0;                    // EDG pattern: the blocks are ELEMENTS (self + facet neighbours), up to n_p + n_enrich rows each
     const double* folded_vals = nullptr;   // value array a Krylov solve has overwritten with A M^-1 (facet block-Jacobi mode)
@@ -133,6 +134,7 @@ struct ehdg_csr {
 namespace ehdg {
 int ensure_colind(const ehdg_csr* A, cudaStream_t st);   // ehdg_solve.cu
 int build_elmap(ehdg_csr* A, const ehdg_mesh* m, cudaStream_t st);   // ehdg_fused.cu
+int build_diag_dst(ehdg_csr* A, cudaStream_t st);                    // ehdg_fused.cu
 struct CsrOut;   // ehdg_fast.h
 // polynomial-path kernels (ehdg_fast.cu)
 int fast_build_tensors(ehdg_ctx* ctx);

@@ -96,6 +96,33 @@ __global__ void csr_fill_kernel(int nf, int f_lo, int f_hi, const int32_t* __res
     }
 }
 
+// mode 1 of the fill, one THREAD per facet: rowptr and row_facet of its rows and the column indices of its FIRST row (all the
+// facet-block SpMV reads).  The warp-per-facet kernel below spends 3.3 ms at 4M on this (6 M warps, each a chain of dependent
+// index loads with 5 of 32 lanes busy); this one is bound by its 1 GB of stores.
+__global__ void csr_fill_first_kernel(int nf, int f_lo, int f_hi, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
+                                      const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len,
+                                      int64_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t* __restrict__ row_facet) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const int r0 = row_start[f], rows = row_start[f + 1] - r0;
+    if (rows == 0) return;
+    const bool mine = f >= f_lo && f < f_hi;
+    const int len = mine ? nbr_len[f] : 0;          // rows outside the window are empty
+    const int64_t base = blk_base[f];
+    for (int i = 0; i < rows; ++i) {
+        rowptr[r0 + i] = base + (int64_t)i * len;
+        row_facet[r0 + i] = f;
+    }
+    if (!mine) return;
+    int32_t* ci = colind + base;
+    for (int t = 0; t < 5; ++t) {
+        const int g = nbr[5 * f + t];
+        if (g < 0) break;
+        const int c0 = row_start[g], nbg = row_start[g + 1] - c0;
+        for (int l = 0; l < nbg; ++l) *ci++ = c0 + l;
+    }
+}
+
 // column indices of rows 2.. of every facet (ehdg_csr_symbolic writes the first rows only)
 int ensure_colind(const ehdg_csr* Ac, cudaStream_t st) {
     ehdg_csr* A = const_cast<ehdg_csr*>(Ac);
@@ -1207,9 +1234,18 @@ __global__ void csr_extent_kernel(int f_lo, int f_hi, const int32_t* __restrict_
         lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
         hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
     }
+    // one pair of global atomics per CTA (190 k warps hammering two addresses cost 0.3 ms at 4M)
+    __shared__ int s_lo, s_hi;
+    if (threadIdx.x == 0) { s_lo = 0x7fffffff; s_hi = -1; }
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) {
-        if (lo != 0x7fffffff) atomicMin(ext, lo);
-        if (hi >= 0) atomicMax(ext + 1, hi);
+        if (lo != 0x7fffffff) atomicMin(&s_lo, lo);
+        if (hi >= 0) atomicMax(&s_hi, hi);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_lo != 0x7fffffff) atomicMin(ext, s_lo);
+        if (s_hi >= 0) atomicMax(ext + 1, s_hi);
     }
 }
 
@@ -1340,7 +1376,7 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     EHDG_CUDA(cudaMallocAsync(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1), st));
     EHDG_CUDA(cudaMallocAsync(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), st));
     EHDG_CUDA(cudaMallocAsync(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1), st));
-    if (nf > 0) csr_fill_kernel<<<(unsigned)(((int64_t)nf * 32 + 255) / 256), 256, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet, 1);
+    if (nf > 0) csr_fill_first_kernel<<<(nf + 127) / 128, 128, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
     EHDG_LAUNCH_CHECK();
     A->colind_full = 0;          // rows 2.. of every facet on first use (ensure_colind): 3 GB of index writes at 4M that a4-a9 never read
     {
@@ -1352,6 +1388,10 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     EHDG_CUDA(cudaStreamSynchronize(st));
     A->dinv = nullptr;
     A->row_facet = row_facet;
+    {
+        const int rcd = build_diag_dst(A, st);     // merge table of the fused store (needs rowptr / row_facet)
+        if (rcd) return rcd;
+    }
     guard.ok = true;
     *out = A;
     return EHDG_OK;
@@ -1590,6 +1630,7 @@ int ehdg_csr_destroy(ehdg_csr* A) {
     if (A->strip) cudaFreeAsync(A->strip, st);
     if (A->elmap) cudaFreeAsync(A->elmap, st);
     if (A->diag_off) cudaFreeAsync(A->diag_off, st);
+    if (A->diag_dst) cudaFreeAsync(A->diag_dst, st);
     cudaFree(A->dinv);
     cudaFree(A->line);
     delete A;
