@@ -397,9 +397,17 @@ class EHDGPipeline:
         m_auto = int(min(200, max(30, chains // 10)))
         # enriched systems: DQGMRES is unreliable on them (config 2 does not converge with it, config 3 takes 2.5x as long as
         # GMRES), so they go straight to GMRES; plain systems try the cheap method first
-        plan = (("dqgmres", 8), ("gmres", m_auto)) if self.nenr == 0 else (("gmres", m_auto),)
-        for method, restart in plan:
-            cap = min(max_iters, 2500) if (method == "dqgmres" and len(plan) > 1) else max_iters      # where DQGMRES(8) works it is done well before
+        # Enriched systems: GMRES(m), and once more with twice the restart if that does not converge within 4 000 iterations
+        # (converging enriched solves need 700-1 900; what made config 2 stall in the r02d / r02g bench lines was a cut strip
+        # chain, see chain_setup, not the restart length)
+        m_enr = m_auto
+        plan = (("dqgmres", 8), ("gmres", m_auto)) if self.nenr == 0 else (("gmres", m_enr), ("gmres", min(240, 2 * m_enr)))
+        for k, (method, restart) in enumerate(plan):
+            cap = max_iters
+            if method == "dqgmres" and len(plan) > 1:
+                cap = min(max_iters, 2500)                # where DQGMRES(8) works it is done well before
+            elif self.nenr and k == 0 and len(plan) > 1:
+                cap = min(max_iters, 4000)                # converging enriched solves need 700-1 900 iterations
             self.gmres(restart=restart, max_iters=cap, rtol=rtol, method=method, precond=precond, drop_tol=drop_tol,
                        strip_block=strip_block, line_max_blocks=line_max_blocks)
             gi = self.gmres_info
