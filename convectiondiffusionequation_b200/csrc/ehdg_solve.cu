@@ -96,30 +96,53 @@ __global__ void csr_fill_kernel(int nf, int f_lo, int f_hi, const int32_t* __res
     }
 }
 
-// mode 1 of the fill, one THREAD per facet: rowptr and row_facet of its rows and the column indices of its FIRST row (all the
-// facet-block SpMV reads).  The warp-per-facet kernel below spends 3.3 ms at 4M on this (6 M warps, each a chain of dependent
-// index loads with 5 of 32 lanes busy); this one is bound by its 1 GB of stores.
-__global__ void csr_fill_first_kernel(int nf, int f_lo, int f_hi, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
-                                      const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len,
-                                      int64_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t* __restrict__ row_facet) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nf) return;
-    const int r0 = row_start[f], rows = row_start[f + 1] - r0;
-    if (rows == 0) return;
-    const bool mine = f >= f_lo && f < f_hi;
-    const int len = mine ? nbr_len[f] : 0;          // rows outside the window are empty
-    const int64_t base = blk_base[f];
-    for (int i = 0; i < rows; ++i) {
-        rowptr[r0 + i] = base + (int64_t)i * len;
-        row_facet[r0 + i] = f;
+// mode 1 of the fill: rowptr and row_facet of every row and the column indices of the FIRST row of every facet (all the
+// facet-block SpMV reads).  A warp takes 32 consecutive facets: every lane loads the metadata of one of them (coalesced), then
+// the warp walks through the 32 facets and its lanes write one facet's entries side by side (coalesced stores).
+// History at 4M: warp per facet with dependent index loads 3.3 ms, thread per facet with strided stores 1.84 ms.
+__global__ void __launch_bounds__(256)
+csr_fill_first_kernel(int nf, int f_lo, int f_hi, const int32_t* __restrict__ row_start, const int64_t* __restrict__ blk_base,
+                      const int32_t* __restrict__ nbr, const int32_t* __restrict__ nbr_len,
+                      int64_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t* __restrict__ row_facet) {
+    const int lane = threadIdx.x & 31;
+    const int fbase = (int)((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5);
+    if (fbase >= nf) return;
+    const int fm = fbase + lane;
+    int r0 = 0, rows = 0, len = 0;
+    int64_t base = 0;
+    int c0[5] = {0, 0, 0, 0, 0}, nbg[5] = {0, 0, 0, 0, 0};
+    bool mine = false;
+    if (fm < nf) {
+        r0 = row_start[fm];
+        rows = row_start[fm + 1] - r0;
+        mine = rows > 0 && fm >= f_lo && fm < f_hi;
+        len = mine ? nbr_len[fm] : 0;             // rows outside the window are empty
+        base = blk_base[fm];
+        if (mine)
+            for (int t = 0; t < 5; ++t) {
+                const int g = nbr[5 * fm + t];
+                if (g < 0) break;
+                c0[t] = row_start[g];
+                nbg[t] = row_start[g + 1] - c0[t];
+            }
     }
-    if (!mine) return;
-    int32_t* ci = colind + base;
-    for (int t = 0; t < 5; ++t) {
-        const int g = nbr[5 * f + t];
-        if (g < 0) break;
-        const int c0 = row_start[g], nbg = row_start[g + 1] - c0;
-        for (int l = 0; l < nbg; ++l) *ci++ = c0 + l;
+    const int nloc = min(32, nf - fbase);
+    for (int j = 0; j < nloc; ++j) {
+        const int jr0 = __shfl_sync(0xffffffffu, r0, j), jrows = __shfl_sync(0xffffffffu, rows, j);
+        const int jlen = __shfl_sync(0xffffffffu, len, j);
+        const int64_t jbase = __shfl_sync(0xffffffffu, base, j);
+        const bool jmine = __shfl_sync(0xffffffffu, mine ? 1 : 0, j) != 0;
+        if (lane < jrows) {
+            rowptr[jr0 + lane] = jbase + (int64_t)lane * jlen;
+            row_facet[jr0 + lane] = fbase + j;
+        }
+        int off = 0;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int jc0 = __shfl_sync(0xffffffffu, c0[t], j), jn = __shfl_sync(0xffffffffu, nbg[t], j);
+            if (jmine && lane < jn) colind[jbase + off + lane] = jc0 + lane;
+            off += jn;
+        }
     }
 }
 
@@ -1376,7 +1399,7 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     EHDG_CUDA(cudaMallocAsync(&A->rowptr, sizeof(int64_t) * (size_t)(nrows + 1), st));
     EHDG_CUDA(cudaMallocAsync(&A->colind, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1), st));
     EHDG_CUDA(cudaMallocAsync(&row_facet, sizeof(int32_t) * (size_t)(nrows > 0 ? nrows : 1), st));
-    if (nf > 0) csr_fill_first_kernel<<<(nf + 127) / 128, 128, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
+    if (nf > 0) csr_fill_first_kernel<<<(unsigned)(((int64_t)((nf + 31) / 32) * 32 + 255) / 256), 256, 0, st>>>(nf, A->f_lo, A->f_hi, A->row_start, A->blk_base, A->nbr, A->nbr_len, A->rowptr, A->colind, row_facet);
     EHDG_LAUNCH_CHECK();
     A->colind_full = 0;          // rows 2.. of every facet on first use (ensure_colind): 3 GB of index writes at 4M that a4-a9 never read
     {
