@@ -76,6 +76,7 @@ SYMBOLS = {
     "ehdg_prune": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, C.c_double, _P, _P, _P, _P]),
     "ehdg_alpha": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P]),
     "ehdg_assemble_condense": (C.c_int, [_P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ehdg_edg_set_boundary_data": (C.c_int, [_P, C.c_int]),
     "ehdg_assemble_condense_csr": (C.c_int, [_P, _P, _P, C.POINTER(Mesh), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ehdg_csr_symbolic": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.POINTER(_P), _P]),
     "ehdg_csr_symbolic_part": (C.c_int, [_P, C.POINTER(Mesh), _P, _P, C.c_int, C.c_int, C.POINTER(_P), _P]),

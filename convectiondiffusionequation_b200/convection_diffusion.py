@@ -57,7 +57,8 @@ class Convection_Diffusion():
                 mesh = mesh_for_size(size, kind=cfg.get('mesh_kind', 'structured'))
                 spec = ProblemSpec(order=order, epsilon=cfg['epsilon'], beta=tuple(cfg['beta']), bonus_int=cfg['bonus_int'],
                                    coeff=self._cf(cfg['coeff']), exact=self._cf(cfg['exact']), enrich_functions=enrich, enrich_domain_ind=inds)
-                pipe = EDGPipeline(mesh, spec, device=cfg.get('device', 'cuda:0'))
+                pipe = EDGPipeline(mesh, spec, device=cfg.get('device', 'cuda:0'),
+                                   boundary_data=bool(cfg.get('dirichlet_lifting', False)))      # debug_edg.py:191-192
                 type = 'edg' if len(enrich) > 0 else 'dg'
                 pipe.setup(theta=cfg.get('theta', 1e-5))     # marking + pruning with config['theta']   (:52-54, :83-123)
                 pipe.alpha()                                # generalised eigenvalue per element         (:129-163)

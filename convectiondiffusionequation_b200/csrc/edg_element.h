@@ -11,6 +11,7 @@
 // size h = |det J| / |e| and alpha_stab are taken from the FIRST element of the facet (facet2el[f][0]); facet points are
 // parametrised from the lower to the higher global vertex number, which both neighbours agree on.
 //   eps [ int grad u . grad v + sum_int ( pen [u][v] - {dn u}[v] - {dn v}[u] ) + sum_bnd ( pen u v - dn u v - dn v u ) ]
+//   right-hand side: int coeff v (+ with pb.edg_bnd_data the boundary data of Python/debug_edg.py:191-192)
 //   - int (b u) . grad v + sum_int (b.n) u_up [v],        pen = 4 alpha_stab p^2 / h^2,  [w] = w_first - w_second.
 #pragma once
 #include "ehdg_general.h"
@@ -140,6 +141,23 @@ EHDG_HD void edg_element_blocks(const Coop& co, const Problem& pb, const RuleSet
                 for (int q = 0; q < nqf; ++q)
                     acc += we[q] * (pen * Up[i * ldf + q] * Up[j * ldf + q] - Up[i * ldf + q] * Ud[j * ldf + q] - Ud[i * ldf + q] * Up[j * ldf + q]);
                 D[idx] += pb.eps * acc;
+            }
+            if (pb.edg_bnd_data) {
+                // debug_edg.py:191-192: f += exact eps (pen v - dn v) dS + b.n IfPos(b.n, 0, -exact) v dS
+                for (int i = co.lane; i < nv; i += co.nl) {
+                    double acc = 0.0;
+                    for (int q = 0; q < nqf; ++q) {
+                        double l[3], ex, egx, egy;
+                        edg_facet_point(g, e, rs.st[q], l);
+                        const double dx = l[0] * g.omx[0] + l[1] * g.omx[1] + l[2] * g.omx[2];
+                        const double dy = l[0] * g.omy[0] + l[1] * g.omy[1] + l[2] * g.omy[2];
+                        problem_exact(pb, dx, dy, &ex, &egx, &egy);
+                        double t = pb.eps * (pen * Up[i * ldf + q] - Ud[i * ldf + q]);
+                        if (!(bn > 0.0)) t -= bn * Up[i * ldf + q];
+                        acc += we[q] * ex * t;
+                    }
+                    F[i] += acc;
+                }
             }
         } else {
             // own sign in the jump: + for the first element, - for the second

@@ -357,6 +357,12 @@ int ehdg_set_expression(ehdg_ctx* c, int which, const int32_t* ops, const double
     return EHDG_OK;
 }
 
+int ehdg_edg_set_boundary_data(ehdg_ctx* c, int enable) {
+    if (!c) { set_error("ehdg_edg_set_boundary_data: null context"); return EHDG_ERR_ARG; }
+    c->pb.edg_bnd_data = enable ? 1 : 0;
+    return EHDG_OK;
+}
+
 int ehdg_set_drop_tol(ehdg_ctx* c, double vol_drop_tol) {
     if (!c || !(vol_drop_tol >= 0.0)) { set_error("ehdg_set_drop_tol: bad argument"); return EHDG_ERR_ARG; }
     c->pb.vol_drop_tol = vol_drop_tol;

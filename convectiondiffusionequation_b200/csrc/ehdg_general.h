@@ -21,6 +21,7 @@ struct Problem {
     int p, n_p, nfl, nenr, nb, nvmax, nfmax, bonus;
     double eps, bx, by;
     double vol_drop_tol;     // selection rule for dependent VOLUME enrichment dofs in the element condensation (0 = off)
+    int edg_bnd_data;        // EDG: right-hand side carries the weakly imposed Dirichlet data (debug_edg.py:191-192)
     int enr_axis[EHDG_MAX_ENRICH];
     double enr_k[EHDG_MAX_ENRICH];
     LayerExpr coeff, exact;

@@ -29,6 +29,7 @@ inline Problem make_problem(const ehdg_problem& ep) {
     pb.bx = ep.beta[0];
     pb.by = ep.beta[1];
     pb.vol_drop_tol = 1e-6;      // ehdg_set_drop_tol
+    pb.edg_bnd_data = 0;         // ehdg_edg_set_boundary_data
     pb.xcoeff = pb.xexact = pb.xexact_dx = pb.xexact_dy = nullptr;      // ehdg_set_expression
     for (int k = 0; k < EHDG_MAX_ENRICH; ++k) {
         pb.enr_axis[k] = k < ep.n_enrich ? ep.enrich_axis[k] : 0;

@@ -19,6 +19,13 @@ class EDGPipeline(EHDGPipeline):
     """One (mesh, order) instance of the EDG path on one GPU.  Marking, the plan and the Krylov entry points are those of the
     EHDG pipeline (the matrix container is shared); pruning, alpha rule, pattern, assembly and error are EDG's own."""
 
+    def __init__(self, *args, boundary_data=False, **kw):
+        """boundary_data: weakly imposed inhomogeneous Dirichlet data on the right-hand side (reference debug_edg.py:191-192)"""
+        super().__init__(*args, **kw)
+        self.boundary_data = bool(boundary_data or self.dirichlet_lifting)
+        self.dirichlet_lifting = False           # the facet lifting is an EHDG notion; EDG imposes the data weakly
+        _lib.check(self.lib.ehdg_edg_set_boundary_data(self.ctx, int(self.boundary_data)), "ehdg_edg_set_boundary_data")
+
     def prune(self, theta=1e-5, want_factors=False):
         m = self.mesh_host
         self.elem_active = torch.zeros(m.ne, dtype=torch.uint8, device=self.dev)

@@ -314,6 +314,11 @@ int ehdg_spmv(ehdg_ctx* ctx, const ehdg_csr* csr, const double* vals, const doub
  *                  - {dn v}[u] (+ boundary terms)] - (b u) . grad v + (b.n) u_up [v],  pen = 4 alpha_stab p^2 / h^2.
  * ehdg_edg_unpack / ehdg_edg_l2_error (:205-210): u f64[ne][n_p + n_enrich] from the solution vector (inactive slots 0);
  *                  err2[2] = squared L2 and H1-seminorm errors against `exact` with the order 5 + bonus rule. */
+/* Inhomogeneous Dirichlet data of the EDG method (reference Python/debug_edg.py:191-192): with enable != 0 ehdg_edg_assemble adds
+ *   f += exact eps (alpha order^2 / h v - n . grad v) dS + b.n IfPos(b.n, 0, -exact) v dS
+ * on the boundary facets (`exact` of the problem / ehdg_set_expression).  The bilinear form is the reference's: it has no
+ * outflow term, the data enter through the Nitsche terms and the inflow flux only. */
+int ehdg_edg_set_boundary_data(ehdg_ctx* ctx, int enable);
 int ehdg_edg_prune(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_mask, double theta,
                    uint8_t* elem_active, double* factors, void* stream);
 int ehdg_edg_alpha(ehdg_ctx* ctx, const ehdg_plan* plan, const ehdg_mesh* mesh, const uint8_t* elem_active, double* lam,

@@ -1,9 +1,10 @@
-"""CPU oracle of the reference's EDG path -- TEST INFRASTRUCTURE ONLY, groundwork for SURVEY.md 8(f) row 1.
+"""CPU oracle of the reference's EDG path -- TEST INFRASTRUCTURE ONLY.
 
 Restates `Convection_Diffusion._solveEDG` (reference Python/convection_diffusion.py:42-219) with numpy, element by
 element and facet by facet: enriched interior-penalty DG for  -eps Lap u + b . grad u = coeff  with weakly imposed
-homogeneous Dirichlet data.  There is NO product path behind it yet (`Convection_Diffusion._solveEDG` of the package
-raises NotImplementedError); nothing outside tests/ imports this module.
+homogeneous Dirichlet data, plus the inhomogeneous boundary terms of the debug variant (Python/debug_edg.py:191-192,
+`assemble(..., boundary_data=True)`).  The product path it checks is csrc/ehdg_edg.cu behind `_solveEDG`; nothing outside
+tests/ imports this module.
 
 PARITY STATUS: UNPINNED.  NGSolve holds the arithmetic and is not available (see oracle/ehdg_oracle.py); the
 reference stores no EDG matrices or solutions.  What IS pinned: the alpha pencil (same known answers as the EHDG path,
@@ -155,7 +156,9 @@ class EDGOracle:
         return out
 
     # ------------------------------------------------------------------ forms (:165-186) and assembly
-    def assemble(self, alpha_stab):
+    def assemble(self, alpha_stab, boundary_data=False):
+        """boundary_data: the right-hand side also carries the weakly imposed Dirichlet data of debug_edg.py:191-192,
+        f += exact eps (alpha order^2 / h v - n . grad v) dS + b.n IfPos(b.n, 0, -exact) v dS"""
         p, eps, b = self.p, self.prob.eps, np.asarray(self.prob.beta)
         order = 2 * self.p + self.prob.bonus
         lam_v, w_v = self.vol_points(order)
@@ -190,6 +193,14 @@ class EDGOracle:
                 M = eps * (pen * np.einsum("in,jn,n->ij", u1, u1, we) - np.einsum("in,jn,n->ij", u1, dn1, we)
                            - np.einsum("in,jn,n->ij", dn1, u1, we))
                 add(d1, d1, M)
+                if boundary_data:
+                    _, _, _, dd1 = self.shapes(e1, lam1)
+                    gD = self.prob.exact(dd1[0], dd1[1])
+                    bn = float(b @ n)
+                    fb = eps * np.einsum("in,n->i", pen * u1 - dn1, we * gD)              # exact eps (pen v - dn v)
+                    if not bn > 0:
+                        fb += -bn * np.einsum("in,n->i", u1, we * gD)                      # b.n IfPos(b.n, 0, -exact) v
+                    F[d1[d1 >= 0]] += fb[d1 >= 0]
                 continue
             lam2, _, _, _ = self.facet_points(e2, f, order)
             u2, gx2, gy2, _ = self.shapes(e2, lam2)
@@ -215,11 +226,11 @@ class EDGOracle:
         A.sum_duplicates()
         return A, F
 
-    def solve(self, alpha_stab=None):
+    def solve(self, alpha_stab=None, boundary_data=False):
         """(:189-203) direct solve on the active dofs; inactive entries of the result are zero"""
         if alpha_stab is None:
             alpha_stab = self.alpha_all()
-        A, F = self.assemble(alpha_stab)
+        A, F = self.assemble(alpha_stab, boundary_data=boundary_data)
         act = np.nonzero(self.active)[0]
         x = np.zeros(self.ndof)
         x[act] = spla.spsolve(A[act][:, act].tocsc(), F[act])

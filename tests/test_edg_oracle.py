@@ -1,5 +1,5 @@
-"""Self-consistency of the EDG oracle (oracle/edg_oracle.py; reference convection_diffusion.py:42-219).  The EDG path has
-no product code yet: these tests pin the oracle the CUDA path will be checked against."""
+"""Self-consistency of the EDG oracle (oracle/edg_oracle.py; reference convection_diffusion.py:42-219, debug_edg.py:191-192):
+these tests pin the oracle the CUDA path (tests/test_gpu_edg.py) is checked against."""
 import json
 import os
 
@@ -67,6 +67,41 @@ def test_polynomial_solution_is_reproduced(beta, eps, kind):
     o = _oracle(mesh, 4, _poly_problem(beta, eps))
     x = o.solve()
     assert o.l2_error(x) < 1e-11
+
+
+@pytest.mark.parametrize("beta,eps,kind,order", [((2.0, 1.0), 0.5, "structured", 2), ((-1.0, 0.7), 0.1, "unstructured", 3)])
+def test_inhomogeneous_boundary_data_are_consistent_up_to_the_outflow_term(beta, eps, kind, order):
+    """debug_edg.py:191-192 puts the Nitsche terms and the INFLOW data on the right-hand side; the reference's convection form
+    (:181-182, skeleton integrals only) has no outflow term  int_{dOmega, b.n > 0} b.n u v  on the left, so the method is
+    consistent for non-vanishing boundary values exactly up to that term.  Check: with it added, u = 1 + x - 2 y + x y (in P2)
+    is reproduced to round-off; without the boundary data the error is O(1)."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+    u = lambda dx, dy: 1.0 + (1 - dx) - 2.0 * (1 - dy) + (1 - dx) * (1 - dy)
+    ux = lambda dx, dy: 1.0 + (1 - dy)
+    uy = lambda dx, dy: -2.0 + (1 - dx)
+    coeff = lambda dx, dy: beta[0] * ux(dx, dy) + beta[1] * uy(dx, dy)          # Lap u = 0
+    prob = orc.Problem(beta, eps, coeff=coeff, exact=u, exact_grad=lambda dx, dy: (ux(dx, dy), uy(dx, dy)), bonus_int=10)
+    mesh = unit_square_mesh(3, kind=kind)
+    o = _oracle(mesh, order, prob)
+    alpha = o.alpha_all()
+    A, F = o.assemble(alpha, boundary_data=True)
+    rows, cols, vals = [], [], []
+    for f in np.nonzero(mesh.facet2el[:, 1] < 0)[0]:
+        e1 = mesh.facet2el[f, 0]
+        lam1, we, n, _ = o.facet_points(e1, f, 2 * order + 10)
+        bn = float(np.asarray(beta) @ n)
+        if bn > 0:
+            u1 = o.shapes(e1, lam1)[0]
+            d = o.el_dofs(e1)
+            M = bn * np.einsum("in,jn,n->ij", u1, u1, we)
+            rr, cc = np.meshgrid(d, d, indexing="ij")
+            rows.append(rr.ravel()); cols.append(cc.ravel()); vals.append(M.ravel())
+    Aout = sps.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=A.shape)
+    x = spla.spsolve((A + Aout).tocsc(), F)
+    assert o.l2_error(x) < 1e-11
+    assert o.l2_error(o.solve(alpha, boundary_data=True)) < 5e-3               # the reference's own (slightly inconsistent) answer
+    assert o.l2_error(o.solve(alpha, boundary_data=False)) > 1e-1              # without the terms the data are taken as zero
 
 
 def test_dg_error_decays_with_the_order():

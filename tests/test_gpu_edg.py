@@ -123,6 +123,46 @@ def test_edg_solution(n, order, eps, beta, enriched, kind):
     P.close()
 
 
+@pytest.mark.parametrize("order,kind,shift,beta", [(2, "structured", 1.5, (2.0, 1.0)), (3, "unstructured", -0.75, (-1.0, 0.5))])
+def test_edg_inhomogeneous_boundary_data(order, kind, shift, beta):
+    """debug_edg.py:191-192: Nitsche + inflow terms of the right-hand side for boundary values that do not vanish; the
+    right-hand side (1e-11) and the solution (L2 error, 1e-8) against the oracle"""
+    from convectiondiffusionequation_b200 import boundary_layer, x, y
+    from convectiondiffusionequation_b200.coefficients import LayerExpr
+    from convectiondiffusionequation_b200.hot_path import ProblemSpec
+    mesh = unit_square_mesh(5, kind=kind)
+    eps = 0.05
+    prob = orc.run_py_problem(beta=beta, eps=eps, enriched=False)
+    base = prob.exact
+    prob.exact = lambda dx, dy: shift + base(dx, dy)
+    o = EDGOracle(mesh.verts, mesh.tris, mesh.el2facet, mesh.facet2el, mesh.maxh, order, prob)
+    p, q = boundary_layer(x, beta[0], eps), boundary_layer(y, beta[1], eps)
+    spec = ProblemSpec(order=order, epsilon=eps, beta=beta, bonus_int=10, coeff=beta[1] * p + beta[0] * q,
+                       exact=p * q + LayerExpr((shift, 0.0, 0.0, 0.0)))
+    P = EDGPipeline(mesh, spec, boundary_data=True).setup(theta=1e-5).alpha()
+    alpha_stab = P.lam.cpu().numpy()
+    _, F = o.assemble(alpha_stab, boundary_data=True)
+    _, F0 = o.assemble(alpha_stab, boundary_data=False)
+    P.assemble()
+    rhs = P.rhs.cpu().numpy()[:o.ndof]                       # no enrichment: rows are the oracle's V dofs in element order
+    perm = _row_to_oracle_dof(o, np.zeros(o.ne, dtype=np.uint8))
+    assert np.abs(rhs - F[perm]).max() < 1e-11 * np.abs(F).max()
+    assert np.abs(F - F0).max() > 1e-3 * np.abs(F).max()      # the boundary terms are not negligible here
+    x_o = o.solve(alpha_stab, boundary_data=True)
+    l2_ref = o.l2_error(x_o)
+    P.gmres(restart=60, max_iters=20000, rtol=1e-10, method="gmres").backsolve()
+    assert P.gmres_info.converged == 1
+    l2, _ = P.errors()
+    # the discrete solutions agree to 1e-8 of their size, 1 + |shift| (the solver tolerance: floor of the line blocks a few
+    # 1e-10); the L2 ERROR is 3e-3 .. 4e-2 of that, so the bound is stated on the scale of the solution
+    assert abs(l2 - l2_ref) < 1e-8 * (1.0 + abs(shift)), (l2, l2_ref)
+    # the driver key: config['dirichlet_lifting'] switches the terms on in _solveEDG
+    Q = EDGPipeline(mesh, spec).setup(theta=1e-5).alpha().assemble()
+    assert np.abs(Q.rhs.cpu().numpy()[:o.ndof] - F0[perm]).max() < 1e-11 * np.abs(F0).max()
+    P.close()
+    Q.close()
+
+
 def test_solveEDG_driver_tables():
     from convectiondiffusionequation_b200 import run
     from convectiondiffusionequation_b200.convection_diffusion import Convection_Diffusion
