@@ -1,6 +1,7 @@
 """Host study: EDG systems from the oracle, block Jacobi over streamline lines vs block Gauss-Seidel across the lines (upwind order)."""
 import sys, time
-sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, scipy.sparse as sps, scipy.sparse.linalg as spla
 from convectiondiffusionequation_b200.mesh import unit_square_mesh
 from oracle import ehdg_oracle as orc

@@ -8,7 +8,7 @@ Recorded (order 4, rtol 1e-8, GMRES(30)):   N=64 structured: facet 1686, lines a
                                            N=64 unstructured: lines along the flow, bin offset 0 / 0.25 / 0.5: 166 / 162 / 346
 """
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import scipy.sparse as sps
 import scipy.sparse.linalg as spla
