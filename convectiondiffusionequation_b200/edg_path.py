@@ -90,11 +90,11 @@ class EDGPipeline(EHDGPipeline):
         return super().gmres(**kw)
 
     def solve_auto(self, rtol=1e-8, max_iters=8000, precond="line", drop_tol=0.0, strip_block=False, line_max_blocks=-1):
-        """GMRES on lines of elements.  At small eps the EDG matrix is upwind DG: preconditioned by exact line solves along the
-        flow it is close to nilpotent ACROSS the lines, so the residual stays at 1 for about as many iterations as there are
-        lines and only then drops (host study on oracle systems: 22 / 43 / 260 iterations for 8 / 16 / 32 lines) -- the restart
-        length has to cover that: m = #lines + 20, at most 300 (beyond that the EDG solve needs a downwind sweep across the
-        lines)."""
+        """GMRES on lines of elements.  Preconditioned by exact solves of the streamline lines, the iteration count grows with the
+        number of lines (host study tests/studies/edg_gs_study.py: 25 / 46 / 127 iterations for 8 / 16 / 32 lines; a Gauss-Seidel
+        sweep across the lines still needs about #lines): across the lines the SIP penalty eps 4 alpha p^2 / h^2 couples like a
+        1-D elliptic operator.  The restart length therefore covers the lines, m = #lines + 20, at most 300; beyond a few dozen
+        lines the EDG solve needs a coarse level -- N = 224 does not converge."""
         if getattr(self, "_lines_csr", None) != self.csr.value:
             self.set_lines()
         chains = int(torch.unique(self.lines()).numel())
