@@ -166,7 +166,6 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
     if (A->nf != m->nf) { set_error("ehdg_assemble_condense_csr: pattern and mesh do not match"); return EHDG_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t rlo = A->windowed ? A->row_lo : 0, rhi = A->windowed ? A->row_hi : A->n_rows;
-    const int fa = A->windowed ? A->f_lo : 0, fb = A->windowed ? A->f_hi : A->nf;
     if (A->folded_vals == vals) A->folded_vals = nullptr;
     if (!A->elmap || A->elmap_ne != m->ne) {
         const int rcm = build_elmap(A, m, st);
@@ -179,6 +178,9 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
     const int nb = c->pb.nb;
     const int64_t nown = rhi > rlo ? rhi - rlo : 0;
     double *diag2 = nullptr, *g2 = nullptr, *Sg = nullptr, *gg = nullptr;
+    // the two scratch buffers go back to the pool on every path out of this function
+    struct AsyncFree { double*& p; cudaStream_t st; ~AsyncFree() { if (p) cudaFreeAsync(p, st); } };
+    AsyncFree free_diag2{diag2, st}, free_sg{Sg, st};
     EHDG_CUDA(cudaMallocAsync(&diag2, sizeof(double) * (size_t)(nown * (nb + 1) + 1), st));
     g2 = diag2 + nown * nb;
     EHDG_CUDA(cudaMemsetAsync(diag2, 0, sizeof(double) * (size_t)(nown * (nb + 1) + 1), st));
@@ -193,7 +195,7 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
     if (p->n_gen > 0) {
         const size_t nfg = (size_t)p->nfmax;
         if (cudaMallocAsync(&Sg, sizeof(double) * (size_t)p->n_gen * (nfg * nfg + nfg), st) != cudaSuccess) {
-            cudaFreeAsync(diag2, st);
+            Sg = nullptr;
             set_error("ehdg_assemble_condense_csr: out of memory for the element blocks of the quadrature path");
             return EHDG_ERR_CUDA;
         }
@@ -216,7 +218,5 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
         merge_diag_kernel<<<(unsigned)((nown + 255) / 256), 256, 0, st>>>(rlo, nown, nb, A->diag_dst, diag2, g2, vals, rhs);
         if (cudaGetLastError() != cudaSuccess) { set_error("ehdg_assemble_condense_csr: merge launch failed"); rc = EHDG_ERR_CUDA; }
     }
-    if (Sg) cudaFreeAsync(Sg, st);
-    cudaFreeAsync(diag2, st);
     return rc;
 }

@@ -212,7 +212,10 @@ const int32_t* ehdg_csr_lines(const ehdg_csr* csr);      /* i32 [nf] device, nul
 int ehdg_csr_destroy(ehdg_csr* csr);
 int ehdg_csr_get_sizes(const ehdg_csr* csr, ehdg_csr_sizes* out);
 const int64_t* ehdg_csr_rowptr(const ehdg_csr* csr);     /* i64 [n_rows+1] device */
-const int32_t* ehdg_csr_colind(const ehdg_csr* csr);     /* i32 [nnz]      device */
+/* i32 [nnz] device.  ehdg_csr_symbolic writes the column indices of the FIRST row of every facet only (all rows of a facet share
+ * one column set and the facet-block SpMV reads just that row); the first call of this accessor -- or the first internal
+ * consumer of whole rows: the chain factorisation, the plain CSR SpMV -- fills the rest on the pattern's stream and waits for it. */
+const int32_t* ehdg_csr_colind(const ehdg_csr* csr);
 const int32_t* ehdg_csr_row_start(const ehdg_csr* csr);  /* i32 [nf+1]     device: first row of facet f */
 const uint16_t* ehdg_csr_dofmask(const ehdg_csr* csr);   /* u16 [nf]       device: active dof slots of facet f */
 /* deterministic numeric fill: every entry gathers its <= 2 element contributions in ascending
