@@ -81,6 +81,9 @@ struct CsrOut {
     double *diag2, *g2;  // second contributions: [own rows][nb] and [own rows]
     int64_t row_lo;
     int nb;
+    int* flags;          // [own rows], zeroed per call; null: the diagonal blocks are merged by a kernel afterwards.
+                         // flags[first own row of a facet] counts the elements that have stored their share of the facet's
+                         // diagonal block and right-hand side; the element that finds 1 there adds the two shares in place.
 };
 
 // exp(-50) = 1.9e-22: below this the exponential of a layer function is dropped next to its polynomial part
@@ -891,6 +894,41 @@ EHDG_HD int fast_assemble_element(const Group<FastDims<P>::LG>& gc, const Proble
             for (int r = l; r < NF; r += LG) gvec[r] = Ss[NF * NF + r];
         }
     EHDG_END_LANES
+#ifdef __CUDA_ARCH__
+    if (em && co->flags) {
+        // In-kernel merge of the two-contributor entries.  Every lane makes its stores visible (fence), then one lane per
+        // group counts this element in on each of its facets; whoever arrives second on a facet (count was 1) finds both
+        // shares in memory -- first element's in the value array, second one's in the side buffer, whichever of the two it
+        // is itself -- and stores first + second: the ascending-element order of the gather, independent of who merges.
+        __threadfence();
+        const int wl = threadIdx.x & 31;
+        const int leader = (wl / LG) * LG;
+        const unsigned gmask = LG >= 32 ? 0xffffffffu : (((1u << (LG & 31)) - 1u) << leader);
+        const int l = gc.lane;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const bool has = store && em->base[a] >= 0;
+            int old = 0;
+            if (has && l == 0) old = atomicAdd(co->flags + (em->row0[a] - co->row_lo), 1);
+            old = __shfl_sync(gmask, old, leader);
+            if (has && old == 1) {
+                __threadfence();
+                const int64_t r0 = em->row0[a] - co->row_lo;
+                double* v = co->vals + em->base[a] + em->coff[a][a];
+                const int64_t len = em->len[a];
+                for (int e = l; e < NFL * NFL; e += LG) {
+                    const int i = e / NFL, c = e - i * NFL;
+                    double* pv = v + i * len + c;
+                    *pv = __ldcg(pv) + __ldcg(co->diag2 + (r0 + i) * co->nb + c);
+                }
+                for (int i = l; i < NFL; i += LG) {
+                    double* pr = co->rhs + em->row0[a] + i;
+                    *pr = __ldcg(pr) + __ldcg(co->g2 + r0 + i);
+                }
+            }
+        }
+    }
+#endif
     return status;
 }
 

@@ -78,6 +78,31 @@ __global__ void scatter_general_kernel(int n_gen, int nb, const int32_t* __restr
     const double gval = gg[(size_t)idx * nfg + rr];
     if (hi) co.g2[m.row0[a] + i - co.row_lo] = gval;
     else co.rhs[m.row0[a] + i] = gval;
+    // in-kernel merge protocol (CsrOut::flags): this element's share of facet a is in memory once the kernel has finished, and
+    // the polynomial kernel that reads the counter starts after it -- where in this kernel the count happens does not matter
+    if (co.flags && k == 0) atomicAdd(co.flags + (m.row0[a] - co.row_lo), 1);
+}
+
+// facets whose TWO elements are on the quadrature path: nobody merges them in the polynomial kernel.  One thread per
+// (general element, local facet); the second element of the facet does the work.
+__global__ void merge_gengen_kernel(int n_gen, int nb, const int32_t* __restrict__ list_gen, const int32_t* __restrict__ el2facet,
+                                    const int32_t* __restrict__ facet2el, const int32_t* __restrict__ eslot,
+                                    const uint16_t* __restrict__ dofmask, const ElMap* __restrict__ em, CsrOut co) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n_gen) return;
+    const int e = list_gen[t / 3], a = t % 3;
+    const ElMap m = em[e];
+    if (m.base[a] < 0 || !((m.hi >> a) & 1)) return;
+    const int f = el2facet[3 * e + a];
+    const int other = facet2el[2 * f];
+    if (!(eslot[other] & EHDG_SLOT_GEN)) return;
+    const int rows = __popc((unsigned)dofmask[f]);
+    const int64_t r0 = m.row0[a] - co.row_lo;
+    double* v = co.vals + m.base[a] + m.coff[a][a];
+    for (int i = 0; i < rows; ++i) {
+        for (int c = 0; c < rows; ++c) v[(int64_t)i * m.len[a] + c] += co.diag2[(r0 + i) * co.nb + c];
+        co.rhs[m.row0[a] + i] += co.g2[r0 + i];
+    }
 }
 
 // column offset of a facet's own (diagonal) block inside its rows; one thread per facet
@@ -181,12 +206,23 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
     // the two scratch buffers go back to the pool on every path out of this function
     struct AsyncFree { double*& p; cudaStream_t st; ~AsyncFree() { if (p) cudaFreeAsync(p, st); } };
     AsyncFree free_diag2{diag2, st}, free_sg{Sg, st};
-    EHDG_CUDA(cudaMallocAsync(&diag2, sizeof(double) * (size_t)(nown * (nb + 1) + 1), st));
-    g2 = diag2 + nown * nb;
-    EHDG_CUDA(cudaMemsetAsync(diag2, 0, sizeof(double) * (size_t)(nown * (nb + 1) + 1), st));
-    CsrOut co{(const ElMap*)A->elmap, vals, rhs, diag2, g2, rlo, nb};
-    int rc = EHDG_OK;
     const bool fork = p->n_gen > 0 && p->n_poly > 0 && c->overlap_general;
+    // Merge of the two-contributor entries: by merge_diag_kernel afterwards (default) or inside the element kernel
+    // (EHDG_INKERNEL_MERGE=1; fence + arrival counter per facet, the second arrival adds the two shares in place).  A/B on
+    // B200, 4M elements (profiles/r02_ab_inkernel_merge.txt): the in-kernel variant is bit-identical and takes the element
+    // kernel from 17.3 to 25.5 ms -- the fences and the L2-only read-modify-writes cost 8 ms where the merge kernel costs 2.3.
+    static const bool want_inkernel = [] { const char* e = getenv("EHDG_INKERNEL_MERGE"); return e && e[0] == '1'; }();
+    const bool inkernel = want_inkernel && !fork;
+    // side buffer [own rows][nb] + [own rows], then (in-kernel merge) the arrival counters, one int per own row
+    const size_t side_doubles = (size_t)(nown * (nb + 1) + 1);
+    const size_t flag_bytes = inkernel ? sizeof(int) * (size_t)(nown + 1) : 0;
+    EHDG_CUDA(cudaMallocAsync(&diag2, sizeof(double) * side_doubles + flag_bytes, st));
+    g2 = diag2 + nown * nb;
+    int* flags = inkernel ? (int*)(diag2 + side_doubles) : nullptr;
+    if (inkernel) EHDG_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, st));
+    else EHDG_CUDA(cudaMemsetAsync(diag2, 0, sizeof(double) * side_doubles, st));
+    CsrOut co{(const ElMap*)A->elmap, vals, rhs, diag2, g2, rlo, nb, flags};
+    int rc = EHDG_OK;
     cudaStream_t sg = fork ? c->side : st;
     if (fork) {
         EHDG_CUDA(cudaEventRecord(c->ev_fork, st));
@@ -207,6 +243,11 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
             scatter_general_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, sg>>>((int)p->n_gen, nb, p->list_gen, m->el2facet, A->dofmask,
                                                                                    (const ElMap*)A->elmap, Sg, gg, co);
             if (cudaGetLastError() != cudaSuccess) rc = EHDG_ERR_CUDA;
+            if (rc == EHDG_OK && inkernel) {
+                merge_gengen_kernel<<<(unsigned)((3 * p->n_gen + 127) / 128), 128, 0, sg>>>((int)p->n_gen, nb, p->list_gen, m->el2facet, m->facet2el,
+                                                                                        p->eslot, A->dofmask, (const ElMap*)A->elmap, co);
+                if (cudaGetLastError() != cudaSuccess) rc = EHDG_ERR_CUDA;
+            }
         }
     }
     if (rc == EHDG_OK && p->n_poly > 0) rc = fast_assemble(c, p, m, lam, nullptr, nullptr, W, z, status, st, &co);
@@ -214,7 +255,7 @@ extern "C" int ehdg_assemble_condense_csr(ehdg_ctx* c, const ehdg_plan* p, ehdg_
         cudaEventRecord(c->ev_join, c->side);
         cudaStreamWaitEvent(st, c->ev_join, 0);
     }
-    if (rc == EHDG_OK && nown > 0) {
+    if (rc == EHDG_OK && nown > 0 && !inkernel) {
         merge_diag_kernel<<<(unsigned)((nown + 255) / 256), 256, 0, st>>>(rlo, nown, nb, A->diag_dst, diag2, g2, vals, rhs);
         if (cudaGetLastError() != cudaSuccess) { set_error("ehdg_assemble_condense_csr: merge launch failed"); rc = EHDG_ERR_CUDA; }
     }
