@@ -88,7 +88,9 @@ typedef struct {
 const char* ehdg_version(void);
 const char* ehdg_last_error(void);
 
-/* context: rules + reference tensors for (order, bonus, enrichment) on the current device */
+/* context: rules + reference tensors for (order, bonus, enrichment) on the current device.  A context owns small device-side
+ * scratch (work counters of the element kernels, timing events, the grow-only plan scratch): calls on ONE context must be issued
+ * from one host thread into one stream at a time; use one context per concurrently running stream. */
 int ehdg_create(const ehdg_problem* prob, ehdg_ctx** out);
 int ehdg_destroy(ehdg_ctx* ctx);
 int ehdg_get_sizes(const ehdg_ctx* ctx, ehdg_sizes* out);
