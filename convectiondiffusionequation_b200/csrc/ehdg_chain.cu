@@ -530,8 +530,10 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
             const int first_blk = chain_ptr.back(), nb_ch = (int)blocks.size() - first_blk;
             int nseg = (max_blocks > 0 && nb_ch > max_blocks) ? (nb_ch + max_blocks - 1) / max_blocks : 1;
             if (max_blocks < 0) nseg = std::max(1, std::min(auto_seg, nb_ch / AUTO_SEG_MIN_BLOCKS));
-            // the strip of marked elements stays whole under the automatic rule: the enriched systems owe their convergence
-            // to its exact solve (config 2: uncut 775-894 iterations; cut in 3 or 4 it stalls at 1e-6, profiles/r02d / r02g)
+            // the strip of marked elements stays whole under the automatic rule: the enriched systems owe their convergence to
+            // its exact solve -- config 2: whole 885 iterations; cut in 2 it stalls at 9e-8, in 3 or 4 at 1e-6 (driver tolerance
+            // 1e-10; profiles/r02d / r02g / r02h bench lines).  The price: at 1M the whole strip (2 800 blocks) is the longest
+            // chain by a factor of 8 and holds every sweep (config 3: 6.5 s whole against 3.3-3.8 s cut, both converging).
             if (max_blocks < 0 && strip && key[part[chain_first[ch]]] == KEY_STRIP) nseg = 1;
             for (int sg = 1; sg <= nseg; ++sg) {
                 const int end_blk = first_blk + (int)(((int64_t)nb_ch * sg) / nseg);
