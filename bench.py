@@ -374,16 +374,23 @@ def main():
         copy_stream.synchronize()
         torch.cuda.synchronize(dev)
 
-    e2e_run(2)
+    # Warm-up: the end-to-end loop is the host-heavy part of the bench (per-mesh set-up with host round trips, pinned copies).
+    # On some boxes of the pool its first repetitions run at a third of the steady speed while the host wakes up from the
+    # GPU-bound phase before it (measured: 135, 55, 44 ms per step in three back-to-back repetitions; 44.4, 44.4, 44.5 on
+    # others), so it is warmed for at least 12 steps / 1 s before the timed repetitions.
+    t_w = time.perf_counter()
+    e2e_run(6)
+    while time.perf_counter() - t_w < 1.0:
+        e2e_run(6)
     e2e_steps = max(2, min(args.steps, 6))
-    e2e_reps = []                      # wall clock with host copies: three repetitions, the median is reported
-    for _ in range(3):
+    e2e_reps = []                      # wall clock with host copies: five repetitions, the median is reported
+    for _ in range(5):
         barrier()
         t0 = time.perf_counter()
         e2e_run(e2e_steps)
         barrier()
         e2e_reps.append((time.perf_counter() - t0) / e2e_steps)
-    e2e_s = sorted(e2e_reps)[1]
+    e2e_s = sorted(e2e_reps)[len(e2e_reps) // 2]
     lam_host = lam_hosts[(e2e_steps - 1) % 2]
     sel_host = P.elem_select.cpu() if getattr(P, "elem_select", None) is not None else None
     lam_chk = lam_host if sel_host is None else lam_host[sel_host.bool()]

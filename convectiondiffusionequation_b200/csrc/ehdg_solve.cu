@@ -1341,7 +1341,12 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     // the row partition (every rank computes the same one from the same replicated masks)
     A->part_facets.assign((size_t)nranks + 1, 0);
     A->part_rows.assign((size_t)nranks + 1, 0);
-    {
+    // One rank: the partition and the column extent are the whole system; the only host round trip left below is the one for
+    // the sizes (rows, nnz) the value storage is allocated by.  Every round trip drains the stream and leaves the GPU idle
+    // while the host wakes up: the per-mesh set-up is latency-bound, not kernel-bound.
+    if (nranks == 1) {
+        A->part_facets[1] = nf;
+    } else {
         int32_t* fb = nullptr;
         EHDG_CUDA(cudaMallocAsync(&fb, sizeof(int32_t) * (size_t)(2 * (nranks + 1)), st));
         struct FreeFb { int32_t* p; cudaStream_t st; ~FreeFb() { if (p) cudaFreeAsync(p, st); } } free_fb{fb, st};
@@ -1371,21 +1376,26 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
     int32_t* d_ext = nullptr;
     EHDG_CUDA(cudaMallocAsync(&d_ext, 2 * sizeof(int32_t), st));
     struct FreeExt { int32_t* p; cudaStream_t st; ~FreeExt() { if (p) cudaFreeAsync(p, st); } } free_ext{d_ext, st};
-    {
+    int32_t nrows = 0, ext[2] = {0, -1};
+    int64_t nnz = 0;
+    if (windowed) {
         const int32_t init[2] = {nf, -1};
         EHDG_CUDA(cudaMemcpyAsync(d_ext, init, sizeof(init), cudaMemcpyHostToDevice, st));
         if (A->f_hi > A->f_lo) csr_extent_kernel<<<(A->f_hi - A->f_lo + 255) / 256, 256, 0, st>>>(A->f_lo, A->f_hi, A->nbr, nbf, d_ext);
         EHDG_LAUNCH_CHECK();
+        EHDG_CUDA(cudaMemcpyAsync(ext, d_ext, sizeof(ext), cudaMemcpyDeviceToHost, st));
     }
-    int32_t nrows = 0, ext[2] = {0, 0};
-    int64_t nnz = 0;
-    EHDG_CUDA(cudaMemcpyAsync(ext, d_ext, sizeof(ext), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaMemcpyAsync(&nrows, A->row_start + nf, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaMemcpyAsync(&nnz, A->blk_base + nf, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     EHDG_CUDA(cudaStreamSynchronize(st));
     A->n_rows = nrows;
     A->nnz = nnz;
-    if (ext[1] >= ext[0]) {
+    if (!windowed) {
+        A->part_rows[1] = nrows;
+        A->row_hi = nrows;
+        A->col_lo = 0;
+        A->col_hi = nrows;
+    } else if (ext[1] >= ext[0]) {
         int32_t rs2[2];
         EHDG_CUDA(cudaMemcpyAsync(&rs2[0], A->row_start + ext[0], sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         EHDG_CUDA(cudaMemcpyAsync(&rs2[1], A->row_start + ext[1] + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1407,8 +1417,8 @@ static int csr_symbolic_impl(ehdg_ctx* c, const ehdg_mesh* m, const uint8_t* fac
         const int rcm = build_elmap(A, m, st);
         if (rcm) return rcm;
     }
-    EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    EHDG_CUDA(cudaStreamSynchronize(st));
+    // rowptr[nrows] = nnz: device to device from the scan's last entry (no host buffer that would have to outlive the call)
+    EHDG_CUDA(cudaMemcpyAsync(A->rowptr + nrows, A->blk_base + nf, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     A->dinv = nullptr;
     A->row_facet = row_facet;
     {
