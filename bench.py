@@ -377,10 +377,9 @@ def main():
     # Warm-up: the end-to-end loop is the host-heavy part of the bench (per-mesh set-up with host round trips, pinned copies).
     # On some boxes of the pool its first repetitions run at a third of the steady speed while the host wakes up from the
     # GPU-bound phase before it (measured: 135, 55, 44 ms per step in three back-to-back repetitions; 44.4, 44.4, 44.5 on
-    # others), so it is warmed for at least 12 steps / 1 s before the timed repetitions.
-    t_w = time.perf_counter()
-    e2e_run(6)
-    while time.perf_counter() - t_w < 1.0:
+    # others), so it is warmed with 18 steps before the timed repetitions (a fixed count: every rank runs the same number of
+    # set-ups, which contain collectives at N > 1).
+    for _ in range(3):
         e2e_run(6)
     e2e_steps = max(2, min(args.steps, 6))
     e2e_reps = []                      # wall clock with host copies: five repetitions, the median is reported
