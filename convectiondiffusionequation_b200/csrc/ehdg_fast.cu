@@ -6,6 +6,30 @@
 namespace ehdg {
 
 constexpr int FAST_THREADS = 128;
+// Threads per CTA at high order.  The reference tensors are staged once per CTA (p = 6: 99.5 KB for the assemble kernel, 73.5 KB
+// for the alpha kernel): more threads per CTA are more element groups sharing one copy of the tables, i.e. more warps per SM.
+// A/B on B200, 1M elements, p = 6 (profiles/r02_ab_p6_threads*.jsonl): assemble 128 / 256 / 384 / 512 threads 51.6 / 31.0 / 21.9 /
+// 21.2 ms (512 spills), alpha 128 / 256 / 384 threads 40.3 / 40.9 / 33.8 ms; p = 5: assemble 128 / 192 / 256 threads 13.4 / 13.3 /
+// 13.8 ms (stays at 128).
+#ifndef EHDG_ASM_THREADS_P5
+#define EHDG_ASM_THREADS_P5 128
+#endif
+#ifndef EHDG_ASM_MINBLOCKS_P5
+#define EHDG_ASM_MINBLOCKS_P5 2
+#endif
+#ifndef EHDG_ASM_THREADS_P6
+#define EHDG_ASM_THREADS_P6 384
+#endif
+#ifndef EHDG_ALPHA_THREADS_P6
+#define EHDG_ALPHA_THREADS_P6 384
+#endif
+#ifndef EHDG_ALPHA_MINBLOCKS_P6
+#define EHDG_ALPHA_MINBLOCKS_P6 1
+#endif
+template <int P>
+constexpr int asm_threads() { return P == 6 ? EHDG_ASM_THREADS_P6 : (P == 5 ? EHDG_ASM_THREADS_P5 : FAST_THREADS); }
+template <int P>
+constexpr int alpha_threads() { return P == 6 ? EHDG_ALPHA_THREADS_P6 : FAST_THREADS; }
 #ifndef EHDG_ASM_MINBLOCKS
 #define EHDG_ASM_MINBLOCKS (EHDG_ASM_R == 2 ? 2 : 4)     // 128 registers without spills since A_FV is built after the elimination
 #endif
@@ -21,16 +45,17 @@ __device__ __forceinline__ int next_work(int* counter, int step) {
 }
 
 template <int P>
-__global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ASM_MINBLOCKS : (P == 5 ? 2 : 1)))
+__global__ void __launch_bounds__(asm_threads<P>(), (P <= 4 ? EHDG_ASM_MINBLOCKS : (P == 5 ? EHDG_ASM_MINBLOCKS_P5 : 1)))
 fast_assemble_kernel(Problem pb, LayerConst cx, LayerConst cy, RuleSet rs, const double* __restrict__ tab_g, int tab_doubles,
                      const double* __restrict__ phi_rhs, int n, const int32_t* __restrict__ list,
                      const double* __restrict__ verts, const int32_t* __restrict__ tris,
                      const double* __restrict__ lam, double* __restrict__ S, double* __restrict__ g,
                      double* __restrict__ W, double* __restrict__ z, int32_t* status, CsrOut co, int* __restrict__ work) {
     typedef FastDims<P> D;
-    constexpr int LG = D::LG, GPC = FAST_THREADS / LG, GPW = 32 / LG;
+    constexpr int TH = asm_threads<P>();
+    constexpr int LG = D::LG, GPC = TH / LG, GPW = 32 / LG;
     extern __shared__ double smem[];
-    for (int i = threadIdx.x; i < tab_doubles; i += FAST_THREADS) smem[i] = tab_g[i];
+    for (int i = threadIdx.x; i < tab_doubles; i += TH) smem[i] = tab_g[i];
     __syncthreads();
     const int gid = threadIdx.x / LG;
     const int scratch = fast_asm_scratch_doubles<P>(rs.nq);
@@ -56,14 +81,15 @@ fast_assemble_kernel(Problem pb, LayerConst cx, LayerConst cy, RuleSet rs, const
 }
 
 template <int P>
-__global__ void __launch_bounds__(FAST_THREADS, (P <= 4 ? EHDG_ALPHA_MINBLOCKS : 2))
+__global__ void __launch_bounds__(alpha_threads<P>(), (P <= 4 ? EHDG_ALPHA_MINBLOCKS : (P == 6 ? EHDG_ALPHA_MINBLOCKS_P6 : 2)))
 fast_alpha_kernel(const double* __restrict__ tab_g, int tab_doubles, int n, const int32_t* __restrict__ list,
                   const uint8_t* __restrict__ skip_if_set, const double* __restrict__ verts, const int32_t* __restrict__ tris,
                   double* __restrict__ lam, int32_t* status, int* __restrict__ work) {
     typedef AlphaDims<P> D;
-    constexpr int LG = D::LG, GPC = FAST_THREADS / LG;
+    constexpr int TH = alpha_threads<P>();
+    constexpr int LG = D::LG, GPC = TH / LG;
     extern __shared__ double smem[];
-    for (int i = threadIdx.x; i < tab_doubles; i += FAST_THREADS) smem[i] = tab_g[i];
+    for (int i = threadIdx.x; i < tab_doubles; i += TH) smem[i] = tab_g[i];
     __syncthreads();
     // interleaved groups (ehdg_fast.h, Group::il): lane l of group g of a warp is thread l * GPW + g
     constexpr int GPW = 32 / LG;
@@ -89,12 +115,13 @@ template <int P>
 static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const int32_t* list, int n, const uint8_t* skip_if_set,
                         double* lam, int32_t* status, cudaStream_t st) {
     typedef AlphaDims<P> D;
-    constexpr int GPC = FAST_THREADS / D::LG;
+    constexpr int TH = alpha_threads<P>();
+    constexpr int GPC = TH / D::LG;
     const int tabd = c->tens.alpha_doubles;
     const size_t smem = (size_t)(((tabd + 1) & ~1) + GPC * fast_alpha_scratch_doubles<P>()) * 8;
     EHDG_CUDA(cudaFuncSetAttribute(fast_alpha_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    EHDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_alpha_kernel<P>, FAST_THREADS, smem));
+    EHDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_alpha_kernel<P>, TH, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t need = ((int64_t)n + GPC - 1) / GPC;
     const int64_t cap = (int64_t)c->sm_count * per_sm;
@@ -106,7 +133,7 @@ static int launch_alpha(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, con
         work = c->work_counters;
         EHDG_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));
     }
-    fast_alpha_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->tens.alpha_tab, tabd, n, list, skip_if_set, m->verts, m->tris, lam, status, work);
+    fast_alpha_kernel<P><<<grid, TH, smem, st>>>(c->tens.alpha_tab, tabd, n, list, skip_if_set, m->verts, m->tris, lam, status, work);
     if (timed) EHDG_CUDA(cudaEventRecord(c->ev_k[1], st));
     EHDG_LAUNCH_CHECK();
     return EHDG_OK;
@@ -116,12 +143,13 @@ template <int P>
 static int launch_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, const double* lam, double* S, double* g,
                            double* W, double* z, int32_t* status, cudaStream_t st, const CsrOut& co) {
     typedef FastDims<P> D;
-    constexpr int GPC = FAST_THREADS / D::LG;
+    constexpr int TH = asm_threads<P>();
+    constexpr int GPC = TH / D::LG;
     const int tabd = c->tens.asm_doubles;
     const size_t smem = (size_t)(((tabd + 1) & ~1) + GPC * fast_asm_scratch_doubles<P>(c->rb.rs.nq)) * 8;
     EHDG_CUDA(cudaFuncSetAttribute(fast_assemble_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    EHDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_assemble_kernel<P>, FAST_THREADS, smem));
+    EHDG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast_assemble_kernel<P>, TH, smem));
     if (per_sm < 1) per_sm = 1;
     const int64_t need = (p->n_poly + GPC - 1) / GPC;
     const int64_t cap = (int64_t)c->sm_count * per_sm;
@@ -132,7 +160,7 @@ static int launch_assemble(ehdg_ctx* c, const ehdg_plan* p, const ehdg_mesh* m, 
         EHDG_CUDA(cudaMemsetAsync(work, 0, sizeof(int), st));
     }
     if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[2], st));
-    fast_assemble_kernel<P><<<grid, FAST_THREADS, smem, st>>>(c->pb, layer_const(c->pb.coeff.k[0]), layer_const(c->pb.coeff.k[1]), c->rb.rs, c->tens.asm_tab, tabd, c->tens.rhs_phi, (int)p->n_poly,
+    fast_assemble_kernel<P><<<grid, TH, smem, st>>>(c->pb, layer_const(c->pb.coeff.k[0]), layer_const(c->pb.coeff.k[1]), c->rb.rs, c->tens.asm_tab, tabd, c->tens.rhs_phi, (int)p->n_poly,
                                                              p->list_poly, m->verts, m->tris, lam, S, g, W, z, status, co, work);
     if (c->time_kernels) EHDG_CUDA(cudaEventRecord(c->ev_k[3], st));
     EHDG_LAUNCH_CHECK();
