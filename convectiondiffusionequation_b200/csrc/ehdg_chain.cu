@@ -486,7 +486,37 @@ int chain_setup(ehdg_csr* A, const double* vals, uint8_t* rowdrop, const int32_t
             bfs(seed0, ch, 0, visit);
             const int far = visit.back();
             for (int u : visit) level[u] = -1;
-            const int maxlev = bfs(far, ch, lev_base, visit2);
+            int maxlev = bfs(far, ch, lev_base, visit2);
+            // The strip of marked elements is ONE chain and, being never cut (below), the longest by far: two arms along the
+            // outflow sides joined at the corner.  Rooting its level structure in the middle of the level range halves the
+            // number of levels (the two halves advance side by side, blocks twice as large) and with it the latency of the
+            // sweep; any root gives a block-tridiagonal matrix.  Taken only if the wider levels still fit one row per lane.
+            // Measured (profiles/r02j / r02k bench lines): config 3 (1M) 8.1 -> 7.1 ms per iteration, 6.4 -> 5.7 s; config 2
+            // through the driver 1.38 -> 1.11 s; same iteration counts (the preconditioner is the same operator).
+            if (strip && key[seed0] == KEY_STRIP && maxlev - lev_base >= 64) {
+                const int mid = lev_base + (maxlev - lev_base) / 2;
+                int center = -1;
+                for (int u : visit2)
+                    if (level[u] == mid) { center = u; break; }
+                std::vector<int32_t> keep_order(visit2);
+                std::vector<int32_t> keep_level(visit2.size());
+                for (size_t k = 0; k < visit2.size(); ++k) keep_level[k] = level[visit2[k]];
+                for (int u : visit2) level[u] = -1;
+                const int maxlev2 = bfs(center, ch, lev_base, visit2);
+                std::vector<int> ldofs((size_t)(maxlev2 - lev_base + 1), 0);
+                for (int u : visit2) ldofs[(size_t)(level[u] - lev_base)] += row_start[u + 1] - row_start[u];
+                bool fits = visit2.size() == keep_order.size();
+                for (int d : ldofs) fits = fits && d <= 32;       // one row per lane in the sweep; beyond that the wider steps cost
+                                                                    // more than the halved length saves (4M unstructured: 25 -> 45 rows,
+                                                                    // 38 -> 44 ms per iteration)
+                if (fits) {
+                    maxlev = maxlev2;
+                } else {                                   // back to the peripheral root
+                    for (int u : visit2) level[u] = -1;
+                    visit2 = keep_order;
+                    for (size_t k = 0; k < visit2.size(); ++k) level[visit2[k]] = keep_level[k];
+                }
+            }
             // BFS order is level order
             for (int u : visit2) { order.push_back(u); lev_of_order.push_back(level[u]); }
             lev_base = maxlev + 2;          // gap: components never share a block boundary coupling
