@@ -96,3 +96,36 @@ def test_fused_pipeline_solves_like_the_two_pass_pipeline():
     assert A.errors() == B.errors()
     A.close()
     B.close()
+
+
+@pytest.mark.parametrize("env", [{"EHDG_INKERNEL_MERGE": "1"}, {"EHDG_OVERLAP": "1"}, {"EHDG_DYNAMIC": "0"}, {"EHDG_DYNAMIC": "3"}])
+def test_opt_in_variants_give_the_same_values(env):
+    """the measured-and-rejected variants stay behind their switches (read once per process, hence the subprocess) and stay
+    correct: in-kernel merge of the diagonal blocks, quadrature path on a side stream, static / drawn work distribution"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import torch\n"
+        "from convectiondiffusionequation_b200.hot_path import EHDGPipeline\n"
+        "from convectiondiffusionequation_b200.mesh import unit_square_mesh\n"
+        "from tests.common import make_pair\n"
+        "for n, order, eps, kind in ((24, 4, 1e-6, 'structured'), (17, 3, 1e-4, 'unstructured'), (40, 2, 1e-3, 'unstructured')):\n"
+        "    mesh = unit_square_mesh(n, kind=kind)\n"
+        "    _, spec = make_pair(mesh, order, eps=eps, enriched=True)\n"
+        "    P = EHDGPipeline(mesh, spec).setup()\n"
+        "    P.csr_pattern()\n"
+        "    P.alpha().assemble_condense()\n"
+        "    P.csr_numeric()\n"
+        "    nnz, nr = P.csr_sizes.nnz, P.csr_sizes.n_rows\n"
+        "    v0, b0 = P.vals[:nnz].clone(), P.rhs[:nr].clone()\n"
+        "    for rep in range(3):\n"
+        "        P.vals.fill_(float('nan')); P.rhs.fill_(float('nan'))\n"
+        "        P.assemble_condense_csr()\n"
+        "        torch.cuda.synchronize()\n"
+        "        assert torch.equal(P.vals[:nnz], v0) and torch.equal(P.rhs[:nr], b0), (n, order, rep)\n"
+        "    P.close()\n"
+        "print('variant ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stderr[-2000:]
