@@ -1,5 +1,5 @@
 """bench.py's output contract, checked on the CPU: the argument surface the driver uses, the reference arm's line shape, and the
-last recorded GPU line (profiles/r02j_bench_1gpu_4M.json) against the key set the task's measurement section asks for."""
+last recorded GPU line (profiles/r02l_bench_1gpu_4M.json) against the key set the task's measurement section asks for."""
 import json
 import os
 import subprocess
@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_recorded_line_has_every_contract_key():
-    line = json.loads(open(os.path.join(ROOT, "profiles", "r02j_bench_1gpu_4M.json")).read().strip().splitlines()[-1])
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r02l_bench_1gpu_4M.json")).read().strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in line, k
